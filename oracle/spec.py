@@ -1,0 +1,342 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement (numpy, fp64) of the reference's
+cross-modal contrastive + retrieval-scoring hot path.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module, and only as the checker; the product
+(vast_b200/) never imports anything under oracle/.
+
+Parity status: the reference ships NO tests, golden vectors or fixtures for this
+path, so the oracle is pinned by *running the reference
+itself* in the authoring container: oracle/make_golden.py drives the reference's
+own `VAST.forward_ret`, `refine_score_matrix`, `compute_metric_ret`,
+`concat_all_gather` and `ddp_allgather` on seeded inputs and commits
+inputs + outputs under tests/golden/; tests/test_oracle_golden.py checks every
+function below against those vectors.
+
+Every function cites the reference lines it restates (paths relative to the
+reference root).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# ----------------------------------------------------------------------------
+# feature build: pool -> concat -> Linear -> L2 normalise
+# ----------------------------------------------------------------------------
+
+
+def pool_vision_for_contra(feature, encoder_type="evaclip"):
+    """model/general_module.py:426-435. feature [b, n, tokens, c] -> [b, c].
+    clip/evaclip: cls token (index 0) then frame mean; swin: token mean then frame mean."""
+    f = np.asarray(feature, dtype=np.float64)
+    if encoder_type.startswith("clip") or encoder_type.startswith("evaclip"):
+        f = f[:, :, 0]
+    elif encoder_type.startswith("swin"):
+        f = f.mean(axis=2)
+    return f.mean(axis=1)
+
+
+def pool_text_for_contra(feature):
+    """model/general_module.py:438-439. [b, L, c] -> cls token [b, c]."""
+    return np.asarray(feature, dtype=np.float64)[:, 0]
+
+
+def pool_audio_for_contra(feature, encoder_type="beats"):
+    """model/general_module.py:441-449. ast: cls token; beats: token mean; then clip mean."""
+    f = np.asarray(feature, dtype=np.float64)
+    if encoder_type.startswith("ast"):
+        f = f[:, :, 0]
+    elif encoder_type.startswith("beats"):
+        f = f.mean(axis=2)
+    else:
+        raise NotImplementedError
+    return f.mean(axis=1)
+
+
+def l2_normalize(x, eps=1e-12):
+    """F.normalize(x, dim=-1) as used at model/vast.py:225-278: x / max(||x||_2, eps)."""
+    x = np.asarray(x, dtype=np.float64)
+    n = np.sqrt((x * x).sum(axis=-1, keepdims=True))
+    return x / np.maximum(n, eps)
+
+
+def fuse_feature(pooled, weight, bias=None):
+    """model/vast.py:269-279 (feat_vas; :254-266 for va/vs, :221-247 single modality):
+    torch.cat(pooled, dim=1) -> Linear(weight [D, sum_dims], bias) -> F.normalize."""
+    x = np.concatenate([np.asarray(p, dtype=np.float64) for p in pooled], axis=1)
+    y = x @ np.asarray(weight, dtype=np.float64).T
+    if bias is not None:
+        y = y + np.asarray(bias, dtype=np.float64)
+    return l2_normalize(y)
+
+
+# ----------------------------------------------------------------------------
+# OMC / ITC loss (label-smoothed bidirectional softmax CE) and its backward
+# ----------------------------------------------------------------------------
+
+
+def _lse(z):
+    m = z.max(axis=1, keepdims=True)
+    return (m + np.log(np.exp(z - m).sum(axis=1, keepdims=True)))[:, 0]
+
+
+def omc_loss(feat_cond, feat_t, feat_t_all, feat_cond_all, contra_temp, rank=0,
+             label_smoothing=0.1, grad_out=1.0):
+    """model/vast.py:405-415 + autograd.
+
+    sim_cond2t = feat_cond @ feat_t_all.T / temp ; sim_t2cond = feat_t @ feat_cond_all.T / temp
+    targets = rank*bs + arange(bs) ; loss = (CE_eps(sim_cond2t) + CE_eps(sim_t2cond)) / 2
+    CE_eps(z)_i = lse_i - (1-eps) z_iy - (eps/C) sum_j z_ij   (== F.cross_entropy(label_smoothing=eps))
+    Gradients flow only to the local rows and to temp (gathered side is no_grad,
+    utils/distributed.py:50).
+    """
+    fc = np.asarray(feat_cond, dtype=np.float64)
+    ft = np.asarray(feat_t, dtype=np.float64)
+    kt = np.asarray(feat_t_all, dtype=np.float64)
+    kc = np.asarray(feat_cond_all, dtype=np.float64)
+    tau = float(contra_temp)
+    eps = float(label_smoothing)
+    bs = fc.shape[0]
+    C = kt.shape[0]
+    y = rank * bs + np.arange(bs)
+    out = {}
+    total = 0.0
+    dtau = 0.0
+    for name, q, k in (("cond2t", fc, kt), ("t2cond", ft, kc)):
+        z = (q @ k.T) / tau
+        lse = _lse(z)
+        zy = z[np.arange(bs), y]
+        ce = lse - (1.0 - eps) * zy - (eps / C) * z.sum(axis=1)
+        total += ce.mean()
+        p = np.exp(z - lse[:, None])
+        ysm = np.full_like(p, eps / C)
+        ysm[np.arange(bs), y] += 1.0 - eps
+        dz = (p - ysm) * (grad_out / (2.0 * bs))
+        out["grad_" + ("cond" if name == "cond2t" else "t")] = (dz @ k) / tau
+        dtau += -(dz * z).sum() / tau
+        out["sim_" + name] = z
+        out["lse_" + name] = lse
+    out["loss"] = total / 2.0
+    out["grad_temp"] = dtau
+    return out
+
+
+def hardneg_weights(sim, rank, floor=1e-4):
+    """model/vast.py:423-427: softmax(sim, 1) + 1e-4, own block's diagonal zeroed."""
+    z = np.asarray(sim, dtype=np.float64)
+    bs = z.shape[0]
+    w = np.exp(z - _lse(z)[:, None]) + floor
+    w[np.arange(bs), rank * bs + np.arange(bs)] = 0.0
+    return w
+
+
+def exp_race_sample(weights, expo):
+    """model/vast.py:430,437: torch.multinomial(w[b], 1).  ATen draws
+    argmax_j w_j / E_j with E_j ~ Exp(1) (same distribution as inverse-CDF
+    sampling); given the noise E explicitly the draw is a deterministic argmax
+    (first index on ties)."""
+    key = np.asarray(weights, dtype=np.float64) / np.asarray(expo, dtype=np.float64)
+    return key.argmax(axis=1)
+
+
+# Philox4x32-10 counter-based generator (Salmon et al. 2011); restated so the
+# CPU can reproduce the exact uniforms the CUDA sampler draws.
+_PH_M0 = np.uint64(0xD2511F53)
+_PH_M1 = np.uint64(0xCD9E8D57)
+_PH_W0 = np.uint32(0x9E3779B9)
+_PH_W1 = np.uint32(0xBB67AE85)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised Philox4x32-10; all inputs uint32 arrays (broadcastable). Returns 4 uint32 arrays."""
+    c0, c1, c2, c3 = [np.asarray(c, dtype=np.uint32) for c in (c0, c1, c2, c3)]
+    c0, c1, c2, c3 = np.broadcast_arrays(c0, c1, c2, c3)
+    k0 = np.uint32(k0)
+    k1 = np.uint32(k1)
+    mask = np.uint64(0xFFFFFFFF)
+    with np.errstate(over="ignore"):
+        for _ in range(10):
+            p0 = _PH_M0 * c0.astype(np.uint64)
+            p1 = _PH_M1 * c2.astype(np.uint64)
+            hi0 = (p0 >> np.uint64(32)).astype(np.uint32)
+            lo0 = (p0 & mask).astype(np.uint32)
+            hi1 = (p1 >> np.uint64(32)).astype(np.uint32)
+            lo1 = (p1 & mask).astype(np.uint32)
+            c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+            k0 = np.uint32((int(k0) + int(_PH_W0)) & 0xFFFFFFFF)
+            k1 = np.uint32((int(k1) + int(_PH_W1)) & 0xFFFFFFFF)
+    return c0, c1, c2, c3
+
+
+def sampler_uniforms(seed, offset, stream, rows, cols, row0=0):
+    """The uniforms the CUDA hard-negative sampler uses for element (row, col):
+    counter = (col >> 2, row, stream, offset), key = (seed lo32, seed hi32),
+    word = col & 3, u = ((x >> 8) + 0.5) * 2^-24 in (0, 1)."""
+    r = (np.arange(rows, dtype=np.uint32) + np.uint32(row0))[:, None]
+    cg = (np.arange((cols + 3) // 4, dtype=np.uint32))[None, :]
+    out = philox4x32_10(cg, r, np.uint32(stream), np.uint32(offset),
+                        seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    x = np.stack(out, axis=-1).reshape(rows, -1)[:, :cols]
+    return ((x >> np.uint32(8)).astype(np.float64) + 0.5) * (2.0 ** -24)
+
+
+def sampler_expo(seed, offset, stream, rows, cols, row0=0):
+    """E = -ln(u) for the uniforms above (Exp(1) race noise)."""
+    return -np.log(sampler_uniforms(seed, offset, stream, rows, cols, row0))
+
+
+def gather_negatives(condition_feats, condition_feats_collate, input_ids, attention_mask,
+                     input_ids_collate, attention_mask_collate, neg_idx_t2cond, neg_idx_cond2t):
+    """model/vast.py:429-448: rows picked by the sampled indices and the 3-way concats
+    input_ids_1 = cat(ids, ids, ids_neg), attention_mask_1 likewise,
+    condition_feats = cat(cond, cond_neg, cond)."""
+    cond_neg = np.asarray(condition_feats_collate)[np.asarray(neg_idx_t2cond)]
+    ids_neg = np.asarray(input_ids_collate)[np.asarray(neg_idx_cond2t)]
+    att_neg = np.asarray(attention_mask_collate)[np.asarray(neg_idx_cond2t)]
+    ids1 = np.concatenate([input_ids, input_ids, ids_neg], axis=0)
+    att1 = np.concatenate([attention_mask, attention_mask, att_neg], axis=0)
+    cond3 = np.concatenate([condition_feats, cond_neg, condition_feats], axis=0)
+    return ids1, att1, cond3
+
+
+# ----------------------------------------------------------------------------
+# retrieval: similarity, top-k, metrics, ITM re-rank bookkeeping
+# ----------------------------------------------------------------------------
+
+
+def score_matrix(feat_t, feat_cond):
+    """evaluation/evaluation_mm.py:223: feat_t @ feat_cond.T (no temperature)."""
+    return np.asarray(feat_t, dtype=np.float64) @ np.asarray(feat_cond, dtype=np.float64).T
+
+
+def score_matrix_f64_lane_order(feat_t, feat_cond, chunk=256):
+    """Exact-mode scores in the *defined* summation order of the CUDA fp64 re-score
+    kernel (vast_b200/csrc/retrieval.cu, rescore_f64): products of two fp32 values are
+    exact in fp64; lane l of a warp accumulates k = l, l+32, ... in increasing k;
+    lanes are combined by the xor-butterfly 16, 8, 4, 2, 1.  Bit-identical to the GPU."""
+    a = np.asarray(feat_t, dtype=np.float32).astype(np.float64)
+    b = np.asarray(feat_cond, dtype=np.float32).astype(np.float64)
+    nt, d = a.shape
+    nv = b.shape[0]
+    dp = (d + 31) // 32 * 32
+    if dp != d:
+        a = np.pad(a, ((0, 0), (0, dp - d)))
+        b = np.pad(b, ((0, 0), (0, dp - d)))
+    out = np.empty((nt, nv), dtype=np.float64)
+    a3 = a.reshape(nt, dp // 32, 32)
+    b3 = b.reshape(nv, dp // 32, 32)
+    for i0 in range(0, nt, chunk):
+        ai = a3[i0:i0 + chunk]
+        acc = np.zeros((ai.shape[0], nv, 32), dtype=np.float64)
+        for s in range(dp // 32):
+            acc = acc + ai[:, None, s, :] * b3[None, :, s, :]
+        for h in (16, 8, 4, 2, 1):
+            acc = acc[..., :h] + acc[..., h:2 * h]
+        out[i0:i0 + chunk] = acc[..., 0]
+    return out
+
+
+def topk_ties(score, k, axis=1):
+    """evaluation/evaluation_mm.py:257,259 `topk(k)`.  torch leaves tie order unspecified;
+    ours is (score descending, index ascending).  Returns (values, indices)."""
+    s = np.asarray(score)
+    if axis == 0:
+        v, i = topk_ties(s.T, k, axis=1)
+        return v.T, i.T
+    order = np.argsort(-s, axis=1, kind="stable")[:, :k]
+    return np.take_along_axis(s, order, axis=1), order
+
+
+def rank_of_gt(score, gt_col):
+    """Rank the gt column would get in a stable descending sort of each row
+    (evaluation_mm.py:333-338: `indice_matrix[i].index(gt_indice)`), lower index first on ties."""
+    s = np.asarray(score)
+    g = s[np.arange(s.shape[0]), gt_col][:, None]
+    cols = np.arange(s.shape[1])[None, :]
+    return ((s > g) | ((s == g) & (cols < np.asarray(gt_col)[:, None]))).sum(axis=1)
+
+
+def compute_metric_ret(score_matrix_, ids, ids_txt, direction="forward"):
+    """evaluation/evaluation_mm.py:326-380, same return dict (values rounded to 0.1).
+    forward: rank of ids.index(ids_txt[i]) in row i; backward: min rank over all texts whose
+    id equals the video id (multi-caption), ranking down columns."""
+    s = np.asarray(score_matrix_)
+    assert s.shape == (len(ids_txt), len(ids))
+    first = {}
+    for j, v in enumerate(ids):
+        first.setdefault(v, j)  # list.index returns the first occurrence
+    if direction == "forward":
+        gt = np.array([first[t] for t in ids_txt])
+        rank = rank_of_gt(s, gt)
+        n = len(ids_txt)
+        tag = "forward"
+    else:
+        st = s.T
+        rank = np.empty(len(ids), dtype=np.int64)
+        ids_txt_arr = list(ids_txt)
+        for i, v in enumerate(ids):
+            gts = [t for t, tv in enumerate(ids_txt_arr) if tv == v]
+            rank[i] = min(rank_of_gt(st[i:i + 1], np.array([g]))[0] for g in gts)
+        n = len(ids)
+        tag = "backward"
+    r1 = int((rank < 1).sum()) / n
+    r5 = int((rank < 5).sum()) / n
+    r10 = int((rank < 10).sum()) / n
+    return {
+        f"{tag}_r1": round(r1 * 100, 1),
+        f"{tag}_recall": f"{round(r1 * 100, 1)}/{round(r5 * 100, 1)}/{round(r10 * 100, 1)}",
+        f"{tag}_ravg": round((r1 + r5 + r10) / 3 * 100, 1),
+    }
+
+
+def refine_score_matrix(condition_feats_per_rank, input_ids, attention_mask, score_matrix_t_cond,
+                        slice_scorer, itm_rerank_num, direction="forward", small_batch=25):
+    """evaluation/evaluation_mm.py:253-319 restated for ALL ranks at once.
+
+    condition_feats_per_rank: list (one entry per rank) of [Nv_r, S, H] arrays (each rank
+    holds only its own videos, :274-286).  For every video column with at least one
+    candidate, the candidate texts (top-k by row for 'forward', by column for 'backward')
+    are scored by `slice_scorer(cond[b,S,H], ids[b,L], mask[b,L]) -> [b]` in chunks of 25
+    (:302) and scattered; everything else stays 0.  Returns the [Nt, Nv] matrix the
+    final ddp_allgather(...).T assembles (:317)."""
+    s = np.asarray(score_matrix_t_cond)
+    nt, nv = s.shape
+    k = itm_rerank_num
+    mask = np.zeros((nt, nv), dtype=bool)
+    if direction == "forward":
+        _, idx = topk_ties(s, k, axis=1)
+        mask[np.arange(nt)[:, None], idx] = True
+    else:
+        _, idx = topk_ties(s, k, axis=0)
+        mask[idx, np.arange(nv)[None, :]] = True
+    out = np.zeros((nt, nv), dtype=np.float64)
+    col = 0
+    for cond in condition_feats_per_rank:
+        for i in range(len(cond)):
+            rows = np.nonzero(mask[:, col])[0]
+            if len(rows):
+                vals = []
+                for c0 in range(0, len(rows), small_batch):
+                    r = rows[c0:c0 + small_batch]
+                    c = np.broadcast_to(np.asarray(cond[i])[None], (len(r),) + np.asarray(cond[i]).shape)
+                    vals.append(np.asarray(slice_scorer(c, np.asarray(input_ids)[r], np.asarray(attention_mask)[r])))
+                out[rows, col] = np.concatenate(vals)
+            col += 1
+    assert col == nv
+    return out
+
+
+# ----------------------------------------------------------------------------
+# collectives (semantics only)
+# ----------------------------------------------------------------------------
+
+
+def concat_all_gather(per_rank):
+    """utils/distributed.py:50-66: concatenate equal-shaped per-rank tensors in rank order."""
+    return np.concatenate([np.asarray(x) for x in per_rank], axis=0)
+
+
+def ddp_allgather(per_rank):
+    """utils/distributed.py:133-149: ragged all-gather (pad to max, gather, trim) ==
+    concatenation of the ragged per-rank tensors in rank order."""
+    return np.concatenate([np.asarray(x) for x in per_rank], axis=0)
