@@ -1,0 +1,221 @@
+/*
+ * vast_b200 -- C-ABI of the B200-native (sm_100a) cross-modal contrastive + retrieval-scoring
+ * hot path of VAST.  Loaded with ctypes from Python (vast_b200/_lib.py); no torch types, no
+ * C++ types, plain pointers and sizes only.
+ *
+ * The reference (DelusionalLogic/VAST) is pure Python/PyTorch and has no FFI of its own: the
+ * "interface each entry point replaces" is therefore the block of reference Python lines cited
+ * beside it (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the library never allocates, frees or synchronises: outputs and workspace are caller
+ *     allocated (query the *_workspace_bytes function), work is only enqueued on `stream`;
+ *   - returns VAST_OK (0) or a negative vast_status; vast_last_error_string() describes the last
+ *     failure on the calling thread.  Nothing throws, nothing exits;
+ *   - stateless and re-entrant; one host thread per GPU (one process per GPU).
+ */
+#ifndef VAST_B200_H_
+#define VAST_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VAST_B200_VERSION 100
+
+#if defined(__GNUC__)
+#define VAST_API __attribute__((visibility("default")))
+#else
+#define VAST_API
+#endif
+
+typedef struct CUstream_st* vast_stream_t; /* == cudaStream_t */
+
+typedef enum { VAST_F32 = 0, VAST_BF16 = 1, VAST_F16 = 2 } vast_dtype;
+
+typedef enum {
+  VAST_OK = 0,
+  VAST_ERR_INVALID = -1,     /* bad argument (null pointer, misaligned, inconsistent sizes) */
+  VAST_ERR_UNSUPPORTED = -2, /* shape / dtype outside what the kernels support            */
+  VAST_ERR_CUDA = -3,        /* a CUDA runtime / driver call failed                        */
+  VAST_ERR_WORKSPACE = -4    /* workspace too small                                        */
+} vast_status;
+
+VAST_API int vast_version(void);
+VAST_API const char* vast_last_error_string(void);
+VAST_API int vast_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Feature build: pool -> concat -> (Linear stays cuBLAS) -> L2 normalise
+ * ---------------------------------------------------------------------------------------- */
+
+/* pool_vision_for_contra + pool_audio_for_contra + pool_text_for_contra + torch.cat(dim=1)
+ * (model/general_module.py:426-449, model/vast.py:269-275) in one pass.
+ * Each modality may be absent (NULL).  vision [bs, n_v, tok_v, c_v], audio [bs, n_a, tok_a, c_a],
+ * subtitle [bs, tok_s, c_s], all contiguous, dtype `dtype`.
+ * *_mode: 0 = take token 0 ("cls": clip/evaclip vision, ast audio, text), 1 = mean over tokens
+ * (swin vision, beats audio); then mean over frames/clips.
+ * out [bs, c_v + c_a + c_s] (dtype out_dtype, leading dimension ldo) = concat of the pooled rows. */
+VAST_API int vast_pool_concat(const void* vision, int64_t n_v, int64_t tok_v, int64_t c_v, int vision_mode,
+                     const void* audio, int64_t n_a, int64_t tok_a, int64_t c_a, int audio_mode,
+                     const void* subtitle, int64_t tok_s, int64_t c_s, int dtype, int64_t bs,
+                     void* out, int out_dtype, int64_t ldo, vast_stream_t stream);
+
+/* Backward of vast_pool_concat: grad_out [bs, c_v+c_a+c_s] (f32) -> dense grads of the encoder
+ * outputs (same shapes/dtype as the inputs; every element written, zeros where no gradient). */
+VAST_API int vast_pool_concat_bwd(const float* grad_out, int64_t ldg, int64_t bs,
+                         void* grad_vision, int64_t n_v, int64_t tok_v, int64_t c_v, int vision_mode,
+                         void* grad_audio, int64_t n_a, int64_t tok_a, int64_t c_a, int audio_mode,
+                         void* grad_subtitle, int64_t tok_s, int64_t c_s, int dtype, vast_stream_t stream);
+
+/* F.normalize(x, dim=-1): y = x / max(||x||_2, eps)  (model/vast.py:225,232,239,246,257,267,278).
+ * x [rows, dim] (dtype x_dtype, leading dim ldx).  Any of the outputs may be NULL:
+ *   y_f32 [rows, dim] (ld ldy), y_16 (bf16, ld ld16; e.g. straight into the all-gather send
+ *   slot), inv_norm [rows] (1 / max(||x||, eps), saved for backward). */
+VAST_API int vast_l2norm(const void* x, int x_dtype, int64_t rows, int64_t dim, int64_t ldx, float eps,
+                float* y_f32, int64_t ldy, void* y_16, int64_t ld16, float* inv_norm, vast_stream_t stream);
+
+/* Backward of F.normalize: dx = inv_norm * (g - y * <g, y>)  (rows whose norm was clamped by eps
+ * get dx = g * inv_norm, like ATen). */
+VAST_API int vast_l2norm_bwd(const float* grad_y, int64_t ldg, const float* y, int64_t ldy, const float* inv_norm,
+                    int64_t rows, int64_t dim, float eps, float* grad_x, int64_t ldgx, vast_stream_t stream);
+
+/* Pack the two local feature blocks into the 16-bit all-gather send buffer:
+ * pack[b, 0:D] = bf16(feat_t[b]), pack[b, D:2D] = bf16(feat_cond[b])   (pack is [bs, 2D]).
+ * Replaces the two separate concat_all_gather payloads of model/vast.py:395,404 by one. */
+VAST_API int vast_pack_pair(const void* feat_t, const void* feat_cond, int dtype, int64_t bs, int64_t dim,
+                   int64_t ld_in, void* pack_bf16, vast_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * OMC / ITC contrastive loss + hard-negative sampling + backward   (model/vast.py:405-440)
+ * ---------------------------------------------------------------------------------------- */
+
+VAST_API size_t vast_omc_workspace_bytes(int64_t bs, int64_t n_total, int64_t dim, int need_sample, int need_grad);
+
+/* One fused contrastive step on this rank's rows.
+ *   pack        [n_total, 2*dim] bf16, row n = (feat_t_all[n] | feat_cond_all[n]) in rank order
+ *               (the output of all_gather_into_tensor over vast_pack_pair buffers); the local
+ *               rows are rows [row_offset, row_offset + bs)   (row_offset = rank * bs).
+ *   loss        [1]  f32: (CE_eps(cond2t) + CE_eps(t2cond)) / 2          (vast.py:412-415)
+ *   neg_idx     [2, bs] int64 or NULL: [0] = negative TEXT index per row drawn from
+ *               softmax(sim_cond2t)+floor, [1] = negative CONDITION index drawn from
+ *               softmax(sim_t2cond)+floor, own positive excluded  (vast.py:423-440).
+ *               Draw = argmax_j w_j / E_j, E ~ Exp(1) from Philox4x32-10(seed, offset) -- the same
+ *               distribution as torch.multinomial(w, 1).  debug_noise [2, bs, n_total] f32 (or
+ *               NULL) replaces the generator's E (index 0 = cond2t) for index-exact tests.
+ *   grad_cond, grad_t [bs, dim] f32, grad_temp [1] f32 (all three or none): d loss / d input
+ *               (unit upstream gradient; gathered side carries no gradient, utils/distributed.py:50).
+ *   lse         [2, bs] f32 or NULL: natural-log row log-sum-exp of (cond2t, t2cond).
+ * The [bs, n_total] logit matrices are never written to HBM. */
+VAST_API int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int64_t dim, int64_t row_offset,
+                  float contra_temp, float label_smoothing, float weight_floor,
+                  uint64_t seed, uint64_t offset, const float* debug_noise,
+                  float* loss, int64_t* neg_idx, float* grad_cond, float* grad_t, float* grad_temp,
+                  float* lse, void* workspace, size_t workspace_bytes, vast_stream_t stream);
+
+/* Negative gather + 3-way concat (model/vast.py:432-448):
+ *   ids_out  [3bs, L]  = cat(ids_local, ids_local, ids_all[neg_text])          (int64)
+ *   mask_out [3bs, L]  = cat(mask_local, mask_local, mask_all[neg_text])       (int64)
+ *   cond_out [3bs, S*H] = cat(cond_local, cond_all[neg_cond], cond_local)      (elem_bytes each)
+ * neg_text / neg_cond are the [bs] int64 rows of vast_omc_step's neg_idx ([0] / [1]).
+ * row_bytes_cond = S*H*elem_bytes must be a multiple of 16. */
+VAST_API int vast_gather_rows_concat3(const int64_t* ids_local, const int64_t* mask_local, const int64_t* ids_all,
+                             const int64_t* mask_all, int64_t L, const void* cond_local, const void* cond_all,
+                             int64_t row_bytes_cond, const int64_t* neg_text, const int64_t* neg_cond,
+                             int64_t bs, int64_t n_total, int64_t* ids_out, int64_t* mask_out, void* cond_out,
+                             vast_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Retrieval scoring   (evaluation/evaluation_mm.py:223,253-380)
+ * ---------------------------------------------------------------------------------------- */
+
+typedef enum {
+  VAST_SIM_BF16 = 0,    /* bf16 inputs, fp32 accumulate on tensor cores                         */
+  VAST_SIM_FP32X3 = 1   /* fp32 inputs split into 3 bf16 terms (6 tensor-core products): fp32-  */
+                        /* grade scores for the exact-ranking pipeline                           */
+} vast_sim_mode;
+
+/* Build the 16-bit tensor-core operand of `x` [rows, dim] (f32 or bf16 input).
+ * mode BF16:   out [rows, dim] bf16.
+ * mode FP32X3: out [rows, 6*dim] bf16; as_query != 0 lays the three split terms out as
+ *              (hi, hi, mid, mid, hi, lo), otherwise as (hi, mid, hi, mid, lo, hi), so that the dot
+ *              product of a query row and a key row sums the six leading cross terms. */
+VAST_API int64_t vast_sim_operand_cols(int64_t dim, int mode);
+VAST_API int vast_sim_pack_operand(const void* x, int x_dtype, int64_t rows, int64_t dim, int64_t ldx, int mode,
+                          int as_query, void* out, vast_stream_t stream);
+
+VAST_API size_t vast_sim_topk_workspace_bytes(int64_t n_q, int64_t n_k, int64_t cols, int64_t k);
+
+/* Streaming similarity + top-k: for every query row i the k best key rows by
+ * (score descending, index ascending) of  q_op[i] . k_op[j], never materialising [n_q, n_k]
+ * (replaces evaluation_mm.py:223 + :257/:259 `score.topk(k)`).  q_op / k_op are packed operands
+ * ([n_q, cols], [n_k, cols] bf16).  Key indices are reported as col_offset + j (column shards).
+ * out_keys [n_q, k] uint64 sortable keys (see vast_topk_unpack); unused tail entries are 0. */
+VAST_API int vast_sim_topk(const void* q_op, const void* k_op, int64_t n_q, int64_t n_k, int64_t cols, int64_t k,
+                  int64_t col_offset, uint64_t* out_keys, void* workspace, size_t workspace_bytes,
+                  vast_stream_t stream);
+
+/* k-way merge of `parts` candidate lists per row ([parts, n_q, k_in] keys, e.g. the all-gather
+ * of every rank's vast_sim_topk output) into the global top-k_out (score desc, index asc). */
+VAST_API int vast_topk_merge(const uint64_t* keys_in, int64_t parts, int64_t n_q, int64_t k_in, int64_t k_out,
+                    uint64_t* keys_out, vast_stream_t stream);
+
+/* keys -> (values f32, indices i32); empty slots give value -inf, index -1. */
+VAST_API int vast_topk_unpack(const uint64_t* keys, int64_t count, float* values, int32_t* indices, vast_stream_t stream);
+
+/* Exact re-scoring of candidate lists: score64[i, c] = sum_k (double)q[i,k] * (double)kk[idx[i,c],k]
+ * in a fixed summation order (lane-strided partials, xor-butterfly), then each row is sorted by
+ * (score desc, index asc).  idx entries < 0 are ignored (sorted last).  q, kk are fp32.
+ * key_offset is subtracted from idx to address `kk` (column shards). */
+VAST_API int vast_rescore_f64(const float* q, int64_t ldq, const float* kk, int64_t ldk, int64_t n_q, int64_t dim,
+                     int32_t* idx /* in/out [n_q, k] */, int64_t k, int64_t key_offset,
+                     double* score64 /* out [n_q, k] */, vast_stream_t stream);
+
+/* Brute-force exact fp64 top-k for the listed rows (fallback of the exact pipeline when the
+ * shortlist cannot be proven complete).  rows_list [n_rows] int32. */
+VAST_API int vast_exact_topk_rows(const float* q, int64_t ldq, const float* kk, int64_t ldk, int64_t n_k, int64_t dim,
+                         const int32_t* rows_list, int64_t n_rows, int64_t k, int64_t col_offset,
+                         int32_t* idx_out /* [n_q, k] rows addressed by rows_list */, double* score_out,
+                         vast_stream_t stream);
+
+/* top-k of an already materialised fp32 score matrix along rows (axis=1) or columns (axis=0),
+ * ties broken by lower index -- the drop-in for `score_matrix.topk(k, dim)` at
+ * evaluation_mm.py:257/:259 when the caller hands refine_score_matrix a dense matrix.
+ * idx_out: axis=1 -> [n_rows, k]; axis=0 -> [k, n_cols]  (int32). */
+VAST_API int vast_dense_topk(const float* score, int64_t n_rows, int64_t n_cols, int64_t ld, int64_t k, int axis,
+                    int32_t* idx_out, float* val_out, vast_stream_t stream);
+
+/* Rank of the ground-truth column in a stable descending sort of each row of an fp32 matrix
+ * (evaluation_mm.py:333-338: sort + list.index), lower index first on ties. */
+VAST_API int vast_dense_rank_of_gt(const float* score, int64_t n_rows, int64_t n_cols, int64_t ld, int axis,
+                          const int32_t* gt, int64_t n_gt, int32_t* rank_out, vast_stream_t stream);
+
+/* Candidate bookkeeping for the ITM re-rank (evaluation_mm.py:264-314 without the dense mask):
+ * bucket the (text, video) candidate pairs by video.  text_idx/video_idx [n_pairs] int32
+ * (video_idx < 0 = empty slot).  Outputs: counts/offsets [n_videos+1] (CSR), order [n_pairs]
+ * = text indices grouped by video, ascending inside a video.  workspace: n_videos+1 int32. */
+VAST_API int vast_bucket_by_video(const int32_t* text_idx, const int32_t* video_idx, int64_t n_pairs, int64_t n_videos,
+                         int32_t* offsets, int32_t* texts_sorted, void* workspace, size_t workspace_bytes,
+                         vast_stream_t stream);
+
+/* out[text, video] = score for every pair (evaluation_mm.py:313); out is pre-zeroed by the caller. */
+VAST_API int vast_scatter_scores(const int32_t* text_idx, const int32_t* video_idx, const float* scores, int64_t n_pairs,
+                        float* out, int64_t ld, vast_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Generic tensor-core NT GEMM (unit-test / building block): C[m, n] = alpha * sum_k A[m,k] B[n,k]
+ * A [M, K], B [N, K] 16-bit (dtype bf16 or f16) with leading dims lda/ldb (multiples of 8), C f32.
+ * ---------------------------------------------------------------------------------------- */
+VAST_API size_t vast_gemm_nt_workspace_bytes(int64_t M, int64_t N, int64_t K);
+VAST_API int vast_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, int dtype, int64_t M, int64_t N,
+                 int64_t K, float alpha, float* C, int64_t ldc, void* workspace, size_t workspace_bytes,
+                 vast_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAST_B200_H_ */

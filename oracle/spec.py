@@ -168,21 +168,23 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
-def sampler_uniforms(seed, offset, stream, rows, cols, row0=0):
-    """The uniforms the CUDA hard-negative sampler uses for element (row, col):
-    counter = (col >> 2, row, stream, offset), key = (seed lo32, seed hi32),
-    word = col & 3, u = ((x >> 8) + 0.5) * 2^-24 in (0, 1)."""
+def sampler_bits(seed, offset, stream, rows, cols, row0=0):
+    """The 32-bit Philox words the CUDA hard-negative sampler (vast_b200/csrc/omc.cu, EpiProb)
+    draws for element (row, col) of direction `stream` (0 = cond2t, 1 = t2cond):
+    counter = (col >> 2, row0 + row, offset lo32, (offset hi32 << 1) | stream),
+    key = (seed lo32, seed hi32), word = col & 3.  row0 = rank * bs (global row)."""
     r = (np.arange(rows, dtype=np.uint32) + np.uint32(row0))[:, None]
     cg = (np.arange((cols + 3) // 4, dtype=np.uint32))[None, :]
-    out = philox4x32_10(cg, r, np.uint32(stream), np.uint32(offset),
-                        seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    x = np.stack(out, axis=-1).reshape(rows, -1)[:, :cols]
-    return ((x >> np.uint32(8)).astype(np.float64) + 0.5) * (2.0 ** -24)
+    c3 = ((((int(offset) >> 32) << 1) | int(stream)) & 0xFFFFFFFF)
+    out = philox4x32_10(cg, r, np.uint32(int(offset) & 0xFFFFFFFF), np.uint32(c3),
+                        int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF)
+    return np.stack(out, axis=-1).reshape(rows, -1)[:, :cols]
 
 
 def sampler_expo(seed, offset, stream, rows, cols, row0=0):
-    """E = -ln(u) for the uniforms above (Exp(1) race noise)."""
-    return -np.log(sampler_uniforms(seed, offset, stream, rows, cols, row0))
+    """Exp(1) race noise of the CUDA sampler: v = (x + 0.5) 2^-32, E = -log1p(-v)."""
+    v = (sampler_bits(seed, offset, stream, rows, cols, row0).astype(np.float64) + 0.5) * (2.0 ** -32)
+    return -np.log1p(-v)
 
 
 def gather_negatives(condition_feats, condition_feats_collate, input_ids, attention_mask,

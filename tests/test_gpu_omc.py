@@ -1,0 +1,175 @@
+"""Fused OMC contrastive step (tcgen05 GEMMs with online-LSE / softmax+race epilogues, dQ GEMM)
+vs the oracle (oracle/spec.py, pinned to the reference by tests/golden) through the C-ABI.
+
+Tolerance (BASELINE.json north_star): loss and gradients within 1e-3 relative of the reference
+math evaluated on the SAME bf16-rounded features (bf16-in / fp32-accumulate mode)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import spec
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-3
+
+
+def bf16_round(x):
+    return torch.from_numpy(np.asarray(x, dtype=np.float32)).bfloat16().float().numpy()
+
+
+def run_step(ft_all, fc_all, bs, rank, temp, **kw):
+    from vast_b200 import ops
+    pack = ops.pack_pair(torch.from_numpy(ft_all).cuda(), torch.from_numpy(fc_all).cuda())
+    out = ops.omc_step(pack, bs, rank * bs, temp, **kw)
+    torch.cuda.synchronize()
+    return out
+
+
+def oracle(ft_all, fc_all, bs, rank, temp):
+    ft_r, fc_r = bf16_round(ft_all), bf16_round(fc_all)
+    sl = slice(rank * bs, (rank + 1) * bs)
+    return spec.omc_loss(fc_r[sl], ft_r[sl], ft_r, fc_r, temp, rank=rank)
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def check_against_oracle(out, o, bs):
+    assert abs(out["loss"].item() - o["loss"]) <= RTOL * abs(o["loss"]), (out["loss"].item(), o["loss"])
+    assert rel(out["grad_cond"].cpu().numpy(), o["grad_cond"]) < RTOL
+    assert rel(out["grad_t"].cpu().numpy(), o["grad_t"]) < RTOL
+    assert abs(out["grad_temp"].item() - o["grad_temp"]) <= RTOL * abs(o["grad_temp"]) + 1e-6
+    lse = out["lse"].cpu().numpy()
+    np.testing.assert_allclose(lse[0], o["lse_cond2t"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(lse[1], o["lse_t2cond"], rtol=1e-4, atol=1e-4)
+
+
+def check_negatives(neg, o, expo, rank, bs, floor=1e-4):
+    """GPU draw must be the oracle's argmax, or a numerical near-tie of it (fp32 vs fp64 keys)."""
+    neg = neg.cpu().numpy()
+    exact = 0
+    for d, name in enumerate(("sim_cond2t", "sim_t2cond")):
+        w = spec.hardneg_weights(o[name], rank, floor)
+        key = w / expo[d]
+        best = key.argmax(axis=1)
+        exact += int((neg[d] == best).sum())
+        got = key[np.arange(bs), neg[d]]
+        assert np.all(got >= key.max(axis=1) * (1 - 2e-3)), (d, np.nonzero(got < key.max(axis=1) * (1 - 2e-3)))
+        assert np.all(neg[d] != rank * bs + np.arange(bs)), "positive sampled as negative"
+    assert exact >= int(0.97 * 2 * bs), exact
+
+
+def test_cfg1_golden_loss_grads_and_reference_negatives(golden):
+    """cfg1 (bs 64, D 512, W 1): loss/grads vs oracle on bf16-rounded inputs and vs the reference's
+    fp32 numbers; with the reference's own Exp(1) noise the sampled negatives reproduce."""
+    g = golden("omc_w1")
+    bs = 64
+    noise = torch.from_numpy(np.ascontiguousarray(g["expo"][::-1])).cuda()  # ours: [0]=cond2t, [1]=t2cond
+    out = run_step(g["feat_t"], g["feat_cond"], bs, 0, float(g["contra_temp"]), debug_noise=noise, want_lse=True)
+    o = oracle(g["feat_t"], g["feat_cond"], bs, 0, float(g["contra_temp"]))
+    check_against_oracle(out, o, bs)
+    # vs the reference run on un-rounded fp32 features: bf16 input rounding only
+    assert abs(out["loss"].item() - float(g["loss_itc"])) < 1e-2 * float(g["loss_itc"])
+    assert rel(out["grad_t"].cpu().numpy(), g["grad_t"]) < 2e-2
+    assert rel(out["grad_cond"].cpu().numpy(), g["grad_cond"]) < 2e-2
+    check_negatives(out["neg_idx"], o, g["expo"][::-1], 0, bs)
+    neg = out["neg_idx"].cpu().numpy()
+    assert (neg[0] == g["neg_cond2t"]).mean() > 0.9 and (neg[1] == g["neg_t2cond"]).mean() > 0.9
+
+
+@pytest.mark.parametrize("rank", [0, 1])
+def test_w2_rank_offsets_golden(golden, rank):
+    g = golden("dist_w2")
+    bs = 16
+    temp = float(g["contra_temp"])
+    noise = torch.from_numpy(np.ascontiguousarray(g[f"r{rank}_expo"][::-1])).cuda()
+    out = run_step(g["feat_t_all"], g["feat_cond_all"], bs, rank, temp, debug_noise=noise, want_lse=True)
+    o = oracle(g["feat_t_all"], g["feat_cond_all"], bs, rank, temp)
+    check_against_oracle(out, o, bs)
+    assert abs(out["loss"].item() - float(g[f"r{rank}_loss_itc"])) < 1e-2 * float(g[f"r{rank}_loss_itc"])
+    check_negatives(out["neg_idx"], o, g[f"r{rank}_expo"][::-1], rank, bs)
+
+
+@pytest.mark.parametrize("bs,world,rank,dim,temp", [(100, 3, 1, 72, 0.07), (1, 1, 0, 8, 0.5), (130, 2, 1, 264, 0.02),
+                                                     (256, 4, 3, 512, 0.07)])
+def test_ragged_shapes_philox(bs, world, rank, dim, temp):
+    n = bs * world
+    gen = torch.Generator().manual_seed(bs + dim)
+    t = torch.nn.functional.normalize(torch.randn(n, dim, generator=gen), dim=-1)
+    c = torch.nn.functional.normalize(t + 0.8 * torch.randn(n, dim, generator=gen), dim=-1)
+    seed, offset = 0x1234567887654321, (7 << 32) | 5
+    out = run_step(t.numpy(), c.numpy(), bs, rank, temp, seed=seed, offset=offset, want_lse=True)
+    o = oracle(t.numpy(), c.numpy(), bs, rank, temp)
+    check_against_oracle(out, o, bs)
+    if n > 1:
+        expo = np.stack([spec.sampler_expo(seed, offset, d, bs, n, row0=rank * bs) for d in (0, 1)])
+        check_negatives(out["neg_idx"], o, expo, rank, bs)
+
+
+def test_cfg3_shape_full_size():
+    """BASELINE cfg3 at W=1: N = 4096, D = 1024 (oracle in fp64 numpy, a few seconds)."""
+    n, dim, temp = 4096, 1024, 0.07
+    gen = torch.Generator().manual_seed(1234)
+    t = torch.nn.functional.normalize(torch.randn(n, dim, generator=gen), dim=-1)
+    c = torch.nn.functional.normalize(t + 0.8 * torch.randn(n, dim, generator=gen), dim=-1)
+    seed, offset = 99, 3
+    out = run_step(t.numpy(), c.numpy(), n, 0, temp, seed=seed, offset=offset, want_lse=True)
+    o = oracle(t.numpy(), c.numpy(), n, 0, temp)
+    check_against_oracle(out, o, n)
+    expo = np.stack([spec.sampler_expo(seed, offset, d, n, n) for d in (0, 1)])
+    check_negatives(out["neg_idx"], o, expo, 0, n)
+    # determinism: same seed/offset -> identical outputs, different offset -> different draws
+    out2 = run_step(t.numpy(), c.numpy(), n, 0, temp, seed=seed, offset=offset)
+    assert torch.equal(out["neg_idx"], out2["neg_idx"]) and torch.equal(out["grad_t"], out2["grad_t"])
+    assert out["loss"].item() == out2["loss"].item()
+    out3 = run_step(t.numpy(), c.numpy(), n, 0, temp, seed=seed, offset=offset + 1)
+    assert (out3["neg_idx"] != out["neg_idx"]).float().mean().item() > 0.3
+
+
+def test_sampler_distribution_chi2():
+    """Distributional parity with torch.multinomial: empirical frequencies over many Philox offsets
+    follow w / sum(w) (chi-square, df = N - 2 per row)."""
+    from vast_b200 import ops
+    bs = n = 8
+    gen = torch.Generator().manual_seed(7)
+    t = torch.nn.functional.normalize(torch.randn(n, 16, generator=gen), dim=-1)
+    c = torch.nn.functional.normalize(t + 1.0 * torch.randn(n, 16, generator=gen), dim=-1)
+    temp = 0.3
+    pack = ops.pack_pair(t.cuda(), c.cuda())
+    draws = 3000
+    counts = np.zeros((2, bs, n))
+    res = []
+    for k in range(draws):
+        res.append(ops.omc_step(pack, bs, 0, temp, seed=42, offset=k, need_grad=False)["neg_idx"])
+    neg = torch.stack(res).cpu().numpy()  # [draws, 2, bs]
+    for d in range(2):
+        for b in range(bs):
+            counts[d, b] = np.bincount(neg[:, d, b], minlength=n)
+    o = oracle(t.numpy(), c.numpy(), bs, 0, temp)
+    for d, name in enumerate(("sim_cond2t", "sim_t2cond")):
+        w = spec.hardneg_weights(o[name], 0)
+        p = w / w.sum(axis=1, keepdims=True)
+        exp = p * draws
+        for b in range(bs):
+            assert counts[d, b, b] == 0
+            m = exp[b] > 0
+            chi2 = ((counts[d, b][m] - exp[b][m]) ** 2 / exp[b][m]).sum()
+            assert chi2 < 35.0, (d, b, chi2)  # df = 6: P(chi2 > 35) ~ 4e-6
+
+
+def test_loss_only_and_errors():
+    from vast_b200 import ops
+    gen = torch.Generator().manual_seed(8)
+    t = torch.nn.functional.normalize(torch.randn(40, 64, generator=gen), dim=-1)
+    c = torch.nn.functional.normalize(t + torch.randn(40, 64, generator=gen), dim=-1)
+    pack = ops.pack_pair(t.cuda(), c.cuda())
+    out = ops.omc_step(pack, 40, 0, 0.07, need_sample=False, need_grad=False)
+    o = oracle(t.numpy(), c.numpy(), 40, 0, 0.07)
+    assert abs(out["loss"].item() - o["loss"]) <= RTOL * abs(o["loss"])
+    with pytest.raises(RuntimeError):
+        ops.omc_step(pack, 40, 8, 0.07)  # local rows outside [0, n_total)
+    with pytest.raises(RuntimeError):
+        ops.omc_step(pack, 40, 0, -1.0)

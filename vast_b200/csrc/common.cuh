@@ -1,0 +1,91 @@
+// Shared host/device helpers for the vast_b200 C-ABI library.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/vast_b200.h"
+
+namespace vast {
+
+void set_last_error(const char* fmt, ...);
+
+#define VAST_REQUIRE(cond, code, ...)    \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::vast::set_last_error(__VA_ARGS__); \
+      return (code);                     \
+    }                                    \
+  } while (0)
+
+#define VAST_CUDA_OK(expr)                                                                         \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      ::vast::set_last_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return VAST_ERR_CUDA;                                                                        \
+    }                                                                                              \
+  } while (0)
+
+// cudaGetLastError after a launch (does not synchronise).
+#define VAST_LAUNCH_OK(name)                                                                \
+  do {                                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess) {                                                                \
+      ::vast::set_last_error("launch of %s failed: %s", name, cudaGetErrorString(_e));      \
+      return VAST_ERR_CUDA;                                                                 \
+    }                                                                                       \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+int device_sm_count();
+
+// Bump allocator over the caller-provided workspace (the library never allocates).
+struct Workspace {
+  char* base;
+  size_t cap;
+  size_t off;
+  Workspace(void* p, size_t n) : base(static_cast<char*>(p)), cap(n), off(0) {}
+  template <class T>
+  T* take(size_t count) {
+    off = align_up(off, 256);
+    T* r = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    return r;
+  }
+  bool ok() const { return base != nullptr ? off <= cap : off == 0; }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// 16-byte streaming load / store (read-once, write-once data).
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream16(void* p, uint4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+}  // namespace vast

@@ -1,0 +1,487 @@
+// HBM-bound kernels of the hot path: pool + concat (+ backward), L2 normalise (+ backward),
+// all-gather send-buffer packing, negative-row gather + 3-way concat.  All coalesced, 128-bit
+// vectorised, warp-shuffle reductions; grids sized so every SM has several CTAs in flight.
+#include "common.cuh"
+
+namespace vast {
+
+// ------------------------------------------------------------------ vector helpers
+template <class T>
+struct Vec;  // 16-byte vector of T <-> floats
+template <>
+struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float (&f)[4]) {
+    const uint4 u = ld_stream16(p);
+    f[0] = __uint_as_float(u.x);
+    f[1] = __uint_as_float(u.y);
+    f[2] = __uint_as_float(u.z);
+    f[3] = __uint_as_float(u.w);
+  }
+  __device__ static void store(float* p, const float (&f)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+template <>
+struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void load(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 u = ld_stream16(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ static void store(__nv_bfloat16* p, const float (&f)[8]) {
+    uint4 u;
+    uint32_t* w = &u.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+template <>
+struct Vec<__half> {
+  static constexpr int N = 8;
+  __device__ static void load(const __half* p, float (&f)[8]) {
+    const uint4 u = ld_stream16(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+  __device__ static void store(__half* p, const float (&f)[8]) {
+    uint4 u;
+    uint32_t* w = &u.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+
+template <class T>
+__device__ __forceinline__ float to_f(T v);
+template <>
+__device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <>
+__device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <class T>
+__device__ __forceinline__ T from_f(float v);
+template <>
+__device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+
+// ------------------------------------------------------------------ pool + concat
+struct PoolSeg {
+  const void* src;  // [bs, n, tok, c]
+  int64_t n, tok, c;
+  int mode;         // 0 = token 0 only, 1 = mean over tokens
+  int64_t out_off;  // column offset in the concat row
+};
+struct PoolParams {
+  PoolSeg seg[3];
+  int64_t bs;
+  void* out;
+  int64_t ldo;
+};
+
+constexpr int POOL_THREADS = 512;
+
+// grid = (bs, 3).  Thread = (vector column, token lane); token lanes stride the (frame, token)
+// list, partial sums are combined through shared memory in a fixed order (deterministic).
+template <class TI, class TO>
+__global__ void __launch_bounds__(POOL_THREADS) pool_concat_kernel(const PoolParams p) {
+  const PoolSeg s = p.seg[blockIdx.y];
+  if (s.src == nullptr) return;
+  constexpr int V = Vec<TI>::N;
+  const int64_t b = blockIdx.x;
+  const int64_t used = s.mode == 0 ? 1 : s.tok;  // tokens that contribute per frame
+  const int64_t count = s.n * used;
+  const bool vec_ok = (s.c % V) == 0;
+  __shared__ float red[POOL_THREADS * 8];
+  const TI* base = static_cast<const TI*>(s.src) + b * s.n * s.tok * s.c;
+  TO* out = static_cast<TO*>(p.out) + b * p.ldo + s.out_off;
+  const float inv = 1.0f / static_cast<float>(count);
+  if (vec_ok) {
+    const int nvec = static_cast<int>(s.c / V);
+    for (int v0 = 0; v0 < nvec; v0 += POOL_THREADS) {  // column super-chunks (c > 512*V only)
+      const int ncol = min(nvec - v0, POOL_THREADS);
+      const int lanes = POOL_THREADS / ncol;  // token lanes
+      const int vc = threadIdx.x % ncol;
+      const int tl = threadIdx.x / ncol;
+      float acc[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] = 0.f;
+      if (tl < lanes) {
+#pragma unroll 4
+        for (int64_t j = tl; j < count; j += lanes) {
+          const int64_t f = j / used, t = j - f * used;
+          float x[V];
+          Vec<TI>::load(base + (f * s.tok + t) * s.c + static_cast<int64_t>(v0 + vc) * V, x);
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc[i] += x[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) red[threadIdx.x * V + i] = acc[i];
+      __syncthreads();
+      if (tl == 0 && vc < ncol) {
+        for (int l = 1; l < lanes; ++l)
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc[i] += red[(l * ncol + vc) * V + i];
+#pragma unroll
+        for (int i = 0; i < V; ++i) out[static_cast<int64_t>(v0 + vc) * V + i] = from_f<TO>(acc[i] * inv);
+      }
+      __syncthreads();
+    }
+  } else {  // scalar fallback for odd channel counts
+    for (int64_t c = threadIdx.x; c < s.c; c += POOL_THREADS) {
+      float a = 0.f;
+      for (int64_t j = 0; j < count; ++j) {
+        const int64_t f = j / used, t = j - f * used;
+        a += to_f<TI>(base[(f * s.tok + t) * s.c + c]);
+      }
+      out[c] = from_f<TO>(a * inv);
+    }
+  }
+}
+
+// Backward: dense gradient of one encoder output, every element written.
+template <class T>
+__global__ void pool_bwd_kernel(const float* __restrict__ g, int64_t ldg, int64_t col_off, T* __restrict__ dst,
+                                int64_t bs, int64_t n, int64_t tok, int64_t c, int mode) {
+  const int64_t total = bs * n * tok * c;
+  const float scale = 1.0f / static_cast<float>(mode == 0 ? n : n * tok);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t ch = i % c;
+    const int64_t t = (i / c) % tok;
+    const int64_t b = i / (c * tok * n);
+    float v = 0.f;
+    if (mode == 1 || t == 0) v = g[b * ldg + col_off + ch] * scale;
+    dst[i] = from_f<T>(v);
+  }
+}
+
+// ------------------------------------------------------------------ L2 normalise
+// One warp per row, two passes over the row (second pass hits L1/L2).
+template <class TI>
+__global__ void __launch_bounds__(128) l2norm_kernel(const TI* __restrict__ x, int64_t rows, int64_t dim, int64_t ldx,
+                                                     float eps, float* __restrict__ y32, int64_t ldy,
+                                                     __nv_bfloat16* __restrict__ y16, int64_t ld16,
+                                                     float* __restrict__ inv_norm) {
+  const int64_t row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const TI* xr = x + row * ldx;
+  float ss = 0.f;
+  for (int64_t c = lane; c < dim; c += 32) {
+    const float v = to_f<TI>(xr[c]);
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  const float denom = fmaxf(sqrtf(ss), eps);
+  if (lane == 0 && inv_norm) inv_norm[row] = 1.0f / denom;
+  for (int64_t c = lane; c < dim; c += 32) {
+    const float v = to_f<TI>(xr[c]) / denom;
+    if (y32) y32[row * ldy + c] = v;
+    if (y16) y16[row * ld16 + c] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void __launch_bounds__(128) l2norm_bwd_kernel(const float* __restrict__ g, int64_t ldg,
+                                                         const float* __restrict__ y, int64_t ldy,
+                                                         const float* __restrict__ inv_norm, int64_t rows, int64_t dim,
+                                                         float eps, float* __restrict__ gx, int64_t ldgx) {
+  const int64_t row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float inv = inv_norm[row];
+  float dot = 0.f;
+  for (int64_t c = lane; c < dim; c += 32) dot = fmaf(g[row * ldg + c], y[row * ldy + c], dot);
+  dot = warp_sum(dot);
+  const bool clamped = inv >= 1.0f / eps;  // ||x|| <= eps: y = x / eps, no projection term
+  for (int64_t c = lane; c < dim; c += 32) {
+    const float gv = g[row * ldg + c];
+    gx[row * ldgx + c] = clamped ? gv * inv : (gv - y[row * ldy + c] * dot) * inv;
+  }
+}
+
+// ------------------------------------------------------------------ all-gather send-buffer packing
+template <class TI>
+__global__ void pack_pair_kernel(const TI* __restrict__ ft, const TI* __restrict__ fc, int64_t bs, int64_t dim,
+                                 int64_t ld, __nv_bfloat16* __restrict__ pack) {
+  const int64_t total = bs * dim;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t b = i / dim, c = i - b * dim;
+    pack[b * 2 * dim + c] = __float2bfloat16_rn(to_f<TI>(ft[b * ld + c]));
+    pack[b * 2 * dim + dim + c] = __float2bfloat16_rn(to_f<TI>(fc[b * ld + c]));
+  }
+}
+
+// ------------------------------------------------------------------ negative gather + 3-way concat
+// Source row r in [0, 2bs): r < bs -> cond_local[r], written to out rows r and r + 2bs (read once,
+// written twice); r >= bs -> cond_all[neg_cond[r - bs]] written to out row r.  Compulsory traffic:
+// 2 reads + 3 writes of a [bs, S*H] block.
+constexpr int GATHER_THREADS = 256;
+constexpr int GATHER_UNROLL = 4;
+__global__ void __launch_bounds__(GATHER_THREADS) gather_cond3_kernel(const uint4* __restrict__ cond_local,
+                                                                     const uint4* __restrict__ cond_all,
+                                                                     const int64_t* __restrict__ neg_cond, int64_t bs,
+                                                                     int64_t n_total, int64_t row_vecs,
+                                                                     uint4* __restrict__ out) {
+  const int64_t r = blockIdx.y;
+  const uint4* src;
+  uint4* dst0 = out + r * row_vecs;
+  uint4* dst1 = nullptr;
+  if (r < bs) {
+    src = cond_local + r * row_vecs;
+    dst1 = out + (r + 2 * bs) * row_vecs;
+  } else {
+    int64_t j = neg_cond[r - bs];
+    j = j < 0 ? 0 : (j >= n_total ? n_total - 1 : j);
+    src = cond_all + j * row_vecs;
+  }
+  const int64_t chunk = static_cast<int64_t>(GATHER_THREADS) * GATHER_UNROLL;
+  for (int64_t base = blockIdx.x * chunk; base < row_vecs; base += gridDim.x * chunk) {
+    uint4 v[GATHER_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GATHER_UNROLL; ++u) {
+      const int64_t i = base + u * GATHER_THREADS + threadIdx.x;
+      if (i < row_vecs) v[u] = ld_stream16(src + i);
+    }
+#pragma unroll
+    for (int u = 0; u < GATHER_UNROLL; ++u) {
+      const int64_t i = base + u * GATHER_THREADS + threadIdx.x;
+      if (i < row_vecs) {
+        st_stream16(dst0 + i, v[u]);
+        if (dst1) st_stream16(dst1 + i, v[u]);
+      }
+    }
+  }
+}
+
+__global__ void gather_ids3_kernel(const int64_t* __restrict__ ids_local, const int64_t* __restrict__ mask_local,
+                                   const int64_t* __restrict__ ids_all, const int64_t* __restrict__ mask_all,
+                                   const int64_t* __restrict__ neg_text, int64_t bs, int64_t n_total, int64_t L,
+                                   int64_t* __restrict__ ids_out, int64_t* __restrict__ mask_out) {
+  const int64_t total = 3 * bs * L;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / L, c = i - r * L;
+    if (r < 2 * bs) {
+      const int64_t s = r < bs ? r : r - bs;
+      ids_out[i] = ids_local[s * L + c];
+      mask_out[i] = mask_local[s * L + c];
+    } else {
+      int64_t j = neg_text[r - 2 * bs];
+      j = j < 0 ? 0 : (j >= n_total ? n_total - 1 : j);
+      ids_out[i] = ids_all[j * L + c];
+      mask_out[i] = mask_all[j * L + c];
+    }
+  }
+}
+
+template <class TI>
+static int launch_pool(const PoolParams& p, int out_dtype, cudaStream_t stream) {
+  dim3 grid(static_cast<unsigned>(p.bs), 3);
+  if (out_dtype == VAST_F32)
+    pool_concat_kernel<TI, float><<<grid, POOL_THREADS, 0, stream>>>(p);
+  else if (out_dtype == VAST_BF16)
+    pool_concat_kernel<TI, __nv_bfloat16><<<grid, POOL_THREADS, 0, stream>>>(p);
+  else
+    pool_concat_kernel<TI, __half><<<grid, POOL_THREADS, 0, stream>>>(p);
+  VAST_LAUNCH_OK("pool_concat");
+  return VAST_OK;
+}
+
+static inline unsigned grid_for(int64_t total, int threads) {
+  const int64_t want = ceil_div64(total, threads);
+  const int64_t cap = static_cast<int64_t>(device_sm_count()) * 16;
+  return static_cast<unsigned>(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+}  // namespace vast
+
+using namespace vast;
+
+extern "C" int vast_pool_concat(const void* vision, int64_t n_v, int64_t tok_v, int64_t c_v, int vision_mode,
+                                const void* audio, int64_t n_a, int64_t tok_a, int64_t c_a, int audio_mode,
+                                const void* subtitle, int64_t tok_s, int64_t c_s, int dtype, int64_t bs, void* out,
+                                int out_dtype, int64_t ldo, vast_stream_t stream) {
+  VAST_REQUIRE(out != nullptr && bs >= 0, VAST_ERR_INVALID, "pool_concat: null output");
+  VAST_REQUIRE(vision || audio || subtitle, VAST_ERR_INVALID, "pool_concat: no modality given");
+  VAST_REQUIRE(dtype >= VAST_F32 && dtype <= VAST_F16 && out_dtype >= VAST_F32 && out_dtype <= VAST_F16,
+               VAST_ERR_UNSUPPORTED, "pool_concat: bad dtype");
+  if (bs == 0) return VAST_OK;
+  PoolParams p;
+  memset(&p, 0, sizeof(p));
+  int64_t off = 0;
+  if (vision) {
+    VAST_REQUIRE(n_v > 0 && tok_v > 0 && c_v > 0, VAST_ERR_INVALID, "pool_concat: bad vision shape");
+    p.seg[0] = {vision, n_v, tok_v, c_v, vision_mode, off};
+    off += c_v;
+  }
+  if (audio) {
+    VAST_REQUIRE(n_a > 0 && tok_a > 0 && c_a > 0, VAST_ERR_INVALID, "pool_concat: bad audio shape");
+    p.seg[1] = {audio, n_a, tok_a, c_a, audio_mode, off};
+    off += c_a;
+  }
+  if (subtitle) {
+    VAST_REQUIRE(tok_s > 0 && c_s > 0, VAST_ERR_INVALID, "pool_concat: bad subtitle shape");
+    p.seg[2] = {subtitle, 1, tok_s, c_s, 0, off};
+    off += c_s;
+  }
+  VAST_REQUIRE(ldo >= off, VAST_ERR_INVALID, "pool_concat: ldo < concat width");
+  // vector loads need 16-byte aligned rows
+  for (int i = 0; i < 3; ++i)
+    if (p.seg[i].src)
+      VAST_REQUIRE((reinterpret_cast<uintptr_t>(p.seg[i].src) & 15) == 0, VAST_ERR_INVALID,
+                   "pool_concat: inputs must be 16-byte aligned");
+  p.bs = bs;
+  p.out = out;
+  p.ldo = ldo;
+  if (dtype == VAST_F32) return launch_pool<float>(p, out_dtype, stream);
+  if (dtype == VAST_BF16) return launch_pool<__nv_bfloat16>(p, out_dtype, stream);
+  return launch_pool<__half>(p, out_dtype, stream);
+}
+
+template <class T>
+static int launch_pool_bwd(const float* g, int64_t ldg, int64_t off, void* dst, int64_t bs, int64_t n, int64_t tok,
+                           int64_t c, int mode, cudaStream_t stream) {
+  const int64_t total = bs * n * tok * c;
+  if (total == 0) return VAST_OK;
+  pool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, stream>>>(g, ldg, off, static_cast<T*>(dst), bs, n, tok, c, mode);
+  VAST_LAUNCH_OK("pool_concat_bwd");
+  return VAST_OK;
+}
+
+extern "C" int vast_pool_concat_bwd(const float* grad_out, int64_t ldg, int64_t bs, void* grad_vision, int64_t n_v,
+                                    int64_t tok_v, int64_t c_v, int vision_mode, void* grad_audio, int64_t n_a,
+                                    int64_t tok_a, int64_t c_a, int audio_mode, void* grad_subtitle, int64_t tok_s,
+                                    int64_t c_s, int dtype, vast_stream_t stream) {
+  VAST_REQUIRE(grad_out != nullptr, VAST_ERR_INVALID, "pool_concat_bwd: null grad");
+  VAST_REQUIRE(dtype >= VAST_F32 && dtype <= VAST_F16, VAST_ERR_UNSUPPORTED, "pool_concat_bwd: bad dtype");
+  int64_t off = 0;
+  struct S {
+    void* dst;
+    int64_t n, tok, c;
+    int mode;
+  } segs[3] = {{grad_vision, n_v, tok_v, c_v, vision_mode},
+               {grad_audio, n_a, tok_a, c_a, audio_mode},
+               {grad_subtitle, 1, tok_s, c_s, 0}};
+  for (auto& s : segs) {
+    if (!s.dst) {
+      continue;
+    }
+    int rc;
+    if (dtype == VAST_F32)
+      rc = launch_pool_bwd<float>(grad_out, ldg, off, s.dst, bs, s.n, s.tok, s.c, s.mode, stream);
+    else if (dtype == VAST_BF16)
+      rc = launch_pool_bwd<__nv_bfloat16>(grad_out, ldg, off, s.dst, bs, s.n, s.tok, s.c, s.mode, stream);
+    else
+      rc = launch_pool_bwd<__half>(grad_out, ldg, off, s.dst, bs, s.n, s.tok, s.c, s.mode, stream);
+    if (rc) return rc;
+    off += s.c;
+  }
+  return VAST_OK;
+}
+
+extern "C" int vast_l2norm(const void* x, int x_dtype, int64_t rows, int64_t dim, int64_t ldx, float eps, float* y_f32,
+                           int64_t ldy, void* y_16, int64_t ld16, float* inv_norm, vast_stream_t stream) {
+  VAST_REQUIRE(x != nullptr && rows >= 0 && dim > 0, VAST_ERR_INVALID, "l2norm: bad arguments");
+  VAST_REQUIRE(ldx >= dim && (!y_f32 || ldy >= dim) && (!y_16 || ld16 >= dim), VAST_ERR_INVALID, "l2norm: bad ld");
+  if (rows == 0) return VAST_OK;
+  const unsigned grid = static_cast<unsigned>(ceil_div64(rows, 4));
+  auto* y16 = static_cast<__nv_bfloat16*>(y_16);
+  if (x_dtype == VAST_F32)
+    l2norm_kernel<float><<<grid, 128, 0, stream>>>(static_cast<const float*>(x), rows, dim, ldx, eps, y_f32, ldy, y16, ld16, inv_norm);
+  else if (x_dtype == VAST_BF16)
+    l2norm_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), rows, dim, ldx, eps, y_f32, ldy, y16, ld16, inv_norm);
+  else if (x_dtype == VAST_F16)
+    l2norm_kernel<__half><<<grid, 128, 0, stream>>>(static_cast<const __half*>(x), rows, dim, ldx, eps, y_f32, ldy, y16, ld16, inv_norm);
+  else
+    VAST_REQUIRE(false, VAST_ERR_UNSUPPORTED, "l2norm: bad dtype");
+  VAST_LAUNCH_OK("l2norm");
+  return VAST_OK;
+}
+
+extern "C" int vast_l2norm_bwd(const float* grad_y, int64_t ldg, const float* y, int64_t ldy, const float* inv_norm,
+                               int64_t rows, int64_t dim, float eps, float* grad_x, int64_t ldgx, vast_stream_t stream) {
+  VAST_REQUIRE(grad_y && y && inv_norm && grad_x && dim > 0, VAST_ERR_INVALID, "l2norm_bwd: null pointer");
+  if (rows == 0) return VAST_OK;
+  l2norm_bwd_kernel<<<static_cast<unsigned>(ceil_div64(rows, 4)), 128, 0, stream>>>(grad_y, ldg, y, ldy, inv_norm, rows,
+                                                                                   dim, eps, grad_x, ldgx);
+  VAST_LAUNCH_OK("l2norm_bwd");
+  return VAST_OK;
+}
+
+extern "C" int vast_pack_pair(const void* feat_t, const void* feat_cond, int dtype, int64_t bs, int64_t dim,
+                              int64_t ld_in, void* pack_bf16, vast_stream_t stream) {
+  VAST_REQUIRE(feat_t && feat_cond && pack_bf16 && dim > 0 && ld_in >= dim, VAST_ERR_INVALID, "pack_pair: bad arguments");
+  if (bs == 0) return VAST_OK;
+  const unsigned grid = grid_for(bs * dim, 256);
+  auto* out = static_cast<__nv_bfloat16*>(pack_bf16);
+  if (dtype == VAST_F32)
+    pack_pair_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(feat_t), static_cast<const float*>(feat_cond), bs, dim, ld_in, out);
+  else if (dtype == VAST_BF16)
+    pack_pair_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(feat_t), static_cast<const __nv_bfloat16*>(feat_cond), bs, dim, ld_in, out);
+  else if (dtype == VAST_F16)
+    pack_pair_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(feat_t), static_cast<const __half*>(feat_cond), bs, dim, ld_in, out);
+  else
+    VAST_REQUIRE(false, VAST_ERR_UNSUPPORTED, "pack_pair: bad dtype");
+  VAST_LAUNCH_OK("pack_pair");
+  return VAST_OK;
+}
+
+extern "C" int vast_gather_rows_concat3(const int64_t* ids_local, const int64_t* mask_local, const int64_t* ids_all,
+                                        const int64_t* mask_all, int64_t L, const void* cond_local, const void* cond_all,
+                                        int64_t row_bytes_cond, const int64_t* neg_text, const int64_t* neg_cond,
+                                        int64_t bs, int64_t n_total, int64_t* ids_out, int64_t* mask_out, void* cond_out,
+                                        vast_stream_t stream) {
+  VAST_REQUIRE(bs >= 0 && n_total >= bs, VAST_ERR_INVALID, "gather_rows_concat3: bad sizes");
+  if (bs == 0) return VAST_OK;
+  if (cond_out) {
+    VAST_REQUIRE(cond_local && cond_all && neg_cond, VAST_ERR_INVALID, "gather_rows_concat3: null cond pointer");
+    VAST_REQUIRE(row_bytes_cond > 0 && row_bytes_cond % 16 == 0, VAST_ERR_UNSUPPORTED,
+                 "gather_rows_concat3: S*H*elem_bytes (%lld) must be a multiple of 16", (long long)row_bytes_cond);
+    VAST_REQUIRE(((reinterpret_cast<uintptr_t>(cond_local) | reinterpret_cast<uintptr_t>(cond_all) |
+                   reinterpret_cast<uintptr_t>(cond_out)) & 15) == 0,
+                 VAST_ERR_INVALID, "gather_rows_concat3: cond pointers must be 16-byte aligned");
+    VAST_REQUIRE(2 * bs <= 65535, VAST_ERR_UNSUPPORTED, "gather_rows_concat3: bs too large");
+    const int64_t row_vecs = row_bytes_cond / 16;
+    const int64_t chunk = GATHER_THREADS * GATHER_UNROLL;
+    int64_t gx = ceil_div64(row_vecs, chunk);
+    if (gx > 64) gx = 64;
+    dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(2 * bs));
+    gather_cond3_kernel<<<grid, GATHER_THREADS, 0, stream>>>(static_cast<const uint4*>(cond_local),
+                                                             static_cast<const uint4*>(cond_all), neg_cond, bs, n_total,
+                                                             row_vecs, static_cast<uint4*>(cond_out));
+    VAST_LAUNCH_OK("gather_cond3");
+  }
+  if (ids_out || mask_out) {
+    VAST_REQUIRE(ids_out && mask_out && ids_local && mask_local && ids_all && mask_all && neg_text && L > 0,
+                 VAST_ERR_INVALID, "gather_rows_concat3: null ids/mask pointer");
+    gather_ids3_kernel<<<grid_for(3 * bs * L, 256), 256, 0, stream>>>(ids_local, mask_local, ids_all, mask_all, neg_text,
+                                                                      bs, n_total, L, ids_out, mask_out);
+    VAST_LAUNCH_OK("gather_ids3");
+  }
+  return VAST_OK;
+}

@@ -1,0 +1,336 @@
+// Warp-specialised, persistent sm_100a "NT" GEMM mainloop with pluggable epilogues.
+//
+//   S[prob][m][n] = sum_k A[prob][m][k] * B[prob][n][k]        (both operands K-major, 16-bit)
+//
+// This is the one tensor-core mainloop behind every dense contraction of the hot path
+// (reference call sites: model/vast.py:405-408 `torch.matmul(feat, feat_all.permute(1,0))`,
+// its autograd backward, and evaluation/evaluation_mm.py:223).  The accumulator tile lives in
+// TMEM and is consumed in place by the epilogue functor (online log-sum-exp, softmax
+// probabilities + hard-negative race, running top-k, or a plain store), so the [M, N] logit
+// matrix never goes to HBM.
+//
+// Roles (one CTA per SM, persistent over work items):
+//   warp 0 / lane 0 : TMA producer    -- cp.async.bulk.tensor into a STAGES-deep smem ring
+//   warp 1 / lane 0 : MMA issuer      -- tcgen05.mma (128 x BN x 16 per instruction), fp32 in TMEM
+//   warps 2..2+NE   : epilogue        -- tcgen05.ld TMEM -> registers -> Epi functor
+// TMEM holds two accumulator stages (2 x BN columns) so the epilogue of tile i overlaps the
+// mainloop of tile i+1.
+//
+// Work item = (problem, 128-row block, contiguous range of N-tiles, contiguous range of K-blocks).
+// Epilogue state (row statistics, top-k lists, ...) persists across the N-tiles of one item and is
+// flushed as a partial ("slot") at the end of the item; a small finalize kernel merges slots.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace vast {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 x 16-bit = one 128-byte swizzle span
+constexpr int MAX_PROBLEMS = 2;
+
+struct GemmShape {
+  int num_problems;
+  int M, N, K;
+  int m_blocks;
+  int n_tiles, n_splits, tiles_per_split;
+  int k_blocks, k_splits, kb_per_split;
+  int num_items;
+  uint32_t idesc;
+};
+
+template <class EpiParams>
+struct alignas(64) KernelParams {
+  CUtensorMap tmA[MAX_PROBLEMS];
+  CUtensorMap tmB[MAX_PROBLEMS];
+  GemmShape g;
+  EpiParams epi;
+};
+
+// What an epilogue thread knows about the work item it is processing.
+struct ItemCtx {
+  int prob, m_blk, n_split, k_split;
+  int row;         // row inside the problem (m_blk * 128 + TMEM lane)
+  bool row_valid;  // row < M
+  int slot;        // partial-result slot = n_split * HALVES + half
+  int M, N;
+  int lane, half;
+};
+
+struct WorkItem {
+  int prob, m_blk, n_split, k_split;
+  int tile_begin, tile_end, kb_begin, kb_end;
+};
+
+__device__ __forceinline__ WorkItem decode_item(const GemmShape& g, int idx) {
+  WorkItem w;
+  w.k_split = idx % g.k_splits;
+  idx /= g.k_splits;
+  w.n_split = idx % g.n_splits;
+  idx /= g.n_splits;
+  w.m_blk = idx % g.m_blocks;
+  w.prob = idx / g.m_blocks;
+  w.tile_begin = w.n_split * g.tiles_per_split;
+  w.tile_end = min(w.tile_begin + g.tiles_per_split, g.n_tiles);
+  w.kb_begin = w.k_split * g.kb_per_split;
+  w.kb_end = min(w.kb_begin + g.kb_per_split, g.k_blocks);
+  return w;
+}
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr uint32_t A_BYTES = BM * BK * 2;
+  static constexpr uint32_t B_BYTES = BN * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr uint32_t BAR_BYTES = 256;  // 2*STAGES + 4 barriers + tmem slot
+  static constexpr uint32_t EPI_OFFSET = BAR_OFFSET + BAR_BYTES;
+  static constexpr uint32_t ALIGN_SLACK = 1024;
+};
+
+template <class Epi, int BN, int STAGES, int NE>
+__global__ void __launch_bounds__(64 + 32 * NE, 1)
+gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
+  static_assert(NE == 4 || NE == 8, "4 or 8 epilogue warps");
+  static_assert(BN == 128 || BN == 256, "BN");
+  using L = SmemLayout<BN, STAGES>;
+  constexpr int HALVES = NE / 4;
+  constexpr int COLS_PER_WARP = BN / HALVES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte aligned bases (in the shared address space).
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* epi_smem = smem + L::EPI_OFFSET;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const GemmShape& g = P.g;
+
+  if (warp == 0 && lane == 0) {
+    for (int p = 0; p < g.num_problems; ++p) {
+      ptx::tma_prefetch_desc(&P.tmA[p]);
+      ptx::tma_prefetch_desc(&P.tmB[p]);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull[a], 1);
+      ptx::mbar_init(&tempty[a], NE);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < g.num_items; item += gridDim.x) {
+        const WorkItem w = decode_item(g, item);
+        for (int t = w.tile_begin; t < w.tile_end; ++t) {
+          for (int kb = w.kb_begin; kb < w.kb_end; ++kb) {
+            ptx::mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * L::STAGE_BYTES;
+            uint8_t* sb = sa + L::A_BYTES;
+            ptx::mbar_arrive_expect_tx(&full[stage], L::STAGE_BYTES);
+            ptx::tma_load_2d(sa, &P.tmA[w.prob], &full[stage], kb * BK, w.m_blk * BM);
+            ptx::tma_load_2d(sb, &P.tmB[w.prob], &full[stage], kb * BK, t * BN);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < g.num_items; item += gridDim.x) {
+        const WorkItem w = decode_item(g, item);
+        for (int t = w.tile_begin; t < w.tile_end; ++t) {
+          ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+          ptx::tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+          for (int kb = w.kb_begin; kb < w.kb_end; ++kb) {
+            ptx::mbar_wait(&full[stage], phase);
+            ptx::tc_fence_after_sync();
+            const uint32_t sa = ptx::smem_u32(smem + stage * L::STAGE_BYTES);
+            const uint64_t da = ptx::umma_desc_sw128_kmajor(sa);
+            const uint64_t db = ptx::umma_desc_sw128_kmajor(sa + L::A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in 16-byte units
+              ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, g.idesc, (kb > w.kb_begin || k > 0) ? 1u : 0u);
+            }
+            ptx::umma_commit(&empty[stage]);  // frees the smem stage once these MMAs retire
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          ptx::umma_commit(&tfull[acc]);  // accumulator tile complete
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps
+    const int ew = warp - 2;
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    Epi epi(P.epi, epi_smem);
+    for (int item = blockIdx.x; item < g.num_items; item += gridDim.x) {
+      const WorkItem w = decode_item(g, item);
+      ItemCtx ctx;
+      ctx.prob = w.prob;
+      ctx.m_blk = w.m_blk;
+      ctx.n_split = w.n_split;
+      ctx.k_split = w.k_split;
+      ctx.row = w.m_blk * BM + q * 32 + lane;
+      ctx.row_valid = ctx.row < g.M;
+      ctx.slot = w.n_split * HALVES + half;
+      ctx.M = g.M;
+      ctx.N = g.N;
+      ctx.lane = lane;
+      ctx.half = half;
+      epi.item_begin(ctx);
+      for (int t = w.tile_begin; t < w.tile_end; ++t) {
+        ptx::mbar_wait(&tfull[acc], acc_phase);
+        ptx::tc_fence_after_sync();
+#pragma unroll 1
+        for (int c = 0; c < COLS_PER_WARP; c += 32) {
+          const int col_in_tile = half * COLS_PER_WARP + c;
+          const uint32_t taddr =
+              tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + col_in_tile);
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(taddr, v);
+          ptx::tmem_ld_wait();
+          epi.chunk(ctx, v, t * BN + col_in_tile);
+          __syncwarp();
+        }
+        ptx::tc_fence_before_sync();
+        if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+      epi.item_end(ctx);
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ host side
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, int64_t rows, int64_t cols, int64_t ld_elems,
+                 int box_rows);
+
+// Pick how many N-splits (and K-splits) to cut each 128-row block into so the persistent grid
+// is evenly loaded.  row_blocks = problems * m_blocks.
+void choose_splits(GemmShape* g, int sm_count, int max_n_splits, int max_k_splits);
+
+inline void fill_shape(GemmShape* g, int problems, int M, int N, int K, int BN, int in_fmt) {
+  g->num_problems = problems;
+  g->M = M;
+  g->N = N;
+  g->K = K;
+  g->m_blocks = ceil_div(M, BM);
+  g->n_tiles = ceil_div(N, BN);
+  g->k_blocks = ceil_div(K, BK);
+  g->n_splits = 1;
+  g->tiles_per_split = g->n_tiles;
+  g->k_splits = 1;
+  g->kb_per_split = g->k_blocks;
+  g->num_items = problems * g->m_blocks;
+  g->idesc = ptx::umma_idesc_f16(static_cast<uint32_t>(in_fmt), BM, static_cast<uint32_t>(BN));
+}
+
+template <class Epi, int BN, int STAGES, int NE>
+int launch_gemm(const KernelParams<typename Epi::Params>& P, cudaStream_t stream, const char* name) {
+  using L = SmemLayout<BN, STAGES>;
+  const size_t smem = L::EPI_OFFSET + L::ALIGN_SLACK + Epi::smem_bytes();
+  auto kern = gemm_tc_kernel<Epi, BN, STAGES, NE>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    VAST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_done = true;
+  }
+  int grid = P.g.num_items < device_sm_count() ? P.g.num_items : device_sm_count();
+  if (grid <= 0) return VAST_OK;
+  kern<<<grid, 64 + 32 * NE, smem, stream>>>(P);
+  VAST_LAUNCH_OK(name);
+  return VAST_OK;
+}
+
+// ------------------------------------------------------------------ plain store epilogue
+// C[k_split][prob][row][col] = alpha * S   (fp32).  Used by the dQ GEMM (split-K partials are
+// summed in a fixed order by the gradient finalize kernel) and by the GEMM unit test.
+struct EpiStore {
+  struct Params {
+    float* C;
+    int64_t ldc;
+    int64_t prob_stride;
+    int64_t ksplit_stride;
+    float alpha;
+  };
+  static size_t smem_bytes() { return 0; }
+  const Params& p;
+  __device__ EpiStore(const Params& p_, uint8_t*) : p(p_) {}
+  __device__ __forceinline__ void item_begin(const ItemCtx&) {}
+  __device__ __forceinline__ void chunk(const ItemCtx& c, const uint32_t (&v)[32], int col0) {
+    if (!c.row_valid || col0 >= c.N) return;
+    float* dst = p.C + c.k_split * p.ksplit_stride + c.prob * p.prob_stride + static_cast<int64_t>(c.row) * p.ldc + col0;
+    const bool vec = (col0 + 32 <= c.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    if (vec) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float4 o;
+        o.x = __uint_as_float(v[i]) * p.alpha;
+        o.y = __uint_as_float(v[i + 1]) * p.alpha;
+        o.z = __uint_as_float(v[i + 2]) * p.alpha;
+        o.w = __uint_as_float(v[i + 3]) * p.alpha;
+        *reinterpret_cast<float4*>(dst + i) = o;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < c.N) dst[i] = __uint_as_float(v[i]) * p.alpha;
+    }
+  }
+  __device__ __forceinline__ void item_end(const ItemCtx&) {}
+};
+
+}  // namespace tc
+}  // namespace vast

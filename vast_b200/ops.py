@@ -1,0 +1,155 @@
+"""Thin Python wrappers, one per C-ABI entry point (include/vast_b200.h).  PyTorch is used for
+device memory and streams only; every op runs the hand-written sm_100a kernels in
+vast_b200/_C/libvast_b200.so and raises if that library (or a CUDA device) is missing."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check, dtype_code, lib, ptr, require_cuda, stream_ptr
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    # torch's caching allocator returns >= 512-byte aligned blocks
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------ generic GEMM (test / building block)
+def gemm_nt(a: torch.Tensor, b: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
+    """C[m, n] = alpha * sum_k a[m, k] b[n, k]; a, b bf16 or fp16 (same dtype), C fp32."""
+    require_cuda(a, b)
+    assert a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[1] and a.dtype == b.dtype
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    m, k = a.shape
+    n = b.shape[0]
+    c = torch.empty(m, n, dtype=torch.float32, device=a.device)
+    nbytes = lib().vast_gemm_nt_workspace_bytes(m, n, k)
+    ws = _ws(nbytes, a.device)
+    check(lib().vast_gemm_nt(ptr(a), a.stride(0), ptr(b), b.stride(0), dtype_code(a.dtype), m, n, k, float(alpha),
+                             ptr(c), c.stride(0), ptr(ws), ws.numel(), stream_ptr()), "gemm_nt")
+    return c
+
+
+# ------------------------------------------------------------------ feature build
+def pool_concat(vision=None, audio=None, subtitle=None, vision_mode=0, audio_mode=1, out_dtype=None):
+    """pool_vision/audio/text_for_contra + torch.cat(dim=1) (general_module.py:426-449, vast.py:269-275).
+    vision [bs,n,tok,c], audio [bs,n,tok,c], subtitle [bs,tok,c]; mode 0 = token 0, 1 = token mean."""
+    xs = [x for x in (vision, audio, subtitle) if x is not None]
+    assert xs, "pool_concat: give at least one modality"
+    require_cuda(*xs)
+    dt = xs[0].dtype
+    assert all(x.dtype == dt and x.is_contiguous() for x in xs)
+    bs = xs[0].shape[0]
+    width = sum(x.shape[-1] for x in xs)
+    out = torch.empty(bs, width, dtype=out_dtype or dt, device=xs[0].device)
+    v, a, s = vision, audio, subtitle
+    check(lib().vast_pool_concat(
+        ptr(v), *(v.shape[1:] if v is not None else (0, 0, 0)), int(vision_mode),
+        ptr(a), *(a.shape[1:] if a is not None else (0, 0, 0)), int(audio_mode),
+        ptr(s), *(s.shape[1:] if s is not None else (0, 0)),
+        dtype_code(dt), bs, ptr(out), dtype_code(out.dtype), out.stride(0), stream_ptr()), "pool_concat")
+    return out
+
+
+def pool_concat_bwd(grad_out, vision_shape=None, audio_shape=None, subtitle_shape=None, vision_mode=0, audio_mode=1,
+                    dtype=torch.float32):
+    require_cuda(grad_out)
+    g = grad_out.contiguous().float()
+    bs = g.shape[0]
+    dev = g.device
+    gv = torch.empty(vision_shape, dtype=dtype, device=dev) if vision_shape is not None else None
+    ga = torch.empty(audio_shape, dtype=dtype, device=dev) if audio_shape is not None else None
+    gs = torch.empty(subtitle_shape, dtype=dtype, device=dev) if subtitle_shape is not None else None
+    check(lib().vast_pool_concat_bwd(
+        ptr(g), g.stride(0), bs,
+        ptr(gv), *(vision_shape[1:] if gv is not None else (0, 0, 0)), int(vision_mode),
+        ptr(ga), *(audio_shape[1:] if ga is not None else (0, 0, 0)), int(audio_mode),
+        ptr(gs), *(subtitle_shape[1:] if gs is not None else (0, 0)),
+        dtype_code(dtype), stream_ptr()), "pool_concat_bwd")
+    return gv, ga, gs
+
+
+def l2norm(x: torch.Tensor, eps: float = 1e-12, want_f32=True, out16: torch.Tensor | None = None, want_inv=False):
+    """F.normalize(x, dim=-1).  Returns (y_f32 or None, inv_norm or None); optionally also writes the
+    bf16 copy into `out16` (any row stride, e.g. the all-gather send slot)."""
+    require_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    rows, dim = x.shape
+    y = torch.empty(rows, dim, dtype=torch.float32, device=x.device) if want_f32 else None
+    inv = torch.empty(rows, dtype=torch.float32, device=x.device) if want_inv else None
+    if out16 is not None:
+        assert out16.dtype == torch.bfloat16 and out16.stride(1) == 1 and out16.shape[0] == rows
+    check(lib().vast_l2norm(ptr(x), dtype_code(x.dtype), rows, dim, x.stride(0), float(eps),
+                            ptr(y), dim, ptr(out16), out16.stride(0) if out16 is not None else 0,
+                            ptr(inv), stream_ptr()), "l2norm")
+    return y, inv
+
+
+def l2norm_bwd(grad_y, y, inv_norm, eps: float = 1e-12):
+    require_cuda(grad_y, y, inv_norm)
+    g = grad_y.contiguous().float()
+    rows, dim = y.shape
+    gx = torch.empty_like(y)
+    check(lib().vast_l2norm_bwd(ptr(g), g.stride(0), ptr(y), y.stride(0), ptr(inv_norm), rows, dim, float(eps),
+                                ptr(gx), gx.stride(0), stream_ptr()), "l2norm_bwd")
+    return gx
+
+
+def pack_pair(feat_t: torch.Tensor, feat_cond: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """[bs, 2D] bf16 = (feat_t | feat_cond): the single all-gather payload."""
+    require_cuda(feat_t, feat_cond)
+    assert feat_t.shape == feat_cond.shape and feat_t.dtype == feat_cond.dtype
+    ft, fc = feat_t.contiguous(), feat_cond.contiguous()
+    bs, dim = ft.shape
+    if out is None:
+        out = torch.empty(bs, 2 * dim, dtype=torch.bfloat16, device=ft.device)
+    assert out.is_contiguous() and out.shape == (bs, 2 * dim) and out.dtype == torch.bfloat16
+    check(lib().vast_pack_pair(ptr(ft), ptr(fc), dtype_code(ft.dtype), bs, dim, dim, ptr(out), stream_ptr()), "pack_pair")
+    return out
+
+
+# ------------------------------------------------------------------ contrastive step
+def omc_step(pack: torch.Tensor, bs: int, row_offset: int, contra_temp: float, label_smoothing: float = 0.1,
+             weight_floor: float = 1e-4, seed: int = 0, offset: int = 0, need_sample: bool = True,
+             need_grad: bool = True, debug_noise: torch.Tensor | None = None, want_lse: bool = False):
+    """Fused OMC step (vast.py:405-440 + backward) on the packed, gathered features.
+    Returns dict(loss[1], neg_idx[2,bs] | None, grad_cond, grad_t, grad_temp | None, lse | None)."""
+    require_cuda(pack)
+    assert pack.dtype == torch.bfloat16 and pack.is_contiguous() and pack.dim() == 2 and pack.shape[1] % 2 == 0
+    n_total, dim = pack.shape[0], pack.shape[1] // 2
+    dev = pack.device
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    neg = torch.empty(2, bs, dtype=torch.int64, device=dev) if need_sample else None
+    gc = torch.empty(bs, dim, dtype=torch.float32, device=dev) if need_grad else None
+    gt = torch.empty(bs, dim, dtype=torch.float32, device=dev) if need_grad else None
+    gtemp = torch.empty(1, dtype=torch.float32, device=dev) if need_grad else None
+    lse = torch.empty(2, bs, dtype=torch.float32, device=dev) if want_lse else None
+    if debug_noise is not None:
+        assert debug_noise.shape == (2, bs, n_total) and debug_noise.dtype == torch.float32 and debug_noise.is_contiguous()
+    nbytes = lib().vast_omc_workspace_bytes(bs, n_total, dim, int(need_sample), int(need_grad))
+    ws = _ws(nbytes, dev)
+    check(lib().vast_omc_step(ptr(pack), bs, n_total, dim, row_offset, float(contra_temp), float(label_smoothing),
+                              float(weight_floor), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1),
+                              ptr(debug_noise), ptr(loss), ptr(neg), ptr(gc), ptr(gt), ptr(gtemp), ptr(lse),
+                              ptr(ws), ws.numel(), stream_ptr()), "omc_step")
+    return dict(loss=loss, neg_idx=neg, grad_cond=gc, grad_t=gt, grad_temp=gtemp, lse=lse, _ws=ws)
+
+
+def gather_rows_concat3(ids_local, mask_local, ids_all, mask_all, cond_local, cond_all, neg_text, neg_cond):
+    """vast.py:432-448: (input_ids_1 [3bs,L], attention_mask_1 [3bs,L], condition_feats [3bs,S,H])."""
+    require_cuda(ids_local, mask_local, ids_all, mask_all, cond_local, cond_all, neg_text, neg_cond)
+    bs, L = ids_local.shape
+    n_total = ids_all.shape[0]
+    il, ml = ids_local.contiguous(), mask_local.contiguous()
+    ia, ma = ids_all.contiguous(), mask_all.contiguous()
+    cl, ca = cond_local.contiguous(), cond_all.contiguous()
+    assert il.dtype == torch.int64 and ml.dtype == torch.int64 and ia.dtype == torch.int64 and ma.dtype == torch.int64
+    assert cl.dtype == ca.dtype and cl.shape[1:] == ca.shape[1:]
+    row_bytes = cl[0].numel() * cl.element_size()
+    ids_out = torch.empty(3 * bs, L, dtype=torch.int64, device=il.device)
+    mask_out = torch.empty(3 * bs, L, dtype=torch.int64, device=il.device)
+    cond_out = torch.empty((3 * bs,) + tuple(cl.shape[1:]), dtype=cl.dtype, device=cl.device)
+    check(lib().vast_gather_rows_concat3(ptr(il), ptr(ml), ptr(ia), ptr(ma), L, ptr(cl), ptr(ca), row_bytes,
+                                         ptr(neg_text.contiguous()), ptr(neg_cond.contiguous()), bs, n_total,
+                                         ptr(ids_out), ptr(mask_out), ptr(cond_out), stream_ptr()), "gather_rows_concat3")
+    return ids_out, mask_out, cond_out
