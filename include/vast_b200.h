@@ -100,6 +100,8 @@ VAST_API size_t vast_omc_workspace_bytes(int64_t bs, int64_t n_total, int64_t di
  *   pack        [n_total, 2*dim] bf16, row n = (feat_t_all[n] | feat_cond_all[n]) in rank order
  *               (the output of all_gather_into_tensor over vast_pack_pair buffers); the local
  *               rows are rows [row_offset, row_offset + bs)   (row_offset = rank * bs).
+ *   contra_temp_dev  optional DEVICE pointer to the temperature (the nn.Parameter itself): when
+ *               non-NULL it is read by the kernels and `contra_temp` is ignored -- no host sync.
  *   loss        [1]  f32: (CE_eps(cond2t) + CE_eps(t2cond)) / 2          (vast.py:412-415)
  *   neg_idx     [2, bs] int64 or NULL: [0] = negative TEXT index per row drawn from
  *               softmax(sim_cond2t)+floor, [1] = negative CONDITION index drawn from
@@ -112,7 +114,7 @@ VAST_API size_t vast_omc_workspace_bytes(int64_t bs, int64_t n_total, int64_t di
  *   lse         [2, bs] f32 or NULL: natural-log row log-sum-exp of (cond2t, t2cond).
  * The [bs, n_total] logit matrices are never written to HBM. */
 VAST_API int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int64_t dim, int64_t row_offset,
-                  float contra_temp, float label_smoothing, float weight_floor,
+                  float contra_temp, const float* contra_temp_dev, float label_smoothing, float weight_floor,
                   uint64_t seed, uint64_t offset, const float* debug_noise,
                   float* loss, int64_t* neg_idx, float* grad_cond, float* grad_t, float* grad_temp,
                   float* lse, void* workspace, size_t workspace_bytes, vast_stream_t stream);
@@ -189,15 +191,18 @@ VAST_API int vast_exact_topk_rows(const float* q, int64_t ldq, const float* kk, 
 VAST_API int vast_dense_topk(const float* score, int64_t n_rows, int64_t n_cols, int64_t ld, int64_t k, int axis,
                     int32_t* idx_out, float* val_out, vast_stream_t stream);
 
-/* Rank of the ground-truth column in a stable descending sort of each row of an fp32 matrix
- * (evaluation_mm.py:333-338: sort + list.index), lower index first on ties. */
+/* Rank of entry (gt_row[g], gt_col[g]) in a stable descending sort of its row (axis=1, over the
+ * columns) or of its column (axis=0, over the rows) of an fp32 matrix, lower index first on ties
+ * (evaluation_mm.py:333-338 and :355-365: sort + list.index). */
 VAST_API int vast_dense_rank_of_gt(const float* score, int64_t n_rows, int64_t n_cols, int64_t ld, int axis,
-                          const int32_t* gt, int64_t n_gt, int32_t* rank_out, vast_stream_t stream);
+                          const int32_t* gt_row, const int32_t* gt_col, int64_t n_gt, int32_t* rank_out,
+                          vast_stream_t stream);
 
 /* Candidate bookkeeping for the ITM re-rank (evaluation_mm.py:264-314 without the dense mask):
  * bucket the (text, video) candidate pairs by video.  text_idx/video_idx [n_pairs] int32
  * (video_idx < 0 = empty slot).  Outputs: counts/offsets [n_videos+1] (CSR), order [n_pairs]
- * = text indices grouped by video, ascending inside a video.  workspace: n_videos+1 int32. */
+ * = text indices grouped by video, ascending inside a video. */
+VAST_API size_t vast_bucket_by_video_workspace_bytes(int64_t n_pairs, int64_t n_videos);
 VAST_API int vast_bucket_by_video(const int32_t* text_idx, const int32_t* video_idx, int64_t n_pairs, int64_t n_videos,
                          int32_t* offsets, int32_t* texts_sorted, void* workspace, size_t workspace_bytes,
                          vast_stream_t stream);

@@ -1,0 +1,75 @@
+"""world_size-2 gloo (CPU) tests of the data-parallel helpers (vast_b200/distributed.py) against the
+golden outputs of the reference's utils/distributed.py, and of the host-side shard logic."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vast_b200 import distributed as D
+    out = {}
+    x = torch.arange(rank * 10, rank * 10 + 6, dtype=torch.float32).reshape(3, 2)
+    out["concat_all_gather"] = D.concat_all_gather(x).numpy()
+    ragged = torch.arange((rank + 2) * 3, dtype=torch.float32).reshape(rank + 2, 3) + 100 * rank
+    out["ddp_allgather"] = D.ddp_allgather(ragged).numpy()
+    out["all_gather_list"] = np.array([len(v) for v in D.all_gather_list(list(range(rank + 1)))])
+    xg = x.clone().requires_grad_()
+    yg = D.all_gather_with_grad(xg)
+    (yg * torch.arange(yg.numel(), dtype=torch.float32).reshape(yg.shape)).sum().backward()
+    out["agwg_out"] = yg.detach().numpy()
+    out["agwg_grad"] = xg.grad.numpy()
+    out["bcast"] = D.any_broadcast({"r": rank}, 1)["r"]
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_collectives_match_reference_w2():
+    g = np.load(os.path.join(GOLD, "dist_w2.npz"))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, 29731, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=100) for _ in range(2))
+    for p in procs:
+        p.join(timeout=30)
+    for r in range(2):
+        for k in ("concat_all_gather", "ddp_allgather", "all_gather_list", "agwg_out", "agwg_grad"):
+            assert np.array_equal(res[r][k], g[f"r{r}_{k}"]), (r, k)
+        assert res[r]["bcast"] == 1
+
+
+def test_single_process_identities():
+    from vast_b200 import distributed as D
+    x = torch.randn(4, 3)
+    assert torch.equal(D.concat_all_gather(x), x) and torch.equal(D.ddp_allgather(x), x)
+    assert D.all_gather_with_grad(x) is x and D.all_gather_list(5) == [5] and D.any_broadcast("a", 0) == "a"
+
+
+def test_shard_bounds_cover_columns():
+    from vast_b200.retrieval import _shard_bounds
+    for n in (1, 7, 100000, 12501):
+        for w in (1, 2, 4, 8):
+            spans = [_shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_metric_helpers_host_logic():
+    from vast_b200.retrieval import _backward_pairs, _first_index, _format
+    assert _first_index(["a", "b", "a"]) == {"a": 0, "b": 1}
+    rows, cols = _backward_pairs(["v0", "v1"], ["v0", "v0", "v1"])
+    assert rows == [0, 1, 2] and cols == [0, 0, 1]
+    assert _format("forward", 0.365, 0.635, 0.75) == {"forward_r1": 36.5, "forward_recall": "36.5/63.5/75.0",
+                                                       "forward_ravg": 58.3}

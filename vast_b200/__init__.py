@@ -1,0 +1,14 @@
+"""vast_b200 -- B200-native (sm_100a) cross-modal contrastive + retrieval-scoring hot path of VAST.
+
+Host side is Python/PyTorch (device memory, streams, torch.distributed); all compute on the path runs in
+hand-written CUDA behind the C-ABI of include/vast_b200.h (vast_b200/_C/libvast_b200.so, loaded with
+ctypes).  There is no CPU or PyTorch fallback: ops raise if the library or a CUDA device is missing."""
+from . import ops  # noqa: F401
+from .contrastive import forward_ret, gather_negatives, omc_loss_and_negatives  # noqa: F401
+from .distributed import (all_gather_list, all_gather_with_grad, any_broadcast, concat_all_gather,  # noqa: F401
+                          ddp_allgather)
+from .features import build_feature, l2_normalize, pool_concat  # noqa: F401
+from .retrieval import (compute_metric_ret, evaluate_ret, recall_from_feats, refine_score_matrix,  # noqa: F401
+                        retrieval_topk)
+
+__version__ = "0.1.0"

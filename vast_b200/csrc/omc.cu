@@ -66,13 +66,14 @@ struct EpiStats {
   struct Params {
     float4* partial;  // [2][M][num_slots] (m2, l, sum s, s_target)
     int num_slots;
-    float scale2;  // log2(e) / tau
+    float scale2;  // log2(e) / tau (used when temp_dev is null)
+    const float* temp_dev;
     int tgt_offset;
   };
   static size_t smem_bytes() { return 0; }
   const Params& p;
-  float m2, l, sz, zt;
-  __device__ EpiStats(const Params& p_, uint8_t*) : p(p_) {}
+  float m2, l, sz, zt, scale2;
+  __device__ EpiStats(const Params& p_, uint8_t*) : p(p_) { scale2 = p.temp_dev ? kLog2e / __ldg(p.temp_dev) : p.scale2; }
   __device__ __forceinline__ void item_begin(const tc::ItemCtx&) {
     m2 = -INFINITY;
     l = 0.f;
@@ -86,7 +87,7 @@ struct EpiStats {
 #pragma unroll
     for (int i = 0; i < 32; ++i)
       if (i < nvalid) cm = fmaxf(cm, __uint_as_float(v[i]));
-    cm *= p.scale2;
+    cm *= scale2;
     if (cm > m2) {
       l *= ex2_approx(m2 - cm);
       m2 = cm;
@@ -96,7 +97,7 @@ struct EpiStats {
     for (int i = 0; i < 32; ++i) {
       if (i < nvalid) {
         const float s = __uint_as_float(v[i]);
-        ls += ex2_approx(fmaf(s, p.scale2, -m2));
+        ls += ex2_approx(fmaf(s, scale2, -m2));
         ss += s;
       }
     }
@@ -124,6 +125,7 @@ struct EpiProb {
     float4* partial;  // [2][M][num_slots] (w_best, e_best, idx_best, sum p*s)
     int num_slots;
     float scale2;
+    const float* temp_dev;
     float floor;
     int tgt_offset;
     int row_offset;  // global row of local row 0 (decorrelates ranks that share a seed)
@@ -133,9 +135,9 @@ struct EpiProb {
   };
   static size_t smem_bytes() { return 0; }
   const Params& p;
-  float lse2, bw, be, pz;
+  float lse2, bw, be, pz, scale2;
   int bidx, tcol;
-  __device__ EpiProb(const Params& p_, uint8_t*) : p(p_) {}
+  __device__ EpiProb(const Params& p_, uint8_t*) : p(p_) { scale2 = p.temp_dev ? kLog2e / __ldg(p.temp_dev) : p.scale2; }
   __device__ __forceinline__ void item_begin(const tc::ItemCtx& c) {
     lse2 = c.row_valid ? p.lse2[static_cast<int64_t>(c.prob) * c.M + c.row] : 0.f;
     bw = -1.f;
@@ -151,12 +153,15 @@ struct EpiProb {
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const float s = __uint_as_float(v[i]);
-      const float q = (i < nvalid) ? ex2_approx(fmaf(s, p.scale2, -lse2)) : 0.f;
+      const float q = (i < nvalid) ? ex2_approx(fmaf(s, scale2, -lse2)) : 0.f;
       pr[i] = q;
       pz = fmaf(q, s, pz);
     }
     if (p.P != nullptr && c.row_valid) {
       __half* dst = p.P + (static_cast<int64_t>(c.prob) * c.M + c.row) * p.ldp + col0;
+      // The target column is excluded from the fp16 P matrix: its coefficient (p_iy - (1 - eps)) is a
+      // cancellation and is applied in fp32 by the gradient finalize kernel.
+      const int tq = tcol - col0;
       if (nvalid >= 32) {
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
@@ -164,7 +169,8 @@ struct EpiProb {
           uint32_t* w = &u.x;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const __half2 h = __floats2half2_rn(pr[i + 2 * j], pr[i + 2 * j + 1]);
+            const __half2 h = __floats2half2_rn((i + 2 * j == tq) ? 0.f : pr[i + 2 * j],
+                                                (i + 2 * j + 1 == tq) ? 0.f : pr[i + 2 * j + 1]);
             w[j] = *reinterpret_cast<const uint32_t*>(&h);
           }
           *reinterpret_cast<uint4*>(dst + i) = u;
@@ -172,7 +178,7 @@ struct EpiProb {
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (i < nvalid) dst[i] = __float2half_rn(pr[i]);
+          if (i < nvalid) dst[i] = __float2half_rn(i == tq ? 0.f : pr[i]);
       }
     }
     if (p.do_sample) {
@@ -277,7 +283,8 @@ __global__ void __launch_bounds__(256) transpose_ksum_kernel(const __nv_bfloat16
 
 // ------------------------------------------------------------------ K3: merge pass-1 partials
 __global__ void __launch_bounds__(128) omc_stats_finalize_kernel(const float4* __restrict__ partial, int slots, int M,
-                                                                int N, float inv_tau, float eps_ls,
+                                                                int N, float inv_tau, const float* __restrict__ temp_dev,
+                                                                float eps_ls,
                                                                 float* __restrict__ lse2, float* __restrict__ zt,
                                                                 float* __restrict__ sz, float* __restrict__ rowce,
                                                                 float* __restrict__ lse_out, int row_blocks,
@@ -295,6 +302,7 @@ __global__ void __launch_bounds__(128) omc_stats_finalize_kernel(const float4* _
   }
   const int r = blockIdx.x * 128 + threadIdx.x;
   if (r >= 2 * M) return;
+  if (temp_dev) inv_tau = 1.0f / __ldg(temp_dev);
   const float4* pp = partial + static_cast<int64_t>(r) * slots;
   float mm = -INFINITY;
   for (int s = 0; s < slots; ++s) mm = fmaxf(mm, pp[s].x);
@@ -316,13 +324,15 @@ __global__ void __launch_bounds__(128) omc_stats_finalize_kernel(const float4* _
 
 // ------------------------------------------------------------------ K5: merge race partials
 __global__ void __launch_bounds__(128) omc_sample_finalize_kernel(const float4* __restrict__ partial, int slots, int M,
-                                                                 int N, float inv_tau, float eps_ls,
+                                                                 int N, float inv_tau, const float* __restrict__ temp_dev,
+                                                                 float eps_ls,
                                                                  const float* __restrict__ zt,
                                                                  const float* __restrict__ sz,
                                                                  int64_t* __restrict__ neg_idx,
                                                                  float* __restrict__ rowdt) {
   const int r = blockIdx.x * 128 + threadIdx.x;
   if (r >= 2 * M) return;
+  if (temp_dev) inv_tau = 1.0f / __ldg(temp_dev);
   const float4* pp = partial + static_cast<int64_t>(r) * slots;
   float bw = -1.f, be = 1.f, pz = 0.f;
   int bidx = -1;
@@ -348,9 +358,15 @@ __global__ void __launch_bounds__(256) omc_grad_finalize_kernel(const float* __r
                                                                int64_t split_stride, int M, int D,
                                                                const float* __restrict__ ksum,
                                                                const __nv_bfloat16* __restrict__ pack, int row_offset,
-                                                               int N, float eps_ls, float gs,
+                                                               int N, float eps_ls, float inv_tau,
+                                                               const float* __restrict__ temp_dev,
+                                                               const float* __restrict__ lse2,
+                                                               const float* __restrict__ zt,
                                                                float* __restrict__ grad_cond, float* __restrict__ grad_t) {
   const int64_t total = 2LL * M * D;
+  if (temp_dev) inv_tau = 1.0f / __ldg(temp_dev);
+  const float gs = inv_tau / (2.0f * M);
+  const float scale2 = kLog2e * inv_tau;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int d = static_cast<int>(i % D);
@@ -361,7 +377,9 @@ __global__ void __launch_bounds__(256) omc_grad_finalize_kernel(const float* __r
     v -= (eps_ls / static_cast<float>(N)) * ksum[p * D + d];
     // target row of the gathered operand: problem 0 -> feat_t_all, problem 1 -> feat_cond_all
     const float kt = __bfloat162float(pack[static_cast<int64_t>(row_offset + row) * 2 * D + p * D + d]);
-    v -= (1.f - eps_ls) * kt;
+    // target column in fp32: coefficient p_iy - (1 - eps)  (P holds 0 there)
+    const float pt = exp2f(fmaf(zt[p * M + row], scale2, -lse2[p * M + row]));
+    v += (pt - (1.f - eps_ls)) * kt;
     (p == 0 ? grad_cond : grad_t)[static_cast<int64_t>(row) * D + d] = gs * v;
   }
 }
@@ -456,7 +474,8 @@ extern "C" size_t vast_omc_workspace_bytes(int64_t bs, int64_t n_total, int64_t 
 }
 
 extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int64_t dim, int64_t row_offset,
-                             float contra_temp, float label_smoothing, float weight_floor, uint64_t seed,
+                             float contra_temp, const float* contra_temp_dev, float label_smoothing,
+                             float weight_floor, uint64_t seed,
                              uint64_t offset, const float* debug_noise, float* loss, int64_t* neg_idx,
                              float* grad_cond, float* grad_t, float* grad_temp, float* lse, void* workspace,
                              size_t workspace_bytes, vast_stream_t stream) {
@@ -465,7 +484,7 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
   VAST_REQUIRE(bs < (1 << 24) && n_total < (1 << 30) && dim <= 16384, VAST_ERR_UNSUPPORTED, "omc_step: sizes too large");
   VAST_REQUIRE(dim % 8 == 0, VAST_ERR_UNSUPPORTED, "omc_step: dim must be a multiple of 8 (got %lld)", (long long)dim);
   VAST_REQUIRE(row_offset >= 0 && row_offset + bs <= n_total, VAST_ERR_INVALID, "omc_step: local rows outside [0, n_total)");
-  VAST_REQUIRE(contra_temp > 0.f, VAST_ERR_INVALID, "omc_step: contra_temp must be positive");
+  VAST_REQUIRE(contra_temp_dev != nullptr || contra_temp > 0.f, VAST_ERR_INVALID, "omc_step: contra_temp must be positive");
   const bool need_grad = grad_cond || grad_t || grad_temp;
   VAST_REQUIRE(!need_grad || (grad_cond && grad_t && grad_temp), VAST_ERR_INVALID,
                "omc_step: give all of grad_cond, grad_t, grad_temp or none");
@@ -489,7 +508,7 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
   float* dqpart = need_grad ? reinterpret_cast<float*>(ws + pl.off_dq) : nullptr;
 
   const auto* pk = static_cast<const __nv_bfloat16*>(pack);
-  const float inv_tau = 1.0f / contra_temp;
+  const float inv_tau = contra_temp_dev ? 0.f : 1.0f / contra_temp;  // device pointer wins (no host sync)
   const int M = static_cast<int>(bs), N = static_cast<int>(n_total), D = static_cast<int>(dim);
   const int row_blocks = ceil_div(2 * M, 128);
   int rc;
@@ -521,14 +540,14 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
       P.tmA[i] = tmA[i];
       P.tmB[i] = tmB[i];
     }
-    P.epi = {partial, pl.slots, kLog2e * inv_tau, static_cast<int>(row_offset)};
+    P.epi = {partial, pl.slots, kLog2e * inv_tau, contra_temp_dev, static_cast<int>(row_offset)};
     rc = tc::launch_gemm<EpiStats, 256, 4, 8>(P, stream, "omc_stats_gemm");
     if (rc) return rc;
   }
   // K3
   {
     const int kblocks = need_grad ? ceil_div(2 * D, 128) : 0;
-    omc_stats_finalize_kernel<<<row_blocks + kblocks, 128, 0, stream>>>(partial, pl.slots, M, N, inv_tau, label_smoothing,
+    omc_stats_finalize_kernel<<<row_blocks + kblocks, 128, 0, stream>>>(partial, pl.slots, M, N, inv_tau, contra_temp_dev, label_smoothing,
                                                                        lse2, zt, sz, rowce, lse, row_blocks, ksump,
                                                                        pl.nrb, D, ksum);
     VAST_LAUNCH_OK("omc_stats_finalize");
@@ -548,6 +567,7 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
     P.epi.partial = partial;
     P.epi.num_slots = pl.slots;
     P.epi.scale2 = kLog2e * inv_tau;
+    P.epi.temp_dev = contra_temp_dev;
     P.epi.floor = weight_floor;
     P.epi.tgt_offset = static_cast<int>(row_offset);
     P.epi.row_offset = static_cast<int>(row_offset);
@@ -559,7 +579,7 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
     P.epi.do_sample = need_sample ? 1 : 0;
     rc = tc::launch_gemm<EpiProb, 256, 4, 8>(P, stream, "omc_prob_gemm");
     if (rc) return rc;
-    omc_sample_finalize_kernel<<<row_blocks, 128, 0, stream>>>(partial, pl.slots, M, N, inv_tau, label_smoothing, zt, sz,
+    omc_sample_finalize_kernel<<<row_blocks, 128, 0, stream>>>(partial, pl.slots, M, N, inv_tau, contra_temp_dev, label_smoothing, zt, sz,
                                                                neg_idx, rowdt);
     VAST_LAUNCH_OK("omc_sample_finalize");
   }
@@ -583,8 +603,8 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
     if (gb > cap) gb = cap;
     omc_grad_finalize_kernel<<<static_cast<unsigned>(gb), 256, 0, stream>>>(dqpart, pl.g_dq.k_splits, 2 * bs * dim, M, D, ksum,
                                                                            pk, static_cast<int>(row_offset), N,
-                                                                           label_smoothing, inv_tau / (2.0f * M), grad_cond,
-                                                                           grad_t);
+                                                                           label_smoothing, inv_tau, contra_temp_dev, lse2, zt,
+                                                                           grad_cond, grad_t);
     VAST_LAUNCH_OK("omc_grad_finalize");
   }
   // K8

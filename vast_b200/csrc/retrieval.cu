@@ -1,18 +1,659 @@
-// placeholder (replaced next): retrieval entry points
+// Retrieval scoring (evaluation/evaluation_mm.py:223,253-380): streaming similarity + top-k on the
+// tensor cores (the [Nt, Nv] score matrix is never materialised), candidate-list merge (split /
+// cross-GPU), exact fp64 re-scoring for bit-exact rankings, dense-matrix top-k / rank drop-ins, and
+// the candidate bookkeeping of the ITM re-rank (bucket by video, scatter scores).
+//
+// Ordering rule everywhere: score descending, index ascending (torch leaves ties unspecified).
 #include "common.cuh"
+#include "gemm_tc.cuh"
+
+namespace vast {
+
+// ------------------------------------------------------------------ sortable keys
+// key = orderable(score) << 32 | (0xFFFFFFFF - index): larger key == better candidate.  0 == empty.
+__device__ __forceinline__ uint32_t f32_orderable(float s) {
+  const uint32_t b = __float_as_uint(s);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float f32_from_orderable(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+__device__ __forceinline__ uint64_t make_key(float s, uint32_t idx) {
+  return (static_cast<uint64_t>(f32_orderable(s)) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - idx);
+}
+
+constexpr int TOPK_MAX = 64;  // list capacity of the GEMM-epilogue selection (smem: 64 x 128 x 8 B)
+
+// ------------------------------------------------------------------ GEMM epilogue: running top-k
+// One thread owns one query row (TMEM lane) and sees that row's scores in increasing column order.
+// Its sorted candidate list lives in shared memory ([pos][row] so lanes hit distinct banks); the
+// current k-th score is kept in a register, so the steady state is one compare per score.
+struct EpiTopK {
+  struct Params {
+    uint64_t* out;  // [M][n_splits][k]
+    int k;
+    int n_splits;
+    uint32_t col_offset;
+  };
+  static size_t smem_bytes() { return static_cast<size_t>(TOPK_MAX) * tc::BM * sizeof(uint64_t); }
+  const Params& p;
+  uint64_t* lists;
+  float thr;
+  int cnt;
+  __device__ EpiTopK(const Params& p_, uint8_t* smem) : p(p_), lists(reinterpret_cast<uint64_t*>(smem)) {}
+  __device__ __forceinline__ void item_begin(const tc::ItemCtx&) {
+    thr = -INFINITY;
+    cnt = 0;
+  }
+  __device__ __noinline__ void insert(uint64_t* my, float s, uint32_t idx) {
+    const uint64_t key = make_key(s, idx);
+    int pos = cnt < p.k ? cnt : p.k - 1;
+    while (pos > 0) {
+      const uint64_t prev = my[(pos - 1) * tc::BM];
+      if (prev >= key) break;
+      my[pos * tc::BM] = prev;
+      --pos;
+    }
+    my[pos * tc::BM] = key;
+    if (cnt < p.k) ++cnt;
+    if (cnt == p.k) thr = f32_from_orderable(static_cast<uint32_t>(my[(p.k - 1) * tc::BM] >> 32));
+  }
+  __device__ __forceinline__ void chunk(const tc::ItemCtx& c, const uint32_t (&v)[32], int col0) {
+    if (col0 >= c.N) return;
+    const int nvalid = c.N - col0;
+    uint64_t* my = lists + (c.row - c.m_blk * tc::BM);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float s = __uint_as_float(v[i]);
+      if (i < nvalid && s > thr) insert(my, s, p.col_offset + static_cast<uint32_t>(col0 + i));
+    }
+  }
+  __device__ __forceinline__ void item_end(const tc::ItemCtx& c) {
+    if (!c.row_valid) return;
+    const uint64_t* my = lists + (c.row - c.m_blk * tc::BM);
+    uint64_t* dst = p.out + (static_cast<int64_t>(c.row) * p.n_splits + c.n_split) * p.k;
+    for (int i = 0; i < p.k; ++i) dst[i] = i < cnt ? my[i * tc::BM] : 0ull;
+  }
+};
+
+// ------------------------------------------------------------------ candidate-list merge
+// One warp per row: `parts` lists of k_in keys -> top k_out.  Each lane holds up to MERGE_CAP keys.
+constexpr int MERGE_CAP = 32;
+__global__ void __launch_bounds__(128) topk_merge_kernel(const uint64_t* __restrict__ in, int64_t part_stride,
+                                                        int64_t row_stride, int parts, int k_in, int64_t n_rows,
+                                                        int k_out, uint64_t* __restrict__ out) {
+  const int64_t row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const int total = parts * k_in;
+  uint64_t mine[MERGE_CAP];
+#pragma unroll
+  for (int j = 0; j < MERGE_CAP; ++j) {
+    const int e = j * 32 + lane;
+    uint64_t key = 0;
+    if (e < total) key = in[(e / k_in) * part_stride + row * row_stride + (e % k_in)];
+    mine[j] = key;
+  }
+  for (int r = 0; r < k_out; ++r) {
+    uint64_t best = 0;
+    int bj = 0;
+#pragma unroll
+    for (int j = 0; j < MERGE_CAP; ++j)
+      if (mine[j] > best) {
+        best = mine[j];
+        bj = j;
+      }
+    uint64_t wbest = best;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint64_t other = __shfl_xor_sync(0xffffffffu, wbest, o);
+      wbest = other > wbest ? other : wbest;
+    }
+    // keys are unique (distinct indices) unless 0 == empty; the owner retires its copy
+    if (wbest != 0 && best == wbest) {
+#pragma unroll
+      for (int j = 0; j < MERGE_CAP; ++j)
+        if (j == bj) mine[j] = 0;
+    }
+    if (lane == 0) out[row * k_out + r] = wbest;
+  }
+}
+
+__global__ void topk_unpack_kernel(const uint64_t* __restrict__ keys, int64_t count, float* __restrict__ vals,
+                                   int32_t* __restrict__ idx) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= count) return;
+  const uint64_t k = keys[i];
+  if (k == 0) {
+    if (vals) vals[i] = -INFINITY;
+    if (idx) idx[i] = -1;
+  } else {
+    if (vals) vals[i] = f32_from_orderable(static_cast<uint32_t>(k >> 32));
+    if (idx) idx[i] = static_cast<int32_t>(0xFFFFFFFFu - static_cast<uint32_t>(k));
+  }
+}
+
+// ------------------------------------------------------------------ operand packing (bf16 / 3-way split)
+template <class TI>
+__global__ void sim_pack_kernel(const TI* __restrict__ x, int64_t rows, int64_t dim, int64_t ldx, int mode,
+                                int as_query, __nv_bfloat16* __restrict__ out) {
+  const int64_t total = rows * dim;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / dim, c = i - r * dim;
+    float v;
+    if constexpr (sizeof(TI) == 4)
+      v = x[r * ldx + c];
+    else
+      v = __bfloat162float(x[r * ldx + c]);
+    if (mode == VAST_SIM_BF16) {
+      out[r * dim + c] = __float2bfloat16_rn(v);
+    } else {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      const float r1 = v - __bfloat162float(hi);
+      const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+      const float r2 = r1 - __bfloat162float(mid);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(r2);
+      __nv_bfloat16* o = out + r * 6 * dim + c;
+      if (as_query) {  // (hi, hi, mid, mid, hi, lo)
+        o[0] = hi; o[dim] = hi; o[2 * dim] = mid; o[3 * dim] = mid; o[4 * dim] = hi; o[5 * dim] = lo;
+      } else {         // (hi, mid, hi, mid, lo, hi)
+        o[0] = hi; o[dim] = mid; o[2 * dim] = hi; o[3 * dim] = mid; o[4 * dim] = lo; o[5 * dim] = hi;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ exact fp64 re-scoring
+// Defined summation order (restated by oracle/spec.py::score_matrix_f64_lane_order): lane l sums
+// k = l, l+32, ... in increasing k; lanes combine by xor-butterfly 16, 8, 4, 2, 1.
+__device__ __forceinline__ double dot_f64_lane_order(const float* __restrict__ a, const float* __restrict__ b, int64_t dim,
+                                                     int lane) {
+  double acc = 0.0;
+  for (int64_t k = lane; k < dim; k += 32) acc = acc + static_cast<double>(a[k]) * static_cast<double>(b[k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
+__global__ void __launch_bounds__(128) rescore_pairs_kernel(const float* __restrict__ q, int64_t ldq,
+                                                           const float* __restrict__ kk, int64_t ldk, int64_t n_q,
+                                                           int64_t dim, const int32_t* __restrict__ idx, int64_t k,
+                                                           int64_t key_offset, double* __restrict__ score) {
+  const int64_t pair = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (pair >= n_q * k) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = pair / k;
+  const int32_t j = idx[pair];
+  double s = -INFINITY;
+  if (j >= 0) s = dot_f64_lane_order(q + row * ldq, kk + (static_cast<int64_t>(j) - key_offset) * ldk, dim, lane);
+  if (lane == 0) score[pair] = s;
+}
+
+// (score desc, idx asc, position asc) in-place sort of each row's k (<= 64) candidates; one warp per row.
+__device__ __forceinline__ bool better64(double sa, int32_t ia, int pa, double sb, int32_t ib, int pb) {
+  if (sa != sb) return sa > sb;
+  if (ia != ib) return ia < ib;
+  return pa < pb;
+}
+__global__ void __launch_bounds__(128) sort_rows_f64_kernel(double* __restrict__ score, int32_t* __restrict__ idx,
+                                                           int64_t n_q, int k) {
+  const int64_t row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= n_q) return;
+  const int lane = threadIdx.x & 31;
+  double* sr = score + row * k;
+  int32_t* ir = idx + row * k;
+  double s[2];
+  int32_t id[2];
+  int rank[2] = {0, 0};
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int e = t * 32 + lane;
+    s[t] = e < k ? sr[e] : -INFINITY;
+    id[t] = e < k ? ir[e] : 0x7fffffff;
+  }
+  for (int e = 0; e < k; ++e) {
+    const double so = __shfl_sync(0xffffffffu, s[e >> 5], e & 31);
+    const int32_t io = __shfl_sync(0xffffffffu, id[e >> 5], e & 31);
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+      if (better64(so, io, e, s[t], id[t], t * 32 + lane)) ++rank[t];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int e = t * 32 + lane;
+    if (e < k) {
+      sr[rank[t]] = s[t];
+      ir[rank[t]] = id[t];
+    }
+  }
+}
+
+// Brute-force exact top-k of listed rows: block per row, 8 warps stride the keys, per-warp sorted
+// lists in shared memory, merged by warp 0.
+constexpr int EXACT_WARPS = 8;
+__global__ void __launch_bounds__(EXACT_WARPS * 32) exact_topk_rows_kernel(
+    const float* __restrict__ q, int64_t ldq, const float* __restrict__ kk, int64_t ldk, int64_t n_k, int64_t dim,
+    const int32_t* __restrict__ rows_list, int k, int64_t col_offset, int32_t* __restrict__ idx_out,
+    double* __restrict__ score_out) {
+  __shared__ double ls[EXACT_WARPS][TOPK_MAX];
+  __shared__ int32_t li[EXACT_WARPS][TOPK_MAX];
+  __shared__ int lc[EXACT_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = rows_list[blockIdx.x];
+  const float* qr = q + row * ldq;
+  int cnt = 0;
+  for (int64_t j = warp; j < n_k; j += EXACT_WARPS) {
+    const double s = dot_f64_lane_order(qr, kk + j * ldk, dim, lane);
+    if (lane == 0) {
+      const int32_t gi = static_cast<int32_t>(j + col_offset);
+      if (cnt < k || better64(s, gi, 0, ls[warp][k - 1], li[warp][k - 1], 0)) {
+        int pos = cnt < k ? cnt : k - 1;
+        while (pos > 0 && better64(s, gi, 0, ls[warp][pos - 1], li[warp][pos - 1], 0)) {
+          ls[warp][pos] = ls[warp][pos - 1];
+          li[warp][pos] = li[warp][pos - 1];
+          --pos;
+        }
+        ls[warp][pos] = s;
+        li[warp][pos] = gi;
+        if (cnt < k) ++cnt;
+      }
+    }
+  }
+  if (lane == 0) lc[warp] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {  // k-way merge of the sorted per-warp lists
+    int head[EXACT_WARPS];
+    for (int w = 0; w < EXACT_WARPS; ++w) head[w] = 0;
+    for (int r = 0; r < k; ++r) {
+      int bw = -1;
+      for (int w = 0; w < EXACT_WARPS; ++w) {
+        if (head[w] >= lc[w]) continue;
+        if (bw < 0 || better64(ls[w][head[w]], li[w][head[w]], 0, ls[bw][head[bw]], li[bw][head[bw]], 0)) bw = w;
+      }
+      if (bw < 0) {
+        idx_out[row * k + r] = -1;
+        score_out[row * k + r] = -INFINITY;
+      } else {
+        idx_out[row * k + r] = li[bw][head[bw]];
+        score_out[row * k + r] = ls[bw][head[bw]];
+        ++head[bw];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ dense-matrix drop-ins
+// top-k along rows: one warp per row, warp-shared sorted list, parallel shift-insert.
+constexpr int DENSE_K_MAX = 128;
+__global__ void __launch_bounds__(128) dense_topk_rows_kernel(const float* __restrict__ score, int64_t n_rows,
+                                                             int64_t n_cols, int64_t ld, int k,
+                                                             int32_t* __restrict__ idx_out, float* __restrict__ val_out) {
+  __shared__ uint64_t lists[4][DENSE_K_MAX];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * 4 + w;
+  if (row >= n_rows) return;
+  uint64_t* my = lists[w];
+  int cnt = 0;
+  float thr = -INFINITY;
+  const float* sr = score + row * ld;
+  for (int64_t c0 = 0; c0 < n_cols; c0 += 32) {
+    const int64_t c = c0 + lane;
+    const float v = c < n_cols ? sr[c] : -INFINITY;
+    unsigned m = __ballot_sync(0xffffffffu, c < n_cols && v > thr);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const float s = __shfl_sync(0xffffffffu, v, src);
+      if (!(s > thr)) continue;  // threshold may have risen inside this chunk
+      const uint64_t key = make_key(s, static_cast<uint32_t>(c0 + src));
+      int gt = 0;
+      for (int i = lane; i < cnt; i += 32) gt += my[i] > key;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) gt += __shfl_xor_sync(0xffffffffu, gt, o);
+      const int last = cnt < k ? cnt : k - 1;  // position that receives the shifted tail
+      uint64_t tmp[DENSE_K_MAX / 32];
+#pragma unroll
+      for (int t = 0; t < DENSE_K_MAX / 32; ++t) {
+        const int i = t * 32 + lane;
+        tmp[t] = (i > gt && i <= last) ? my[i - 1] : 0;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < DENSE_K_MAX / 32; ++t) {
+        const int i = t * 32 + lane;
+        if (i > gt && i <= last) my[i] = tmp[t];
+      }
+      if (lane == 0) my[gt] = key;
+      __syncwarp();
+      if (cnt < k) ++cnt;
+      if (cnt == k) thr = f32_from_orderable(static_cast<uint32_t>(my[k - 1] >> 32));
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < k; i += 32) {
+    const bool ok = i < cnt;
+    idx_out[row * k + i] = ok ? static_cast<int32_t>(0xFFFFFFFFu - static_cast<uint32_t>(my[i])) : -1;
+    if (val_out) val_out[row * k + i] = ok ? f32_from_orderable(static_cast<uint32_t>(my[i] >> 32)) : -INFINITY;
+  }
+}
+
+// top-k down columns: one thread per column (coalesced across the warp), per-thread list [pos][lane].
+__global__ void __launch_bounds__(32) dense_topk_cols_kernel(const float* __restrict__ score, int64_t n_rows,
+                                                            int64_t n_cols, int64_t ld, int k,
+                                                            int32_t* __restrict__ idx_out, float* __restrict__ val_out) {
+  extern __shared__ uint64_t clists[];  // [k][32]
+  const int lane = threadIdx.x;
+  const int64_t col = blockIdx.x * 32 + lane;
+  if (col >= n_cols) return;
+  uint64_t* my = clists + lane;
+  int cnt = 0;
+  float thr = -INFINITY;
+  for (int64_t r = 0; r < n_rows; ++r) {
+    const float s = score[r * ld + col];
+    if (s > thr) {
+      const uint64_t key = make_key(s, static_cast<uint32_t>(r));
+      int pos = cnt < k ? cnt : k - 1;
+      while (pos > 0) {
+        const uint64_t prev = my[(pos - 1) * 32];
+        if (prev >= key) break;
+        my[pos * 32] = prev;
+        --pos;
+      }
+      my[pos * 32] = key;
+      if (cnt < k) ++cnt;
+      if (cnt == k) thr = f32_from_orderable(static_cast<uint32_t>(my[(k - 1) * 32] >> 32));
+    }
+  }
+  for (int i = 0; i < k; ++i) {  // output layout [k][n_cols] like torch.topk(dim=0)
+    const bool ok = i < cnt;
+    idx_out[i * n_cols + col] = ok ? static_cast<int32_t>(0xFFFFFFFFu - static_cast<uint32_t>(my[i * 32])) : -1;
+    if (val_out) val_out[i * n_cols + col] = ok ? f32_from_orderable(static_cast<uint32_t>(my[i * 32] >> 32)) : -INFINITY;
+  }
+}
+
+// rank of (gt_row, gt_col) inside its row (axis=1) or column (axis=0): one warp per query.
+__global__ void __launch_bounds__(128) dense_rank_kernel(const float* __restrict__ score, int64_t n_rows, int64_t n_cols,
+                                                        int64_t ld, int axis, const int32_t* __restrict__ gt_row,
+                                                        const int32_t* __restrict__ gt_col, int64_t n_gt,
+                                                        int32_t* __restrict__ rank_out) {
+  const int64_t g = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (g >= n_gt) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t r = gt_row[g], c = gt_col[g];
+  const float ref = score[r * ld + c];
+  int cnt = 0;
+  if (axis == 1) {
+    for (int64_t j = lane; j < n_cols; j += 32) {
+      const float s = score[r * ld + j];
+      cnt += (s > ref) || (s == ref && j < c);
+    }
+  } else {
+    for (int64_t i = lane; i < n_rows; i += 32) {
+      const float s = score[i * ld + c];
+      cnt += (s > ref) || (s == ref && i < r);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) rank_out[g] = cnt;
+}
+
+// ------------------------------------------------------------------ ITM re-rank bookkeeping
+__global__ void bucket_count_kernel(const int32_t* __restrict__ video_idx, int64_t n_pairs, int64_t n_videos,
+                                    int32_t* __restrict__ counts) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n_pairs) return;
+  const int32_t v = video_idx[i];
+  if (v >= 0 && v < n_videos) atomicAdd(&counts[v], 1);
+}
+// exclusive scan of counts[0..n) into offsets[0..n] (single block, fixed order)
+__global__ void __launch_bounds__(1024) bucket_scan_kernel(const int32_t* __restrict__ counts, int64_t n,
+                                                          int32_t* __restrict__ offsets, int32_t* __restrict__ cursor) {
+  __shared__ int32_t part[1024];
+  __shared__ int32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    const int32_t v = i < n ? counts[i] : 0;
+    part[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      int32_t t = 0;
+      if (static_cast<int>(threadIdx.x) >= o) t = part[threadIdx.x - o];
+      __syncthreads();
+      part[threadIdx.x] += t;
+      __syncthreads();
+    }
+    const int32_t excl = carry + part[threadIdx.x] - v;
+    if (i < n) {
+      offsets[i] = excl;
+      cursor[i] = excl;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += part[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[n] = carry;
+}
+__global__ void bucket_fill_kernel(const int32_t* __restrict__ text_idx, const int32_t* __restrict__ video_idx,
+                                   int64_t n_pairs, int64_t n_videos, int32_t* __restrict__ cursor,
+                                   int32_t* __restrict__ unsorted) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n_pairs) return;
+  const int32_t v = video_idx[i];
+  if (v >= 0 && v < n_videos) unsorted[atomicAdd(&cursor[v], 1)] = text_idx[i];
+}
+// ascending text order inside each bucket (rank sort; pairs are unique): one warp per video
+__global__ void __launch_bounds__(128) bucket_sort_kernel(const int32_t* __restrict__ offsets,
+                                                         const int32_t* __restrict__ unsorted, int64_t n_videos,
+                                                         int32_t* __restrict__ sorted) {
+  const int64_t v = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (v >= n_videos) return;
+  const int lane = threadIdx.x & 31;
+  const int32_t b = offsets[v], e = offsets[v + 1];
+  for (int32_t i = b + lane; i < e; i += 32) {
+    const int32_t x = unsorted[i];
+    int32_t rank = 0;
+    for (int32_t j = b; j < e; ++j) {
+      const int32_t y = unsorted[j];
+      rank += (y < x) || (y == x && j < i);
+    }
+    sorted[b + rank] = x;
+  }
+}
+__global__ void scatter_scores_kernel(const int32_t* __restrict__ text_idx, const int32_t* __restrict__ video_idx,
+                                      const float* __restrict__ scores, int64_t n_pairs, float* __restrict__ out,
+                                      int64_t ld) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n_pairs) return;
+  const int32_t t = text_idx[i], v = video_idx[i];
+  if (t >= 0 && v >= 0) out[static_cast<int64_t>(t) * ld + v] = scores[i];
+}
+
+static inline unsigned blocks_for(int64_t n, int per_block) { return static_cast<unsigned>(ceil_div64(n, per_block)); }
+
+struct TopkPlan {
+  tc::GemmShape g;
+  size_t ws_bytes;
+};
+static void topk_plan(TopkPlan* pl, int64_t n_q, int64_t n_k, int64_t cols, int64_t k) {
+  tc::fill_shape(&pl->g, 1, (int)n_q, (int)n_k, (int)cols, 256, 1);
+  int max_splits = static_cast<int>(MERGE_CAP * 32 / (k > 0 ? k : 1));
+  if (max_splits > 64) max_splits = 64;
+  if (max_splits < 1) max_splits = 1;
+  tc::choose_splits(&pl->g, device_sm_count(), max_splits, 1);
+  pl->ws_bytes = pl->g.n_splits > 1 ? align_up(sizeof(uint64_t) * n_q * pl->g.n_splits * k, 256) : 0;
+}
+
+}  // namespace vast
+
 using namespace vast;
-#define NOTYET(name) do { set_last_error(name ": not implemented yet"); return VAST_ERR_UNSUPPORTED; } while (0)
-extern "C" {
-int64_t vast_sim_operand_cols(int64_t dim, int mode) { return mode == VAST_SIM_FP32X3 ? 6 * dim : dim; }
-int vast_sim_pack_operand(const void*, int, int64_t, int64_t, int64_t, int, int, void*, vast_stream_t) { NOTYET("sim_pack_operand"); }
-size_t vast_sim_topk_workspace_bytes(int64_t, int64_t, int64_t, int64_t) { return 0; }
-int vast_sim_topk(const void*, const void*, int64_t, int64_t, int64_t, int64_t, int64_t, uint64_t*, void*, size_t, vast_stream_t) { NOTYET("sim_topk"); }
-int vast_topk_merge(const uint64_t*, int64_t, int64_t, int64_t, int64_t, uint64_t*, vast_stream_t) { NOTYET("topk_merge"); }
-int vast_topk_unpack(const uint64_t*, int64_t, float*, int32_t*, vast_stream_t) { NOTYET("topk_unpack"); }
-int vast_rescore_f64(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int32_t*, int64_t, int64_t, double*, vast_stream_t) { NOTYET("rescore_f64"); }
-int vast_exact_topk_rows(const float*, int64_t, const float*, int64_t, int64_t, int64_t, const int32_t*, int64_t, int64_t, int64_t, int32_t*, double*, vast_stream_t) { NOTYET("exact_topk_rows"); }
-int vast_dense_topk(const float*, int64_t, int64_t, int64_t, int64_t, int, int32_t*, float*, vast_stream_t) { NOTYET("dense_topk"); }
-int vast_dense_rank_of_gt(const float*, int64_t, int64_t, int64_t, int, const int32_t*, int64_t, int32_t*, vast_stream_t) { NOTYET("dense_rank_of_gt"); }
-int vast_bucket_by_video(const int32_t*, const int32_t*, int64_t, int64_t, int32_t*, int32_t*, void*, size_t, vast_stream_t) { NOTYET("bucket_by_video"); }
-int vast_scatter_scores(const int32_t*, const int32_t*, const float*, int64_t, float*, int64_t, vast_stream_t) { NOTYET("scatter_scores"); }
+
+extern "C" int64_t vast_sim_operand_cols(int64_t dim, int mode) { return mode == VAST_SIM_FP32X3 ? 6 * dim : dim; }
+
+extern "C" int vast_sim_pack_operand(const void* x, int x_dtype, int64_t rows, int64_t dim, int64_t ldx, int mode,
+                                     int as_query, void* out, vast_stream_t stream) {
+  VAST_REQUIRE(x && out && rows >= 0 && dim > 0 && ldx >= dim, VAST_ERR_INVALID, "sim_pack_operand: bad arguments");
+  VAST_REQUIRE(mode == VAST_SIM_BF16 || mode == VAST_SIM_FP32X3, VAST_ERR_UNSUPPORTED, "sim_pack_operand: bad mode");
+  VAST_REQUIRE(dim % 8 == 0, VAST_ERR_UNSUPPORTED, "sim_pack_operand: dim must be a multiple of 8");
+  if (rows == 0) return VAST_OK;
+  int64_t nb = ceil_div64(rows * dim, 256);
+  const int64_t cap = static_cast<int64_t>(device_sm_count()) * 16;
+  if (nb > cap) nb = cap;
+  auto* o = static_cast<__nv_bfloat16*>(out);
+  if (x_dtype == VAST_F32)
+    sim_pack_kernel<float><<<static_cast<unsigned>(nb), 256, 0, stream>>>(static_cast<const float*>(x), rows, dim, ldx, mode, as_query, o);
+  else if (x_dtype == VAST_BF16)
+    sim_pack_kernel<__nv_bfloat16><<<static_cast<unsigned>(nb), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), rows, dim, ldx, mode, as_query, o);
+  else
+    VAST_REQUIRE(false, VAST_ERR_UNSUPPORTED, "sim_pack_operand: f32 or bf16 input");
+  VAST_LAUNCH_OK("sim_pack_operand");
+  return VAST_OK;
+}
+
+extern "C" size_t vast_sim_topk_workspace_bytes(int64_t n_q, int64_t n_k, int64_t cols, int64_t k) {
+  if (n_q <= 0 || n_k <= 0 || cols <= 0 || k <= 0 || k > TOPK_MAX) return 0;
+  TopkPlan pl;
+  topk_plan(&pl, n_q, n_k, cols, k);
+  return pl.ws_bytes;
+}
+
+extern "C" int vast_sim_topk(const void* q_op, const void* k_op, int64_t n_q, int64_t n_k, int64_t cols, int64_t k,
+                             int64_t col_offset, uint64_t* out_keys, void* workspace, size_t workspace_bytes,
+                             vast_stream_t stream) {
+  VAST_REQUIRE(q_op && k_op && out_keys, VAST_ERR_INVALID, "sim_topk: null pointer");
+  VAST_REQUIRE(n_q > 0 && n_k > 0 && cols > 0 && n_q < (1 << 30) && n_k < (1 << 30), VAST_ERR_INVALID, "sim_topk: bad sizes");
+  VAST_REQUIRE(k >= 1 && k <= TOPK_MAX, VAST_ERR_UNSUPPORTED, "sim_topk: k must be in [1, %d] (got %lld)", TOPK_MAX, (long long)k);
+  VAST_REQUIRE(cols % 8 == 0, VAST_ERR_UNSUPPORTED, "sim_topk: operand width must be a multiple of 8");
+  VAST_REQUIRE(col_offset >= 0 && col_offset + n_k < 0xFFFFFFFFll, VAST_ERR_INVALID, "sim_topk: col_offset out of range");
+  TopkPlan pl;
+  topk_plan(&pl, n_q, n_k, cols, k);
+  VAST_REQUIRE(workspace_bytes >= pl.ws_bytes && (pl.ws_bytes == 0 || workspace), VAST_ERR_WORKSPACE,
+               "sim_topk: workspace %zu < required %zu", workspace_bytes, pl.ws_bytes);
+  tc::KernelParams<EpiTopK::Params> P;
+  memset(&P, 0, sizeof(P));
+  P.g = pl.g;
+  int rc = tc::make_tmap_2d(&P.tmA[0], q_op, VAST_BF16, n_q, cols, cols, tc::BM);
+  if (rc) return rc;
+  rc = tc::make_tmap_2d(&P.tmB[0], k_op, VAST_BF16, n_k, cols, cols, 256);
+  if (rc) return rc;
+  uint64_t* part = pl.g.n_splits > 1 ? static_cast<uint64_t*>(workspace) : out_keys;
+  P.epi = {part, static_cast<int>(k), pl.g.n_splits, static_cast<uint32_t>(col_offset)};
+  rc = tc::launch_gemm<EpiTopK, 256, 3, 4>(P, stream, "sim_topk_gemm");
+  if (rc) return rc;
+  if (pl.g.n_splits > 1) {
+    topk_merge_kernel<<<blocks_for(n_q, 4), 128, 0, stream>>>(part, k, pl.g.n_splits * k, pl.g.n_splits, (int)k, n_q, (int)k, out_keys);
+    VAST_LAUNCH_OK("topk_merge(splits)");
+  }
+  return VAST_OK;
+}
+
+extern "C" int vast_topk_merge(const uint64_t* keys_in, int64_t parts, int64_t n_q, int64_t k_in, int64_t k_out,
+                               uint64_t* keys_out, vast_stream_t stream) {
+  VAST_REQUIRE(keys_in && keys_out && parts > 0 && n_q >= 0 && k_in > 0 && k_out > 0, VAST_ERR_INVALID, "topk_merge: bad arguments");
+  VAST_REQUIRE(parts * k_in <= MERGE_CAP * 32, VAST_ERR_UNSUPPORTED, "topk_merge: parts*k_in must be <= %d", MERGE_CAP * 32);
+  if (n_q == 0) return VAST_OK;
+  topk_merge_kernel<<<blocks_for(n_q, 4), 128, 0, stream>>>(keys_in, n_q * k_in, k_in, (int)parts, (int)k_in, n_q, (int)k_out, keys_out);
+  VAST_LAUNCH_OK("topk_merge");
+  return VAST_OK;
+}
+
+extern "C" int vast_topk_unpack(const uint64_t* keys, int64_t count, float* values, int32_t* indices, vast_stream_t stream) {
+  VAST_REQUIRE(keys && count >= 0, VAST_ERR_INVALID, "topk_unpack: bad arguments");
+  if (count == 0) return VAST_OK;
+  topk_unpack_kernel<<<blocks_for(count, 256), 256, 0, stream>>>(keys, count, values, indices);
+  VAST_LAUNCH_OK("topk_unpack");
+  return VAST_OK;
+}
+
+extern "C" int vast_rescore_f64(const float* q, int64_t ldq, const float* kk, int64_t ldk, int64_t n_q, int64_t dim,
+                                int32_t* idx, int64_t k, int64_t key_offset, double* score64, vast_stream_t stream) {
+  VAST_REQUIRE(q && kk && idx && score64 && dim > 0, VAST_ERR_INVALID, "rescore_f64: null pointer");
+  VAST_REQUIRE(k >= 1 && k <= 64, VAST_ERR_UNSUPPORTED, "rescore_f64: k must be in [1, 64]");
+  if (n_q == 0) return VAST_OK;
+  rescore_pairs_kernel<<<blocks_for(n_q * k, 4), 128, 0, stream>>>(q, ldq, kk, ldk, n_q, dim, idx, k, key_offset, score64);
+  VAST_LAUNCH_OK("rescore_pairs");
+  sort_rows_f64_kernel<<<blocks_for(n_q, 4), 128, 0, stream>>>(score64, idx, n_q, (int)k);
+  VAST_LAUNCH_OK("sort_rows_f64");
+  return VAST_OK;
+}
+
+extern "C" int vast_exact_topk_rows(const float* q, int64_t ldq, const float* kk, int64_t ldk, int64_t n_k, int64_t dim,
+                                    const int32_t* rows_list, int64_t n_rows, int64_t k, int64_t col_offset,
+                                    int32_t* idx_out, double* score_out, vast_stream_t stream) {
+  VAST_REQUIRE(q && kk && rows_list && idx_out && score_out, VAST_ERR_INVALID, "exact_topk_rows: null pointer");
+  VAST_REQUIRE(k >= 1 && k <= TOPK_MAX, VAST_ERR_UNSUPPORTED, "exact_topk_rows: k must be in [1, %d]", TOPK_MAX);
+  if (n_rows == 0) return VAST_OK;
+  exact_topk_rows_kernel<<<static_cast<unsigned>(n_rows), EXACT_WARPS * 32, 0, stream>>>(q, ldq, kk, ldk, n_k, dim, rows_list, (int)k,
+                                                                                        col_offset, idx_out, score_out);
+  VAST_LAUNCH_OK("exact_topk_rows");
+  return VAST_OK;
+}
+
+extern "C" int vast_dense_topk(const float* score, int64_t n_rows, int64_t n_cols, int64_t ld, int64_t k, int axis,
+                               int32_t* idx_out, float* val_out, vast_stream_t stream) {
+  VAST_REQUIRE(score && idx_out && n_rows > 0 && n_cols > 0 && ld >= n_cols, VAST_ERR_INVALID, "dense_topk: bad arguments");
+  VAST_REQUIRE(k >= 1 && k <= DENSE_K_MAX, VAST_ERR_UNSUPPORTED, "dense_topk: k must be in [1, %d]", DENSE_K_MAX);
+  if (axis == 1) {
+    dense_topk_rows_kernel<<<blocks_for(n_rows, 4), 128, 0, stream>>>(score, n_rows, n_cols, ld, (int)k, idx_out, val_out);
+  } else if (axis == 0) {
+    dense_topk_cols_kernel<<<blocks_for(n_cols, 32), 32, k * 32 * sizeof(uint64_t), stream>>>(score, n_rows, n_cols, ld, (int)k, idx_out, val_out);
+  } else {
+    VAST_REQUIRE(false, VAST_ERR_INVALID, "dense_topk: axis must be 0 or 1");
+  }
+  VAST_LAUNCH_OK("dense_topk");
+  return VAST_OK;
+}
+
+extern "C" int vast_dense_rank_of_gt(const float* score, int64_t n_rows, int64_t n_cols, int64_t ld, int axis,
+                                     const int32_t* gt_row, const int32_t* gt_col, int64_t n_gt, int32_t* rank_out,
+                                     vast_stream_t stream) {
+  VAST_REQUIRE(score && gt_row && gt_col && rank_out && (axis == 0 || axis == 1), VAST_ERR_INVALID, "dense_rank_of_gt: bad arguments");
+  if (n_gt == 0) return VAST_OK;
+  dense_rank_kernel<<<blocks_for(n_gt, 4), 128, 0, stream>>>(score, n_rows, n_cols, ld, axis, gt_row, gt_col, n_gt, rank_out);
+  VAST_LAUNCH_OK("dense_rank_of_gt");
+  return VAST_OK;
+}
+
+extern "C" size_t vast_bucket_by_video_workspace_bytes(int64_t n_pairs, int64_t n_videos) {
+  return align_up(sizeof(int32_t) * (n_videos + 1), 256) * 2 + align_up(sizeof(int32_t) * (n_pairs > 0 ? n_pairs : 1), 256);
+}
+
+extern "C" int vast_bucket_by_video(const int32_t* text_idx, const int32_t* video_idx, int64_t n_pairs, int64_t n_videos,
+                                    int32_t* offsets, int32_t* texts_sorted, void* workspace, size_t workspace_bytes,
+                                    vast_stream_t stream) {
+  VAST_REQUIRE(text_idx && video_idx && offsets && texts_sorted && workspace, VAST_ERR_INVALID, "bucket_by_video: null pointer");
+  VAST_REQUIRE(n_pairs >= 0 && n_videos > 0 && n_pairs < (1ll << 31), VAST_ERR_INVALID, "bucket_by_video: bad sizes");
+  VAST_REQUIRE(workspace_bytes >= vast_bucket_by_video_workspace_bytes(n_pairs, n_videos), VAST_ERR_WORKSPACE,
+               "bucket_by_video: workspace too small");
+  Workspace ws(workspace, workspace_bytes);
+  int32_t* counts = ws.take<int32_t>(n_videos + 1);
+  int32_t* cursor = ws.take<int32_t>(n_videos + 1);
+  int32_t* unsorted = ws.take<int32_t>(n_pairs > 0 ? n_pairs : 1);
+  VAST_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (n_videos + 1), stream));
+  if (n_pairs > 0) {
+    bucket_count_kernel<<<blocks_for(n_pairs, 256), 256, 0, stream>>>(video_idx, n_pairs, n_videos, counts);
+    VAST_LAUNCH_OK("bucket_count");
+  }
+  bucket_scan_kernel<<<1, 1024, 0, stream>>>(counts, n_videos, offsets, cursor);
+  VAST_LAUNCH_OK("bucket_scan");
+  if (n_pairs > 0) {
+    bucket_fill_kernel<<<blocks_for(n_pairs, 256), 256, 0, stream>>>(text_idx, video_idx, n_pairs, n_videos, cursor, unsorted);
+    VAST_LAUNCH_OK("bucket_fill");
+    bucket_sort_kernel<<<blocks_for(n_videos, 4), 128, 0, stream>>>(offsets, unsorted, n_videos, texts_sorted);
+    VAST_LAUNCH_OK("bucket_sort");
+  }
+  return VAST_OK;
+}
+
+extern "C" int vast_scatter_scores(const int32_t* text_idx, const int32_t* video_idx, const float* scores, int64_t n_pairs,
+                                   float* out, int64_t ld, vast_stream_t stream) {
+  VAST_REQUIRE(text_idx && video_idx && scores && out, VAST_ERR_INVALID, "scatter_scores: null pointer");
+  if (n_pairs == 0) return VAST_OK;
+  scatter_scores_kernel<<<blocks_for(n_pairs, 256), 256, 0, stream>>>(text_idx, video_idx, scores, n_pairs, out, ld);
+  VAST_LAUNCH_OK("scatter_scores");
+  return VAST_OK;
 }

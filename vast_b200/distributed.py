@@ -1,0 +1,104 @@
+"""Data-parallel helpers with the reference's names and semantics (utils/distributed.py), built on
+`all_gather_into_tensor` (no list-of-tensors + torch.cat copy).  Work with NCCL on GPUs and gloo on CPU."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def _rank():
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def _gather_equal(t: torch.Tensor) -> torch.Tensor:
+    w = _world()
+    t = t.contiguous()
+    if w == 1:
+        return t.clone()
+    out = torch.empty((w * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t)
+    return out
+
+
+@torch.no_grad()
+def concat_all_gather(tensor: torch.Tensor) -> torch.Tensor:
+    """utils/distributed.py:50-66: all-gather equal-shaped tensors, concatenated in rank order, no grad."""
+    return _gather_equal(tensor)
+
+
+class _GatherWithGrad(torch.autograd.Function):
+    """utils/distributed.py:12-30 (GatherLayer): forward all-gather; backward returns this rank's slice of
+    the SUM over ranks of the gathered gradient (the reference all-reduces the whole [W, bs, ...] stack and
+    slices; a reduce-scatter moves W x less data for the same result)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.bs = x.shape[0]
+        return _gather_equal(x)
+
+    @staticmethod
+    def backward(ctx, grad):
+        w = _world()
+        grad = grad.contiguous()
+        if w == 1:
+            return grad
+        out = torch.empty((ctx.bs,) + tuple(grad.shape[1:]), dtype=grad.dtype, device=grad.device)
+        if grad.is_cuda:
+            dist.reduce_scatter_tensor(out, grad)
+        else:  # gloo has no reduce_scatter
+            g = grad.clone()
+            dist.all_reduce(g)
+            out = g[_rank() * ctx.bs:(_rank() + 1) * ctx.bs].clone()
+        return out
+
+
+def all_gather_with_grad(tensors: torch.Tensor) -> torch.Tensor:
+    """utils/distributed.py:33-47."""
+    if _world() == 1:
+        return tensors
+    return _GatherWithGrad.apply(tensors)
+
+
+def ddp_allgather(input: torch.Tensor) -> torch.Tensor:
+    """utils/distributed.py:133-149: ragged all-gather along dim 0 (sizes exchanged once, pad to max,
+    one all_gather_into_tensor, trim)."""
+    w = _world()
+    if w == 1:
+        return input.clone()
+    x = input.contiguous()
+    size = torch.tensor([x.shape[0]], dtype=torch.int64, device=x.device)
+    sizes = torch.empty(w, dtype=torch.int64, device=x.device)
+    dist.all_gather_into_tensor(sizes, size)
+    sizes = sizes.tolist()
+    mx = max(sizes)
+    if x.shape[0] < mx:
+        pad = torch.zeros((mx - x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        x = torch.cat((x, pad), dim=0)
+    out = torch.empty((w * mx,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x)
+    if all(s == mx for s in sizes):
+        return out
+    return torch.cat([out[r * mx:r * mx + s] for r, s in enumerate(sizes)], dim=0)
+
+
+def all_gather_list(data):
+    """utils/distributed.py:98-114: gather arbitrary picklable data from all ranks into a list."""
+    w = _world()
+    if w == 1:
+        return [data]
+    out = [None] * w
+    dist.all_gather_object(out, data)
+    return out
+
+
+def any_broadcast(data, root_rank):
+    """utils/distributed.py:117-128."""
+    if _world() == 1:
+        return data
+    box = [data]
+    dist.broadcast_object_list(box, src=root_rank)
+    return box[0]

@@ -109,7 +109,7 @@ def pack_pair(feat_t: torch.Tensor, feat_cond: torch.Tensor, out: torch.Tensor |
 
 
 # ------------------------------------------------------------------ contrastive step
-def omc_step(pack: torch.Tensor, bs: int, row_offset: int, contra_temp: float, label_smoothing: float = 0.1,
+def omc_step(pack: torch.Tensor, bs: int, row_offset: int, contra_temp, label_smoothing: float = 0.1,
              weight_floor: float = 1e-4, seed: int = 0, offset: int = 0, need_sample: bool = True,
              need_grad: bool = True, debug_noise: torch.Tensor | None = None, want_lse: bool = False):
     """Fused OMC step (vast.py:405-440 + backward) on the packed, gathered features.
@@ -128,11 +128,16 @@ def omc_step(pack: torch.Tensor, bs: int, row_offset: int, contra_temp: float, l
         assert debug_noise.shape == (2, bs, n_total) and debug_noise.dtype == torch.float32 and debug_noise.is_contiguous()
     nbytes = lib().vast_omc_workspace_bytes(bs, n_total, dim, int(need_sample), int(need_grad))
     ws = _ws(nbytes, dev)
-    check(lib().vast_omc_step(ptr(pack), bs, n_total, dim, row_offset, float(contra_temp), float(label_smoothing),
+    temp_dev = None
+    if isinstance(contra_temp, torch.Tensor):  # device scalar: read by the kernels, no host sync
+        require_cuda(contra_temp)
+        temp_dev = contra_temp.detach().reshape(1).float()
+        contra_temp = 0.0
+    check(lib().vast_omc_step(ptr(pack), bs, n_total, dim, row_offset, float(contra_temp), ptr(temp_dev), float(label_smoothing),
                               float(weight_floor), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1),
                               ptr(debug_noise), ptr(loss), ptr(neg), ptr(gc), ptr(gt), ptr(gtemp), ptr(lse),
                               ptr(ws), ws.numel(), stream_ptr()), "omc_step")
-    return dict(loss=loss, neg_idx=neg, grad_cond=gc, grad_t=gt, grad_temp=gtemp, lse=lse, _ws=ws)
+    return dict(loss=loss, neg_idx=neg, grad_cond=gc, grad_t=gt, grad_temp=gtemp, lse=lse, _ws=(ws, temp_dev))
 
 
 def gather_rows_concat3(ids_local, mask_local, ids_all, mask_all, cond_local, cond_all, neg_text, neg_cond):
@@ -153,3 +158,126 @@ def gather_rows_concat3(ids_local, mask_local, ids_all, mask_all, cond_local, co
                                          ptr(neg_text.contiguous()), ptr(neg_cond.contiguous()), bs, n_total,
                                          ptr(ids_out), ptr(mask_out), ptr(cond_out), stream_ptr()), "gather_rows_concat3")
     return ids_out, mask_out, cond_out
+
+
+# ------------------------------------------------------------------ retrieval scoring
+SIM_BF16, SIM_FP32X3 = _lib.SIM_BF16, _lib.SIM_FP32X3
+TOPK_MAX = 64
+
+
+def sim_pack_operand(x: torch.Tensor, mode: int = SIM_BF16, as_query: bool = True) -> torch.Tensor:
+    """16-bit tensor-core operand of x [rows, dim]: bf16 cast, or the 6-block 3-term split (fp32 grade)."""
+    require_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype in (torch.float32, torch.bfloat16)
+    rows, dim = x.shape
+    cols = lib().vast_sim_operand_cols(dim, mode)
+    out = torch.empty(rows, cols, dtype=torch.bfloat16, device=x.device)
+    check(lib().vast_sim_pack_operand(ptr(x), dtype_code(x.dtype), rows, dim, x.stride(0), mode, int(as_query),
+                                      ptr(out), stream_ptr()), "sim_pack_operand")
+    return out
+
+
+def sim_topk(q_op: torch.Tensor, k_op: torch.Tensor, k: int, col_offset: int = 0) -> torch.Tensor:
+    """Streaming similarity + top-k on packed operands; returns sortable keys [n_q, k] (int64 storage)."""
+    require_cuda(q_op, k_op)
+    assert q_op.dtype == torch.bfloat16 and k_op.dtype == torch.bfloat16 and q_op.is_contiguous() and k_op.is_contiguous()
+    assert q_op.shape[1] == k_op.shape[1]
+    n_q, cols = q_op.shape
+    n_k = k_op.shape[0]
+    keys = torch.empty(n_q, k, dtype=torch.int64, device=q_op.device)
+    nbytes = lib().vast_sim_topk_workspace_bytes(n_q, n_k, cols, k)
+    ws = _ws(nbytes, q_op.device)
+    check(lib().vast_sim_topk(ptr(q_op), ptr(k_op), n_q, n_k, cols, k, col_offset, ptr(keys), ptr(ws), ws.numel(),
+                              stream_ptr()), "sim_topk")
+    return keys
+
+
+def topk_merge(keys_parts: torch.Tensor, k_out: int) -> torch.Tensor:
+    """[parts, n_q, k_in] keys -> [n_q, k_out] (score desc, index asc)."""
+    require_cuda(keys_parts)
+    assert keys_parts.dim() == 3 and keys_parts.dtype == torch.int64 and keys_parts.is_contiguous()
+    parts, n_q, k_in = keys_parts.shape
+    out = torch.empty(n_q, k_out, dtype=torch.int64, device=keys_parts.device)
+    check(lib().vast_topk_merge(ptr(keys_parts), parts, n_q, k_in, k_out, ptr(out), stream_ptr()), "topk_merge")
+    return out
+
+
+def topk_unpack(keys: torch.Tensor):
+    require_cuda(keys)
+    keys = keys.contiguous()
+    vals = torch.empty(keys.shape, dtype=torch.float32, device=keys.device)
+    idx = torch.empty(keys.shape, dtype=torch.int32, device=keys.device)
+    check(lib().vast_topk_unpack(ptr(keys), keys.numel(), ptr(vals), ptr(idx), stream_ptr()), "topk_unpack")
+    return vals, idx
+
+
+def rescore_f64(q: torch.Tensor, kk: torch.Tensor, idx: torch.Tensor, key_offset: int = 0):
+    """Exact fp64 scores of candidate lists, rows re-sorted by (score desc, index asc).  idx is modified in place."""
+    require_cuda(q, kk, idx)
+    assert q.dtype == torch.float32 and kk.dtype == torch.float32 and idx.dtype == torch.int32 and idx.is_contiguous()
+    assert q.stride(1) == 1 and kk.stride(1) == 1
+    n_q, k = idx.shape
+    score = torch.empty(n_q, k, dtype=torch.float64, device=q.device)
+    check(lib().vast_rescore_f64(ptr(q), q.stride(0), ptr(kk), kk.stride(0), n_q, q.shape[1], ptr(idx), k, key_offset,
+                                 ptr(score), stream_ptr()), "rescore_f64")
+    return idx, score
+
+
+def exact_topk_rows(q, kk, rows_list, k, idx_out, score_out, col_offset: int = 0):
+    require_cuda(q, kk, rows_list, idx_out, score_out)
+    assert rows_list.dtype == torch.int32 and idx_out.dtype == torch.int32 and score_out.dtype == torch.float64
+    check(lib().vast_exact_topk_rows(ptr(q), q.stride(0), ptr(kk), kk.stride(0), kk.shape[0], q.shape[1],
+                                     ptr(rows_list), rows_list.numel(), k, col_offset, ptr(idx_out), ptr(score_out),
+                                     stream_ptr()), "exact_topk_rows")
+
+
+def dense_topk(score: torch.Tensor, k: int, axis: int = 1):
+    """top-k of a materialised fp32 matrix, ties -> lower index.  axis=1: [n_rows,k]; axis=0: [k,n_cols]."""
+    require_cuda(score)
+    assert score.dtype == torch.float32 and score.dim() == 2 and score.stride(1) == 1
+    n_rows, n_cols = score.shape
+    shape = (n_rows, k) if axis == 1 else (k, n_cols)
+    idx = torch.empty(shape, dtype=torch.int32, device=score.device)
+    vals = torch.empty(shape, dtype=torch.float32, device=score.device)
+    check(lib().vast_dense_topk(ptr(score), n_rows, n_cols, score.stride(0), k, axis, ptr(idx), ptr(vals), stream_ptr()),
+          "dense_topk")
+    return vals, idx
+
+
+def dense_rank_of_gt(score: torch.Tensor, gt_row: torch.Tensor, gt_col: torch.Tensor, axis: int = 1) -> torch.Tensor:
+    require_cuda(score, gt_row, gt_col)
+    assert score.dtype == torch.float32 and score.stride(1) == 1
+    gt_row, gt_col = gt_row.int().contiguous(), gt_col.int().contiguous()
+    out = torch.empty(gt_row.numel(), dtype=torch.int32, device=score.device)
+    check(lib().vast_dense_rank_of_gt(ptr(score), score.shape[0], score.shape[1], score.stride(0), axis, ptr(gt_row),
+                                      ptr(gt_col), gt_row.numel(), ptr(out), stream_ptr()), "dense_rank_of_gt")
+    return out
+
+
+def bucket_by_video(text_idx: torch.Tensor, video_idx: torch.Tensor, n_videos: int):
+    """Candidate pairs -> CSR by video: (offsets [n_videos+1] int32, texts [n_valid_pairs...] int32 ascending per video)."""
+    require_cuda(text_idx, video_idx)
+    t, v = text_idx.int().contiguous().reshape(-1), video_idx.int().contiguous().reshape(-1)
+    n = t.numel()
+    offsets = torch.empty(n_videos + 1, dtype=torch.int32, device=t.device)
+    texts = torch.full((max(n, 1),), -1, dtype=torch.int32, device=t.device)
+    ws = _ws(lib().vast_bucket_by_video_workspace_bytes(n, n_videos), t.device)
+    check(lib().vast_bucket_by_video(ptr(t), ptr(v), n, n_videos, ptr(offsets), ptr(texts), ptr(ws), ws.numel(),
+                                     stream_ptr()), "bucket_by_video")
+    return offsets, texts[:n]
+
+
+def scatter_scores(text_idx, video_idx, scores, out: torch.Tensor) -> torch.Tensor:
+    require_cuda(text_idx, video_idx, scores, out)
+    assert out.dtype == torch.float32 and out.stride(1) == 1
+    t, v = text_idx.int().contiguous().reshape(-1), video_idx.int().contiguous().reshape(-1)
+    s = scores.float().contiguous().reshape(-1)
+    check(lib().vast_scatter_scores(ptr(t), ptr(v), ptr(s), t.numel(), ptr(out), out.stride(0), stream_ptr()),
+          "scatter_scores")
+    return out
+
+
+def gemm_nt_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """fp32-grade a @ b.T for fp32 inputs on the bf16 tensor cores: 3-term bf16 splits, six leading cross
+    products accumulated in fp32 (replaces the fp32 `torch.matmul` of evaluation_mm.py:223)."""
+    return gemm_nt(sim_pack_operand(a.contiguous(), SIM_FP32X3, True), sim_pack_operand(b.contiguous(), SIM_FP32X3, False))
