@@ -49,6 +49,13 @@ VAST_API int vast_version(void);
 VAST_API const char* vast_last_error_string(void);
 VAST_API int vast_sm_count(void);
 
+/* Developer / benchmark aid (the only calls that synchronise): when enabled, every kernel launch of
+ * the library is bracketed by CUDA events on its stream; vast_timing_read waits for them, returns how
+ * many launches were recorded since the last read (<= max_entries) and fills ms_out[i] and the
+ * 48-byte name slots names_out[48*i]. */
+VAST_API int vast_timing_enable(int on);
+VAST_API int vast_timing_read(float* ms_out, char* names_out, int max_entries);
+
 /* ------------------------------------------------------------------------------------------
  * Feature build: pool -> concat -> (Linear stays cuBLAS) -> L2 normalise
  * ---------------------------------------------------------------------------------------- */

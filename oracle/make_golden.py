@@ -218,19 +218,20 @@ def golden_retrieval():
         log = ns.E.compute_metric_ret(score_b, ids_b, ids_txt_b, direction)
         out[f"b_metric_{direction}"] = np.array([log[f"{direction}_r1"], log[f"{direction}_ravg"]])
         out[f"b_recall_{direction}"] = np.array(log[f"{direction}_recall"])
-    # (c) refine_score_matrix W=1, both directions, k=7 (> one ITM chunk when many texts pick one video)
+    # (c) refine_score_matrix W=1, both directions; k >= 10 so R@10 does not depend on torch's unspecified
+    #     tie order among the exact zeros of the refined matrix
     g2 = torch.Generator().manual_seed(8)
     cond = torch.randn(nv_b, s, h, generator=g2)
     tids = torch.randint(0, 30522, (nt_b, l), generator=g2)
     tmask = (torch.rand(nt_b, l, generator=g2) > 0.1).long()
     m = R.make_stub_model(hidden=h)
     out.update(c_cond=cond.numpy(), c_ids=tids.numpy(), c_mask=tmask.numpy())
-    for direction, k in (("forward", 7), ("backward", 30)):
+    for direction, k in (("forward", 12), ("backward", 30)):
         r = ns.E.refine_score_matrix(cond, tids, tmask, score_b, m, k, direction=direction)
         out[f"c_refine_{direction}"] = r.numpy()
         log = ns.E.compute_metric_ret(r, ids_b, ids_txt_b, direction)
         out[f"c_recall_{direction}"] = np.array(log[f"{direction}_recall"])
-    out["c_k"] = np.array([7, 30])
+    out["c_k"] = np.array([12, 30])
     np.savez_compressed(os.path.join(GOLD, "retrieval.npz"), **out)
     print("retrieval:", out["a_recall_forward"], out["b_recall_backward"], out["c_recall_forward"])
 

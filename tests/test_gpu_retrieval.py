@@ -149,7 +149,7 @@ class _StubModel:
         return torch.softmax(h[:, 0] @ self.w, dim=1)[:, 1]
 
 
-@pytest.mark.parametrize("direction,k", [("forward", 7), ("backward", 30)])
+@pytest.mark.parametrize("direction,k", [("forward", 12), ("backward", 30)])
 def test_refine_score_matrix_golden(golden, direction, k):
     import vast_b200
     g = golden("retrieval")

@@ -17,6 +17,8 @@ SIGNATURES = {
     "vast_version": (i32, []),
     "vast_last_error_string": (C.c_char_p, []),
     "vast_sm_count": (i32, []),
+    "vast_timing_enable": (i32, [i32]),
+    "vast_timing_read": (i32, [vp, vp, i32]),
     "vast_pool_concat": (i32, [vp, i64, i64, i64, i32, vp, i64, i64, i64, i32, vp, i64, i64, i32, i64, vp, i32, i64, vp]),
     "vast_pool_concat_bwd": (i32, [vp, i64, i64, vp, i64, i64, i64, i32, vp, i64, i64, i64, i32, vp, i64, i64, i32, vp]),
     "vast_l2norm": (i32, [vp, i32, i64, i64, i64, f32, vp, i64, vp, i64, vp, vp]),

@@ -47,6 +47,17 @@ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int device_sm_count();
 
+// Optional per-kernel timing (bench.py's roofline leg): when enabled through vast_timing_enable,
+// every launch wrapped in VAST_TIMED is bracketed by CUDA events on its own stream.
+int timing_begin(const char* name, cudaStream_t stream);
+void timing_end(int slot, cudaStream_t stream);
+#define VAST_TIMED(stream, name, ...)                        \
+  do {                                                       \
+    const int _ts = ::vast::timing_begin(name, stream);      \
+    __VA_ARGS__;                                             \
+    ::vast::timing_end(_ts, stream);                         \
+  } while (0)
+
 // Bump allocator over the caller-provided workspace (the library never allocates).
 struct Workspace {
   char* base;

@@ -289,7 +289,7 @@ int launch_gemm(const KernelParams<typename Epi::Params>& P, cudaStream_t stream
   }
   int grid = P.g.num_items < device_sm_count() ? P.g.num_items : device_sm_count();
   if (grid <= 0) return VAST_OK;
-  kern<<<grid, 64 + 32 * NE, smem, stream>>>(P);
+  VAST_TIMED(stream, name, (kern<<<grid, 64 + 32 * NE, smem, stream>>>(P)));
   VAST_LAUNCH_OK(name);
   return VAST_OK;
 }

@@ -230,10 +230,12 @@ __global__ void __launch_bounds__(256) transpose_ksum_kernel(const __nv_bfloat16
   __shared__ __half tile[64][66];
   __shared__ float csum[8][64];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * 64;  // column in [0, 2D)
+  // blockIdx.x = prob * ceil(D/64) + column block inside that problem's D columns (any D)
+  const int nblk = static_cast<int>((dim + 63) / 64);
+  const int prob = static_cast<int>(blockIdx.x) / nblk;
+  const int64_t d0 = static_cast<int64_t>(static_cast<int>(blockIdx.x) - prob * nblk) * 64;
+  const int64_t c0 = prob * dim + d0;  // column in [0, 2D) of the packed row
   const int64_t r0 = static_cast<int64_t>(blockIdx.y) * TR_ROWS;
-  const int prob = c0 >= dim ? 1 : 0;
-  const int64_t d0 = c0 - prob * dim;
   float s0 = 0.f, s1 = 0.f;
   for (int sub = 0; sub < TR_ROWS / 64; ++sub) {
     const int64_t rb = r0 + sub * 64;
@@ -515,8 +517,8 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
 
   // K1
   if (need_grad) {
-    dim3 grid(static_cast<unsigned>(ceil_div(2 * D, 64)), static_cast<unsigned>(pl.nrb));
-    transpose_ksum_kernel<<<grid, 256, 0, stream>>>(pk, n_total, dim, pl.npad, KT, ksump, pl.nrb);
+    dim3 grid(static_cast<unsigned>(2 * ceil_div(D, 64)), static_cast<unsigned>(pl.nrb));
+    VAST_TIMED(stream, "transpose_ksum", (transpose_ksum_kernel<<<grid, 256, 0, stream>>>(pk, n_total, dim, pl.npad, KT, ksump, pl.nrb)));
     VAST_LAUNCH_OK("transpose_ksum");
   }
 
@@ -547,9 +549,10 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
   // K3
   {
     const int kblocks = need_grad ? ceil_div(2 * D, 128) : 0;
-    omc_stats_finalize_kernel<<<row_blocks + kblocks, 128, 0, stream>>>(partial, pl.slots, M, N, inv_tau, contra_temp_dev, label_smoothing,
-                                                                       lse2, zt, sz, rowce, lse, row_blocks, ksump,
-                                                                       pl.nrb, D, ksum);
+    VAST_TIMED(stream, "omc_stats_finalize",
+               (omc_stats_finalize_kernel<<<row_blocks + kblocks, 128, 0, stream>>>(
+                   partial, pl.slots, M, N, inv_tau, contra_temp_dev, label_smoothing, lse2, zt, sz, rowce, lse, row_blocks,
+                   ksump, pl.nrb, D, ksum)));
     VAST_LAUNCH_OK("omc_stats_finalize");
   }
   // K4 + K5: pass 2
@@ -579,8 +582,9 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
     P.epi.do_sample = need_sample ? 1 : 0;
     rc = tc::launch_gemm<EpiProb, 256, 4, 8>(P, stream, "omc_prob_gemm");
     if (rc) return rc;
-    omc_sample_finalize_kernel<<<row_blocks, 128, 0, stream>>>(partial, pl.slots, M, N, inv_tau, contra_temp_dev, label_smoothing, zt, sz,
-                                                               neg_idx, rowdt);
+    VAST_TIMED(stream, "omc_sample_finalize",
+               (omc_sample_finalize_kernel<<<row_blocks, 128, 0, stream>>>(partial, pl.slots, M, N, inv_tau, contra_temp_dev,
+                                                                           label_smoothing, zt, sz, neg_idx, rowdt)));
     VAST_LAUNCH_OK("omc_sample_finalize");
   }
   // K6 + K7: dQ
@@ -601,15 +605,16 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
     int64_t gb = ceil_div64(total, 256 * 4);
     const int64_t cap = static_cast<int64_t>(device_sm_count()) * 8;
     if (gb > cap) gb = cap;
-    omc_grad_finalize_kernel<<<static_cast<unsigned>(gb), 256, 0, stream>>>(dqpart, pl.g_dq.k_splits, 2 * bs * dim, M, D, ksum,
-                                                                           pk, static_cast<int>(row_offset), N,
-                                                                           label_smoothing, inv_tau, contra_temp_dev, lse2, zt,
-                                                                           grad_cond, grad_t);
+    VAST_TIMED(stream, "omc_grad_finalize",
+               (omc_grad_finalize_kernel<<<static_cast<unsigned>(gb), 256, 0, stream>>>(
+                   dqpart, pl.g_dq.k_splits, 2 * bs * dim, M, D, ksum, pk, static_cast<int>(row_offset), N, label_smoothing,
+                   inv_tau, contra_temp_dev, lse2, zt, grad_cond, grad_t)));
     VAST_LAUNCH_OK("omc_grad_finalize");
   }
   // K8
-  omc_final_reduce_kernel<<<1, 1024, 0, stream>>>(rowce, need_grad ? rowdt : nullptr, 2 * M, 1.0f / (2.0f * M), loss,
-                                                  need_grad ? grad_temp : nullptr);
+  VAST_TIMED(stream, "omc_final_reduce",
+             (omc_final_reduce_kernel<<<1, 1024, 0, stream>>>(rowce, need_grad ? rowdt : nullptr, 2 * M, 1.0f / (2.0f * M), loss,
+                                                             need_grad ? grad_temp : nullptr)));
   VAST_LAUNCH_OK("omc_final_reduce");
   return VAST_OK;
 }

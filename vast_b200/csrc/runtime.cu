@@ -30,6 +30,28 @@ int device_sm_count() {
   return cached[dev];
 }
 
+struct KTimer {
+  static constexpr int MAX = 8192;
+  bool enabled = false, created = false;
+  cudaEvent_t ev[MAX][2];
+  char names[MAX][48];
+  int n = 0;
+};
+static KTimer g_timer;
+
+int timing_begin(const char* name, cudaStream_t stream) {
+  KTimer& t = g_timer;
+  if (!t.enabled || t.n >= KTimer::MAX) return -1;
+  const int slot = t.n++;
+  strncpy(t.names[slot], name, 47);
+  t.names[slot][47] = 0;
+  cudaEventRecord(t.ev[slot][0], stream);
+  return slot;
+}
+void timing_end(int slot, cudaStream_t stream) {
+  if (slot >= 0) cudaEventRecord(g_timer.ev[slot][1], stream);
+}
+
 namespace tc {
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -113,5 +135,35 @@ const char* vast_last_error_string(void) { return vast::g_last_error; }
 int vast_version(void) { return VAST_B200_VERSION; }
 
 int vast_sm_count(void) { return vast::device_sm_count(); }
+
+int vast_timing_enable(int on) {
+  vast::KTimer& t = vast::g_timer;
+  if (on && !t.created) {
+    for (int i = 0; i < vast::KTimer::MAX; ++i)
+      for (int j = 0; j < 2; ++j)
+        if (cudaEventCreate(&t.ev[i][j]) != cudaSuccess) {
+          vast::set_last_error("timing_enable: cudaEventCreate failed");
+          return VAST_ERR_CUDA;
+        }
+    t.created = true;
+  }
+  t.enabled = on != 0;
+  t.n = 0;
+  return VAST_OK;
+}
+
+int vast_timing_read(float* ms_out, char* names_out, int max_entries) {
+  vast::KTimer& t = vast::g_timer;
+  int n = t.n < max_entries ? t.n : max_entries;
+  for (int i = 0; i < n; ++i) {
+    if (cudaEventSynchronize(t.ev[i][1]) != cudaSuccess || cudaEventElapsedTime(&ms_out[i], t.ev[i][0], t.ev[i][1]) != cudaSuccess) {
+      vast::set_last_error("timing_read: event query failed");
+      return VAST_ERR_CUDA;
+    }
+    if (names_out) memcpy(names_out + 48 * i, t.names[i], 48);
+  }
+  t.n = 0;
+  return n;
+}
 
 }  // extern "C"

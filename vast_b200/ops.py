@@ -14,6 +14,22 @@ def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
+def kernel_timing(enable: bool) -> None:
+    """Bracket every library kernel launch with CUDA events (benchmark aid)."""
+    check(lib().vast_timing_enable(int(enable)), "timing_enable")
+
+
+def kernel_timing_read(max_entries: int = 8192):
+    """[(kernel name, milliseconds), ...] for the launches recorded since the last read (synchronises)."""
+    import ctypes
+    ms = (ctypes.c_float * max_entries)()
+    names = ctypes.create_string_buffer(48 * max_entries)
+    n = lib().vast_timing_read(ms, names, max_entries)
+    if n < 0:
+        check(n, "timing_read")
+    return [(names.raw[48 * i:48 * i + 48].split(b"\0", 1)[0].decode(), float(ms[i])) for i in range(n)]
+
+
 # ------------------------------------------------------------------ generic GEMM (test / building block)
 def gemm_nt(a: torch.Tensor, b: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
     """C[m, n] = alpha * sum_k a[m, k] b[n, k]; a, b bf16 or fp16 (same dtype), C fp32."""
@@ -111,23 +127,30 @@ def pack_pair(feat_t: torch.Tensor, feat_cond: torch.Tensor, out: torch.Tensor |
 # ------------------------------------------------------------------ contrastive step
 def omc_step(pack: torch.Tensor, bs: int, row_offset: int, contra_temp, label_smoothing: float = 0.1,
              weight_floor: float = 1e-4, seed: int = 0, offset: int = 0, need_sample: bool = True,
-             need_grad: bool = True, debug_noise: torch.Tensor | None = None, want_lse: bool = False):
+             need_grad: bool = True, debug_noise: torch.Tensor | None = None, want_lse: bool = False,
+             buffers: dict | None = None):
     """Fused OMC step (vast.py:405-440 + backward) on the packed, gathered features.
-    Returns dict(loss[1], neg_idx[2,bs] | None, grad_cond, grad_t, grad_temp | None, lse | None)."""
+    Returns dict(loss[1], neg_idx[2,bs] | None, grad_cond, grad_t, grad_temp | None, lse | None).
+    `buffers` (a dict returned by an earlier call with the same shapes/flags) re-uses outputs + workspace."""
     require_cuda(pack)
     assert pack.dtype == torch.bfloat16 and pack.is_contiguous() and pack.dim() == 2 and pack.shape[1] % 2 == 0
     n_total, dim = pack.shape[0], pack.shape[1] // 2
     dev = pack.device
-    loss = torch.empty(1, dtype=torch.float32, device=dev)
-    neg = torch.empty(2, bs, dtype=torch.int64, device=dev) if need_sample else None
-    gc = torch.empty(bs, dim, dtype=torch.float32, device=dev) if need_grad else None
-    gt = torch.empty(bs, dim, dtype=torch.float32, device=dev) if need_grad else None
-    gtemp = torch.empty(1, dtype=torch.float32, device=dev) if need_grad else None
-    lse = torch.empty(2, bs, dtype=torch.float32, device=dev) if want_lse else None
     if debug_noise is not None:
         assert debug_noise.shape == (2, bs, n_total) and debug_noise.dtype == torch.float32 and debug_noise.is_contiguous()
-    nbytes = lib().vast_omc_workspace_bytes(bs, n_total, dim, int(need_sample), int(need_grad))
-    ws = _ws(nbytes, dev)
+    if buffers is not None:
+        loss, neg, gc, gt, gtemp, lse = (buffers[k] for k in ("loss", "neg_idx", "grad_cond", "grad_t", "grad_temp", "lse"))
+        ws = buffers["_ws"][0]
+        assert (neg is not None) == need_sample and (gc is not None) == need_grad and (lse is not None) == want_lse
+        assert gc is None or gc.shape == (bs, dim)
+    else:
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        neg = torch.empty(2, bs, dtype=torch.int64, device=dev) if need_sample else None
+        gc = torch.empty(bs, dim, dtype=torch.float32, device=dev) if need_grad else None
+        gt = torch.empty(bs, dim, dtype=torch.float32, device=dev) if need_grad else None
+        gtemp = torch.empty(1, dtype=torch.float32, device=dev) if need_grad else None
+        lse = torch.empty(2, bs, dtype=torch.float32, device=dev) if want_lse else None
+        ws = _ws(lib().vast_omc_workspace_bytes(bs, n_total, dim, int(need_sample), int(need_grad)), dev)
     temp_dev = None
     if isinstance(contra_temp, torch.Tensor):  # device scalar: read by the kernels, no host sync
         require_cuda(contra_temp)
