@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of the VAST contrastive + retrieval-scoring hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's torch CPU path (host cores)
+
+Primary line (one JSON object on stdout, rank 0):
+  metric  contrastive_fwd_bwd_pairs_per_sec on BASELINE config 3 (global batch 4096, 1024-d, tau .07):
+          a "step" = pack -> all-gather (N > 1) -> fused OMC loss + hard-negative sampling + backward.
+  value   device-timed throughput with the fp32 features already resident in HBM.
+  e2e     the same step through the public API (vast_b200.omc_loss_and_negatives + .backward()) with
+          pinned HOST feature buffers: H2D of the step's inputs and D2H of the loss inside the timed region.
+  roofline  the dominant kernel of the step, per-launch CUDA-event time vs the measured bf16 peak.
+  cpu_baseline  oracle/torch_ref.py (operation-for-operation torch CPU port of model/vast.py:405-440,
+          pinned bit-for-bit to the reference by tests/golden) on the box's host cores.
+  retrieval  secondary metric of the same BASELINE metric string: streaming similarity + top-16 queries/s
+          at config 5 (100k x 100k x 512), column-sharded over the N GPUs.
+Scaling is STRONG: the global batch (and the retrieval problem) is fixed, per-GPU work shrinks with N."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_GLOBAL, DIM, TEMP = 4096, 1024, 0.07          # BASELINE.json configs[2] / north_star target shape
+RET_N, RET_D, RET_K = 100_000, 512, 16           # BASELINE.json configs[4]
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+def synth(n, d, seed, rows=None):
+    """SURVEY 8d synthetic features: t = randn, c = t + 0.8 randn, L2-normalised (host, fp32)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    t = torch.randn(n, d, generator=g)
+    c = t + 0.8 * torch.randn(n, d, generator=g)
+    t = torch.nn.functional.normalize(t, dim=-1)
+    c = torch.nn.functional.normalize(c, dim=-1)
+    if rows is not None:
+        t, c = t[rows], c[rows]
+    return t.contiguous(), c.contiguous()
+
+
+class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region (NVML; nvidia-smi fallback)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        self.index = index
+        self.th = None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {getattr(nv, k): k.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", "")
+                     for k in dir(nv) if k.startswith(("nvmlClocksEventReason", "nvmlClocksThrottleReason"))
+                     and isinstance(getattr(nv, k), int)}
+            while not self._stop.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if bit and (r & bit) == bit and bit & (bit - 1) == 0:
+                        self.reasons.add(nm)
+                time.sleep(0.02)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f"sampler_error:{type(e).__name__}")
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.th:
+            self.th.join(timeout=2)
+        drop = {"None", "GpuIdle", "ApplicationsClocksSetting", "All"}
+        rs = sorted(r for r in self.reasons if r not in drop)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": rs, "samples": len(self.samples)}
+
+
+def timed_loop(torch, dist, world, fn, steps):
+    """barrier + sync | K steps between CUDA events on the current stream | sync; max over ranks (ms)."""
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    return ms
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import vast_b200
+    from vast_b200 import ops
+    peaks = load_peaks()
+    dev = torch.device("cuda", local_rank)
+    K, W = args.steps, max(args.warmup, 3)
+    assert N_GLOBAL % world == 0
+    bs = N_GLOBAL // world
+    rows = slice(rank * bs, (rank + 1) * bs)
+
+    # ---- inputs: R rotating sets so consecutive steps never find their inputs in the 126 MB L2
+    per_set = 2 * bs * DIM * 4
+    R = max(2, -(-160 * 2 ** 20 // per_set))
+    host_sets = [synth(N_GLOBAL, DIM, 1234 + s, rows) for s in range(R)]
+    dev_sets = [(t.to(dev), c.to(dev)) for t, c in host_sets]
+    temp = torch.full((1,), TEMP, device=dev)
+    local_pack = torch.empty(bs, 2 * DIM, dtype=torch.bfloat16, device=dev)
+    pack_all = torch.empty(N_GLOBAL, 2 * DIM, dtype=torch.bfloat16, device=dev) if world > 1 else local_pack
+    state = {"buf": None}
+
+    def step_dev(i):
+        ft, fc = dev_sets[i % R]
+        ops.pack_pair(ft, fc, out=local_pack)
+        if world > 1:
+            dist.all_gather_into_tensor(pack_all, local_pack)
+        state["buf"] = ops.omc_step(pack_all, bs, rank * bs, temp, 0.1, 1e-4, seed=1234, offset=i, need_sample=True,
+                                    need_grad=True, buffers=state["buf"])
+
+    for i in range(W):
+        step_dev(i)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = timed_loop(torch, dist, world, step_dev, K)
+    clocks = sampler.stop()
+    loss_val = state["buf"]["loss"].item()
+    value = N_GLOBAL * K / (ms * 1e-3)
+    launches_per_step = 1 + 8  # pack_pair + the 8 kernels of vast_omc_step
+
+    # ---- per-kernel breakdown: the same K steps again with every launch bracketed by CUDA events
+    ops.kernel_timing(True)
+    if world > 1:
+        dist.barrier()
+    for i in range(min(K, 400)):
+        step_dev(i)
+    torch.cuda.synchronize()
+    recs = ops.kernel_timing_read()
+    ops.kernel_timing(False)
+    agg = {}
+    for nm, t in recs:
+        a = agg.setdefault(nm, [0.0, 0])
+        a[0] += t
+        a[1] += 1
+    kern = {nm: {"avg_us": 1e3 * a[0] / a[1], "launches": a[1]} for nm, a in agg.items()}
+    step_sum_us = sum(v["avg_us"] for v in kern.values())
+    gemm_flops = 4.0 * bs * N_GLOBAL * DIM  # two problems x 2*bs*N*D per GEMM launch (algorithmic)
+    gemms = {k: v for k, v in kern.items() if k.endswith("_gemm")}
+    dom = max(gemms, key=lambda k: gemms[k]["avg_us"])
+    achieved = gemm_flops / (gemms[dom]["avg_us"] * 1e-6) / 1e12
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": round(achieved, 1), "peak": peaks["tf_sustained"],
+                "unit": "TFLOP/s", "frac": round(achieved / peaks["tf_sustained"], 4), "traffic": None,
+                "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
+                "how": "per-launch CUDA events on the launch stream, second pass of the same steps",
+                "share_of_step": round(gemms[dom]["avg_us"] / step_sum_us, 3),
+                "kernels_us": {k: round(v["avg_us"], 2) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["avg_us"])},
+                "step_algorithmic_tflops": round(8.0 * bs * N_GLOBAL * DIM * world / (ms / K * 1e-3) / 1e12 / world, 1),
+                "step_frac": round(8.0 * bs * N_GLOBAL * DIM / (ms / K * 1e-3) / 1e12 / peaks["tf_sustained"], 4)}
+
+    # ---- e2e: public API, pinned host inputs (bf16), H2D + D2H inside the timed region
+    pin = [(t.bfloat16().pin_memory(), c.bfloat16().pin_memory()) for t, c in host_sets]
+    d_t = torch.empty(bs, DIM, dtype=torch.bfloat16, device=dev)
+    d_c = torch.empty(bs, DIM, dtype=torch.bfloat16, device=dev)
+    temp_param = torch.nn.Parameter(torch.tensor(TEMP, device=dev))
+    sink = {"loss": 0.0}
+
+    def step_e2e(i):
+        ht, hc = pin[i % R]
+        d_t.copy_(ht, non_blocking=True)
+        d_c.copy_(hc, non_blocking=True)
+        ft = d_t.detach().requires_grad_()
+        fc = d_c.detach().requires_grad_()
+        temp_param.grad = None
+        loss, neg_text, neg_cond = vast_b200.omc_loss_and_negatives(fc, ft, temp_param, rank=rank, world_size=world)
+        loss.backward()
+        sink["loss"] = loss.item()  # D2H read of the step's result
+
+    for i in range(W):
+        step_e2e(i)
+    Ke = min(K, 200)
+    ms_e = timed_loop(torch, dist, world, step_e2e, Ke)
+    e2e = {"value": N_GLOBAL * Ke / (ms_e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": 2 * bs * DIM * 2,
+           "d2h_bytes_per_step": 4, "ms_per_step": ms_e / Ke, "steps": Ke,
+           "api": "vast_b200.omc_loss_and_negatives(...) + loss.backward() + loss.item()"}
+
+    # ---- retrieval (config 5): streaming similarity + top-16, columns sharded over the ranks
+    ret = None
+    if not args.no_retrieval:
+        g = torch.Generator().manual_seed(4321)
+        rt = torch.nn.functional.normalize(torch.randn(RET_N, RET_D, generator=g), dim=-1).to(dev)
+        rv = torch.nn.functional.normalize(torch.randn(RET_N, RET_D, generator=g), dim=-1).to(dev)
+        shard = (rank, world)
+
+        def step_ret(i):
+            vast_b200.retrieval_topk(rt, rv, RET_K, mode="bf16", shard=shard)
+
+        for i in range(2):
+            step_ret(i)
+        Kr = 5
+        ops.kernel_timing(True)
+        ms_r = timed_loop(torch, dist, world, step_ret, Kr)
+        recs = ops.kernel_timing_read()
+        ops.kernel_timing(False)
+        g_us = [t * 1e3 for nm, t in recs if nm == "sim_topk_gemm"]
+        fl = 2.0 * RET_N * (RET_N / world) * RET_D
+        ach = fl / (statistics.mean(g_us) * 1e-6) / 1e12 if g_us else None
+        ret = {"metric": "retrieval_topk_queries_per_sec", "value": RET_N * Kr / (ms_r * 1e-3), "unit": "queries/s",
+               "ms_per_step": ms_r / Kr, "steps": Kr,
+               "config": {"workload": f"BASELINE cfg5: {RET_N}x{RET_N} similarity, D={RET_D}, top-{RET_K}, bf16 mode, "
+                                      f"columns sharded over {world} GPU(s), candidate all-gather + merge"},
+               "roofline": {"bound": "tensor", "kernel": "sim_topk_gemm", "achieved": round(ach, 1) if ach else None,
+                            "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                            "frac": round(ach / peaks["tf_burst"], 4) if ach else None,
+                            "peak_source": f"{peaks['src']} bf16 burst (kernel dominates a short step)"}}
+        del rt, rv
+
+    # ---- CPU baseline: the torch port of the reference path on the host cores (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_contrastive(sample_steps=3)
+
+    if rank == 0:
+        line = {
+            "metric": "contrastive_fwd_bwd_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"BASELINE cfg3: OMC contrastive loss + hard-negative sampling + backward, global batch "
+                                   f"{N_GLOBAL}, D={DIM}, tau={TEMP}, label smoothing 0.1, bf16-in/fp32-accumulate, "
+                                   f"{world} rank(s) x {bs} rows, one packed NCCL all-gather per step",
+                       "l2": f"inputs rotate over {R} distinct sets ({R * per_set >> 20} MiB > 126 MB L2)",
+                       "loss_last_step": loss_val},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * K, "roofline": roofline,
+            "cpu_baseline": cpu, "retrieval": ret,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_contrastive(sample_steps=3, budget_s=None, steps=None, warmup=1):
+    """Times oracle/torch_ref.contrastive_step (the reference's torch CPU math, vast.py:405-440 + backward +
+    per-row multinomial loops) on the host cores.  Returns the cpu_baseline object."""
+    import torch
+    from oracle import torch_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    t, c = synth(N_GLOBAL, DIM, 1234)
+    m = N_GLOBAL
+    torch.manual_seed(0)
+    t0 = time.perf_counter()
+    run_cpu_sample(torch_ref, t, c, m)
+    first = time.perf_counter() - t0
+    n = steps if steps is not None else sample_steps
+    if budget_s is not None and first * (n + warmup) > budget_s:   # bound the work: a row sample of the same step
+        m = max(64, int(N_GLOBAL * budget_s / (first * (n + warmup))) // 64 * 64)
+    for _ in range(max(0, warmup - (1 if m == N_GLOBAL else 0))):
+        run_cpu_sample(torch_ref, t, c, m)
+    times = []
+    for _ in range(n):
+        t0 = time.perf_counter()
+        run_cpu_sample(torch_ref, t, c, m)
+        times.append(time.perf_counter() - t0)
+    sec = statistics.median(times)
+    return {"value": m / sec, "unit": "pairs/s", "cores": cores, "kind": "port", "ms_per_step": sec * 1e3,
+            "sample": f"{m} of {N_GLOBAL} local rows vs all {N_GLOBAL} columns per step (fp32, torch {torch.__version__} CPU, "
+                      f"{cores} threads), median of {n}",
+            "what": "oracle/torch_ref.py: torch-CPU port of model/vast.py:405-440 + autograd, bit-for-bit equal to the "
+                    "reference on tests/golden/omc_w1.npz"}
+
+
+def run_cpu_sample(torch_ref, t, c, m):
+    import torch
+    fc = c[:m].detach().requires_grad_()
+    ft = t[:m].detach().requires_grad_()
+    temp = torch.tensor(TEMP, requires_grad=True)
+    loss, n1, n2 = torch_ref.itc_and_negatives(fc, ft, t, c, temp)
+    loss.backward()
+    return loss.item()
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (torch ops on the host cores).
+    /root/reference is not present on the GPU box, so this is the operation-for-operation port
+    (oracle/torch_ref.py); rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    cpu = cpu_contrastive(budget_s=150.0, steps=K, warmup=max(W, 1))
+    line = {"impl": "reference", "metric": "contrastive_fwd_bwd_pairs_per_sec", "value": cpu["value"], "unit": "pairs/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": cpu["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"BASELINE cfg3: OMC contrastive loss + hard-negative sampling + backward, global batch "
+                                   f"{N_GLOBAL}, D={DIM}, tau={TEMP}; reference torch CPU path on the host cores"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-retrieval", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
