@@ -161,17 +161,18 @@ def run_ours(args):
     clocks = sampler.stop()
     loss_val = state["buf"]["loss"].item()
     value = N_GLOBAL * K / (ms * 1e-3)
-    launches_per_step = 1 + 8  # pack_pair + the 8 kernels of vast_omc_step
 
     # ---- per-kernel breakdown: the same K steps again with every launch bracketed by CUDA events
     ops.kernel_timing(True)
     if world > 1:
         dist.barrier()
-    for i in range(min(K, 400)):
+    kt_steps = min(K, 400)
+    for i in range(kt_steps):
         step_dev(i)
     torch.cuda.synchronize()
     recs = ops.kernel_timing_read()
     ops.kernel_timing(False)
+    launches_per_step = len(recs) // kt_steps   # every kernel of the step is bracketed (pack_pair + vast_omc_step's)
     agg = {}
     for nm, t in recs:
         a = agg.setdefault(nm, [0.0, 0])

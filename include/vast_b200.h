@@ -103,6 +103,9 @@ VAST_API int vast_pack_pair(const void* feat_t, const void* feat_cond, int dtype
 
 VAST_API size_t vast_omc_workspace_bytes(int64_t bs, int64_t n_total, int64_t dim, int need_sample, int need_grad);
 
+/* vast_omc_step flags */
+#define VAST_OMC_TWO_PASS 1 /* evaluate the logits twice (row max / sum-exp pass first) instead of once */
+
 /* One fused contrastive step on this rank's rows.
  *   pack        [n_total, 2*dim] bf16, row n = (feat_t_all[n] | feat_cond_all[n]) in rank order
  *               (the output of all_gather_into_tensor over vast_pack_pair buffers); the local
@@ -113,16 +116,25 @@ VAST_API size_t vast_omc_workspace_bytes(int64_t bs, int64_t n_total, int64_t di
  *   neg_idx     [2, bs] int64 or NULL: [0] = negative TEXT index per row drawn from
  *               softmax(sim_cond2t)+floor, [1] = negative CONDITION index drawn from
  *               softmax(sim_t2cond)+floor, own positive excluded  (vast.py:423-440).
- *               Draw = argmax_j w_j / E_j, E ~ Exp(1) from Philox4x32-10(seed, offset) -- the same
- *               distribution as torch.multinomial(w, 1).  debug_noise [2, bs, n_total] f32 (or
- *               NULL) replaces the generator's E (index 0 = cond2t) for index-exact tests.
+ *               The draw has the distribution of torch.multinomial(w, 1).  torch draws
+ *               argmax_j w_j / E_j (E ~ Exp(1)); here the same race runs between 32-column chunks
+ *               (a chunk's min of E_j / w_j is Exp(sum of its w_j)), the column inside the winning
+ *               chunk is drawn by inverse CDF, and the constant floor is the uniform component of a
+ *               two-part mixture; all randomness is Philox4x32-10(seed, offset), restated by
+ *               oracle/spec.py::hardneg_hier_sample.
+ *   debug_noise [2, bs, n_total] f32 or NULL: caller-supplied Exp(1) variates; the draw is then
+ *               literally argmax_j w_j / debug_noise_j (index 0 = cond2t) -- index-exact parity tests
+ *               against the reference's own draws.  Implies VAST_OMC_TWO_PASS.
+ *   flags       0 (default): logits evaluated once, exponent reference = the positive pair's logit,
+ *               automatic on-device fallback to the two-pass form if a probability numerator would leave
+ *               the fp16 range; VAST_OMC_TWO_PASS: always two passes.
  *   grad_cond, grad_t [bs, dim] f32, grad_temp [1] f32 (all three or none): d loss / d input
  *               (unit upstream gradient; gathered side carries no gradient, utils/distributed.py:50).
  *   lse         [2, bs] f32 or NULL: natural-log row log-sum-exp of (cond2t, t2cond).
  * The [bs, n_total] logit matrices are never written to HBM. */
 VAST_API int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int64_t dim, int64_t row_offset,
                   float contra_temp, const float* contra_temp_dev, float label_smoothing, float weight_floor,
-                  uint64_t seed, uint64_t offset, const float* debug_noise,
+                  uint64_t seed, uint64_t offset, const float* debug_noise, int flags,
                   float* loss, int64_t* neg_idx, float* grad_cond, float* grad_t, float* grad_temp,
                   float* lse, void* workspace, size_t workspace_bytes, vast_stream_t stream);
 
@@ -225,6 +237,12 @@ VAST_API int vast_scatter_scores(const int32_t* text_idx, const int32_t* video_i
 VAST_API size_t vast_gemm_nt_workspace_bytes(int64_t M, int64_t N, int64_t K);
 VAST_API int vast_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, int dtype, int64_t M, int64_t N,
                  int64_t K, float alpha, float* C, int64_t ldc, void* workspace, size_t workspace_bytes,
+                 vast_stream_t stream);
+/* C[m, n] = alpha * sum_k A[m, k] * B[k, n]: B row-major [K, N] (ldb >= N) is fed to the tensor cores as
+ * the MN-major operand straight from its row-major layout (no transposed copy); dtype_a must equal
+ * dtype_b (VAST_BF16 or VAST_F16).  Workspace as for vast_gemm_nt. */
+VAST_API int vast_gemm_nn(const void* A, int64_t lda, int dtype_a, const void* B, int64_t ldb, int dtype_b, int64_t M,
+                 int64_t N, int64_t K, float alpha, float* C, int64_t ldc, void* workspace, size_t workspace_bytes,
                  vast_stream_t stream);
 
 #ifdef __cplusplus

@@ -169,8 +169,9 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def sampler_bits(seed, offset, stream, rows, cols, row0=0):
-    """The 32-bit Philox words the CUDA hard-negative sampler (vast_b200/csrc/omc.cu, EpiProb)
-    draws for element (row, col) of direction `stream` (0 = cond2t, 1 = t2cond):
+    """The 32-bit Philox words the CUDA hard-negative sampler (vast_b200/csrc/omc.cu, EpiSoft)
+    draws for CHUNK `col` (32 consecutive logit columns) of row `row`, direction `stream`
+    (0 = cond2t, 1 = t2cond):
     counter = (col >> 2, row0 + row, offset lo32, (offset hi32 << 1) | stream),
     key = (seed lo32, seed hi32), word = col & 3.  row0 = rank * bs (global row)."""
     r = (np.arange(rows, dtype=np.uint32) + np.uint32(row0))[:, None]
@@ -185,6 +186,60 @@ def sampler_expo(seed, offset, stream, rows, cols, row0=0):
     """Exp(1) race noise of the CUDA sampler: v = (x + 0.5) 2^-32, E = -log1p(-v)."""
     v = (sampler_bits(seed, offset, stream, rows, cols, row0).astype(np.float64) + 0.5) * (2.0 ** -32)
     return -np.log1p(-v)
+
+
+def sampler_tail_units(seed, offset, stream, rows, row0=0):
+    """The three uniforms (within-chunk, mixture, uniform-component) of the CUDA sampler's finalize step:
+    Philox counter = (0xFFFFFFFF, row0 + row, offset lo32, (offset hi32 << 1) | stream), words 0..2,
+    u = (x + 0.5) 2^-32."""
+    r = np.arange(rows, dtype=np.uint32) + np.uint32(row0)
+    c3 = ((((int(offset) >> 32) << 1) | int(stream)) & 0xFFFFFFFF)
+    out = philox4x32_10(np.full(rows, 0xFFFFFFFF, dtype=np.uint32), r, np.uint32(int(offset) & 0xFFFFFFFF), np.uint32(c3),
+                        int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF)
+    return (np.stack(out[:3], axis=-1).astype(np.float64) + 0.5) * (2.0 ** -32)
+
+
+def hardneg_hier_sample(sim, rank, chunk_expo, units, floor=1e-4, chunk=32):
+    """The production hard-negative draw of vast_b200 (csrc/omc.cu: EpiSoft<false> + row finalize), an
+    exact re-formulation of `torch.multinomial(softmax(sim) + floor with the positive zeroed, 1)`
+    (model/vast.py:423-440):
+      * w_j = p_j + floor (j != target) is the mixture  (1 - p_t) * [p_j / (1 - p_t)]  +  floor (N-1) * [1 / (N-1)];
+      * the softmax component is drawn by the exponential race BETWEEN chunks of `chunk` columns
+        (argmax_c  sum_{j in c} p_j / E_c: the minimum of independent E_j / p_j over a chunk is
+        Exp(sum p_j) and its argmin is independent of it) followed by inverse CDF inside the chunk.
+    sim [bs, N] logits; chunk_expo [bs, ceil(N/chunk)] Exp(1); units [bs, 3] uniforms.  Returns
+    (index [bs], used_softmax_component [bs] bool, winning chunk [bs])."""
+    z = np.asarray(sim, dtype=np.float64)
+    bs, n = z.shape
+    p = np.exp(z - _lse(z)[:, None])
+    tcol = rank * bs + np.arange(bs)
+    pt = p[np.arange(bs), tcol].copy()
+    p[np.arange(bs), tcol] = 0.0
+    nch = (n + chunk - 1) // chunk
+    pad = np.zeros((bs, nch * chunk))
+    pad[:, :n] = p
+    cs = pad.reshape(bs, nch, chunk).sum(axis=2)
+    key = cs / np.asarray(chunk_expo, dtype=np.float64)[:, :nch]
+    win = key.argmax(axis=1)
+    out = np.zeros(bs, dtype=np.int64)
+    used_a = np.zeros(bs, dtype=bool)
+    for i in range(bs):
+        w_a = 1.0 - pt[i]
+        w_b = floor * (n - 1)
+        take_a = cs[i, win[i]] > 0 and units[i, 1] * (w_a + w_b) < w_a
+        if n == 1:
+            out[i] = -1
+        elif take_a:
+            seg = pad[i, win[i] * chunk:(win[i] + 1) * chunk]
+            pre = np.cumsum(seg)
+            hit = np.nonzero((seg > 0) & (pre >= units[i, 0] * pre[-1]))[0]
+            j = hit[0] if hit.size else np.nonzero(seg > 0)[0][-1]
+            out[i] = win[i] * chunk + j
+            used_a[i] = True
+        else:
+            j = min(int(units[i, 2] * (n - 1)), n - 2)
+            out[i] = j + 1 if j >= tcol[i] else j
+    return out, used_a, win
 
 
 def gather_negatives(condition_feats, condition_feats_collate, input_ids, attention_mask,

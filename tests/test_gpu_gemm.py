@@ -25,6 +25,35 @@ def test_gemm_exact_grid(m, n, k, dtype):
     assert torch.equal(c.double(), ref), f"max abs err {(c.double() - ref).abs().max().item()}"
 
 
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (128, 256, 128), (256, 512, 1024), (200, 304, 136), (1, 8, 8),
+                                   (129, 264, 72), (512, 1024, 4096), (100, 72, 304)])
+@pytest.mark.parametrize("da,db", [(torch.bfloat16, torch.bfloat16), (torch.float16, torch.float16)])
+def test_gemm_nn_mn_major_b_exact_grid(m, n, k, da, db):
+    """B row-major [K, N] consumed as the MN-major UMMA operand (no transpose): the dQ GEMM of the contrastive
+    step multiplies the fp16 probabilities by the row-major gathered features.  (Mixed fp16 x bf16 operands
+    are rejected: tcgen05.mma kind::f16 raises an illegal-instruction fault for them on sm_100a.)"""
+    from vast_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(m * 5 + n * 11 + k)
+    a = _grid((m, k), g, da)
+    b = _grid((k, n), g, db)
+    c = ops.gemm_nn(a, b)
+    ref = a.double() @ b.double()
+    torch.cuda.synchronize()
+    assert torch.equal(c.double(), ref), f"max abs err {(c.double() - ref).abs().max().item()}"
+
+
+def test_gemm_nn_strided_view_of_packed_buffer():
+    from vast_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    pack = torch.randn(700, 2 * 264, generator=g, device="cuda").half()
+    p = torch.rand(300, 704, generator=g, device="cuda").half()[:, :700]   # ld 704 >= 700
+    for half in (0, 1):
+        b = pack[:, half * 264:(half + 1) * 264]
+        c = ops.gemm_nn(p, b)
+        ref = p.double() @ b.double()
+        assert (c.double() - ref).abs().max().item() < 2e-4 * ref.abs().max().item()
+
+
 def test_gemm_random_and_alpha_and_strides():
     from vast_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(0)

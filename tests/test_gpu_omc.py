@@ -68,6 +68,23 @@ def check_negatives(neg, o, expo, rank, bs, floor=1e-4):
     assert exact >= int(0.97 * 2 * bs), exact
 
 
+def check_negatives_hier(neg, o, seed, offset, rank, bs, n, floor=1e-4):
+    """Production sampler (chunk race + inverse CDF + uniform floor component) vs its oracle restatement fed
+    with the same Philox words; fp32 / fp16 near-ties may flip a few draws."""
+    neg = neg.cpu().numpy()
+    nch = (n + 31) // 32
+    exact = 0
+    for d, name in enumerate(("sim_cond2t", "sim_t2cond")):
+        expo = spec.sampler_expo(seed, offset, d, bs, nch, row0=rank * bs)
+        units = spec.sampler_tail_units(seed, offset, d, bs, row0=rank * bs)
+        want, _, _ = spec.hardneg_hier_sample(o[name], rank, expo, units, floor)
+        exact += int((neg[d] == want).sum())
+        if n > 1:
+            assert np.all(neg[d] != rank * bs + np.arange(bs)), "positive sampled as negative"
+            assert np.all((neg[d] >= 0) & (neg[d] < n))
+    assert exact >= int(0.97 * 2 * bs), (exact, 2 * bs)
+
+
 def test_cfg1_golden_loss_grads_and_reference_negatives(golden):
     """cfg1 (bs 64, D 512, W 1): loss/grads vs oracle on bf16-rounded inputs and vs the reference's
     fp32 numbers; with the reference's own Exp(1) noise the sampled negatives reproduce."""
@@ -99,20 +116,51 @@ def test_w2_rank_offsets_golden(golden, rank):
     check_negatives(out["neg_idx"], o, g[f"r{rank}_expo"][::-1], rank, bs)
 
 
+@pytest.mark.parametrize("two_pass", [False, True])
 @pytest.mark.parametrize("bs,world,rank,dim,temp", [(100, 3, 1, 72, 0.07), (1, 1, 0, 8, 0.5), (130, 2, 1, 264, 0.02),
                                                      (256, 4, 3, 512, 0.07)])
-def test_ragged_shapes_philox(bs, world, rank, dim, temp):
+def test_ragged_shapes_philox(bs, world, rank, dim, temp, two_pass):
     n = bs * world
     gen = torch.Generator().manual_seed(bs + dim)
     t = torch.nn.functional.normalize(torch.randn(n, dim, generator=gen), dim=-1)
     c = torch.nn.functional.normalize(t + 0.8 * torch.randn(n, dim, generator=gen), dim=-1)
     seed, offset = 0x1234567887654321, (7 << 32) | 5
-    out = run_step(t.numpy(), c.numpy(), bs, rank, temp, seed=seed, offset=offset, want_lse=True)
+    out = run_step(t.numpy(), c.numpy(), bs, rank, temp, seed=seed, offset=offset, want_lse=True, two_pass=two_pass)
     o = oracle(t.numpy(), c.numpy(), bs, rank, temp)
     check_against_oracle(out, o, bs)
-    if n > 1:
-        expo = np.stack([spec.sampler_expo(seed, offset, d, bs, n, row0=rank * bs) for d in (0, 1)])
-        check_negatives(out["neg_idx"], o, expo, rank, bs)
+    check_negatives_hier(out["neg_idx"], o, seed, offset, rank, bs, n)
+
+
+@pytest.mark.parametrize("case", ["hard_rows", "small_tau", "untrained"])
+def test_single_pass_range_and_fallback(case):
+    """The single-pass form keeps softmax numerators relative to the positive pair in fp16.  Rows whose best
+    negative beats the positive by more than 16 ln2 nats overflow that range: the on-device fallback must
+    redo the step in two passes and still match the oracle.  'untrained' (positives indistinguishable from
+    negatives) must stay within range and match as well."""
+    n, dim = 192, 128
+    gen = torch.Generator().manual_seed(5)
+    t = torch.nn.functional.normalize(torch.randn(n, dim, generator=gen), dim=-1)
+    if case == "untrained":
+        c = torch.nn.functional.normalize(torch.randn(n, dim, generator=gen), dim=-1)
+        temp = 0.07
+    else:
+        c = torch.nn.functional.normalize(t + 0.5 * torch.randn(n, dim, generator=gen), dim=-1)
+        temp = 0.07
+        if case == "hard_rows":   # mislabeled pairs: positive anti-correlated, a perfect negative elsewhere
+            c[3] = -t[3]
+            c[77] = t[3]
+            c[150] = -t[150]
+        else:
+            temp = 0.004          # 1 / tau = 250: ordinary negatives already exceed the range
+    seed, offset = 17, 9
+    out = run_step(t.numpy(), c.numpy(), n, 0, temp, seed=seed, offset=offset, want_lse=True)
+    ref = run_step(t.numpy(), c.numpy(), n, 0, temp, seed=seed, offset=offset, want_lse=True, two_pass=True)
+    o = oracle(t.numpy(), c.numpy(), n, 0, temp)
+    check_against_oracle(out, o, n)
+    check_against_oracle(ref, o, n)
+    check_negatives_hier(out["neg_idx"], o, seed, offset, 0, n)
+    if case != "untrained":       # the fallback IS the two-pass form: identical bits
+        assert torch.equal(out["grad_t"], ref["grad_t"]) and torch.equal(out["neg_idx"], ref["neg_idx"])
 
 
 def test_cfg3_shape_full_size():
@@ -125,8 +173,7 @@ def test_cfg3_shape_full_size():
     out = run_step(t.numpy(), c.numpy(), n, 0, temp, seed=seed, offset=offset, want_lse=True)
     o = oracle(t.numpy(), c.numpy(), n, 0, temp)
     check_against_oracle(out, o, n)
-    expo = np.stack([spec.sampler_expo(seed, offset, d, n, n) for d in (0, 1)])
-    check_negatives(out["neg_idx"], o, expo, 0, n)
+    check_negatives_hier(out["neg_idx"], o, seed, offset, 0, n)
     # determinism: same seed/offset -> identical outputs, different offset -> different draws
     out2 = run_step(t.numpy(), c.numpy(), n, 0, temp, seed=seed, offset=offset)
     assert torch.equal(out["neg_idx"], out2["neg_idx"]) and torch.equal(out["grad_t"], out2["grad_t"])

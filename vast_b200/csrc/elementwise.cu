@@ -1,6 +1,8 @@
 // HBM-bound kernels of the hot path: pool + concat (+ backward), L2 normalise (+ backward),
 // all-gather send-buffer packing, negative-row gather + 3-way concat.  All coalesced, 128-bit
 // vectorised, warp-shuffle reductions; grids sized so every SM has several CTAs in flight.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace vast {
@@ -236,6 +238,44 @@ __global__ void pack_pair_kernel(const TI* __restrict__ ft, const TI* __restrict
   }
 }
 
+// Vectorised variant (dim % 8 == 0, ld % 8 == 0, 16-byte aligned pointers): one thread converts 8
+// consecutive elements of one of the two inputs -> one 16-byte store.
+template <class TI>
+__global__ void __launch_bounds__(256) pack_pair_vec_kernel(const TI* __restrict__ ft, const TI* __restrict__ fc, int64_t bs,
+                                                           int dim8, int64_t ld, __nv_bfloat16* __restrict__ pack) {
+  const int64_t total = bs * 2 * dim8;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t b = i / (2 * dim8);
+    const int v = static_cast<int>(i - b * 2 * dim8);  // 16-byte vector inside the packed row
+    const bool second = v >= dim8;
+    const TI* src = (second ? fc : ft) + b * ld + static_cast<int64_t>(second ? v - dim8 : v) * 8;
+    uint4 o;
+    if constexpr (sizeof(TI) == 4) {
+      const float4 a = ld_stream_f4(src), c = ld_stream_f4(src + 4);
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(c.x, c.y), h3 = __floats2bfloat162_rn(c.z, c.w);
+      o.x = *reinterpret_cast<uint32_t*>(&h0);
+      o.y = *reinterpret_cast<uint32_t*>(&h1);
+      o.z = *reinterpret_cast<uint32_t*>(&h2);
+      o.w = *reinterpret_cast<uint32_t*>(&h3);
+    } else if constexpr (std::is_same<TI, __nv_bfloat16>::value) {
+      o = ld_stream16(src);
+    } else {
+      const uint4 raw = ld_stream16(src);
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+      uint32_t* ow = &o.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        __nv_bfloat162 r = __floats2bfloat162_rn(f.x, f.y);
+        ow[j] = *reinterpret_cast<uint32_t*>(&r);
+      }
+    }
+    *reinterpret_cast<uint4*>(pack + b * 16 * dim8 + static_cast<int64_t>(v) * 8) = o;
+  }
+}
+
 // ------------------------------------------------------------------ negative gather + 3-way concat
 // Source row r in [0, 2bs): r < bs -> cond_local[r], written to out rows r and r + 2bs (read once,
 // written twice); r >= bs -> cond_all[neg_cond[r - bs]] written to out row r.  Compulsory traffic:
@@ -437,8 +477,22 @@ extern "C" int vast_pack_pair(const void* feat_t, const void* feat_cond, int dty
                               int64_t ld_in, void* pack_bf16, vast_stream_t stream) {
   VAST_REQUIRE(feat_t && feat_cond && pack_bf16 && dim > 0 && ld_in >= dim, VAST_ERR_INVALID, "pack_pair: bad arguments");
   if (bs == 0) return VAST_OK;
-  const unsigned grid = grid_for(bs * dim, 256);
   auto* out = static_cast<__nv_bfloat16*>(pack_bf16);
+  const bool vec = dim % 8 == 0 && ld_in % 8 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(feat_t) | reinterpret_cast<uintptr_t>(feat_cond) | reinterpret_cast<uintptr_t>(pack_bf16)) & 15) == 0;
+  if (vec && (dtype == VAST_F32 || dtype == VAST_BF16 || dtype == VAST_F16)) {
+    const int dim8 = static_cast<int>(dim / 8);
+    const unsigned g = grid_for(bs * 2 * dim8, 256);
+    if (dtype == VAST_F32)
+      VAST_TIMED(stream, "pack_pair", (pack_pair_vec_kernel<float><<<g, 256, 0, stream>>>(static_cast<const float*>(feat_t), static_cast<const float*>(feat_cond), bs, dim8, ld_in, out)));
+    else if (dtype == VAST_BF16)
+      VAST_TIMED(stream, "pack_pair", (pack_pair_vec_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(feat_t), static_cast<const __nv_bfloat16*>(feat_cond), bs, dim8, ld_in, out)));
+    else
+      VAST_TIMED(stream, "pack_pair", (pack_pair_vec_kernel<__half><<<g, 256, 0, stream>>>(static_cast<const __half*>(feat_t), static_cast<const __half*>(feat_cond), bs, dim8, ld_in, out)));
+    VAST_LAUNCH_OK("pack_pair");
+    return VAST_OK;
+  }
+  const unsigned grid = grid_for(bs * dim, 256);
   if (dtype == VAST_F32)
     pack_pair_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(feat_t), static_cast<const float*>(feat_cond), bs, dim, ld_in, out);
   else if (dtype == VAST_BF16)

@@ -26,28 +26,30 @@ extern "C" size_t vast_gemm_nt_workspace_bytes(int64_t M, int64_t N, int64_t K) 
   return g.k_splits > 1 ? static_cast<size_t>(g.k_splits) * M * N * sizeof(float) + 256 : 0;
 }
 
-extern "C" int vast_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, int dtype, int64_t M, int64_t N,
-                            int64_t K, float alpha, float* C, int64_t ldc, void* workspace, size_t workspace_bytes,
-                            vast_stream_t stream) {
-  VAST_REQUIRE(A && B && C, VAST_ERR_INVALID, "gemm_nt: null pointer");
+template <bool B_MN>
+static int gemm_impl(const void* A, int64_t lda, int dtype_a, const void* B, int64_t ldb, int dtype_b, int64_t M, int64_t N,
+                     int64_t K, float alpha, float* C, int64_t ldc, void* workspace, size_t workspace_bytes,
+                     vast_stream_t stream, const char* name) {
+  VAST_REQUIRE(A && B && C, VAST_ERR_INVALID, "%s: null pointer", name);
   VAST_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1 << 30) && N < (1 << 30) && K < (1 << 30), VAST_ERR_INVALID,
-               "gemm_nt: bad sizes");
-  VAST_REQUIRE(dtype == VAST_BF16 || dtype == VAST_F16, VAST_ERR_UNSUPPORTED, "gemm_nt: bf16/f16 only");
+               "%s: bad sizes", name);
+  VAST_REQUIRE((dtype_a == VAST_BF16 || dtype_a == VAST_F16) && dtype_b == dtype_a, VAST_ERR_UNSUPPORTED,
+               "%s: both operands bf16 or both f16 (tcgen05 kind::f16 faults on mixed formats)", name);
   using Epi = tc::EpiStore;
   tc::KernelParams<Epi::Params> P;
   memset(&P, 0, sizeof(P));
-  tc::fill_shape(&P.g, 1, (int)M, (int)N, (int)K, 256, dtype == VAST_BF16 ? 1 : 0);
+  tc::fill_shape(&P.g, 1, (int)M, (int)N, (int)K, 256, dtype_a == VAST_BF16 ? 1 : 0, dtype_b == VAST_BF16 ? 1 : 0, B_MN);
   tc::choose_splits(&P.g, device_sm_count(), 64, 8);
-  int rc = tc::make_tmap_2d(&P.tmA[0], A, dtype, M, K, lda, tc::BM);
+  int rc = tc::make_tmap_2d(&P.tmA[0], A, dtype_a, M, K, lda, tc::BM);
   if (rc) return rc;
-  rc = tc::make_tmap_2d(&P.tmB[0], B, dtype, N, K, ldb, 256);
+  rc = B_MN ? tc::make_tmap_2d(&P.tmB[0], B, dtype_b, K, N, ldb, tc::BK) : tc::make_tmap_2d(&P.tmB[0], B, dtype_b, N, K, ldb, 256);
   if (rc) return rc;
   if (P.g.k_splits > 1) {
     Workspace ws(workspace, workspace_bytes);
     float* part = ws.take<float>(static_cast<size_t>(P.g.k_splits) * M * N);
-    VAST_REQUIRE(workspace && ws.ok(), VAST_ERR_WORKSPACE, "gemm_nt: workspace too small");
+    VAST_REQUIRE(workspace && ws.ok(), VAST_ERR_WORKSPACE, "%s: workspace too small", name);
     P.epi = {part, N, 0, M * N, alpha};
-    rc = tc::launch_gemm<Epi, 256, 4, 4>(P, stream, "gemm_nt");
+    rc = tc::launch_gemm<Epi, 256, 4, 4, B_MN>(P, stream, name);
     if (rc) return rc;
     const int64_t total = M * N;
     reduce_ksplit_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(part, M * N, P.g.k_splits, C, ldc, M, N);
@@ -55,5 +57,20 @@ extern "C" int vast_gemm_nt(const void* A, int64_t lda, const void* B, int64_t l
     return VAST_OK;
   }
   P.epi = {C, ldc, 0, 0, alpha};
-  return tc::launch_gemm<Epi, 256, 4, 4>(P, stream, "gemm_nt");
+  return tc::launch_gemm<Epi, 256, 4, 4, B_MN>(P, stream, name);
+}
+
+// C[m, n] = alpha * sum_k A[m, k] * B[n, k]   (both operands K-major)
+extern "C" int vast_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, int dtype, int64_t M, int64_t N,
+                            int64_t K, float alpha, float* C, int64_t ldc, void* workspace, size_t workspace_bytes,
+                            vast_stream_t stream) {
+  return gemm_impl<false>(A, lda, dtype, B, ldb, dtype, M, N, K, alpha, C, ldc, workspace, workspace_bytes, stream, "gemm_nt");
+}
+
+// C[m, n] = alpha * sum_k A[m, k] * B[k, n]   (B row-major = MN-major operand, consumed without a transpose;
+// A and B share one 16-bit format)
+extern "C" int vast_gemm_nn(const void* A, int64_t lda, int dtype_a, const void* B, int64_t ldb, int dtype_b, int64_t M,
+                            int64_t N, int64_t K, float alpha, float* C, int64_t ldc, void* workspace,
+                            size_t workspace_bytes, vast_stream_t stream) {
+  return gemm_impl<true>(A, lda, dtype_a, B, ldb, dtype_b, M, N, K, alpha, C, ldc, workspace, workspace_bytes, stream, "gemm_nn");
 }

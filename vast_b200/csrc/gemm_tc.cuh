@@ -45,6 +45,7 @@ struct alignas(64) KernelParams {
   CUtensorMap tmA[MAX_PROBLEMS];
   CUtensorMap tmB[MAX_PROBLEMS];
   GemmShape g;
+  const int* gate;  // optional device flag: the whole launch is a no-op while *gate == 0
   EpiParams epi;
 };
 
@@ -89,11 +90,16 @@ struct SmemLayout {
   static constexpr uint32_t ALIGN_SLACK = 1024;
 };
 
-template <class Epi, int BN, int STAGES, int NE>
+// B_MN = false: B is [N rows, K cols] K-major (an "NT" GEMM, S = A . B^T with B given row-wise).
+// B_MN = true : B is [K rows, N cols] row-major, i.e. the MN-major UMMA operand: each pipeline stage holds
+//               BN/64 TMA boxes of 64 K-rows x 64 N-columns (128-byte swizzle atoms stacked along K),
+//               so a row-major matrix is consumed as the right-hand side WITHOUT a transposed copy.
+template <class Epi, int BN, int STAGES, int NE, bool B_MN>
 __global__ void __launch_bounds__(64 + 32 * NE, 1)
 gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
   static_assert(NE == 4 || NE == 8, "4 or 8 epilogue warps");
   static_assert(BN == 128 || BN == 256, "BN");
+  if (P.gate != nullptr && *reinterpret_cast<const volatile int*>(P.gate) == 0) return;
   using L = SmemLayout<BN, STAGES>;
   constexpr int HALVES = NE / 4;
   constexpr int COLS_PER_WARP = BN / HALVES;
@@ -153,7 +159,13 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
             uint8_t* sb = sa + L::A_BYTES;
             ptx::mbar_arrive_expect_tx(&full[stage], L::STAGE_BYTES);
             ptx::tma_load_2d(sa, &P.tmA[w.prob], &full[stage], kb * BK, w.m_blk * BM);
-            ptx::tma_load_2d(sb, &P.tmB[w.prob], &full[stage], kb * BK, t * BN);
+            if constexpr (B_MN) {
+#pragma unroll
+              for (int nb = 0; nb < BN / 64; ++nb)
+                ptx::tma_load_2d(sb + nb * (BK * 128), &P.tmB[w.prob], &full[stage], t * BN + nb * 64, kb * BK);
+            } else {
+              ptx::tma_load_2d(sb, &P.tmB[w.prob], &full[stage], kb * BK, t * BN);
+            }
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -180,11 +192,14 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
             ptx::tc_fence_after_sync();
             const uint32_t sa = ptx::smem_u32(smem + stage * L::STAGE_BYTES);
             const uint64_t da = ptx::umma_desc_sw128_kmajor(sa);
-            const uint64_t db = ptx::umma_desc_sw128_kmajor(sa + L::A_BYTES);
+            const uint64_t db = B_MN ? ptx::umma_desc_sw128_mnmajor(sa + L::A_BYTES, BK * 128)
+                                     : ptx::umma_desc_sw128_kmajor(sa + L::A_BYTES);
+            // K-major: advance 16 elements (32 bytes) along K inside the swizzle span: +2 in 16-byte units.
+            // MN-major: 16 K-rows of 128 bytes = 2048 bytes: +128.
+            constexpr uint64_t B_KSTEP = B_MN ? 128 : 2;
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in 16-byte units
-              ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, g.idesc, (kb > w.kb_begin || k > 0) ? 1u : 0u);
+              ptx::umma_f16(d_tmem, da + 2 * k, db + B_KSTEP * k, g.idesc, (kb > w.kb_begin || k > 0) ? 1u : 0u);
             }
             ptx::umma_commit(&empty[stage]);  // frees the smem stage once these MMAs retire
             if (++stage == STAGES) {
@@ -261,7 +276,10 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, int64_t rows, int
 // is evenly loaded.  row_blocks = problems * m_blocks.
 void choose_splits(GemmShape* g, int sm_count, int max_n_splits, int max_k_splits);
 
-inline void fill_shape(GemmShape* g, int problems, int M, int N, int K, int BN, int in_fmt) {
+// a_fmt / b_fmt: 0 = fp16, 1 = bf16 (may differ); b_mn: B operand is MN-major (see gemm_tc_kernel).
+inline void fill_shape(GemmShape* g, int problems, int M, int N, int K, int BN, int a_fmt, int b_fmt = -1,
+                       bool b_mn = false) {
+  if (b_fmt < 0) b_fmt = a_fmt;
   g->num_problems = problems;
   g->M = M;
   g->N = N;
@@ -274,18 +292,21 @@ inline void fill_shape(GemmShape* g, int problems, int M, int N, int K, int BN, 
   g->k_splits = 1;
   g->kb_per_split = g->k_blocks;
   g->num_items = problems * g->m_blocks;
-  g->idesc = ptx::umma_idesc_f16(static_cast<uint32_t>(in_fmt), BM, static_cast<uint32_t>(BN));
+  g->idesc = ptx::umma_idesc_f16(static_cast<uint32_t>(a_fmt), static_cast<uint32_t>(b_fmt), b_mn ? 1u : 0u, BM,
+                                 static_cast<uint32_t>(BN));
 }
 
-template <class Epi, int BN, int STAGES, int NE>
-int launch_gemm(const KernelParams<typename Epi::Params>& P, cudaStream_t stream, const char* name) {
+template <class Epi, int BN, int STAGES, int NE, bool B_MN = false>
+int launch_gemm(const KernelParams<typename Epi::Params>& P, cudaStream_t stream, const char* name,
+                size_t epi_smem_bytes = 0) {
   using L = SmemLayout<BN, STAGES>;
-  const size_t smem = L::EPI_OFFSET + L::ALIGN_SLACK + Epi::smem_bytes();
-  auto kern = gemm_tc_kernel<Epi, BN, STAGES, NE>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  const size_t smem = L::EPI_OFFSET + L::ALIGN_SLACK + epi_smem_bytes;
+  VAST_REQUIRE(smem <= 232448, VAST_ERR_UNSUPPORTED, "%s: %zu bytes of shared memory exceed the 227 KB limit", name, smem);
+  auto kern = gemm_tc_kernel<Epi, BN, STAGES, NE, B_MN>;
+  static size_t attr_smem = 0;  // per instantiation; grows monotonically
+  if (smem > attr_smem) {
     VAST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_done = true;
+    attr_smem = smem;
   }
   int grid = P.g.num_items < device_sm_count() ? P.g.num_items : device_sm_count();
   if (grid <= 0) return VAST_OK;
@@ -305,7 +326,6 @@ struct EpiStore {
     int64_t ksplit_stride;
     float alpha;
   };
-  static size_t smem_bytes() { return 0; }
   const Params& p;
   __device__ EpiStore(const Params& p_, uint8_t*) : p(p_) {}
   __device__ __forceinline__ void item_begin(const ItemCtx&) {}

@@ -3,22 +3,29 @@
 //   problem 0 "cond2t": rows = local feat_cond, columns = all feat_t
 //   problem 1 "t2cond": rows = local feat_t,    columns = all feat_cond
 //
-//   K1 transpose_ksum     : B operands -> fp16 transposes (dQ GEMM operand) + column sums
-//   K2 stats GEMM         : S tile in TMEM -> online (max, sum-exp, sum z, z_target) per row   [pass 1]
-//   K3 stats_finalize     : merge partials -> lse, per-row CE terms, ksum
-//   K4 prob GEMM          : S tile recomputed -> p = exp(z - lse): fp16 P tile (L2-resident
-//                           workspace), sum p*z (for d temp), exponential-race hard negatives [pass 2]
-//   K5 sample_finalize    : merge race partials -> negative indices, d temp row terms
-//   K6 dQ GEMM            : dQ = P . K  (fp16 x fp16 -> fp32, split-K partials)
-//   K7 grad_finalize      : dQ = (1/(2 bs tau)) (P.K - (eps/N) sum_j K_j - (1-eps) K_target)
-//   K8 final_reduce       : loss, d temp (single block, fixed order -> deterministic)
+// Single-pass flow (default):
+//   K1 prep          : column sums of the gathered features (label-smoothing term), their fp16 copy (the dQ
+//                      GEMM needs both operands in one 16-bit format), target logits z_t = <t_i, c_i> of the
+//                      local rows, per-row exponent reference ref_i = z_t / tau
+//   K2 soft GEMM     : S tile in TMEM -> Pt_ij = exp(z_ij - ref_i)  ("softmax numerators" relative to the
+//                      positive pair, so Pt_target = 1): fp16 Pt tile to the L2-resident workspace (target
+//                      column zeroed), row sums l_i, chunk-level exponential race for the hard negatives
+//   K3 dQ GEMM       : dQraw = Pt . K, the gathered features read ROW-MAJOR as the MN-major UMMA operand
+//                      (fp16 x fp16 -> fp32; no transposed copy)
+//   K4 row finalize  : per row: l_i -> lse, loss terms, hard-negative draw, gradient assembly
+//                      dQ = (1/(2 bs tau)) (dQraw / l - (eps/N) sum_j K_j - ((1-eps) - p_target) K_target),
+//                      d tau terms; the last block reduces loss and d tau in a fixed order.
+// The [bs, N] logits are evaluated exactly ONCE.  Pt needs the fp16 range: an entry overflows only if
+// some negative beats its positive by more than 16 ln2 = 11.09 nats ((s_ij - s_ii) > 0.78 at tau = 0.07).
+// The soft epilogue detects that (chunk sum >= 65504) and raises a device flag; three flag-gated
+// launches then redo the step in the two-pass form (K2a stats GEMM: online row max / sum-exp; K2b
+// finalize: ref_i = lse_i; K2c soft GEMM again, now Pt = softmax <= 1).  No host synchronisation
+// either way.  VAST_OMC_TWO_PASS / debug noise select the two-pass form directly.
 //
-// Why dQ is not fused FlashAttention-style into K4: the dQ accumulator of a 128-row block is
-// 128 x D fp32; at D = 1024 that is 512 KB, twice the 256 KB of TMEM (512 columns x 128 lanes),
-// so an output-stationary fused backward would have to recompute S once per 256-column slice of
-// D (4x the S work).  Staging P in fp16 through L2 costs one extra write+read of bs x N x 2 B
-// (32 MB per direction at bs = N = 4096, L2-resident on a 126 MB L2) and keeps S at exactly two
-// evaluations.  The fp32 logits / log-softmax / gradient matrices are never materialised.
+// Why dQ is not fused FlashAttention-style into K2: the dQ accumulator of a 128-row block is
+// 128 x D fp32; at D = 1024 that is 512 KB, twice the 256 KB of TMEM (512 columns x 128 lanes).
+// Staging Pt in fp16 through L2 (32 MB per direction at bs = N = 4096; the L2 holds 126 MB) keeps S at
+// one evaluation; fp32 logits / log-softmax / gradient matrices are never materialised.
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
@@ -61,24 +68,25 @@ __device__ __forceinline__ float expo_from_bits(uint32_t x) {
   return v < 9.765625e-4f ? small : big;
 }
 
-// ------------------------------------------------------------------ pass 1 epilogue: row statistics
+// u in (0, 1) from a 32-bit word
+__device__ __forceinline__ float unit_from_bits(uint32_t x) {
+  return fminf(fmaf(__uint2float_rn(x), 2.3283064365386963e-10f, 1.1641532182693481e-10f), 0.99999994f);
+}
+
+// ------------------------------------------------------------------ two-pass form, pass 1: row statistics
 struct EpiStats {
   struct Params {
-    float4* partial;  // [2][M][num_slots] (m2, l, sum s, s_target)
+    float2* partial;  // [2][M][num_slots] (max2, sum exp2)
     int num_slots;
     float scale2;  // log2(e) / tau (used when temp_dev is null)
     const float* temp_dev;
-    int tgt_offset;
   };
-  static size_t smem_bytes() { return 0; }
   const Params& p;
-  float m2, l, sz, zt, scale2;
+  float m2, l, scale2;
   __device__ EpiStats(const Params& p_, uint8_t*) : p(p_) { scale2 = p.temp_dev ? kLog2e / __ldg(p.temp_dev) : p.scale2; }
   __device__ __forceinline__ void item_begin(const tc::ItemCtx&) {
     m2 = -INFINITY;
     l = 0.f;
-    sz = 0.f;
-    zt = 0.f;
   }
   __device__ __forceinline__ void chunk(const tc::ItemCtx& c, const uint32_t (&v)[32], int col0) {
     if (col0 >= c.N) return;
@@ -92,37 +100,32 @@ struct EpiStats {
       l *= ex2_approx(m2 - cm);
       m2 = cm;
     }
-    float ls = 0.f, ss = 0.f;
+    float ls = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (i < nvalid) {
-        const float s = __uint_as_float(v[i]);
-        ls += ex2_approx(fmaf(s, scale2, -m2));
-        ss += s;
-      }
-    }
+    for (int i = 0; i < 32; ++i)
+      if (i < nvalid) ls += ex2_approx(fmaf(__uint_as_float(v[i]), scale2, -m2));
     l += ls;
-    sz += ss;
-    const int t = p.tgt_offset + c.row - col0;
-    if (static_cast<unsigned>(t) < 32u) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i == t) zt = __uint_as_float(v[i]);
-    }
   }
   __device__ __forceinline__ void item_end(const tc::ItemCtx& c) {
     if (c.row_valid)
-      p.partial[(static_cast<int64_t>(c.prob) * c.M + c.row) * p.num_slots + c.slot] = make_float4(m2, l, sz, zt);
+      p.partial[(static_cast<int64_t>(c.prob) * c.M + c.row) * p.num_slots + c.slot] = make_float2(m2, l);
   }
 };
 
-// ------------------------------------------------------------------ pass 2 epilogue: probabilities + race
-struct EpiProb {
+// ------------------------------------------------------------------ soft epilogue: numerators + race
+// Pt_ij = exp2(s_ij * scale2 - ref2_i).  ELEM = false (production): hard negatives by a chunk-level
+// exponential race -- the chunk (32 consecutive columns) with the largest (sum of Pt over the chunk) / E_c
+// wins, E_c ~ Exp(1) from Philox; the column inside the winning chunk and the uniform "floor" component are
+// drawn by the row-finalize kernel.  ELEM = true (index-exact parity tests with injected per-element noise,
+// two-pass form only so that Pt is the softmax probability): the reference's formulation literally,
+// argmax_j (p_ij + floor) / E_ij.
+template <bool ELEM>
+struct EpiSoft {
   struct Params {
-    const float* lse2;  // [2][M] log2-domain row log-sum-exp
-    __half* P;          // [2][M][ldp] softmax probabilities (dQ GEMM A operand) or nullptr
+    const float* ref2;  // [2][M] log2-domain exponent reference per row
+    __half* P;          // [2][M][ldp] Pt (dQ GEMM A operand), target column zeroed; or nullptr
     int64_t ldp;
-    float4* partial;  // [2][M][num_slots] (w_best, e_best, idx_best, sum p*s)
+    float4* partial;  // [2][M][num_slots] (sum Pt excl. target, best weight, best E, best chunk / index)
     int num_slots;
     float scale2;
     const float* temp_dev;
@@ -130,38 +133,51 @@ struct EpiProb {
     int tgt_offset;
     int row_offset;  // global row of local row 0 (decorrelates ranks that share a seed)
     uint32_t seed_lo, seed_hi, off_lo, off_hi;
-    const float* noise;  // [2][M][N] caller-supplied Exp(1) noise (debug) or nullptr
+    const float* noise;  // ELEM only: [2][M][N] caller-supplied Exp(1) noise
+    int64_t noise_ld;
     int do_sample;
+    int* ovf;  // raised when a chunk sum leaves the fp16 range (single-pass form) or nullptr
   };
-  static size_t smem_bytes() { return 0; }
   const Params& p;
-  float lse2, bw, be, pz, scale2;
+  float ref, l, bw, be, scale2;
   int bidx, tcol;
-  __device__ EpiProb(const Params& p_, uint8_t*) : p(p_) { scale2 = p.temp_dev ? kLog2e / __ldg(p.temp_dev) : p.scale2; }
+  uint4 rnd;
+  __device__ EpiSoft(const Params& p_, uint8_t*) : p(p_) { scale2 = p.temp_dev ? kLog2e / __ldg(p.temp_dev) : p.scale2; }
   __device__ __forceinline__ void item_begin(const tc::ItemCtx& c) {
-    lse2 = c.row_valid ? p.lse2[static_cast<int64_t>(c.prob) * c.M + c.row] : 0.f;
-    bw = -1.f;
+    ref = c.row_valid ? p.ref2[static_cast<int64_t>(c.prob) * c.M + c.row] : 0.f;
+    l = 0.f;
+    bw = ELEM ? -1.f : 0.f;
     be = 1.f;
     bidx = -1;
-    pz = 0.f;
     tcol = p.tgt_offset + c.row;
+    rnd = make_uint4(0, 0, 0, 0);
   }
   __device__ __forceinline__ void chunk(const tc::ItemCtx& c, const uint32_t (&v)[32], int col0) {
     if (col0 >= c.N) return;
     const int nvalid = c.N - col0;
     float pr[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float s = __uint_as_float(v[i]);
-      const float q = (i < nvalid) ? ex2_approx(fmaf(s, scale2, -lse2)) : 0.f;
-      pr[i] = q;
-      pz = fmaf(q, s, pz);
+    for (int i = 0; i < 32; ++i) pr[i] = ex2_approx(fmaf(__uint_as_float(v[i]), scale2, -ref));
+    if (nvalid < 32) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i >= nvalid) pr[i] = 0.f;
     }
+    // The target column is excluded from Pt: its coefficient (p_iy - (1 - eps)) is a cancellation and is
+    // applied in fp32 by the row-finalize kernel; it is not a negative either.
+    const int tq = tcol - col0;
+    if (static_cast<unsigned>(tq) < 32u) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i == tq) pr[i] = 0.f;
+    }
+    float cs = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) cs += (pr[i] + pr[i + 1]) + (pr[i + 2] + pr[i + 3]);
+    l += cs;
+    if (p.ovf != nullptr && !(cs < 65504.f)) *p.ovf = 1;  // also catches inf / nan
     if (p.P != nullptr && c.row_valid) {
       __half* dst = p.P + (static_cast<int64_t>(c.prob) * c.M + c.row) * p.ldp + col0;
-      // The target column is excluded from the fp16 P matrix: its coefficient (p_iy - (1 - eps)) is a
-      // cancellation and is applied in fp32 by the gradient finalize kernel.
-      const int tq = tcol - col0;
       if (nvalid >= 32) {
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
@@ -169,8 +185,7 @@ struct EpiProb {
           uint32_t* w = &u.x;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const __half2 h = __floats2half2_rn((i + 2 * j == tq) ? 0.f : pr[i + 2 * j],
-                                                (i + 2 * j + 1 == tq) ? 0.f : pr[i + 2 * j + 1]);
+            const __half2 h = __floats2half2_rn(pr[i + 2 * j], pr[i + 2 * j + 1]);
             w[j] = *reinterpret_cast<const uint32_t*>(&h);
           }
           *reinterpret_cast<uint4*>(dst + i) = u;
@@ -178,228 +193,365 @@ struct EpiProb {
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (i < nvalid) dst[i] = __float2half_rn(i == tq ? 0.f : pr[i]);
+          if (i < nvalid) dst[i] = __float2half_rn(pr[i]);
       }
     }
-    if (p.do_sample) {
-      const float* nz =
-          p.noise ? p.noise + (static_cast<int64_t>(c.prob) * c.M + (c.row_valid ? c.row : 0)) * c.N + col0 : nullptr;
+    if (!p.do_sample) return;
+    if constexpr (ELEM) {
+      const float* nz = p.noise + (static_cast<int64_t>(c.prob) * c.M + (c.row_valid ? c.row : 0)) * p.noise_ld + col0;
 #pragma unroll
-      for (int g4 = 0; g4 < 8; ++g4) {
-        uint4 r = make_uint4(0, 0, 0, 0);
-        if (nz == nullptr)
-          r = philox4x32_10(make_uint4(static_cast<uint32_t>((col0 >> 2) + g4), static_cast<uint32_t>(p.row_offset + c.row),
-                                       p.off_lo, (p.off_hi << 1) | static_cast<uint32_t>(c.prob)),
-                            make_uint2(p.seed_lo, p.seed_hi));
-        const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i = g4 * 4 + j;
-          const int col = col0 + i;
-          float e;
-          if (nz != nullptr)
-            e = (i < nvalid) ? nz[i] : 1.f;
-          else
-            e = expo_from_bits(rw[j]);
-          float w = pr[i] + p.floor;
-          if (col == tcol) w = 0.f;
-          // argmax of w / e without the division; strict > keeps the first (lowest) index on ties
-          if (i < nvalid && w * be > bw * e) {
-            bw = w;
-            be = e;
-            bidx = col;
-          }
+      for (int i = 0; i < 32; ++i) {
+        const float e = (i < nvalid) ? nz[i] : 1.f;
+        const float w = (i == tq) ? 0.f : pr[i] + p.floor;
+        // argmax of w / e without the division; strict > keeps the first (lowest) index on ties
+        if (i < nvalid && w * be > bw * e) {
+          bw = w;
+          be = e;
+          bidx = col0 + i;
         }
+      }
+    } else {
+      const int gc = col0 >> 5;  // global chunk index
+      // one Philox call serves four chunks; a warp's column ranges start at multiples of 128 columns
+      if ((gc & 3) == 0)
+        rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(gc >> 2), static_cast<uint32_t>(p.row_offset + c.row), p.off_lo,
+                                       (p.off_hi << 1) | static_cast<uint32_t>(c.prob)),
+                            make_uint2(p.seed_lo, p.seed_hi));
+      const uint32_t w = (gc & 3) == 0 ? rnd.x : (gc & 3) == 1 ? rnd.y : (gc & 3) == 2 ? rnd.z : rnd.w;
+      const float e = expo_from_bits(w);
+      // race between chunks: argmax cs / e; strict > keeps the first chunk on ties, empty chunks never win
+      if (cs * be > bw * e) {
+        bw = cs;
+        be = e;
+        bidx = gc;
       }
     }
   }
   __device__ __forceinline__ void item_end(const tc::ItemCtx& c) {
     if (c.row_valid)
       p.partial[(static_cast<int64_t>(c.prob) * c.M + c.row) * p.num_slots + c.slot] =
-          make_float4(bw, be, __int_as_float(bidx), pz);
+          make_float4(l, bw, be, __int_as_float(bidx));
   }
 };
 
-// ------------------------------------------------------------------ K1: transposes + column sums
-// pack [N, 2D] bf16 -> KT [2][D][Npad] fp16 with KT[0] = feat_t_all^T, KT[1] = feat_cond_all^T, and
-// ksum_partial [2][nrb][D] = per-256-row-block column sums (fixed order).
-constexpr int TR_ROWS = 256;
-__global__ void __launch_bounds__(256) transpose_ksum_kernel(const __nv_bfloat16* __restrict__ pack, int64_t n_total,
-                                                            int64_t dim, int64_t npad, __half* __restrict__ kt,
-                                                            float* __restrict__ ksum_partial, int nrb) {
-  __shared__ __half tile[64][66];
-  __shared__ float csum[8][64];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  // blockIdx.x = prob * ceil(D/64) + column block inside that problem's D columns (any D)
-  const int nblk = static_cast<int>((dim + 63) / 64);
-  const int prob = static_cast<int>(blockIdx.x) / nblk;
-  const int64_t d0 = static_cast<int64_t>(static_cast<int>(blockIdx.x) - prob * nblk) * 64;
-  const int64_t c0 = prob * dim + d0;  // column in [0, 2D) of the packed row
-  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * TR_ROWS;
-  float s0 = 0.f, s1 = 0.f;
-  for (int sub = 0; sub < TR_ROWS / 64; ++sub) {
-    const int64_t rb = r0 + sub * 64;
-    if (rb >= n_total) break;
+// ------------------------------------------------------------------ K1: prep
+// blocks [0, ncs):   column sums of pack [N, 2D] over 64-row slabs -> ksum_partial[slab][2D] (fixed order)
+// blocks [ncs, ..):  one warp per local row: z_t = <t_i, c_i> (fp32 over the bf16 features), and in the
+//                    single-pass form the exponent reference ref2 = z_t * log2(e) / tau for both directions
+// The last block to finish (ticket) reduces the slab partials into ksum[2D]; block 0 clears the overflow flag.
+constexpr int PREP_ROWS = 64;
+__global__ void __launch_bounds__(256) omc_prep_kernel(const __nv_bfloat16* __restrict__ pack, int n_total, int dim, int bs,
+                                                      int row_offset, int ncs, int nslab,
+                                                      float* __restrict__ ksum_partial, float* __restrict__ ksum,
+                                                      float* __restrict__ zt, float* __restrict__ ref2, float scale2,
+                                                      const float* __restrict__ temp_dev, int* __restrict__ flags,
+                                                      __half* __restrict__ pack16) {
+  __shared__ float red[8][264];
+  __shared__ int is_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cols = 2 * dim;
+  if (static_cast<int>(blockIdx.x) < ncs) {
+    const int ctiles = (cols + 255) / 256;
+    const int slab = blockIdx.x / ctiles;
+    const int c0 = (blockIdx.x - slab * ctiles) * 256 + lane * 8;  // 8 columns per lane, 256 per warp pass
+    const int r0 = slab * PREP_ROWS + warp * (PREP_ROWS / 8);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (c0 < cols) {
+      uint4 raw[PREP_ROWS / 8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = ty * 8 + i;
-      float a = 0.f, b = 0.f;
-      if (rb + r < n_total) {
-        const int64_t col = c0 + 2 * tx;
-        const __nv_bfloat16* src = pack + (rb + r) * 2 * dim + col;
-        if (d0 + 2 * tx < dim) a = __bfloat162float(src[0]);
-        if (d0 + 2 * tx + 1 < dim) b = __bfloat162float(src[1]);
+      for (int i = 0; i < PREP_ROWS / 8; ++i) {
+        const int r = r0 + i;
+        raw[i] = r < n_total ? *reinterpret_cast<const uint4*>(pack + static_cast<int64_t>(r) * cols + c0) : make_uint4(0, 0, 0, 0);
       }
-      s0 += a;
-      s1 += b;
-      tile[r][2 * tx] = __float2half_rn(a);
-      tile[r][2 * tx + 1] = __float2half_rn(b);
-    }
-    __syncthreads();
-    // write 64 d-rows x 64 n: each thread one (d, pair of n)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int d = ty * 8 + i;
-      if (d0 + d < dim) {
-        const int64_t n = rb + 2 * tx;
-        __half* dst = kt + (static_cast<int64_t>(prob) * dim + d0 + d) * npad + n;
-        if (n + 1 < npad)
-          *reinterpret_cast<__half2*>(dst) = __halves2half2(tile[2 * tx][d], tile[2 * tx + 1][d]);
-        else if (n < npad)
-          dst[0] = tile[2 * tx][d];
+      for (int i = 0; i < PREP_ROWS / 8; ++i) {
+        const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+        uint4 h16;
+        uint32_t* hw = &h16.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xffff0000u);
+          acc[2 * j] += lo;
+          acc[2 * j + 1] += hi;
+          const __half2 h = __floats2half2_rn(lo, hi);
+          hw[j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        // fp16 copy of the gathered features (dQ GEMM right-hand side; kind::f16 needs A and B in ONE format,
+        // and the probabilities need fp16's mantissa).  Exact for 2^-14 <= |x| <= 65504.
+        if (pack16 != nullptr && r0 + i < n_total)
+          *reinterpret_cast<uint4*>(pack16 + static_cast<int64_t>(r0 + i) * cols + c0) = h16;
       }
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
     __syncthreads();
+    {
+      const int c = (blockIdx.x - slab * ctiles) * 256 + threadIdx.x;
+      if (c < cols) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        ksum_partial[static_cast<int64_t>(slab) * cols + c] = s;
+      }
+    }
+  } else {
+    const int i = (blockIdx.x - ncs) * 8 + warp;
+    if (i < bs) {
+      const __nv_bfloat16* row = pack + static_cast<int64_t>(row_offset + i) * cols;
+      float acc = 0.f;
+      for (int d = lane * 8; d < dim; d += 256) {
+        const uint4 a = *reinterpret_cast<const uint4*>(row + d);
+        const uint4 b = *reinterpret_cast<const uint4*>(row + dim + d);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc = fmaf(__uint_as_float(aw[j] << 16), __uint_as_float(bw[j] << 16), acc);
+          acc = fmaf(__uint_as_float(aw[j] & 0xffff0000u), __uint_as_float(bw[j] & 0xffff0000u), acc);
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        zt[i] = acc;
+        zt[bs + i] = acc;
+        if (ref2 != nullptr) {
+          if (temp_dev) scale2 = kLog2e / __ldg(temp_dev);
+          ref2[i] = acc * scale2;
+          ref2[bs + i] = acc * scale2;
+        }
+      }
+    }
   }
-  csum[ty][2 * tx] = s0;
-  csum[ty][2 * tx + 1] = s1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) flags[0] = 0;
+  // last block: ksum[c] = sum over slabs (fixed order -> deterministic)
+  __threadfence();
   __syncthreads();
-  if (threadIdx.x < 64) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += csum[i][threadIdx.x];
-    if (d0 + threadIdx.x < dim)
-      ksum_partial[(static_cast<int64_t>(prob) * nrb + blockIdx.y) * dim + d0 + threadIdx.x] = s;
+  if (threadIdx.x == 0) is_last = (atomicAdd(&flags[1], 1) == static_cast<int>(gridDim.x) - 1);
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    for (int c = threadIdx.x; c < cols; c += 256) {
+      float s = 0.f;
+      for (int b = 0; b < nslab; ++b) s += __ldcg(ksum_partial + static_cast<int64_t>(b) * cols + c);
+      ksum[c] = s;
+    }
+    if (threadIdx.x == 0) flags[1] = 0;
   }
 }
 
-// ------------------------------------------------------------------ K3: merge pass-1 partials
-__global__ void __launch_bounds__(128) omc_stats_finalize_kernel(const float4* __restrict__ partial, int slots, int M,
-                                                                int N, float inv_tau, const float* __restrict__ temp_dev,
-                                                                float eps_ls,
-                                                                float* __restrict__ lse2, float* __restrict__ zt,
-                                                                float* __restrict__ sz, float* __restrict__ rowce,
-                                                                float* __restrict__ lse_out, int row_blocks,
-                                                                const float* __restrict__ ksum_partial, int nrb, int D,
-                                                                float* __restrict__ ksum) {
-  if (static_cast<int>(blockIdx.x) >= row_blocks) {  // trailing blocks: ksum[p][d] = sum of row-block partials
-    const int idx = (blockIdx.x - row_blocks) * 128 + threadIdx.x;
-    if (idx < 2 * D) {
-      const int p = idx / D, d = idx - p * D;
-      float s = 0.f;
-      for (int b = 0; b < nrb; ++b) s += ksum_partial[(static_cast<int64_t>(p) * nrb + b) * D + d];
-      ksum[idx] = s;
-    }
-    return;
-  }
+// ------------------------------------------------------------------ two-pass form: merge pass-1 partials
+__global__ void __launch_bounds__(128) omc_stats_finalize_kernel(const float2* __restrict__ partial, int slots, int rows2,
+                                                                float* __restrict__ ref2, const int* __restrict__ gate) {
+  if (gate != nullptr && *gate == 0) return;
   const int r = blockIdx.x * 128 + threadIdx.x;
-  if (r >= 2 * M) return;
-  if (temp_dev) inv_tau = 1.0f / __ldg(temp_dev);
-  const float4* pp = partial + static_cast<int64_t>(r) * slots;
+  if (r >= rows2) return;
+  const float2* pp = partial + static_cast<int64_t>(r) * slots;
   float mm = -INFINITY;
   for (int s = 0; s < slots; ++s) mm = fmaxf(mm, pp[s].x);
-  float l = 0.f, ssum = 0.f, t = 0.f;
+  float l = 0.f;
   for (int s = 0; s < slots; ++s) {
-    const float4 q = pp[s];
+    const float2 q = pp[s];
     if (q.y > 0.f) l += q.y * exp2f(q.x - mm);
-    ssum += q.z;
-    t += q.w;
   }
-  const float l2 = mm + log2f(l);
-  lse2[r] = l2;
-  zt[r] = t;
-  sz[r] = ssum;
-  const float lse = l2 * kLn2;
-  if (lse_out) lse_out[r] = lse;
-  rowce[r] = lse - (1.f - eps_ls) * inv_tau * t - (eps_ls / static_cast<float>(N)) * inv_tau * ssum;
+  ref2[r] = mm + log2f(l);  // log2-domain log-sum-exp: Pt becomes the softmax probability
 }
 
-// ------------------------------------------------------------------ K5: merge race partials
-__global__ void __launch_bounds__(128) omc_sample_finalize_kernel(const float4* __restrict__ partial, int slots, int M,
-                                                                 int N, float inv_tau, const float* __restrict__ temp_dev,
-                                                                 float eps_ls,
-                                                                 const float* __restrict__ zt,
-                                                                 const float* __restrict__ sz,
-                                                                 int64_t* __restrict__ neg_idx,
-                                                                 float* __restrict__ rowdt) {
-  const int r = blockIdx.x * 128 + threadIdx.x;
-  if (r >= 2 * M) return;
-  if (temp_dev) inv_tau = 1.0f / __ldg(temp_dev);
-  const float4* pp = partial + static_cast<int64_t>(r) * slots;
-  float bw = -1.f, be = 1.f, pz = 0.f;
-  int bidx = -1;
-  for (int s = 0; s < slots; ++s) {
-    const float4 q = pp[s];
-    pz += q.w;
-    const int idx = __float_as_int(q.z);
-    if (idx < 0) continue;
-    const float lhs = q.x * be, rhs = bw * q.y;
-    if (lhs > rhs || (lhs == rhs && idx < bidx)) {
-      bw = q.x;
-      be = q.y;
-      bidx = idx;
+// ------------------------------------------------------------------ K4: row finalize
+// One warp per (direction, local row).
+struct RowFinParams {
+  const float4* partial;
+  int slots;
+  int M, N, D;
+  int row_offset;
+  const float* ref2;
+  const float* zt;
+  float inv_tau;
+  const float* temp_dev;
+  float eps_ls, floor;
+  // sampling
+  int64_t* neg_idx;  // [2][M] or nullptr
+  int elem_mode;     // partial.w already holds the winning column (ELEM epilogue)
+  const __half* P;
+  int64_t ldp;
+  uint32_t seed_lo, seed_hi, off_lo, off_hi;
+  // gradient
+  const float* dq_part;  // [ks][2][M][D] or nullptr
+  int ksplits;
+  int64_t split_stride;
+  const float* ksum;  // [2][D]
+  const __nv_bfloat16* pack;
+  float* grad_cond;
+  float* grad_t;
+  // outputs
+  float* lse_out;  // [2][M] or nullptr
+  float* rowce;    // [2][M]
+  float* rowdt;    // [2][M]
+  float* loss;
+  float* grad_temp;  // or nullptr
+  int* ticket;
+};
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[2 * j] = __uint_as_float(w[j] << 16);
+    f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+  }
+}
+
+__global__ void __launch_bounds__(256) omc_row_finalize_kernel(const RowFinParams p) {
+  __shared__ float red[2][256];
+  __shared__ int is_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  const float inv_tau = p.temp_dev ? 1.0f / __ldg(p.temp_dev) : p.inv_tau;
+  if (r < 2 * p.M) {
+    const int prob = r / p.M, row = r - prob * p.M;
+    const int tcol = p.row_offset + row;
+    // ---- merge the per-slot partials (lane-strided, then butterfly: fixed order)
+    const float4* pp = p.partial + static_cast<int64_t>(r) * p.slots;
+    float l = 0.f, bw = p.elem_mode ? -1.f : 0.f, be = 1.f;
+    int bidx = -1;
+    for (int s = lane; s < p.slots; s += 32) {
+      const float4 q = pp[s];
+      l += q.x;
+      const int idx = __float_as_int(q.w);
+      if (idx >= 0) {
+        const float lhs = q.y * be, rhs = bw * q.z;
+        if (bidx < 0 || lhs > rhs || (lhs == rhs && idx < bidx)) {
+          bw = q.y;
+          be = q.z;
+          bidx = idx;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      l += __shfl_xor_sync(0xffffffffu, l, o);
+      const float ow = __shfl_xor_sync(0xffffffffu, bw, o), oe = __shfl_xor_sync(0xffffffffu, be, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (oi >= 0) {
+        const float lhs = ow * be, rhs = bw * oe;
+        if (bidx < 0 || lhs > rhs || (lhs == rhs && oi < bidx)) {
+          bw = ow;
+          be = oe;
+          bidx = oi;
+        }
+      }
+    }
+    const float ref = p.ref2[r], zt = p.zt[r];
+    const float scale2 = kLog2e * inv_tau;
+    const float pt_un = exp2f(fmaf(zt, scale2, -ref));  // numerator of the positive pair
+    const float ltot = l + pt_un;
+    const float rho = 1.0f / ltot;
+    const float pt = pt_un * rho;
+    const float lse = (ref + log2f(ltot)) * kLn2;
+
+    // ---- hard negative
+    if (p.neg_idx != nullptr) {
+      int pick = -1;
+      if (p.elem_mode) {
+        pick = bidx;
+      } else if (p.N > 1) {
+        const uint4 rnd = philox4x32_10(make_uint4(0xFFFFFFFFu, static_cast<uint32_t>(p.row_offset + row), p.off_lo,
+                                                   (p.off_hi << 1) | static_cast<uint32_t>(prob)),
+                                        make_uint2(p.seed_lo, p.seed_hi));
+        const float u_in = unit_from_bits(rnd.x), u_mix = unit_from_bits(rnd.y), u_uni = unit_from_bits(rnd.z);
+        // mixture: softmax part (mass l, column drawn in proportion to Pt) vs floor part (uniform, mass floor*ltot*(N-1))
+        const float w_a = l, w_b = p.floor * ltot * static_cast<float>(p.N - 1);
+        const bool take_a = bidx >= 0 && u_mix * (w_a + w_b) < w_a;
+        if (take_a) {
+          const int col = bidx * 32 + lane;
+          float v = 0.f;
+          if (col < p.N) v = __half2float(p.P[static_cast<int64_t>(r) * p.ldp + col]);
+          float pre = v;  // inclusive prefix over the chunk (Kogge-Stone: fixed order)
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(0xffffffffu, pre, o);
+            if (lane >= o) pre += t;
+          }
+          const float tot = __shfl_sync(0xffffffffu, pre, 31);
+          const float target = u_in * tot;
+          const unsigned hit = __ballot_sync(0xffffffffu, v > 0.f && pre >= target);
+          const unsigned any = __ballot_sync(0xffffffffu, v > 0.f);
+          if (hit)
+            pick = bidx * 32 + (__ffs(hit) - 1);
+          else if (any)
+            pick = bidx * 32 + (31 - __clz(any));
+        }
+        if (pick < 0) {  // uniform over the N - 1 non-target columns
+          int j = static_cast<int>(u_uni * static_cast<float>(p.N - 1));
+          j = j > p.N - 2 ? p.N - 2 : j;
+          pick = j >= tcol ? j + 1 : j;
+        }
+      }
+      if (lane == 0) p.neg_idx[r] = pick;
+    }
+
+    // ---- gradient + the two row dot products (q . dQraw for d tau, q . ksum for the smoothing term)
+    const __nv_bfloat16* prow = p.pack + static_cast<int64_t>(p.row_offset + row) * 2 * p.D;
+    const __nv_bfloat16* qv = prow + (prob == 0 ? p.D : 0);   // this direction's query row
+    const __nv_bfloat16* kv = prow + (prob == 0 ? 0 : p.D);   // the positive row of the gathered side
+    const float* ks = p.ksum + prob * p.D;
+    float dot_q = 0.f, dot_s = 0.f;
+    const bool grad = p.dq_part != nullptr;
+    const float gs = inv_tau / (2.0f * p.M);
+    const float c_sm = p.eps_ls / static_cast<float>(p.N);
+    const float c_t = pt - (1.f - p.eps_ls);
+    float* gout = grad ? (prob == 0 ? p.grad_cond : p.grad_t) + static_cast<int64_t>(row) * p.D : nullptr;
+    for (int d = lane * 8; d < p.D; d += 256) {
+      float q[8], k[8], ksv[8];
+      bf16x8_to_f32(*reinterpret_cast<const uint4*>(qv + d), q);
+      *reinterpret_cast<float4*>(&ksv[0]) = *reinterpret_cast<const float4*>(ks + d);
+      *reinterpret_cast<float4*>(&ksv[4]) = *reinterpret_cast<const float4*>(ks + d + 4);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dot_s = fmaf(q[j], ksv[j], dot_s);
+      if (grad) {
+        bf16x8_to_f32(*reinterpret_cast<const uint4*>(kv + d), k);
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const float* src = p.dq_part + (static_cast<int64_t>(prob) * p.M + row) * p.D + d;
+        for (int s = 0; s < p.ksplits; ++s) {
+          const float4 a = __ldcs(reinterpret_cast<const float4*>(src + s * p.split_stride));
+          const float4 b = __ldcs(reinterpret_cast<const float4*>(src + s * p.split_stride + 4));
+          acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+          acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+        }
+        float g[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dot_q = fmaf(q[j], acc[j], dot_q);
+          g[j] = gs * (rho * acc[j] - c_sm * ksv[j] + c_t * k[j]);
+        }
+        *reinterpret_cast<float4*>(gout + d) = make_float4(g[0], g[1], g[2], g[3]);
+        *reinterpret_cast<float4*>(gout + d + 4) = make_float4(g[4], g[5], g[6], g[7]);
+      }
+    }
+    dot_q = warp_sum(dot_q);
+    dot_s = warp_sum(dot_s);
+    if (lane == 0) {
+      const float pz = rho * dot_q + pt * zt;  // sum_j p_ij s_ij
+      p.rowce[r] = lse - (1.f - p.eps_ls) * inv_tau * zt - c_sm * inv_tau * dot_s;
+      // d loss / d tau row term: -(1/tau) sum_j (p_ij - y_ij) z_ij   (scaled by 1/(2 bs) below)
+      p.rowdt[r] = -inv_tau * inv_tau * (pz - (1.f - p.eps_ls) * zt - c_sm * dot_s);
+      if (p.lse_out) p.lse_out[r] = lse;
     }
   }
-  if (neg_idx) neg_idx[r] = bidx;
-  // d loss / d tau row term: -(1/tau) * sum_j (p_ij - y_ij) z_ij   (scaled by 1/(2 bs) in final_reduce)
-  rowdt[r] = -inv_tau * inv_tau * (pz - (1.f - eps_ls) * zt[r] - (eps_ls / static_cast<float>(N)) * sz[r]);
-}
-
-// ------------------------------------------------------------------ K7: gradient assembly
-__global__ void __launch_bounds__(256) omc_grad_finalize_kernel(const float* __restrict__ part, int ksplits,
-                                                               int64_t split_stride, int M, int D,
-                                                               const float* __restrict__ ksum,
-                                                               const __nv_bfloat16* __restrict__ pack, int row_offset,
-                                                               int N, float eps_ls, float inv_tau,
-                                                               const float* __restrict__ temp_dev,
-                                                               const float* __restrict__ lse2,
-                                                               const float* __restrict__ zt,
-                                                               float* __restrict__ grad_cond, float* __restrict__ grad_t) {
-  const int64_t total = 2LL * M * D;
-  if (temp_dev) inv_tau = 1.0f / __ldg(temp_dev);
-  const float gs = inv_tau / (2.0f * M);
-  const float scale2 = kLog2e * inv_tau;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int d = static_cast<int>(i % D);
-    const int row = static_cast<int>((i / D) % M);
-    const int p = static_cast<int>(i / (static_cast<int64_t>(D) * M));
-    float v = 0.f;
-    for (int k = 0; k < ksplits; ++k) v += part[k * split_stride + i];
-    v -= (eps_ls / static_cast<float>(N)) * ksum[p * D + d];
-    // target row of the gathered operand: problem 0 -> feat_t_all, problem 1 -> feat_cond_all
-    const float kt = __bfloat162float(pack[static_cast<int64_t>(row_offset + row) * 2 * D + p * D + d]);
-    // target column in fp32: coefficient p_iy - (1 - eps)  (P holds 0 there)
-    const float pt = exp2f(fmaf(zt[p * M + row], scale2, -lse2[p * M + row]));
-    v += (pt - (1.f - eps_ls)) * kt;
-    (p == 0 ? grad_cond : grad_t)[static_cast<int64_t>(row) * D + d] = gs * v;
-  }
-}
-
-// ------------------------------------------------------------------ K8: scalar reductions (one block)
-__global__ void __launch_bounds__(1024) omc_final_reduce_kernel(const float* __restrict__ rowce,
-                                                               const float* __restrict__ rowdt, int rows2, float scale,
-                                                               float* __restrict__ loss, float* __restrict__ grad_temp) {
-  __shared__ float red[2][1024];
+  // ---- last block: loss and d tau (fixed order -> deterministic)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(p.ticket, 1) == static_cast<int>(gridDim.x) - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
   float a = 0.f, b = 0.f;
-  for (int i = threadIdx.x; i < rows2; i += 1024) {
-    a += rowce[i];
-    if (rowdt) b += rowdt[i];
+  for (int i = threadIdx.x; i < 2 * p.M; i += 256) {
+    a += __ldcg(p.rowce + i);
+    b += __ldcg(p.rowdt + i);
   }
   red[0][threadIdx.x] = a;
   red[1][threadIdx.x] = b;
   __syncthreads();
-  for (int s = 512; s > 0; s >>= 1) {
+  for (int s = 128; s > 0; s >>= 1) {
     if (static_cast<int>(threadIdx.x) < s) {
       red[0][threadIdx.x] += red[0][threadIdx.x + s];
       red[1][threadIdx.x] += red[1][threadIdx.x + s];
@@ -407,32 +559,35 @@ __global__ void __launch_bounds__(1024) omc_final_reduce_kernel(const float* __r
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    if (loss) loss[0] = red[0][0] * scale;
-    if (grad_temp) grad_temp[0] = red[1][0] * scale;
+    const float scale = 1.0f / (2.0f * p.M);
+    p.loss[0] = red[0][0] * scale;
+    if (p.grad_temp) p.grad_temp[0] = red[1][0] * scale;
+    *p.ticket = 0;
   }
 }
 
 // ------------------------------------------------------------------ host orchestration
 struct OmcPlan {
-  tc::GemmShape g_s;   // S GEMMs (pass 1 and pass 2)
+  tc::GemmShape g_s;   // S GEMMs
   tc::GemmShape g_dq;  // dQ GEMM
   int bn_dq;
   int slots;
-  int nrb;
+  int nslab, ncs;
   int64_t npad;
   // workspace offsets (bytes)
-  size_t off_partial, off_lse2, off_zt, off_sz, off_rowce, off_rowdt, off_P, off_KT, off_ksump, off_ksum, off_dq, total;
+  size_t off_flags, off_partial, off_ref2, off_zt, off_rowce, off_rowdt, off_ksump, off_ksum, off_P, off_dq, off_k16, total;
 };
 
-static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, int need_sample, int need_grad) {
+static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, bool need_p, bool need_grad) {
   const int sms = device_sm_count();
   tc::fill_shape(&pl->g_s, 2, (int)bs, (int)n_total, (int)dim, 256, 1);
   tc::choose_splits(&pl->g_s, sms, 32, 1);
   pl->slots = pl->g_s.n_splits * 2;  // NE = 8 -> two column halves per split
   pl->npad = static_cast<int64_t>(align_up(static_cast<size_t>(n_total), 8));
-  pl->nrb = ceil_div((int)n_total, TR_ROWS);
-  pl->bn_dq = dim >= 256 ? 256 : 128;
-  tc::fill_shape(&pl->g_dq, 2, (int)bs, (int)dim, (int)n_total, pl->bn_dq, 0);
+  pl->nslab = ceil_div((int)n_total, PREP_ROWS);
+  pl->ncs = pl->nslab * ceil_div(2 * (int)dim, 256);
+  pl->bn_dq = dim > 128 ? 256 : 128;
+  tc::fill_shape(&pl->g_dq, 2, (int)bs, (int)dim, (int)n_total, pl->bn_dq, /*a: fp16*/ 0, /*b: fp16*/ 0, /*b_mn*/ true);
   tc::choose_splits(&pl->g_dq, sms, 64, 4);
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -441,27 +596,22 @@ static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, int 
     off += bytes;
     return r;
   };
+  pl->off_flags = take(256);
   pl->off_partial = take(sizeof(float4) * 2 * bs * pl->slots);
-  pl->off_lse2 = take(sizeof(float) * 2 * bs);
+  pl->off_ref2 = take(sizeof(float) * 2 * bs);
   pl->off_zt = take(sizeof(float) * 2 * bs);
-  pl->off_sz = take(sizeof(float) * 2 * bs);
   pl->off_rowce = take(sizeof(float) * 2 * bs);
   pl->off_rowdt = take(sizeof(float) * 2 * bs);
-  pl->off_P = pl->off_KT = pl->off_ksump = pl->off_ksum = pl->off_dq = 0;
+  pl->off_ksump = take(sizeof(float) * 2 * dim * pl->nslab);
+  pl->off_ksum = take(sizeof(float) * 2 * dim);
+  pl->off_P = pl->off_dq = 0;
+  if (need_p) pl->off_P = take(sizeof(__half) * 2 * bs * pl->npad);
+  pl->off_k16 = 0;
   if (need_grad) {
-    pl->off_P = take(sizeof(__half) * 2 * bs * pl->npad);
-    pl->off_KT = take(sizeof(__half) * 2 * dim * pl->npad);
-    pl->off_ksump = take(sizeof(float) * 2 * pl->nrb * dim);
-    pl->off_ksum = take(sizeof(float) * 2 * dim);
     pl->off_dq = take(sizeof(float) * pl->g_dq.k_splits * 2 * bs * dim);
+    pl->off_k16 = take(sizeof(__half) * 2 * dim * n_total);
   }
-  (void)need_sample;
   pl->total = align_up(off, 256);
-}
-
-template <int BN>
-static int launch_dq(tc::KernelParams<tc::EpiStore::Params>& P, cudaStream_t stream) {
-  return tc::launch_gemm<tc::EpiStore, BN, 4, 4>(P, stream, "omc_dq_gemm");
 }
 
 }  // namespace vast
@@ -471,56 +621,58 @@ using namespace vast;
 extern "C" size_t vast_omc_workspace_bytes(int64_t bs, int64_t n_total, int64_t dim, int need_sample, int need_grad) {
   if (bs <= 0 || n_total <= 0 || dim <= 0) return 0;
   OmcPlan pl;
-  omc_plan(&pl, bs, n_total, dim, need_sample, need_grad);
+  omc_plan(&pl, bs, n_total, dim, need_sample || need_grad, need_grad != 0);
   return pl.total;
 }
 
 extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int64_t dim, int64_t row_offset,
                              float contra_temp, const float* contra_temp_dev, float label_smoothing,
-                             float weight_floor, uint64_t seed,
-                             uint64_t offset, const float* debug_noise, float* loss, int64_t* neg_idx,
-                             float* grad_cond, float* grad_t, float* grad_temp, float* lse, void* workspace,
-                             size_t workspace_bytes, vast_stream_t stream) {
+                             float weight_floor, uint64_t seed, uint64_t offset, const float* debug_noise, int flags,
+                             float* loss, int64_t* neg_idx, float* grad_cond, float* grad_t, float* grad_temp, float* lse,
+                             void* workspace, size_t workspace_bytes, vast_stream_t stream) {
   VAST_REQUIRE(pack && loss && workspace, VAST_ERR_INVALID, "omc_step: null pointer");
   VAST_REQUIRE(bs > 0 && n_total >= bs && dim > 0, VAST_ERR_INVALID, "omc_step: bad sizes");
   VAST_REQUIRE(bs < (1 << 24) && n_total < (1 << 30) && dim <= 16384, VAST_ERR_UNSUPPORTED, "omc_step: sizes too large");
   VAST_REQUIRE(dim % 8 == 0, VAST_ERR_UNSUPPORTED, "omc_step: dim must be a multiple of 8 (got %lld)", (long long)dim);
+  VAST_REQUIRE((reinterpret_cast<uintptr_t>(pack) & 15) == 0, VAST_ERR_INVALID, "omc_step: pack must be 16-byte aligned");
   VAST_REQUIRE(row_offset >= 0 && row_offset + bs <= n_total, VAST_ERR_INVALID, "omc_step: local rows outside [0, n_total)");
   VAST_REQUIRE(contra_temp_dev != nullptr || contra_temp > 0.f, VAST_ERR_INVALID, "omc_step: contra_temp must be positive");
   const bool need_grad = grad_cond || grad_t || grad_temp;
   VAST_REQUIRE(!need_grad || (grad_cond && grad_t && grad_temp), VAST_ERR_INVALID,
                "omc_step: give all of grad_cond, grad_t, grad_temp or none");
   const bool need_sample = neg_idx != nullptr;
+  const bool elem = debug_noise != nullptr;                         // reference-literal per-element race
+  const bool two_pass = elem || (flags & VAST_OMC_TWO_PASS) != 0;  // otherwise: single pass + gated fallback
   OmcPlan pl;
-  omc_plan(&pl, bs, n_total, dim, need_sample, need_grad);
+  omc_plan(&pl, bs, n_total, dim, need_sample || need_grad, need_grad);
   VAST_REQUIRE(workspace_bytes >= pl.total, VAST_ERR_WORKSPACE, "omc_step: workspace %zu < required %zu", workspace_bytes, pl.total);
   VAST_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, VAST_ERR_INVALID, "omc_step: workspace must be 256-byte aligned");
 
   char* ws = static_cast<char*>(workspace);
+  int* wflags = reinterpret_cast<int*>(ws + pl.off_flags);  // [0] fp16-range overflow, [1] prep ticket, [2] finalize ticket
   float4* partial = reinterpret_cast<float4*>(ws + pl.off_partial);
-  float* lse2 = reinterpret_cast<float*>(ws + pl.off_lse2);
+  float* ref2 = reinterpret_cast<float*>(ws + pl.off_ref2);
   float* zt = reinterpret_cast<float*>(ws + pl.off_zt);
-  float* sz = reinterpret_cast<float*>(ws + pl.off_sz);
   float* rowce = reinterpret_cast<float*>(ws + pl.off_rowce);
   float* rowdt = reinterpret_cast<float*>(ws + pl.off_rowdt);
-  __half* Pbuf = need_grad ? reinterpret_cast<__half*>(ws + pl.off_P) : nullptr;
-  __half* KT = need_grad ? reinterpret_cast<__half*>(ws + pl.off_KT) : nullptr;
-  float* ksump = need_grad ? reinterpret_cast<float*>(ws + pl.off_ksump) : nullptr;
-  float* ksum = need_grad ? reinterpret_cast<float*>(ws + pl.off_ksum) : nullptr;
+  float* ksump = reinterpret_cast<float*>(ws + pl.off_ksump);
+  float* ksum = reinterpret_cast<float*>(ws + pl.off_ksum);
+  __half* Pbuf = (need_grad || need_sample) ? reinterpret_cast<__half*>(ws + pl.off_P) : nullptr;
   float* dqpart = need_grad ? reinterpret_cast<float*>(ws + pl.off_dq) : nullptr;
+  __half* pack16 = need_grad ? reinterpret_cast<__half*>(ws + pl.off_k16) : nullptr;
 
   const auto* pk = static_cast<const __nv_bfloat16*>(pack);
   const float inv_tau = contra_temp_dev ? 0.f : 1.0f / contra_temp;  // device pointer wins (no host sync)
   const int M = static_cast<int>(bs), N = static_cast<int>(n_total), D = static_cast<int>(dim);
-  const int row_blocks = ceil_div(2 * M, 128);
   int rc;
 
+  VAST_CUDA_OK(cudaMemsetAsync(wflags, 0, 16, stream));
   // K1
-  if (need_grad) {
-    dim3 grid(static_cast<unsigned>(2 * ceil_div(D, 64)), static_cast<unsigned>(pl.nrb));
-    VAST_TIMED(stream, "transpose_ksum", (transpose_ksum_kernel<<<grid, 256, 0, stream>>>(pk, n_total, dim, pl.npad, KT, ksump, pl.nrb)));
-    VAST_LAUNCH_OK("transpose_ksum");
-  }
+  VAST_TIMED(stream, "omc_prep",
+             (omc_prep_kernel<<<pl.ncs + ceil_div(M, 8), 256, 0, stream>>>(pk, N, D, M, static_cast<int>(row_offset), pl.ncs, pl.nslab,
+                                                                            ksump, ksum, zt, two_pass ? nullptr : ref2,
+                                                                            kLog2e * inv_tau, contra_temp_dev, wflags, pack16)));
+  VAST_LAUNCH_OK("omc_prep");
 
   // tensor maps of the S GEMMs: A = local rows, B = all rows, both strided views of `pack`
   CUtensorMap tmA[2], tmB[2];
@@ -533,38 +685,33 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
   rc = tc::make_tmap_2d(&tmB[1], pk + dim, VAST_BF16, n_total, dim, 2 * dim, 256);  // all cond
   if (rc) return rc;
 
-  // K2: pass 1
-  {
+  auto run_stats = [&](const int* gate) -> int {
     tc::KernelParams<EpiStats::Params> P;
     memset(&P, 0, sizeof(P));
     P.g = pl.g_s;
+    P.gate = gate;
     for (int i = 0; i < 2; ++i) {
       P.tmA[i] = tmA[i];
       P.tmB[i] = tmB[i];
     }
-    P.epi = {partial, pl.slots, kLog2e * inv_tau, contra_temp_dev, static_cast<int>(row_offset)};
-    rc = tc::launch_gemm<EpiStats, 256, 4, 8>(P, stream, "omc_stats_gemm");
-    if (rc) return rc;
-  }
-  // K3
-  {
-    const int kblocks = need_grad ? ceil_div(2 * D, 128) : 0;
-    VAST_TIMED(stream, "omc_stats_finalize",
-               (omc_stats_finalize_kernel<<<row_blocks + kblocks, 128, 0, stream>>>(
-                   partial, pl.slots, M, N, inv_tau, contra_temp_dev, label_smoothing, lse2, zt, sz, rowce, lse, row_blocks,
-                   ksump, pl.nrb, D, ksum)));
+    P.epi = {reinterpret_cast<float2*>(partial), pl.slots, kLog2e * inv_tau, contra_temp_dev};
+    int r = tc::launch_gemm<EpiStats, 256, 4, 8>(P, stream, gate ? "omc_stats_gemm_gated" : "omc_stats_gemm");
+    if (r) return r;
+    VAST_TIMED(stream, gate ? "omc_stats_finalize_gated" : "omc_stats_finalize",
+               (omc_stats_finalize_kernel<<<ceil_div(2 * M, 128), 128, 0, stream>>>(reinterpret_cast<const float2*>(partial), pl.slots,
+                                                                                    2 * M, ref2, gate)));
     VAST_LAUNCH_OK("omc_stats_finalize");
-  }
-  // K4 + K5: pass 2
-  if (need_sample || need_grad) {
-    tc::KernelParams<EpiProb::Params> P;
+    return VAST_OK;
+  };
+  auto fill_soft = [&](auto& P, const int* gate, int* ovf) {
     memset(&P, 0, sizeof(P));
     P.g = pl.g_s;
+    P.gate = gate;
     for (int i = 0; i < 2; ++i) {
       P.tmA[i] = tmA[i];
       P.tmB[i] = tmB[i];
     }
-    P.epi.lse2 = lse2;
+    P.epi.ref2 = ref2;
     P.epi.P = Pbuf;
     P.epi.ldp = pl.npad;
     P.epi.partial = partial;
@@ -579,15 +726,36 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
     P.epi.off_lo = static_cast<uint32_t>(offset);
     P.epi.off_hi = static_cast<uint32_t>(offset >> 32);
     P.epi.noise = debug_noise;
+    P.epi.noise_ld = n_total;
     P.epi.do_sample = need_sample ? 1 : 0;
-    rc = tc::launch_gemm<EpiProb, 256, 4, 8>(P, stream, "omc_prob_gemm");
+    P.epi.ovf = ovf;
+  };
+  auto run_soft = [&](const int* gate, int* ovf) -> int {
+    if (elem) {
+      tc::KernelParams<EpiSoft<true>::Params> P;
+      fill_soft(P, gate, ovf);
+      return tc::launch_gemm<EpiSoft<true>, 256, 4, 8>(P, stream, "omc_soft_gemm_elem");
+    }
+    tc::KernelParams<EpiSoft<false>::Params> P;
+    fill_soft(P, gate, ovf);
+    return tc::launch_gemm<EpiSoft<false>, 256, 4, 8>(P, stream, gate ? "omc_soft_gemm_gated" : "omc_soft_gemm");
+  };
+
+  if (two_pass) {
+    rc = run_stats(nullptr);
     if (rc) return rc;
-    VAST_TIMED(stream, "omc_sample_finalize",
-               (omc_sample_finalize_kernel<<<row_blocks, 128, 0, stream>>>(partial, pl.slots, M, N, inv_tau, contra_temp_dev,
-                                                                           label_smoothing, zt, sz, neg_idx, rowdt)));
-    VAST_LAUNCH_OK("omc_sample_finalize");
+    rc = run_soft(nullptr, nullptr);
+    if (rc) return rc;
+  } else {
+    rc = run_soft(nullptr, &wflags[0]);  // K2: exponent reference = the positive pair's logit
+    if (rc) return rc;
+    rc = run_stats(&wflags[0]);          // the next three launches are no-ops unless the fp16 range overflowed
+    if (rc) return rc;
+    rc = run_soft(&wflags[0], nullptr);
+    if (rc) return rc;
   }
-  // K6 + K7: dQ
+
+  // K3: dQraw = Pt . K   (fp16 x fp16, the gathered features as the MN-major operand in their row-major layout)
   if (need_grad) {
     tc::KernelParams<tc::EpiStore::Params> P;
     memset(&P, 0, sizeof(P));
@@ -595,26 +763,54 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
     for (int i = 0; i < 2; ++i) {
       rc = tc::make_tmap_2d(&P.tmA[i], Pbuf + static_cast<int64_t>(i) * bs * pl.npad, VAST_F16, bs, n_total, pl.npad, tc::BM);
       if (rc) return rc;
-      rc = tc::make_tmap_2d(&P.tmB[i], KT + static_cast<int64_t>(i) * dim * pl.npad, VAST_F16, dim, n_total, pl.npad, pl.bn_dq);
+      rc = tc::make_tmap_2d(&P.tmB[i], pack16 + static_cast<int64_t>(i) * dim, VAST_F16, n_total, dim, 2 * dim, tc::BK);
       if (rc) return rc;
     }
     P.epi = {dqpart, dim, bs * dim, 2 * bs * dim, 1.0f};
-    rc = pl.bn_dq == 256 ? launch_dq<256>(P, stream) : launch_dq<128>(P, stream);
+    rc = pl.bn_dq == 256 ? tc::launch_gemm<tc::EpiStore, 256, 4, 4, true>(P, stream, "omc_dq_gemm")
+                         : tc::launch_gemm<tc::EpiStore, 128, 4, 4, true>(P, stream, "omc_dq_gemm");
     if (rc) return rc;
-    const int64_t total = 2LL * M * D;
-    int64_t gb = ceil_div64(total, 256 * 4);
-    const int64_t cap = static_cast<int64_t>(device_sm_count()) * 8;
-    if (gb > cap) gb = cap;
-    VAST_TIMED(stream, "omc_grad_finalize",
-               (omc_grad_finalize_kernel<<<static_cast<unsigned>(gb), 256, 0, stream>>>(
-                   dqpart, pl.g_dq.k_splits, 2 * bs * dim, M, D, ksum, pk, static_cast<int>(row_offset), N, label_smoothing,
-                   inv_tau, contra_temp_dev, lse2, zt, grad_cond, grad_t)));
-    VAST_LAUNCH_OK("omc_grad_finalize");
   }
-  // K8
-  VAST_TIMED(stream, "omc_final_reduce",
-             (omc_final_reduce_kernel<<<1, 1024, 0, stream>>>(rowce, need_grad ? rowdt : nullptr, 2 * M, 1.0f / (2.0f * M), loss,
-                                                             need_grad ? grad_temp : nullptr)));
-  VAST_LAUNCH_OK("omc_final_reduce");
+
+  // K4
+  {
+    RowFinParams R;
+    memset(&R, 0, sizeof(R));
+    R.partial = partial;
+    R.slots = pl.slots;
+    R.M = M;
+    R.N = N;
+    R.D = D;
+    R.row_offset = static_cast<int>(row_offset);
+    R.ref2 = ref2;
+    R.zt = zt;
+    R.inv_tau = inv_tau;
+    R.temp_dev = contra_temp_dev;
+    R.eps_ls = label_smoothing;
+    R.floor = weight_floor;
+    R.neg_idx = neg_idx;
+    R.elem_mode = elem ? 1 : 0;
+    R.P = Pbuf;
+    R.ldp = pl.npad;
+    R.seed_lo = static_cast<uint32_t>(seed);
+    R.seed_hi = static_cast<uint32_t>(seed >> 32);
+    R.off_lo = static_cast<uint32_t>(offset);
+    R.off_hi = static_cast<uint32_t>(offset >> 32);
+    R.dq_part = dqpart;
+    R.ksplits = pl.g_dq.k_splits;
+    R.split_stride = 2 * bs * dim;
+    R.ksum = ksum;
+    R.pack = pk;
+    R.grad_cond = grad_cond;
+    R.grad_t = grad_t;
+    R.lse_out = lse;
+    R.rowce = rowce;
+    R.rowdt = rowdt;
+    R.loss = loss;
+    R.grad_temp = need_grad ? grad_temp : nullptr;
+    R.ticket = &wflags[2];
+    VAST_TIMED(stream, "omc_row_finalize", (omc_row_finalize_kernel<<<ceil_div(2 * M, 8), 256, 0, stream>>>(R)));
+    VAST_LAUNCH_OK("omc_row_finalize");
+  }
   return VAST_OK;
 }

@@ -142,10 +142,24 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor, kind::f16: fp32 accumulate, A/B both K-major, 16-bit inputs.
-// in_fmt: 0 = fp16, 1 = bf16.
-__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t in_fmt, uint32_t m, uint32_t n) {
-  return (1u << 4) | (in_fmt << 7) | (in_fmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+// MN-major operand tile (rows = K, 64 MN-elements = one 128-byte swizzle span per row), written by TMA
+// with CU_TENSOR_MAP_SWIZZLE_128B as boxes of 64 K-rows x 64 MN-elements: 8-row K groups are 1024 B
+// apart (SBO); the next 64 MN-elements start `mn_atom_bytes` later (LBO = one whole box).
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t mn_atom_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);            // start address
+  d |= static_cast<uint64_t>((mn_atom_bytes >> 4) & 0x3FFF) << 16;  // LBO
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                      // SBO
+  d |= static_cast<uint64_t>(1) << 46;                              // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                              // SWIZZLE_128B
+  return d;
+}
+
+// Instruction descriptor, kind::f16: fp32 accumulate, A K-major, B K-major (b_mn = 0) or MN-major (1),
+// 16-bit inputs.  a_fmt / b_fmt: 0 = fp16, 1 = bf16 (the two operand formats are independent fields).
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t a_fmt, uint32_t b_fmt, uint32_t b_mn, uint32_t m,
+                                                      uint32_t n) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | (b_mn << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 }  // namespace ptx

@@ -22,57 +22,180 @@ __device__ __forceinline__ uint64_t make_key(float s, uint32_t idx) {
   return (static_cast<uint64_t>(f32_orderable(s)) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - idx);
 }
 
-constexpr int TOPK_MAX = 64;  // list capacity of the GEMM-epilogue selection (smem: 64 x 128 x 8 B)
+constexpr int TOPK_MAX = 64;  // largest k of the GEMM-epilogue selection
 
 // ------------------------------------------------------------------ GEMM epilogue: running top-k
 // One thread owns one query row (TMEM lane) and sees that row's scores in increasing column order.
-// Its sorted candidate list lives in shared memory ([pos][row] so lanes hit distinct banks); the
-// current k-th score is kept in a register, so the steady state is one compare per score.
+// Steady state is ONE compare per score against the row's current k-th best (a register).  Scores that
+// pass are appended to the row's candidate buffer in shared memory ([row][pos], capacity CAP > k); when
+// a buffer of the warp is full the warp compacts all 32 of its rows together: each row's candidates are
+// bitonic-sorted across the lanes (keys are unique, so (score desc, index asc) is a strict order), the
+// best k stay, and the k-th becomes the new threshold.  Compactions are rare (the number of candidates
+// that beat the running k-th grows only logarithmically with the columns seen) and warp-converged, so
+// the epilogue stays hidden behind the MMAs of the next accumulator tile.
+//   E = 32-bit... number of key registers per lane in the sort: CAP <= 32 * E.
+__device__ __forceinline__ void sts_u64(uint32_t addr, uint64_t v) {
+  asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t lds_u64(uint32_t addr) {
+  uint64_t v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+template <int E>
 struct EpiTopK {
   struct Params {
-    uint64_t* out;  // [M][n_splits][k]
+    uint64_t* out;  // [M][n_splits][k], each list sorted best-first, 0 = empty
     int k;
+    int cap;  // buffer capacity per row, k < cap <= 32 * E
     int n_splits;
     uint32_t col_offset;
   };
-  static size_t smem_bytes() { return static_cast<size_t>(TOPK_MAX) * tc::BM * sizeof(uint64_t); }
+  static size_t smem_bytes(int cap) { return static_cast<size_t>(cap + 1) * tc::BM * sizeof(uint64_t); }
   const Params& p;
-  uint64_t* lists;
+  uint32_t lists;  // shared-space address of this warp's 32 rows: [32][cap + 1] keys
+  uint32_t my;     // this lane's row
+  uint32_t stride_b;
   float thr;
   int cnt;
-  __device__ EpiTopK(const Params& p_, uint8_t* smem) : p(p_), lists(reinterpret_cast<uint64_t*>(smem)) {}
+  __device__ EpiTopK(const Params& p_, uint8_t* smem) : p(p_) {
+    // odd row stride (in 8-byte words): simultaneous appends of different rows spread over the banks
+    stride_b = static_cast<uint32_t>(p.cap + 1) * 8u;
+    const uint32_t q = (threadIdx.x >> 5) & 3;  // one epilogue warp per TMEM lane quadrant (NE == 4)
+    lists = ptx::smem_u32(smem) + q * 32u * stride_b;
+    my = lists + (threadIdx.x & 31) * stride_b;
+    thr = -INFINITY;
+    cnt = 0;
+  }
   __device__ __forceinline__ void item_begin(const tc::ItemCtx&) {
     thr = -INFINITY;
     cnt = 0;
   }
-  __device__ __noinline__ void insert(uint64_t* my, float s, uint32_t idx) {
-    const uint64_t key = make_key(s, idx);
-    int pos = cnt < p.k ? cnt : p.k - 1;
-    while (pos > 0) {
-      const uint64_t prev = my[(pos - 1) * tc::BM];
-      if (prev >= key) break;
-      my[pos * tc::BM] = prev;
-      --pos;
+
+  // Sort 32*E keys (register e of lane l holds element e*32 + l) in descending order (bitonic network).
+  __device__ __forceinline__ static void sort_desc(uint64_t (&key)[E], int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32 * E; size <<= 1) {
+#pragma unroll
+      for (int st = size >> 1; st > 0; st >>= 1) {
+        if (st >= 32) {  // partner lives in another register of the same lane
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const int pe = e ^ (st >> 5);
+            if (pe > e) {
+              const bool desc = (((e << 5) & size) == 0);
+              const uint64_t a = key[e], b = key[pe];
+              const bool sw = desc ? (a < b) : (a > b);
+              key[e] = sw ? b : a;
+              key[pe] = sw ? a : b;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const int idx = (e << 5) | lane;
+            const uint64_t other = __shfl_xor_sync(0xffffffffu, key[e], st);
+            const bool desc = ((idx & size) == 0);
+            const bool lower = ((lane & st) == 0);  // this lane holds the lower index of the pair
+            const bool keep_max = (desc == lower);  // descending run: the lower index keeps the larger key
+            const bool gt = key[e] > other;
+            key[e] = (gt == keep_max) ? key[e] : other;
+          }
+        }
+      }
     }
-    my[pos * tc::BM] = key;
-    if (cnt < p.k) ++cnt;
-    if (cnt == p.k) thr = f32_from_orderable(static_cast<uint32_t>(my[(p.k - 1) * tc::BM] >> 32));
   }
+
+  // Warp-collective: every row of the warp holding more than k candidates (or any, if `all`) is sorted,
+  // cut to its best k, and gets its threshold refreshed.
+  __device__ __forceinline__ void compact(int lane, bool all, int& n_mine, float& thr_mine) const {
+    __syncwarp();
+#pragma unroll 1
+    for (int r = 0; r < 32; ++r) {
+      const int n = __shfl_sync(0xffffffffu, n_mine, r);
+      if (!(n > p.k || (all && n > 0))) continue;
+      const uint32_t row = lists + static_cast<uint32_t>(r) * stride_b;
+      uint64_t key[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int pos = e * 32 + lane;
+        key[e] = pos < n ? lds_u64(row + pos * 8) : 0ull;
+      }
+      sort_desc(key, lane);
+      const int keep = n < p.k ? n : p.k;
+      uint64_t kth = 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int pos = e * 32 + lane;
+        if (pos < keep) sts_u64(row + pos * 8, key[e]);
+        const uint64_t cand = __shfl_sync(0xffffffffu, key[e], (p.k - 1) & 31);
+        if (e == ((p.k - 1) >> 5)) kth = cand;
+      }
+      if (lane == r) {
+        n_mine = keep;
+        if (keep == p.k) thr_mine = f32_from_orderable(static_cast<uint32_t>(kth >> 32));
+      }
+    }
+    __syncwarp();
+  }
+
   __device__ __forceinline__ void chunk(const tc::ItemCtx& c, const uint32_t (&v)[32], int col0) {
     if (col0 >= c.N) return;
     const int nvalid = c.N - col0;
-    uint64_t* my = lists + (c.row - c.m_blk * tc::BM);
+    const uint32_t gcol = p.col_offset + static_cast<uint32_t>(col0);
+    const int cap = p.cap;
+    float t = thr;
+    int n = cnt;
+    int resume = 32;  // first column of this chunk that could not be appended (buffer full)
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const float s = __uint_as_float(v[i]);
-      if (i < nvalid && s > thr) insert(my, s, p.col_offset + static_cast<uint32_t>(col0 + i));
+      if (i < nvalid && s > t) {
+        if (n < cap) {
+          sts_u64(my + n * 8, make_key(s, gcol + i));
+          ++n;
+        } else if (resume == 32) {
+          resume = i;
+        }
+      }
     }
+    while (__any_sync(0xffffffffu, resume < 32)) {
+      compact(c.lane, false, n, t);
+      const int from = resume;
+      resume = 32;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float s = __uint_as_float(v[i]);
+        if (i >= from && i < nvalid && s > t) {
+          if (n < cap) {
+            sts_u64(my + n * 8, make_key(s, gcol + i));
+            ++n;
+          } else if (resume == 32) {
+            resume = i;
+          }
+        }
+      }
+    }
+    thr = t;
+    cnt = n;
   }
+
   __device__ __forceinline__ void item_end(const tc::ItemCtx& c) {
-    if (!c.row_valid) return;
-    const uint64_t* my = lists + (c.row - c.m_blk * tc::BM);
-    uint64_t* dst = p.out + (static_cast<int64_t>(c.row) * p.n_splits + c.n_split) * p.k;
-    for (int i = 0; i < p.k; ++i) dst[i] = i < cnt ? my[i * tc::BM] : 0ull;
+    float t = thr;
+    int n_mine = cnt;
+    compact(c.lane, true, n_mine, t);
+    const int row0 = c.row - c.lane;  // first row of this warp
+#pragma unroll 1
+    for (int r = 0; r < 32; ++r) {
+      const int row = row0 + r;
+      if (row >= c.M) break;
+      const int n = __shfl_sync(0xffffffffu, n_mine, r);
+      const uint32_t src = lists + static_cast<uint32_t>(r) * stride_b;
+      uint64_t* dst = p.out + (static_cast<int64_t>(row) * p.n_splits + c.n_split) * p.k;
+      for (int i = c.lane; i < p.k; i += 32) dst[i] = i < n ? lds_u64(src + i * 8) : 0ull;
+    }
+    __syncwarp();
   }
 };
 
@@ -475,9 +598,17 @@ __global__ void scatter_scores_kernel(const int32_t* __restrict__ text_idx, cons
 
 static inline unsigned blocks_for(int64_t n, int per_block) { return static_cast<unsigned>(ceil_div64(n, per_block)); }
 
+template <class T, int S>
+struct TopkTag {
+  using type = T;
+  static constexpr int stages = S;
+};
+
 struct TopkPlan {
   tc::GemmShape g;
   size_t ws_bytes;
+  int e;    // key registers per lane in the epilogue sort
+  int cap;  // candidate buffer capacity per row
 };
 static void topk_plan(TopkPlan* pl, int64_t n_q, int64_t n_k, int64_t cols, int64_t k) {
   tc::fill_shape(&pl->g, 1, (int)n_q, (int)n_k, (int)cols, 256, 1);
@@ -486,6 +617,17 @@ static void topk_plan(TopkPlan* pl, int64_t n_q, int64_t n_k, int64_t cols, int6
   if (max_splits < 1) max_splits = 1;
   tc::choose_splits(&pl->g, device_sm_count(), max_splits, 1);
   pl->ws_bytes = pl->g.n_splits > 1 ? align_up(sizeof(uint64_t) * n_q * pl->g.n_splits * k, 256) : 0;
+  // k <= 16: 32 slots (>= 16 spare); k <= 48: 64 slots; k <= 64: 80 slots (shared memory bound), sorted as 128
+  if (k <= 16) {
+    pl->e = 1;
+    pl->cap = 32;
+  } else if (k <= 48) {
+    pl->e = 2;
+    pl->cap = 64;
+  } else {
+    pl->e = 4;
+    pl->cap = 80;
+  }
 }
 
 }  // namespace vast
@@ -533,16 +675,27 @@ extern "C" int vast_sim_topk(const void* q_op, const void* k_op, int64_t n_q, in
   topk_plan(&pl, n_q, n_k, cols, k);
   VAST_REQUIRE(workspace_bytes >= pl.ws_bytes && (pl.ws_bytes == 0 || workspace), VAST_ERR_WORKSPACE,
                "sim_topk: workspace %zu < required %zu", workspace_bytes, pl.ws_bytes);
-  tc::KernelParams<EpiTopK::Params> P;
-  memset(&P, 0, sizeof(P));
-  P.g = pl.g;
-  int rc = tc::make_tmap_2d(&P.tmA[0], q_op, VAST_BF16, n_q, cols, cols, tc::BM);
-  if (rc) return rc;
-  rc = tc::make_tmap_2d(&P.tmB[0], k_op, VAST_BF16, n_k, cols, cols, 256);
-  if (rc) return rc;
   uint64_t* part = pl.g.n_splits > 1 ? static_cast<uint64_t*>(workspace) : out_keys;
-  P.epi = {part, static_cast<int>(k), pl.g.n_splits, static_cast<uint32_t>(col_offset)};
-  rc = tc::launch_gemm<EpiTopK, 256, 3, 4>(P, stream, "sim_topk_gemm");
+  int rc;
+  auto run = [&](auto tag) -> int {
+    using Epi = typename decltype(tag)::type;
+    constexpr int STAGES = decltype(tag)::stages;
+    tc::KernelParams<typename Epi::Params> P;
+    memset(&P, 0, sizeof(P));
+    P.g = pl.g;
+    int r = tc::make_tmap_2d(&P.tmA[0], q_op, VAST_BF16, n_q, cols, cols, tc::BM);
+    if (r) return r;
+    r = tc::make_tmap_2d(&P.tmB[0], k_op, VAST_BF16, n_k, cols, cols, 256);
+    if (r) return r;
+    P.epi = {part, static_cast<int>(k), pl.cap, pl.g.n_splits, static_cast<uint32_t>(col_offset)};
+    return tc::launch_gemm<Epi, 256, STAGES, 4>(P, stream, "sim_topk_gemm", Epi::smem_bytes(pl.cap));
+  };
+  if (pl.e == 1)
+    rc = run(TopkTag<EpiTopK<1>, 4>{});
+  else if (pl.e == 2)
+    rc = run(TopkTag<EpiTopK<2>, 3>{});
+  else
+    rc = run(TopkTag<EpiTopK<4>, 3>{});
   if (rc) return rc;
   if (pl.g.n_splits > 1) {
     topk_merge_kernel<<<blocks_for(n_q, 4), 128, 0, stream>>>(part, k, pl.g.n_splits * k, pl.g.n_splits, (int)k, n_q, (int)k, out_keys);

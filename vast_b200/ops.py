@@ -46,6 +46,21 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, alpha: float = 1.0) -> torch.Tenso
     return c
 
 
+def gemm_nn(a: torch.Tensor, b: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
+    """C[m, n] = alpha * sum_k a[m, k] b[k, n]; b row-major (MN-major tensor-core operand, no transpose);
+    a, b bf16 or fp16, formats may differ; C fp32."""
+    require_cuda(a, b)
+    assert a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[0]
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    m, k = a.shape
+    n = b.shape[1]
+    c = torch.empty(m, n, dtype=torch.float32, device=a.device)
+    ws = _ws(lib().vast_gemm_nt_workspace_bytes(m, n, k), a.device)
+    check(lib().vast_gemm_nn(ptr(a), a.stride(0), dtype_code(a.dtype), ptr(b), b.stride(0), dtype_code(b.dtype), m, n, k,
+                             float(alpha), ptr(c), c.stride(0), ptr(ws), ws.numel(), stream_ptr()), "gemm_nn")
+    return c
+
+
 # ------------------------------------------------------------------ feature build
 def pool_concat(vision=None, audio=None, subtitle=None, vision_mode=0, audio_mode=1, out_dtype=None):
     """pool_vision/audio/text_for_contra + torch.cat(dim=1) (general_module.py:426-449, vast.py:269-275).
@@ -125,13 +140,19 @@ def pack_pair(feat_t: torch.Tensor, feat_cond: torch.Tensor, out: torch.Tensor |
 
 
 # ------------------------------------------------------------------ contrastive step
+OMC_TWO_PASS = 1
+
+
 def omc_step(pack: torch.Tensor, bs: int, row_offset: int, contra_temp, label_smoothing: float = 0.1,
              weight_floor: float = 1e-4, seed: int = 0, offset: int = 0, need_sample: bool = True,
              need_grad: bool = True, debug_noise: torch.Tensor | None = None, want_lse: bool = False,
-             buffers: dict | None = None):
+             buffers: dict | None = None, two_pass: bool = False):
     """Fused OMC step (vast.py:405-440 + backward) on the packed, gathered features.
     Returns dict(loss[1], neg_idx[2,bs] | None, grad_cond, grad_t, grad_temp | None, lse | None).
-    `buffers` (a dict returned by an earlier call with the same shapes/flags) re-uses outputs + workspace."""
+    `buffers` (a dict returned by an earlier call with the same shapes/flags) re-uses outputs + workspace.
+    two_pass: evaluate the logits twice (VAST_OMC_TWO_PASS) instead of the default single pass with the
+    on-device fallback; debug_noise [2, bs, n_total] (Exp(1) variates) switches to the reference-literal
+    per-element race argmax_j w_j / E_j for index-exact tests."""
     require_cuda(pack)
     assert pack.dtype == torch.bfloat16 and pack.is_contiguous() and pack.dim() == 2 and pack.shape[1] % 2 == 0
     n_total, dim = pack.shape[0], pack.shape[1] // 2
@@ -158,7 +179,8 @@ def omc_step(pack: torch.Tensor, bs: int, row_offset: int, contra_temp, label_sm
         contra_temp = 0.0
     check(lib().vast_omc_step(ptr(pack), bs, n_total, dim, row_offset, float(contra_temp), ptr(temp_dev), float(label_smoothing),
                               float(weight_floor), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1),
-                              ptr(debug_noise), ptr(loss), ptr(neg), ptr(gc), ptr(gt), ptr(gtemp), ptr(lse),
+                              ptr(debug_noise), OMC_TWO_PASS if two_pass else 0, ptr(loss), ptr(neg), ptr(gc), ptr(gt),
+                              ptr(gtemp), ptr(lse),
                               ptr(ws), ws.numel(), stream_ptr()), "omc_step")
     return dict(loss=loss, neg_idx=neg, grad_cond=gc, grad_t=gt, grad_temp=gtemp, lse=lse, _ws=(ws, temp_dev))
 
