@@ -158,7 +158,7 @@ def test_single_pass_range_and_fallback(case):
     o = oracle(t.numpy(), c.numpy(), n, 0, temp)
     check_against_oracle(out, o, n)
     check_against_oracle(ref, o, n)
-    check_negatives_hier(out["neg_idx"], o, seed, offset, 0, n)
+    check_negatives_hier(out["neg_idx"], o, seed, offset, 0, n, n)
     if case != "untrained":       # the fallback IS the two-pass form: identical bits
         assert torch.equal(out["grad_t"], ref["grad_t"]) and torch.equal(out["neg_idx"], ref["neg_idx"])
 
@@ -173,7 +173,7 @@ def test_cfg3_shape_full_size():
     out = run_step(t.numpy(), c.numpy(), n, 0, temp, seed=seed, offset=offset, want_lse=True)
     o = oracle(t.numpy(), c.numpy(), n, 0, temp)
     check_against_oracle(out, o, n)
-    check_negatives_hier(out["neg_idx"], o, seed, offset, 0, n)
+    check_negatives_hier(out["neg_idx"], o, seed, offset, 0, n, n)
     # determinism: same seed/offset -> identical outputs, different offset -> different draws
     out2 = run_step(t.numpy(), c.numpy(), n, 0, temp, seed=seed, offset=offset)
     assert torch.equal(out["neg_idx"], out2["neg_idx"]) and torch.equal(out["grad_t"], out2["grad_t"])

@@ -482,7 +482,7 @@ extern "C" int vast_pack_pair(const void* feat_t, const void* feat_cond, int dty
                    ((reinterpret_cast<uintptr_t>(feat_t) | reinterpret_cast<uintptr_t>(feat_cond) | reinterpret_cast<uintptr_t>(pack_bf16)) & 15) == 0;
   if (vec && (dtype == VAST_F32 || dtype == VAST_BF16 || dtype == VAST_F16)) {
     const int dim8 = static_cast<int>(dim / 8);
-    const unsigned g = grid_for(bs * 2 * dim8, 256);
+    const unsigned g = static_cast<unsigned>(ceil_div64(bs * 2 * dim8, 256));  // one 16-byte vector per thread
     if (dtype == VAST_F32)
       VAST_TIMED(stream, "pack_pair", (pack_pair_vec_kernel<float><<<g, 256, 0, stream>>>(static_cast<const float*>(feat_t), static_cast<const float*>(feat_cond), bs, dim8, ld_in, out)));
     else if (dtype == VAST_BF16)

@@ -10,11 +10,13 @@
 //   K2 soft GEMM     : S tile in TMEM -> Pt_ij = exp(z_ij - ref_i)  ("softmax numerators" relative to the
 //                      positive pair, so Pt_target = 1): fp16 Pt tile to the L2-resident workspace (target
 //                      column zeroed), row sums l_i, chunk-level exponential race for the hard negatives
-//   K3 dQ GEMM       : dQraw = Pt . K, the gathered features read ROW-MAJOR as the MN-major UMMA operand
-//                      (fp16 x fp16 -> fp32; no transposed copy)
-//   K4 row finalize  : per row: l_i -> lse, loss terms, hard-negative draw, gradient assembly
+//   K3 row stats     : per row: l_i -> lse, CE term, 1 / l_i, p_target, and the hard-negative draw
+//   K4 dQ GEMM       : dQraw = Pt . K, the gathered features read ROW-MAJOR as the MN-major UMMA operand
+//                      (fp16 x fp16 -> fp32; no transposed copy); the epilogue assembles the gradient in place,
 //                      dQ = (1/(2 bs tau)) (dQraw / l - (eps/N) sum_j K_j - ((1-eps) - p_target) K_target),
-//                      d tau terms; the last block reduces loss and d tau in a fixed order.
+//                      and <q_i, dQraw_i> for d tau.  (Small per-rank problems split K instead and a reduce
+//                      kernel sums the partials in a fixed order.)
+//   K5 final         : loss and d tau, block sums + last-block ticket (fixed order -> deterministic)
 // The [bs, N] logits are evaluated exactly ONCE.  Pt needs the fp16 range: an entry overflows only if
 // some negative beats its positive by more than 16 ln2 = 11.09 nats ((s_ij - s_ii) > 0.78 at tau = 0.07).
 // The soft epilogue detects that (chunk sum >= 65504) and raises a device flag; three flag-gated
@@ -235,11 +237,14 @@ struct EpiSoft {
 };
 
 // ------------------------------------------------------------------ K1: prep
-// blocks [0, ncs):   column sums of pack [N, 2D] over 64-row slabs -> ksum_partial[slab][2D] (fixed order)
+// blocks [0, ncs):   column sums of pack [N, 2D] over PREP_ROWS-row slabs -> ksum_partial[slab][2D] (fixed order),
+//                    plus the fp16 copy of those rows
 // blocks [ncs, ..):  one warp per local row: z_t = <t_i, c_i> (fp32 over the bf16 features), and in the
 //                    single-pass form the exponent reference ref2 = z_t * log2(e) / tau for both directions
-// The last block to finish (ticket) reduces the slab partials into ksum[2D]; block 0 clears the overflow flag.
-constexpr int PREP_ROWS = 64;
+// Per 256-column tile, the last slab block to finish (ticket) reduces that tile's slab partials into ksum
+// in a fixed order (deterministic, and the reduction is spread over the column tiles).
+constexpr int PREP_ROWS = 128;
+constexpr int FLAG_INTS = 256;  // [0] fp16-range overflow, [1] finalize ticket, [8 + ctile] prep tickets per 256-column tile
 __global__ void __launch_bounds__(256) omc_prep_kernel(const __nv_bfloat16* __restrict__ pack, int n_total, int dim, int bs,
                                                       int row_offset, int ncs, int nslab,
                                                       float* __restrict__ ksum_partial, float* __restrict__ ksum,
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__(256) omc_prep_kernel(const __nv_bfloat16* __re
 #pragma unroll
       for (int i = 0; i < PREP_ROWS / 8; ++i) {
         const int r = r0 + i;
-        raw[i] = r < n_total ? *reinterpret_cast<const uint4*>(pack + static_cast<int64_t>(r) * cols + c0) : make_uint4(0, 0, 0, 0);
+        raw[i] = r < n_total ? ld_stream16(pack + static_cast<int64_t>(r) * cols + c0) : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
       for (int i = 0; i < PREP_ROWS / 8; ++i) {
@@ -294,6 +299,28 @@ __global__ void __launch_bounds__(256) omc_prep_kernel(const __nv_bfloat16* __re
         ksum_partial[static_cast<int64_t>(slab) * cols + c] = s;
       }
     }
+    // last slab block of this column tile: ksum[c] = sum over slabs, fixed order
+    const int ctile = blockIdx.x - slab * ctiles;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&flags[8 + ctile], 1) == nslab - 1);
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      const int c = ctile * 256 + threadIdx.x;
+      if (c < cols) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int b = 0;
+        for (; b + 4 <= nslab; b += 4) {
+          a0 += __ldcg(ksum_partial + static_cast<int64_t>(b) * cols + c);
+          a1 += __ldcg(ksum_partial + static_cast<int64_t>(b + 1) * cols + c);
+          a2 += __ldcg(ksum_partial + static_cast<int64_t>(b + 2) * cols + c);
+          a3 += __ldcg(ksum_partial + static_cast<int64_t>(b + 3) * cols + c);
+        }
+        for (; b < nslab; ++b) a0 += __ldcg(ksum_partial + static_cast<int64_t>(b) * cols + c);
+        ksum[c] = (a0 + a1) + (a2 + a3);
+      }
+    }
   } else {
     const int i = (blockIdx.x - ncs) * 8 + warp;
     if (i < bs) {
@@ -321,21 +348,6 @@ __global__ void __launch_bounds__(256) omc_prep_kernel(const __nv_bfloat16* __re
       }
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) flags[0] = 0;
-  // last block: ksum[c] = sum over slabs (fixed order -> deterministic)
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(&flags[1], 1) == static_cast<int>(gridDim.x) - 1);
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    for (int c = threadIdx.x; c < cols; c += 256) {
-      float s = 0.f;
-      for (int b = 0; b < nslab; ++b) s += __ldcg(ksum_partial + static_cast<int64_t>(b) * cols + c);
-      ksum[c] = s;
-    }
-    if (threadIdx.x == 0) flags[1] = 0;
-  }
 }
 
 // ------------------------------------------------------------------ two-pass form: merge pass-1 partials
@@ -355,9 +367,11 @@ __global__ void __launch_bounds__(128) omc_stats_finalize_kernel(const float2* _
   ref2[r] = mm + log2f(l);  // log2-domain log-sum-exp: Pt becomes the softmax probability
 }
 
-// ------------------------------------------------------------------ K4: row finalize
-// One warp per (direction, local row).
-struct RowFinParams {
+// ------------------------------------------------------------------ K3: row statistics + hard negatives
+// One warp per (direction, local row): merges the soft epilogue's per-slot partials, draws the hard
+// negative, and leaves what the gradient epilogue and the final reduction need:
+//   rowstat[r] = (rho = 1 / l, c_t = p_target - (1 - eps), p_target, <q, sum_j K_j>),  rowce[r] = CE row term.
+struct RowStatParams {
   const float4* partial;
   int slots;
   int M, N, D;
@@ -367,27 +381,16 @@ struct RowFinParams {
   float inv_tau;
   const float* temp_dev;
   float eps_ls, floor;
-  // sampling
   int64_t* neg_idx;  // [2][M] or nullptr
   int elem_mode;     // partial.w already holds the winning column (ELEM epilogue)
   const __half* P;
   int64_t ldp;
   uint32_t seed_lo, seed_hi, off_lo, off_hi;
-  // gradient
-  const float* dq_part;  // [ks][2][M][D] or nullptr
-  int ksplits;
-  int64_t split_stride;
   const float* ksum;  // [2][D]
   const __nv_bfloat16* pack;
-  float* grad_cond;
-  float* grad_t;
-  // outputs
-  float* lse_out;  // [2][M] or nullptr
-  float* rowce;    // [2][M]
-  float* rowdt;    // [2][M]
-  float* loss;
-  float* grad_temp;  // or nullptr
-  int* ticket;
+  float4* rowstat;  // [2][M]
+  float* rowce;     // [2][M]
+  float* lse_out;   // [2][M] or nullptr
 };
 
 __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
@@ -399,154 +402,274 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
   }
 }
 
-__global__ void __launch_bounds__(256) omc_row_finalize_kernel(const RowFinParams p) {
-  __shared__ float red[2][256];
-  __shared__ int is_last;
+__global__ void __launch_bounds__(256) omc_row_stats_kernel(const RowStatParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;
+  if (r >= 2 * p.M) return;
   const float inv_tau = p.temp_dev ? 1.0f / __ldg(p.temp_dev) : p.inv_tau;
-  if (r < 2 * p.M) {
-    const int prob = r / p.M, row = r - prob * p.M;
-    const int tcol = p.row_offset + row;
-    // ---- merge the per-slot partials (lane-strided, then butterfly: fixed order)
-    const float4* pp = p.partial + static_cast<int64_t>(r) * p.slots;
-    float l = 0.f, bw = p.elem_mode ? -1.f : 0.f, be = 1.f;
-    int bidx = -1;
-    for (int s = lane; s < p.slots; s += 32) {
-      const float4 q = pp[s];
-      l += q.x;
-      const int idx = __float_as_int(q.w);
-      if (idx >= 0) {
-        const float lhs = q.y * be, rhs = bw * q.z;
-        if (bidx < 0 || lhs > rhs || (lhs == rhs && idx < bidx)) {
-          bw = q.y;
-          be = q.z;
-          bidx = idx;
-        }
+  const int prob = r / p.M, row = r - prob * p.M;
+  const int tcol = p.row_offset + row;
+  // ---- <q, ksum> (label-smoothing term of the loss and of d tau): issue these loads first
+  const __nv_bfloat16* qv = p.pack + static_cast<int64_t>(p.row_offset + row) * 2 * p.D + (prob == 0 ? p.D : 0);
+  const float* ks = p.ksum + prob * p.D;
+  float dot_s = 0.f;
+#pragma unroll 2
+  for (int d = lane * 8; d < p.D; d += 256) {
+    float q[8];
+    bf16x8_to_f32(*reinterpret_cast<const uint4*>(qv + d), q);
+    const float4 k0 = *reinterpret_cast<const float4*>(ks + d), k1 = *reinterpret_cast<const float4*>(ks + d + 4);
+    dot_s = fmaf(q[0], k0.x, dot_s); dot_s = fmaf(q[1], k0.y, dot_s); dot_s = fmaf(q[2], k0.z, dot_s); dot_s = fmaf(q[3], k0.w, dot_s);
+    dot_s = fmaf(q[4], k1.x, dot_s); dot_s = fmaf(q[5], k1.y, dot_s); dot_s = fmaf(q[6], k1.z, dot_s); dot_s = fmaf(q[7], k1.w, dot_s);
+  }
+  // ---- merge the per-slot partials (lane-strided, then butterfly: fixed order)
+  const float4* pp = p.partial + static_cast<int64_t>(r) * p.slots;
+  float l = 0.f, bw = p.elem_mode ? -1.f : 0.f, be = 1.f;
+  int bidx = -1;
+  for (int s = lane; s < p.slots; s += 32) {
+    const float4 q = pp[s];
+    l += q.x;
+    const int idx = __float_as_int(q.w);
+    if (idx >= 0) {
+      const float lhs = q.y * be, rhs = bw * q.z;
+      if (bidx < 0 || lhs > rhs || (lhs == rhs && idx < bidx)) {
+        bw = q.y;
+        be = q.z;
+        bidx = idx;
       }
     }
+  }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      l += __shfl_xor_sync(0xffffffffu, l, o);
-      const float ow = __shfl_xor_sync(0xffffffffu, bw, o), oe = __shfl_xor_sync(0xffffffffu, be, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-      if (oi >= 0) {
-        const float lhs = ow * be, rhs = bw * oe;
-        if (bidx < 0 || lhs > rhs || (lhs == rhs && oi < bidx)) {
-          bw = ow;
-          be = oe;
-          bidx = oi;
-        }
+  for (int o = 16; o > 0; o >>= 1) {
+    l += __shfl_xor_sync(0xffffffffu, l, o);
+    const float ow = __shfl_xor_sync(0xffffffffu, bw, o), oe = __shfl_xor_sync(0xffffffffu, be, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (oi >= 0) {
+      const float lhs = ow * be, rhs = bw * oe;
+      if (bidx < 0 || lhs > rhs || (lhs == rhs && oi < bidx)) {
+        bw = ow;
+        be = oe;
+        bidx = oi;
       }
     }
-    const float ref = p.ref2[r], zt = p.zt[r];
-    const float scale2 = kLog2e * inv_tau;
-    const float pt_un = exp2f(fmaf(zt, scale2, -ref));  // numerator of the positive pair
-    const float ltot = l + pt_un;
-    const float rho = 1.0f / ltot;
-    const float pt = pt_un * rho;
-    const float lse = (ref + log2f(ltot)) * kLn2;
+  }
+  dot_s = warp_sum(dot_s);
+  const float ref = p.ref2[r], zt = p.zt[r];
+  const float scale2 = kLog2e * inv_tau;
+  const float pt_un = exp2f(fmaf(zt, scale2, -ref));  // numerator of the positive pair
+  const float ltot = l + pt_un;
+  const float rho = 1.0f / ltot;
+  const float pt = pt_un * rho;
+  const float lse = (ref + log2f(ltot)) * kLn2;
 
-    // ---- hard negative
-    if (p.neg_idx != nullptr) {
-      int pick = -1;
-      if (p.elem_mode) {
-        pick = bidx;
-      } else if (p.N > 1) {
-        const uint4 rnd = philox4x32_10(make_uint4(0xFFFFFFFFu, static_cast<uint32_t>(p.row_offset + row), p.off_lo,
-                                                   (p.off_hi << 1) | static_cast<uint32_t>(prob)),
-                                        make_uint2(p.seed_lo, p.seed_hi));
-        const float u_in = unit_from_bits(rnd.x), u_mix = unit_from_bits(rnd.y), u_uni = unit_from_bits(rnd.z);
-        // mixture: softmax part (mass l, column drawn in proportion to Pt) vs floor part (uniform, mass floor*ltot*(N-1))
-        const float w_a = l, w_b = p.floor * ltot * static_cast<float>(p.N - 1);
-        const bool take_a = bidx >= 0 && u_mix * (w_a + w_b) < w_a;
-        if (take_a) {
-          const int col = bidx * 32 + lane;
-          float v = 0.f;
-          if (col < p.N) v = __half2float(p.P[static_cast<int64_t>(r) * p.ldp + col]);
-          float pre = v;  // inclusive prefix over the chunk (Kogge-Stone: fixed order)
+  // ---- hard negative
+  if (p.neg_idx != nullptr) {
+    int pick = -1;
+    if (p.elem_mode) {
+      pick = bidx;
+    } else if (p.N > 1) {
+      const uint4 rnd = philox4x32_10(make_uint4(0xFFFFFFFFu, static_cast<uint32_t>(p.row_offset + row), p.off_lo,
+                                                 (p.off_hi << 1) | static_cast<uint32_t>(prob)),
+                                      make_uint2(p.seed_lo, p.seed_hi));
+      const float u_in = unit_from_bits(rnd.x), u_mix = unit_from_bits(rnd.y), u_uni = unit_from_bits(rnd.z);
+      // mixture: softmax part (mass l, column drawn in proportion to Pt) vs floor part (uniform, mass floor*ltot*(N-1))
+      const float w_a = l, w_b = p.floor * ltot * static_cast<float>(p.N - 1);
+      const bool take_a = bidx >= 0 && u_mix * (w_a + w_b) < w_a;
+      if (take_a) {
+        const int col = bidx * 32 + lane;
+        float v = 0.f;
+        if (col < p.N) v = __half2float(p.P[static_cast<int64_t>(r) * p.ldp + col]);
+        float pre = v;  // inclusive prefix over the chunk (Kogge-Stone: fixed order)
 #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const float t = __shfl_up_sync(0xffffffffu, pre, o);
-            if (lane >= o) pre += t;
-          }
-          const float tot = __shfl_sync(0xffffffffu, pre, 31);
-          const float target = u_in * tot;
-          const unsigned hit = __ballot_sync(0xffffffffu, v > 0.f && pre >= target);
-          const unsigned any = __ballot_sync(0xffffffffu, v > 0.f);
-          if (hit)
-            pick = bidx * 32 + (__ffs(hit) - 1);
-          else if (any)
-            pick = bidx * 32 + (31 - __clz(any));
+        for (int o = 1; o < 32; o <<= 1) {
+          const float t = __shfl_up_sync(0xffffffffu, pre, o);
+          if (lane >= o) pre += t;
         }
-        if (pick < 0) {  // uniform over the N - 1 non-target columns
-          int j = static_cast<int>(u_uni * static_cast<float>(p.N - 1));
-          j = j > p.N - 2 ? p.N - 2 : j;
-          pick = j >= tcol ? j + 1 : j;
-        }
+        const float tot = __shfl_sync(0xffffffffu, pre, 31);
+        const float target = u_in * tot;
+        const unsigned hit = __ballot_sync(0xffffffffu, v > 0.f && pre >= target);
+        const unsigned any = __ballot_sync(0xffffffffu, v > 0.f);
+        if (hit)
+          pick = bidx * 32 + (__ffs(hit) - 1);
+        else if (any)
+          pick = bidx * 32 + (31 - __clz(any));
       }
-      if (lane == 0) p.neg_idx[r] = pick;
+      if (pick < 0) {  // uniform over the N - 1 non-target columns
+        int j = static_cast<int>(u_uni * static_cast<float>(p.N - 1));
+        j = j > p.N - 2 ? p.N - 2 : j;
+        pick = j >= tcol ? j + 1 : j;
+      }
     }
-
-    // ---- gradient + the two row dot products (q . dQraw for d tau, q . ksum for the smoothing term)
-    const __nv_bfloat16* prow = p.pack + static_cast<int64_t>(p.row_offset + row) * 2 * p.D;
-    const __nv_bfloat16* qv = prow + (prob == 0 ? p.D : 0);   // this direction's query row
-    const __nv_bfloat16* kv = prow + (prob == 0 ? 0 : p.D);   // the positive row of the gathered side
-    const float* ks = p.ksum + prob * p.D;
-    float dot_q = 0.f, dot_s = 0.f;
-    const bool grad = p.dq_part != nullptr;
-    const float gs = inv_tau / (2.0f * p.M);
+    if (lane == 0) p.neg_idx[r] = pick;
+  }
+  if (lane == 0) {
     const float c_sm = p.eps_ls / static_cast<float>(p.N);
-    const float c_t = pt - (1.f - p.eps_ls);
-    float* gout = grad ? (prob == 0 ? p.grad_cond : p.grad_t) + static_cast<int64_t>(row) * p.D : nullptr;
-    for (int d = lane * 8; d < p.D; d += 256) {
-      float q[8], k[8], ksv[8];
-      bf16x8_to_f32(*reinterpret_cast<const uint4*>(qv + d), q);
-      *reinterpret_cast<float4*>(&ksv[0]) = *reinterpret_cast<const float4*>(ks + d);
-      *reinterpret_cast<float4*>(&ksv[4]) = *reinterpret_cast<const float4*>(ks + d + 4);
+    p.rowstat[r] = make_float4(rho, pt - (1.f - p.eps_ls), pt, dot_s);
+    p.rowce[r] = lse - (1.f - p.eps_ls) * inv_tau * zt - c_sm * inv_tau * dot_s;
+    if (p.lse_out) p.lse_out[r] = lse;
+  }
+}
+
+// ------------------------------------------------------------------ K4 epilogue: gradient assembly in the dQ GEMM
+// acc = sum_{j != target} Pt_ij K_j  (TMEM)  ->  dQ_i = (1/(2 bs tau)) (rho_i acc - (eps/N) sum_j K_j + c_t,i K_target)
+// written straight to the gradient tensors; <q_i, acc> (for d tau) leaves as one partial per column range.
+struct EpiGrad {
+  struct Params {
+    const float4* rowstat;  // [2][M]
+    const float* ksum;      // [2][D]
+    const __nv_bfloat16* pack;
+    int row_offset;
+    int D;
+    float inv_tau;
+    const float* temp_dev;
+    float c_sm;  // eps / N_total
+    float* grad_cond;
+    float* grad_t;
+    float* dotq;  // [2][M][num_slots]
+    int num_slots;
+  };
+  const Params& p;
+  float rho, c_t, gs, dotq;
+  const __nv_bfloat16* qrow;
+  const __nv_bfloat16* krow;
+  float* grow;
+  __device__ EpiGrad(const Params& p_, uint8_t*) : p(p_) {
+    const float inv_tau = p.temp_dev ? 1.0f / __ldg(p.temp_dev) : p.inv_tau;
+    gs = inv_tau;  // scaled by 1 / (2 M) in item_begin (M comes with the item)
+  }
+  __device__ __forceinline__ void item_begin(const tc::ItemCtx& c) {
+    const int row = c.row_valid ? c.row : 0;
+    const float4 st = p.rowstat[static_cast<int64_t>(c.prob) * c.M + row];
+    rho = st.x;
+    c_t = st.y;
+    dotq = 0.f;
+    const __nv_bfloat16* prow = p.pack + static_cast<int64_t>(p.row_offset + row) * 2 * p.D;
+    qrow = prow + (c.prob == 0 ? p.D : 0);  // this direction's query row
+    krow = prow + (c.prob == 0 ? 0 : p.D);  // the positive row of the gathered side
+    grow = (c.prob == 0 ? p.grad_cond : p.grad_t) + static_cast<int64_t>(row) * p.D;
+  }
+  __device__ __forceinline__ void chunk(const tc::ItemCtx& c, const uint32_t (&v)[32], int col0) {
+    if (!c.row_valid || col0 >= c.N) return;
+    const float g1 = gs / (2.0f * c.M);
+    const float* ks = p.ksum + c.prob * p.D + col0;
+    if (col0 + 32 <= c.N) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dot_s = fmaf(q[j], ksv[j], dot_s);
-      if (grad) {
-        bf16x8_to_f32(*reinterpret_cast<const uint4*>(kv + d), k);
-        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        const float* src = p.dq_part + (static_cast<int64_t>(prob) * p.M + row) * p.D + d;
-        for (int s = 0; s < p.ksplits; ++s) {
-          const float4 a = __ldcs(reinterpret_cast<const float4*>(src + s * p.split_stride));
-          const float4 b = __ldcs(reinterpret_cast<const float4*>(src + s * p.split_stride + 4));
-          acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-          acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
-        }
+      for (int i = 0; i < 32; i += 8) {
+        float q[8], k[8];
+        bf16x8_to_f32(*reinterpret_cast<const uint4*>(qrow + col0 + i), q);
+        bf16x8_to_f32(*reinterpret_cast<const uint4*>(krow + col0 + i), k);
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(ks + i)), s1 = __ldg(reinterpret_cast<const float4*>(ks + i + 4));
+        const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
         float g[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          dot_q = fmaf(q[j], acc[j], dot_q);
-          g[j] = gs * (rho * acc[j] - c_sm * ksv[j] + c_t * k[j]);
+          const float a = __uint_as_float(v[i + j]);
+          dotq = fmaf(q[j], a, dotq);
+          g[j] = g1 * (fmaf(rho, a, c_t * k[j]) - p.c_sm * sv[j]);
         }
-        *reinterpret_cast<float4*>(gout + d) = make_float4(g[0], g[1], g[2], g[3]);
-        *reinterpret_cast<float4*>(gout + d + 4) = make_float4(g[4], g[5], g[6], g[7]);
+        *reinterpret_cast<float4*>(grow + col0 + i) = make_float4(g[0], g[1], g[2], g[3]);
+        *reinterpret_cast<float4*>(grow + col0 + i + 4) = make_float4(g[4], g[5], g[6], g[7]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (col0 + i < c.N) {
+          const float a = __uint_as_float(v[i]);
+          const float q = __bfloat162float(qrow[col0 + i]), k = __bfloat162float(krow[col0 + i]);
+          dotq = fmaf(q, a, dotq);
+          grow[col0 + i] = g1 * (fmaf(rho, a, c_t * k) - p.c_sm * ks[i]);
+        }
       }
     }
-    dot_q = warp_sum(dot_q);
-    dot_s = warp_sum(dot_s);
-    if (lane == 0) {
-      const float pz = rho * dot_q + pt * zt;  // sum_j p_ij s_ij
-      p.rowce[r] = lse - (1.f - p.eps_ls) * inv_tau * zt - c_sm * inv_tau * dot_s;
-      // d loss / d tau row term: -(1/tau) sum_j (p_ij - y_ij) z_ij   (scaled by 1/(2 bs) below)
-      p.rowdt[r] = -inv_tau * inv_tau * (pz - (1.f - p.eps_ls) * zt - c_sm * dot_s);
-      if (p.lse_out) p.lse_out[r] = lse;
-    }
   }
-  // ---- last block: loss and d tau (fixed order -> deterministic)
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(p.ticket, 1) == static_cast<int>(gridDim.x) - 1);
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
+  __device__ __forceinline__ void item_end(const tc::ItemCtx& c) {
+    if (c.row_valid) p.dotq[(static_cast<int64_t>(c.prob) * c.M + c.row) * p.num_slots + c.slot] = dotq;
+  }
+};
+
+// ------------------------------------------------------------------ K4': gradient from split-K partials
+// (small per-rank problems cut the dQ GEMM along K to fill the SMs; partials are summed in a fixed order)
+struct GradReduceParams {
+  const float* dq_part;  // [ks][2][M][D]
+  int ksplits;
+  int64_t split_stride;
+  int M, D, row_offset;
+  const float4* rowstat;
+  const float* ksum;
+  const __nv_bfloat16* pack;
+  float inv_tau;
+  const float* temp_dev;
+  float c_sm;
+  float* grad_cond;
+  float* grad_t;
+  float* dotq;  // [2][M]
+};
+__global__ void __launch_bounds__(256) omc_grad_reduce_kernel(const GradReduceParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= 2 * p.M) return;
+  const float inv_tau = p.temp_dev ? 1.0f / __ldg(p.temp_dev) : p.inv_tau;
+  const int prob = r / p.M, row = r - prob * p.M;
+  const float4 st = p.rowstat[r];
+  const float rho = st.x, c_t = st.y;
+  const float g1 = inv_tau / (2.0f * p.M);
+  const __nv_bfloat16* prow = p.pack + static_cast<int64_t>(p.row_offset + row) * 2 * p.D;
+  const __nv_bfloat16* qv = prow + (prob == 0 ? p.D : 0);
+  const __nv_bfloat16* kv = prow + (prob == 0 ? 0 : p.D);
+  const float* ks = p.ksum + prob * p.D;
+  float* gout = (prob == 0 ? p.grad_cond : p.grad_t) + static_cast<int64_t>(row) * p.D;
+  float dot_q = 0.f;
+#pragma unroll 2
+  for (int d = lane * 8; d < p.D; d += 256) {
+    float q[8], k[8], ksv[8];
+    bf16x8_to_f32(*reinterpret_cast<const uint4*>(qv + d), q);
+    bf16x8_to_f32(*reinterpret_cast<const uint4*>(kv + d), k);
+    *reinterpret_cast<float4*>(&ksv[0]) = *reinterpret_cast<const float4*>(ks + d);
+    *reinterpret_cast<float4*>(&ksv[4]) = *reinterpret_cast<const float4*>(ks + d + 4);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const float* src = p.dq_part + (static_cast<int64_t>(prob) * p.M + row) * p.D + d;
+    for (int s = 0; s < p.ksplits; ++s) {
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(src + s * p.split_stride));
+      const float4 b = __ldcs(reinterpret_cast<const float4*>(src + s * p.split_stride + 4));
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+    float g[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      dot_q = fmaf(q[j], acc[j], dot_q);
+      g[j] = g1 * (fmaf(rho, acc[j], c_t * k[j]) - p.c_sm * ksv[j]);
+    }
+    *reinterpret_cast<float4*>(gout + d) = make_float4(g[0], g[1], g[2], g[3]);
+    *reinterpret_cast<float4*>(gout + d + 4) = make_float4(g[4], g[5], g[6], g[7]);
+  }
+  dot_q = warp_sum(dot_q);
+  if (lane == 0) p.dotq[r] = dot_q;
+}
+
+// ------------------------------------------------------------------ K5: loss and d tau
+// One thread per (direction, row); per-block sums in a fixed order, the last block (ticket) adds the block sums.
+__global__ void __launch_bounds__(256) omc_final_kernel(const float* __restrict__ rowce, const float4* __restrict__ rowstat,
+                                                       const float* __restrict__ zt, const float* __restrict__ dotq,
+                                                       int dslots, int rows2, int M, float inv_tau,
+                                                       const float* __restrict__ temp_dev, float eps_ls, float c_sm,
+                                                       float2* __restrict__ blockpart, int* __restrict__ ticket,
+                                                       float* __restrict__ loss, float* __restrict__ grad_temp) {
+  __shared__ float red[2][256];
+  __shared__ int is_last;
+  const int r = blockIdx.x * 256 + threadIdx.x;
   float a = 0.f, b = 0.f;
-  for (int i = threadIdx.x; i < 2 * p.M; i += 256) {
-    a += __ldcg(p.rowce + i);
-    b += __ldcg(p.rowdt + i);
+  if (r < rows2) {
+    a = rowce[r];
+    if (dotq != nullptr) {
+      if (temp_dev) inv_tau = 1.0f / __ldg(temp_dev);
+      const float4 st = rowstat[r];  // (rho, c_t, p_target, <q, ksum>)
+      float dq = 0.f;
+      for (int s = 0; s < dslots; ++s) dq += dotq[static_cast<int64_t>(r) * dslots + s];
+      const float z = zt[r];
+      const float pz = st.x * dq + st.z * z;  // sum_j p_ij s_ij
+      // d loss / d tau row term: -(1/tau) sum_j (p_ij - y_ij) z_ij
+      b = -inv_tau * inv_tau * (pz - (1.f - eps_ls) * z - c_sm * st.w);
+    }
   }
   red[0][threadIdx.x] = a;
   red[1][threadIdx.x] = b;
@@ -559,10 +682,34 @@ __global__ void __launch_bounds__(256) omc_row_finalize_kernel(const RowFinParam
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    const float scale = 1.0f / (2.0f * p.M);
-    p.loss[0] = red[0][0] * scale;
-    if (p.grad_temp) p.grad_temp[0] = red[1][0] * scale;
-    *p.ticket = 0;
+    blockpart[blockIdx.x] = make_float2(red[0][0], red[1][0]);
+    __threadfence();
+    is_last = (atomicAdd(ticket, 1) == static_cast<int>(gridDim.x) - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  a = 0.f;
+  b = 0.f;
+  for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += 256) {
+    const float2 v = __ldcg(blockpart + i);
+    a += v.x;
+    b += v.y;
+  }
+  red[0][threadIdx.x] = a;
+  red[1][threadIdx.x] = b;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (static_cast<int>(threadIdx.x) < s) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + s];
+      red[1][threadIdx.x] += red[1][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float scale = 1.0f / (2.0f * M);
+    loss[0] = red[0][0] * scale;
+    if (grad_temp) grad_temp[0] = red[1][0] * scale;
   }
 }
 
@@ -575,7 +722,9 @@ struct OmcPlan {
   int nslab, ncs;
   int64_t npad;
   // workspace offsets (bytes)
-  size_t off_flags, off_partial, off_ref2, off_zt, off_rowce, off_rowdt, off_ksump, off_ksum, off_P, off_dq, off_k16, total;
+  int dslots;  // <q, dQraw> partials per row
+  size_t off_flags, off_partial, off_ref2, off_zt, off_rowce, off_rowstat, off_blockpart, off_dotq, off_ksump, off_ksum, off_P,
+      off_dq, off_k16, total;
 };
 
 static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, bool need_p, bool need_grad) {
@@ -596,19 +745,22 @@ static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, bool
     off += bytes;
     return r;
   };
-  pl->off_flags = take(256);
+  pl->off_flags = take(sizeof(int) * FLAG_INTS);
   pl->off_partial = take(sizeof(float4) * 2 * bs * pl->slots);
   pl->off_ref2 = take(sizeof(float) * 2 * bs);
   pl->off_zt = take(sizeof(float) * 2 * bs);
   pl->off_rowce = take(sizeof(float) * 2 * bs);
-  pl->off_rowdt = take(sizeof(float) * 2 * bs);
+  pl->off_rowstat = take(sizeof(float4) * 2 * bs);
+  pl->off_blockpart = take(sizeof(float2) * ceil_div64(2 * bs, 256));
+  pl->dslots = pl->g_dq.k_splits == 1 ? pl->g_dq.n_splits : 1;
+  pl->off_dotq = take(sizeof(float) * 2 * bs * pl->dslots);
   pl->off_ksump = take(sizeof(float) * 2 * dim * pl->nslab);
   pl->off_ksum = take(sizeof(float) * 2 * dim);
   pl->off_P = pl->off_dq = 0;
   if (need_p) pl->off_P = take(sizeof(__half) * 2 * bs * pl->npad);
   pl->off_k16 = 0;
   if (need_grad) {
-    pl->off_dq = take(sizeof(float) * pl->g_dq.k_splits * 2 * bs * dim);
+    if (pl->g_dq.k_splits > 1) pl->off_dq = take(sizeof(float) * pl->g_dq.k_splits * 2 * bs * dim);
     pl->off_k16 = take(sizeof(__half) * 2 * dim * n_total);
   }
   pl->total = align_up(off, 256);
@@ -649,16 +801,18 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
   VAST_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, VAST_ERR_INVALID, "omc_step: workspace must be 256-byte aligned");
 
   char* ws = static_cast<char*>(workspace);
-  int* wflags = reinterpret_cast<int*>(ws + pl.off_flags);  // [0] fp16-range overflow, [1] prep ticket, [2] finalize ticket
+  int* wflags = reinterpret_cast<int*>(ws + pl.off_flags);  // see FLAG_INTS
   float4* partial = reinterpret_cast<float4*>(ws + pl.off_partial);
   float* ref2 = reinterpret_cast<float*>(ws + pl.off_ref2);
   float* zt = reinterpret_cast<float*>(ws + pl.off_zt);
   float* rowce = reinterpret_cast<float*>(ws + pl.off_rowce);
-  float* rowdt = reinterpret_cast<float*>(ws + pl.off_rowdt);
   float* ksump = reinterpret_cast<float*>(ws + pl.off_ksump);
   float* ksum = reinterpret_cast<float*>(ws + pl.off_ksum);
   __half* Pbuf = (need_grad || need_sample) ? reinterpret_cast<__half*>(ws + pl.off_P) : nullptr;
-  float* dqpart = need_grad ? reinterpret_cast<float*>(ws + pl.off_dq) : nullptr;
+  float* dqpart = (need_grad && pl.g_dq.k_splits > 1) ? reinterpret_cast<float*>(ws + pl.off_dq) : nullptr;
+  float4* rowstat = reinterpret_cast<float4*>(ws + pl.off_rowstat);
+  float2* blockpart = reinterpret_cast<float2*>(ws + pl.off_blockpart);
+  float* dotq = reinterpret_cast<float*>(ws + pl.off_dotq);
   __half* pack16 = need_grad ? reinterpret_cast<__half*>(ws + pl.off_k16) : nullptr;
 
   const auto* pk = static_cast<const __nv_bfloat16*>(pack);
@@ -666,7 +820,7 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
   const int M = static_cast<int>(bs), N = static_cast<int>(n_total), D = static_cast<int>(dim);
   int rc;
 
-  VAST_CUDA_OK(cudaMemsetAsync(wflags, 0, 16, stream));
+  VAST_CUDA_OK(cudaMemsetAsync(wflags, 0, sizeof(int) * FLAG_INTS, stream));
   // K1
   VAST_TIMED(stream, "omc_prep",
              (omc_prep_kernel<<<pl.ncs + ceil_div(M, 8), 256, 0, stream>>>(pk, N, D, M, static_cast<int>(row_offset), pl.ncs, pl.nslab,
@@ -755,26 +909,9 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
     if (rc) return rc;
   }
 
-  // K3: dQraw = Pt . K   (fp16 x fp16, the gathered features as the MN-major operand in their row-major layout)
-  if (need_grad) {
-    tc::KernelParams<tc::EpiStore::Params> P;
-    memset(&P, 0, sizeof(P));
-    P.g = pl.g_dq;
-    for (int i = 0; i < 2; ++i) {
-      rc = tc::make_tmap_2d(&P.tmA[i], Pbuf + static_cast<int64_t>(i) * bs * pl.npad, VAST_F16, bs, n_total, pl.npad, tc::BM);
-      if (rc) return rc;
-      rc = tc::make_tmap_2d(&P.tmB[i], pack16 + static_cast<int64_t>(i) * dim, VAST_F16, n_total, dim, 2 * dim, tc::BK);
-      if (rc) return rc;
-    }
-    P.epi = {dqpart, dim, bs * dim, 2 * bs * dim, 1.0f};
-    rc = pl.bn_dq == 256 ? tc::launch_gemm<tc::EpiStore, 256, 4, 4, true>(P, stream, "omc_dq_gemm")
-                         : tc::launch_gemm<tc::EpiStore, 128, 4, 4, true>(P, stream, "omc_dq_gemm");
-    if (rc) return rc;
-  }
-
-  // K4
+  // K3: row statistics + hard negatives
   {
-    RowFinParams R;
+    RowStatParams R;
     memset(&R, 0, sizeof(R));
     R.partial = partial;
     R.slots = pl.slots;
@@ -796,21 +933,76 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
     R.seed_hi = static_cast<uint32_t>(seed >> 32);
     R.off_lo = static_cast<uint32_t>(offset);
     R.off_hi = static_cast<uint32_t>(offset >> 32);
-    R.dq_part = dqpart;
-    R.ksplits = pl.g_dq.k_splits;
-    R.split_stride = 2 * bs * dim;
     R.ksum = ksum;
     R.pack = pk;
-    R.grad_cond = grad_cond;
-    R.grad_t = grad_t;
-    R.lse_out = lse;
+    R.rowstat = rowstat;
     R.rowce = rowce;
-    R.rowdt = rowdt;
-    R.loss = loss;
-    R.grad_temp = need_grad ? grad_temp : nullptr;
-    R.ticket = &wflags[2];
-    VAST_TIMED(stream, "omc_row_finalize", (omc_row_finalize_kernel<<<ceil_div(2 * M, 8), 256, 0, stream>>>(R)));
-    VAST_LAUNCH_OK("omc_row_finalize");
+    R.lse_out = lse;
+    VAST_TIMED(stream, "omc_row_stats", (omc_row_stats_kernel<<<ceil_div(2 * M, 8), 256, 0, stream>>>(R)));
+    VAST_LAUNCH_OK("omc_row_stats");
   }
+
+  // K4: dQ = Pt . K   (fp16 x fp16, the gathered features as the MN-major operand in their row-major layout)
+  const float c_sm = label_smoothing / static_cast<float>(N);
+  if (need_grad) {
+    CUtensorMap tmPa[2], tmKb[2];
+    for (int i = 0; i < 2; ++i) {
+      rc = tc::make_tmap_2d(&tmPa[i], Pbuf + static_cast<int64_t>(i) * bs * pl.npad, VAST_F16, bs, n_total, pl.npad, tc::BM);
+      if (rc) return rc;
+      rc = tc::make_tmap_2d(&tmKb[i], pack16 + static_cast<int64_t>(i) * dim, VAST_F16, n_total, dim, 2 * dim, tc::BK);
+      if (rc) return rc;
+    }
+    if (pl.g_dq.k_splits == 1) {  // gradient assembled in the GEMM epilogue
+      tc::KernelParams<EpiGrad::Params> P;
+      memset(&P, 0, sizeof(P));
+      P.g = pl.g_dq;
+      for (int i = 0; i < 2; ++i) {
+        P.tmA[i] = tmPa[i];
+        P.tmB[i] = tmKb[i];
+      }
+      P.epi = {rowstat, ksum, pk, static_cast<int>(row_offset), D, inv_tau, contra_temp_dev, c_sm, grad_cond, grad_t, dotq, pl.dslots};
+      rc = pl.bn_dq == 256 ? tc::launch_gemm<EpiGrad, 256, 4, 4, true>(P, stream, "omc_dq_gemm")
+                           : tc::launch_gemm<EpiGrad, 128, 4, 4, true>(P, stream, "omc_dq_gemm");
+      if (rc) return rc;
+    } else {  // split-K partials, summed in a fixed order by the reduce kernel
+      tc::KernelParams<tc::EpiStore::Params> P;
+      memset(&P, 0, sizeof(P));
+      P.g = pl.g_dq;
+      for (int i = 0; i < 2; ++i) {
+        P.tmA[i] = tmPa[i];
+        P.tmB[i] = tmKb[i];
+      }
+      P.epi = {dqpart, dim, bs * dim, 2 * bs * dim, 1.0f};
+      rc = pl.bn_dq == 256 ? tc::launch_gemm<tc::EpiStore, 256, 4, 4, true>(P, stream, "omc_dq_gemm")
+                           : tc::launch_gemm<tc::EpiStore, 128, 4, 4, true>(P, stream, "omc_dq_gemm");
+      if (rc) return rc;
+      GradReduceParams G;
+      memset(&G, 0, sizeof(G));
+      G.dq_part = dqpart;
+      G.ksplits = pl.g_dq.k_splits;
+      G.split_stride = 2 * bs * dim;
+      G.M = M;
+      G.D = D;
+      G.row_offset = static_cast<int>(row_offset);
+      G.rowstat = rowstat;
+      G.ksum = ksum;
+      G.pack = pk;
+      G.inv_tau = inv_tau;
+      G.temp_dev = contra_temp_dev;
+      G.c_sm = c_sm;
+      G.grad_cond = grad_cond;
+      G.grad_t = grad_t;
+      G.dotq = dotq;
+      VAST_TIMED(stream, "omc_grad_reduce", (omc_grad_reduce_kernel<<<ceil_div(2 * M, 8), 256, 0, stream>>>(G)));
+      VAST_LAUNCH_OK("omc_grad_reduce");
+    }
+  }
+
+  // K5
+  VAST_TIMED(stream, "omc_final",
+             (omc_final_kernel<<<ceil_div(2 * M, 256), 256, 0, stream>>>(rowce, rowstat, zt, need_grad ? dotq : nullptr, pl.dslots,
+                                                                        2 * M, M, inv_tau, contra_temp_dev, label_smoothing, c_sm,
+                                                                        blockpart, &wflags[1], loss, need_grad ? grad_temp : nullptr)));
+  VAST_LAUNCH_OK("omc_final");
   return VAST_OK;
 }

@@ -116,21 +116,34 @@ struct EpiTopK {
       const int n = __shfl_sync(0xffffffffu, n_mine, r);
       if (!(n > p.k || (all && n > 0))) continue;
       const uint32_t row = lists + static_cast<uint32_t>(r) * stride_b;
-      uint64_t key[E];
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const int pos = e * 32 + lane;
-        key[e] = pos < n ? lds_u64(row + pos * 8) : 0ull;
-      }
-      sort_desc(key, lane);
       const int keep = n < p.k ? n : p.k;
       uint64_t kth = 0;
+      if constexpr (E == 1) {
+        // <= 32 candidates: rank each key by counting the larger ones (32 independent broadcast loads, no
+        // dependent shuffle chain), then write the best `keep` to their sorted positions.
+        const uint64_t key = lane < n ? lds_u64(row + lane * 8) : 0ull;
+        int rank = 0;
 #pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const int pos = e * 32 + lane;
-        if (pos < keep) sts_u64(row + pos * 8, key[e]);
-        const uint64_t cand = __shfl_sync(0xffffffffu, key[e], (p.k - 1) & 31);
-        if (e == ((p.k - 1) >> 5)) kth = cand;
+        for (int j = 0; j < 32; ++j) rank += (lds_u64(row + j * 8) > key && j < n) ? 1 : 0;
+        __syncwarp();
+        if (lane < n && rank < keep) sts_u64(row + rank * 8, key);
+        const unsigned m = __ballot_sync(0xffffffffu, lane < n && rank == p.k - 1);
+        if (m) kth = __shfl_sync(0xffffffffu, key, __ffs(m) - 1);
+      } else {
+        uint64_t key[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int pos = e * 32 + lane;
+          key[e] = pos < n ? lds_u64(row + pos * 8) : 0ull;
+        }
+        sort_desc(key, lane);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int pos = e * 32 + lane;
+          if (pos < keep) sts_u64(row + pos * 8, key[e]);
+          const uint64_t cand = __shfl_sync(0xffffffffu, key[e], (p.k - 1) & 31);
+          if (e == ((p.k - 1) >> 5)) kth = cand;
+        }
       }
       if (lane == r) {
         n_mine = keep;
