@@ -21,7 +21,7 @@ using namespace vast;
 
 extern "C" size_t vast_gemm_nt_workspace_bytes(int64_t M, int64_t N, int64_t K) {
   tc::GemmShape g;
-  tc::fill_shape(&g, 1, (int)M, (int)N, (int)K, 256, 1);
+  tc::fill_shape(&g, 1, (int)M, (int)N, (int)K, 256, 1, 1, false, tc::pick_cluster((int)M));
   tc::choose_splits(&g, device_sm_count(), 64, 8);
   return g.k_splits > 1 ? static_cast<size_t>(g.k_splits) * M * N * sizeof(float) + 256 : 0;
 }
@@ -38,11 +38,12 @@ static int gemm_impl(const void* A, int64_t lda, int dtype_a, const void* B, int
   using Epi = tc::EpiStore;
   tc::KernelParams<Epi::Params> P;
   memset(&P, 0, sizeof(P));
-  tc::fill_shape(&P.g, 1, (int)M, (int)N, (int)K, 256, dtype_a == VAST_BF16 ? 1 : 0, dtype_b == VAST_BF16 ? 1 : 0, B_MN);
+  const int cl = tc::pick_cluster((int)M);
+  tc::fill_shape(&P.g, 1, (int)M, (int)N, (int)K, 256, dtype_a == VAST_BF16 ? 1 : 0, dtype_b == VAST_BF16 ? 1 : 0, B_MN, cl);
   tc::choose_splits(&P.g, device_sm_count(), 64, 8);
   int rc = tc::make_tmap_2d(&P.tmA[0], A, dtype_a, M, K, lda, tc::BM);
   if (rc) return rc;
-  rc = B_MN ? tc::make_tmap_2d(&P.tmB[0], B, dtype_b, K, N, ldb, tc::BK) : tc::make_tmap_2d(&P.tmB[0], B, dtype_b, N, K, ldb, 256);
+  rc = B_MN ? tc::make_tmap_2d(&P.tmB[0], B, dtype_b, K, N, ldb, tc::BK) : tc::make_tmap_2d(&P.tmB[0], B, dtype_b, N, K, ldb, 256 / cl);
   if (rc) return rc;
   if (P.g.k_splits > 1) {
     Workspace ws(workspace, workspace_bytes);

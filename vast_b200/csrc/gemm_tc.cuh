@@ -33,7 +33,9 @@ constexpr int MAX_PROBLEMS = 2;
 struct GemmShape {
   int num_problems;
   int M, N, K;
-  int m_blocks;
+  int cl;        // CTAs per cluster (stacked along M, sharing every B tile through TMA multicast)
+  int m_blocks;  // 128-row blocks
+  int m_groups;  // groups of `cl` row blocks = what one cluster works on
   int n_tiles, n_splits, tiles_per_split;
   int k_blocks, k_splits, kb_per_split;
   int num_items;
@@ -64,14 +66,16 @@ struct WorkItem {
   int tile_begin, tile_end, kb_begin, kb_end;
 };
 
-__device__ __forceinline__ WorkItem decode_item(const GemmShape& g, int idx) {
+// idx enumerates (problem, row-block group, N-split, K-split); the CTA's own row block inside the group
+// is its rank in the cluster.
+__device__ __forceinline__ WorkItem decode_item(const GemmShape& g, int idx, int cta_rank) {
   WorkItem w;
   w.k_split = idx % g.k_splits;
   idx /= g.k_splits;
   w.n_split = idx % g.n_splits;
   idx /= g.n_splits;
-  w.m_blk = idx % g.m_blocks;
-  w.prob = idx / g.m_blocks;
+  w.m_blk = (idx % g.m_groups) * g.cl + cta_rank;
+  w.prob = idx / g.m_groups;
   w.tile_begin = w.n_split * g.tiles_per_split;
   w.tile_end = min(w.tile_begin + g.tiles_per_split, g.n_tiles);
   w.kb_begin = w.k_split * g.kb_per_split;
@@ -79,31 +83,46 @@ __device__ __forceinline__ WorkItem decode_item(const GemmShape& g, int idx) {
   return w;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CL>
 struct SmemLayout {
   static constexpr uint32_t A_BYTES = BM * BK * 2;
-  static constexpr uint32_t B_BYTES = BN * BK * 2;
+  static constexpr uint32_t B_BYTES = BN * BK * 2 / CL;  // a CTA pair keeps half of every B tile per CTA
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr uint32_t BAR_BYTES = 256;  // 2*STAGES + 4 barriers + tmem slot
   static constexpr uint32_t EPI_OFFSET = BAR_OFFSET + BAR_BYTES;
   static constexpr uint32_t ALIGN_SLACK = 1024;
+  static_assert(2 * STAGES * 8 + 4 * 8 + 8 <= BAR_BYTES, "barrier block too small");
 };
 
 // B_MN = false: B is [N rows, K cols] K-major (an "NT" GEMM, S = A . B^T with B given row-wise).
 // B_MN = true : B is [K rows, N cols] row-major, i.e. the MN-major UMMA operand: each pipeline stage holds
 //               BN/64 TMA boxes of 64 K-rows x 64 N-columns (128-byte swizzle atoms stacked along K),
 //               so a row-major matrix is consumed as the right-hand side WITHOUT a transposed copy.
-template <class Epi, int BN, int STAGES, int NE, bool B_MN>
+// CL = 1: one CTA per tile, tcgen05.mma.cta_group::1 (M = 128).
+// CL = 2: CTA PAIRS (clusters of two SMs of one TPC) with tcgen05.mma.cta_group::2: one instruction of the
+//         leader CTA multiplies a 256 x BN tile -- each CTA contributes its own 128 A rows and HALF of the B
+//         tile from its shared memory and receives its 128 accumulator rows in its own TMEM.  Per CTA and
+//         k-block that is 16 + 16 KB of TMA writes and 4 + 4 KB of operand reads per MMA instead of
+//         16 + 32 and 4 + 8: a lone CTA at 128 x 256 needs ~190 B/clk of shared-memory traffic (TMA fill +
+//         UMMA operand reads) against the 128 B/clk an SM has, which is what caps cta_group::1 near 60 % of
+//         the tensor peak; the pair needs exactly 128 B/clk.
+//         Protocol: both CTAs run their own TMA producer (transaction bytes of both land on the LEADER's
+//         `full` barrier); only the leader issues MMAs; its tcgen05.commit is multicast to both CTAs' `empty`
+//         (stage free) and `tfull` (accumulator ready) barriers; both CTAs' epilogue warps arrive on the
+//         leader's `tempty` barrier (accumulator drained).
+template <class Epi, int BN, int STAGES, int NE, bool B_MN, int CL>
 __global__ void __launch_bounds__(64 + 32 * NE, 1)
 gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
   static_assert(NE == 4 || NE == 8, "4 or 8 epilogue warps");
   static_assert(BN == 128 || BN == 256, "BN");
+  static_assert(CL == 1 || CL == 2, "single CTA or CTA pair");
   if (P.gate != nullptr && *reinterpret_cast<const volatile int*>(P.gate) == 0) return;
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, CL>;
   constexpr int HALVES = NE / 4;
   constexpr int COLS_PER_WARP = BN / HALVES;
   constexpr uint32_t TMEM_COLS = 2 * BN;
+  constexpr bool PAIR = CL == 2;
 
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte aligned bases (in the shared address space).
@@ -120,6 +139,10 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const GemmShape& g = P.g;
+  const int cta_rank = PAIR ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  const bool leader = cta_rank == 0;
+  const int cluster_id = static_cast<int>(blockIdx.x) / CL;
+  const int num_clusters = static_cast<int>(gridDim.x) / CL;
 
   if (warp == 0 && lane == 0) {
     for (int p = 0; p < g.num_problems; ++p) {
@@ -132,39 +155,57 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull[a], 1);
-      ptx::mbar_init(&tempty[a], NE);
+      ptx::mbar_init(&tempty[a], NE * CL);
     }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
-    ptx::tmem_relinquish();
+    ptx::tmem_alloc<CL>(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish<CL>();
   }
   ptx::tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (PAIR)
+    ptx::cluster_sync_all();  // the peer's barriers and TMEM must exist before anything remote touches them
+  else
+    __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------ TMA producer (every CTA)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < g.num_items; item += gridDim.x) {
-        const WorkItem w = decode_item(g, item);
+      for (int item = cluster_id; item < g.num_items; item += num_clusters) {
+        const WorkItem w = decode_item(g, item, cta_rank);
         for (int t = w.tile_begin; t < w.tile_end; ++t) {
           for (int kb = w.kb_begin; kb < w.kb_end; ++kb) {
             ptx::mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * L::STAGE_BYTES;
             uint8_t* sb = sa + L::A_BYTES;
-            ptx::mbar_arrive_expect_tx(&full[stage], L::STAGE_BYTES);
-            ptx::tma_load_2d(sa, &P.tmA[w.prob], &full[stage], kb * BK, w.m_blk * BM);
-            if constexpr (B_MN) {
+            if constexpr (!PAIR) {
+              ptx::mbar_arrive_expect_tx(&full[stage], L::STAGE_BYTES);
+              ptx::tma_load_2d(sa, &P.tmA[w.prob], &full[stage], kb * BK, w.m_blk * BM);
+              if constexpr (B_MN) {
 #pragma unroll
-              for (int nb = 0; nb < BN / 64; ++nb)
-                ptx::tma_load_2d(sb + nb * (BK * 128), &P.tmB[w.prob], &full[stage], t * BN + nb * 64, kb * BK);
+                for (int nb = 0; nb < BN / 64; ++nb)
+                  ptx::tma_load_2d(sb + nb * (BK * 128), &P.tmB[w.prob], &full[stage], t * BN + nb * 64, kb * BK);
+              } else {
+                ptx::tma_load_2d(sb, &P.tmB[w.prob], &full[stage], kb * BK, t * BN);
+              }
             } else {
-              ptx::tma_load_2d(sb, &P.tmB[w.prob], &full[stage], kb * BK, t * BN);
+              // the leader's barrier collects the bytes of BOTH CTAs' loads
+              if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * L::STAGE_BYTES);
+              ptx::tma_load_2d_pair(sa, &P.tmA[w.prob], &full[stage], kb * BK, w.m_blk * BM);
+              constexpr int HALF_N = BN / 2;  // this CTA's half of the B tile
+              if constexpr (B_MN) {
+#pragma unroll
+                for (int nb = 0; nb < HALF_N / 64; ++nb)
+                  ptx::tma_load_2d_pair(sb + nb * (BK * 128), &P.tmB[w.prob], &full[stage],
+                                        t * BN + cta_rank * HALF_N + nb * 64, kb * BK);
+              } else {
+                ptx::tma_load_2d_pair(sb, &P.tmB[w.prob], &full[stage], kb * BK, t * BN + cta_rank * HALF_N);
+              }
             }
             if (++stage == STAGES) {
               stage = 0;
@@ -175,14 +216,14 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA of a pair)
+    if (lane == 0 && leader) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < g.num_items; item += gridDim.x) {
-        const WorkItem w = decode_item(g, item);
+      for (int item = cluster_id; item < g.num_items; item += num_clusters) {
+        const WorkItem w = decode_item(g, item, cta_rank);
         for (int t = w.tile_begin; t < w.tile_end; ++t) {
           ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
           ptx::tc_fence_after_sync();
@@ -199,15 +240,15 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
             constexpr uint64_t B_KSTEP = B_MN ? 128 : 2;
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              ptx::umma_f16(d_tmem, da + 2 * k, db + B_KSTEP * k, g.idesc, (kb > w.kb_begin || k > 0) ? 1u : 0u);
+              ptx::umma_f16<CL>(d_tmem, da + 2 * k, db + B_KSTEP * k, g.idesc, (kb > w.kb_begin || k > 0) ? 1u : 0u);
             }
-            ptx::umma_commit(&empty[stage]);  // frees the smem stage once these MMAs retire
+            ptx::umma_commit<CL>(&empty[stage]);  // frees the smem stage (in both CTAs) once these MMAs retire
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
             }
           }
-          ptx::umma_commit(&tfull[acc]);  // accumulator tile complete
+          ptx::umma_commit<CL>(&tfull[acc]);  // accumulator tile complete (in both CTAs' TMEM)
           if (++acc == 2) {
             acc = 0;
             acc_phase ^= 1;
@@ -216,15 +257,15 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps
+    // ------------------------------------------------------------ epilogue warps (every CTA)
     const int ew = warp - 2;
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int half = ew >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     Epi epi(P.epi, epi_smem);
-    for (int item = blockIdx.x; item < g.num_items; item += gridDim.x) {
-      const WorkItem w = decode_item(g, item);
+    for (int item = cluster_id; item < g.num_items; item += num_clusters) {
+      const WorkItem w = decode_item(g, item, cta_rank);
       ItemCtx ctx;
       ctx.prob = w.prob;
       ctx.m_blk = w.m_blk;
@@ -239,21 +280,30 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
       ctx.half = half;
       epi.item_begin(ctx);
       for (int t = w.tile_begin; t < w.tile_end; ++t) {
+        // Epilogues with global operands (EpiGrad) start loading the first chunk's rows while the MMAs finish.
+        epi.prefetch(ctx, t * BN + half * COLS_PER_WARP);
         ptx::mbar_wait(&tfull[acc], acc_phase);
         ptx::tc_fence_after_sync();
-#pragma unroll 1
+#pragma unroll(Epi::kUnrollChunks ? COLS_PER_WARP / 32 : 1)
         for (int c = 0; c < COLS_PER_WARP; c += 32) {
           const int col_in_tile = half * COLS_PER_WARP + c;
           const uint32_t taddr =
               tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + col_in_tile);
           uint32_t v[32];
           ptx::tmem_ld_32x32b_x32(taddr, v);
+          // software pipeline: the next chunk's global operands are requested before this chunk's wait
+          epi.advance(ctx, t * BN + col_in_tile + 32, c + 32 < COLS_PER_WARP);
           ptx::tmem_ld_wait();
           epi.chunk(ctx, v, t * BN + col_in_tile);
           __syncwarp();
         }
         ptx::tc_fence_before_sync();
-        if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+        if (lane == 0) {
+          if constexpr (PAIR)
+            ptx::mbar_arrive_leader(&tempty[acc]);  // the MMA issuer lives in the leader CTA
+          else
+            ptx::mbar_arrive(&tempty[acc]);
+        }
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -264,8 +314,11 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
   }
 
   ptx::tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  if constexpr (PAIR)
+    ptx::cluster_sync_all();  // no CTA may leave while its peer can still reach its barriers / TMEM
+  else
+    __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<CL>(tmem_base, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------ host side
@@ -278,41 +331,73 @@ void choose_splits(GemmShape* g, int sm_count, int max_n_splits, int max_k_split
 
 // a_fmt / b_fmt: 0 = fp16, 1 = bf16 (may differ); b_mn: B operand is MN-major (see gemm_tc_kernel).
 inline void fill_shape(GemmShape* g, int problems, int M, int N, int K, int BN, int a_fmt, int b_fmt = -1,
-                       bool b_mn = false) {
+                       bool b_mn = false, int cl = 1) {
   if (b_fmt < 0) b_fmt = a_fmt;
   g->num_problems = problems;
   g->M = M;
   g->N = N;
   g->K = K;
+  g->cl = cl;
   g->m_blocks = ceil_div(M, BM);
+  g->m_groups = ceil_div(g->m_blocks, cl);
   g->n_tiles = ceil_div(N, BN);
   g->k_blocks = ceil_div(K, BK);
   g->n_splits = 1;
   g->tiles_per_split = g->n_tiles;
   g->k_splits = 1;
   g->kb_per_split = g->k_blocks;
-  g->num_items = problems * g->m_blocks;
-  g->idesc = ptx::umma_idesc_f16(static_cast<uint32_t>(a_fmt), static_cast<uint32_t>(b_fmt), b_mn ? 1u : 0u, BM,
-                                 static_cast<uint32_t>(BN));
+  g->num_items = problems * g->m_groups;
+  g->idesc = ptx::umma_idesc_f16(static_cast<uint32_t>(a_fmt), static_cast<uint32_t>(b_fmt), b_mn ? 1u : 0u,
+                                 static_cast<uint32_t>(BM * cl), static_cast<uint32_t>(BN));
 }
 
-template <class Epi, int BN, int STAGES, int NE, bool B_MN = false>
-int launch_gemm(const KernelParams<typename Epi::Params>& P, cudaStream_t stream, const char* name,
-                size_t epi_smem_bytes = 0) {
-  using L = SmemLayout<BN, STAGES>;
+// CTA pairs (cta_group::2) as soon as there are two 128-row blocks to pair.
+inline int pick_cluster(int M) { return ceil_div(M, BM) >= 2 ? 2 : 1; }
+
+template <class Epi, int BN, int STAGES, int NE, bool B_MN, int CL>
+int launch_gemm_cl(const KernelParams<typename Epi::Params>& P, cudaStream_t stream, const char* name, size_t epi_smem_bytes) {
+  using L = SmemLayout<BN, STAGES, CL>;
   const size_t smem = L::EPI_OFFSET + L::ALIGN_SLACK + epi_smem_bytes;
   VAST_REQUIRE(smem <= 232448, VAST_ERR_UNSUPPORTED, "%s: %zu bytes of shared memory exceed the 227 KB limit", name, smem);
-  auto kern = gemm_tc_kernel<Epi, BN, STAGES, NE, B_MN>;
+  VAST_REQUIRE(P.g.cl == CL, VAST_ERR_INVALID, "%s: shape planned for clusters of %d, launched with %d", name, P.g.cl, CL);
+  auto kern = gemm_tc_kernel<Epi, BN, STAGES, NE, B_MN, CL>;
   static size_t attr_smem = 0;  // per instantiation; grows monotonically
   if (smem > attr_smem) {
     VAST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr_smem = smem;
   }
-  int grid = P.g.num_items < device_sm_count() ? P.g.num_items : device_sm_count();
-  if (grid <= 0) return VAST_OK;
-  VAST_TIMED(stream, name, (kern<<<grid, 64 + 32 * NE, smem, stream>>>(P)));
+  const int clusters_max = device_sm_count() / CL;
+  const int clusters = P.g.num_items < clusters_max ? P.g.num_items : clusters_max;
+  if (clusters <= 0) return VAST_OK;
+  if constexpr (CL == 1) {
+    VAST_TIMED(stream, name, (kern<<<clusters, 64 + 32 * NE, smem, stream>>>(P)));
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(static_cast<unsigned>(clusters * CL), 1, 1);
+    cfg.blockDim = dim3(64 + 32 * NE, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VAST_TIMED(stream, name, (cudaLaunchKernelEx(&cfg, kern, P)));
+  }
   VAST_LAUNCH_OK(name);
   return VAST_OK;
+}
+
+// STAGES is the ring depth of a lone CTA (48 KB stages at BN = 256); a CTA pair has 32 KB stages and takes
+// STAGES2 of them (default: the same shared-memory footprint -> 1.5x the depth).
+template <class Epi, int BN, int STAGES, int NE, bool B_MN = false, int STAGES2 = STAGES + STAGES / 2>
+int launch_gemm(const KernelParams<typename Epi::Params>& P, cudaStream_t stream, const char* name,
+                size_t epi_smem_bytes = 0) {
+  if (P.g.cl == 2) return launch_gemm_cl<Epi, BN, STAGES2, NE, B_MN, 2>(P, stream, name, epi_smem_bytes);
+  return launch_gemm_cl<Epi, BN, STAGES, NE, B_MN, 1>(P, stream, name, epi_smem_bytes);
 }
 
 // ------------------------------------------------------------------ plain store epilogue
@@ -326,9 +411,12 @@ struct EpiStore {
     int64_t ksplit_stride;
     float alpha;
   };
+  static constexpr bool kUnrollChunks = false;
   const Params& p;
   __device__ EpiStore(const Params& p_, uint8_t*) : p(p_) {}
   __device__ __forceinline__ void item_begin(const ItemCtx&) {}
+  __device__ __forceinline__ void prefetch(const ItemCtx&, int) {}
+  __device__ __forceinline__ void advance(const ItemCtx&, int, bool) {}
   __device__ __forceinline__ void chunk(const ItemCtx& c, const uint32_t (&v)[32], int col0) {
     if (!c.row_valid || col0 >= c.N) return;
     float* dst = p.C + c.k_split * p.ksplit_stride + c.prob * p.prob_stride + static_cast<int64_t>(c.row) * p.ldc + col0;

@@ -83,6 +83,7 @@ struct EpiStats {
     float scale2;  // log2(e) / tau (used when temp_dev is null)
     const float* temp_dev;
   };
+  static constexpr bool kUnrollChunks = false;
   const Params& p;
   float m2, l, scale2;
   __device__ EpiStats(const Params& p_, uint8_t*) : p(p_) { scale2 = p.temp_dev ? kLog2e / __ldg(p.temp_dev) : p.scale2; }
@@ -90,6 +91,8 @@ struct EpiStats {
     m2 = -INFINITY;
     l = 0.f;
   }
+  __device__ __forceinline__ void prefetch(const tc::ItemCtx&, int) {}
+  __device__ __forceinline__ void advance(const tc::ItemCtx&, int, bool) {}
   __device__ __forceinline__ void chunk(const tc::ItemCtx& c, const uint32_t (&v)[32], int col0) {
     if (col0 >= c.N) return;
     const int nvalid = c.N - col0;  // >= 1; >= 32 for a full chunk
@@ -140,6 +143,7 @@ struct EpiSoft {
     int do_sample;
     int* ovf;  // raised when a chunk sum leaves the fp16 range (single-pass form) or nullptr
   };
+  static constexpr bool kUnrollChunks = false;
   const Params& p;
   float ref, l, bw, be, scale2;
   int bidx, tcol;
@@ -154,6 +158,8 @@ struct EpiSoft {
     tcol = p.tgt_offset + c.row;
     rnd = make_uint4(0, 0, 0, 0);
   }
+  __device__ __forceinline__ void prefetch(const tc::ItemCtx&, int) {}
+  __device__ __forceinline__ void advance(const tc::ItemCtx&, int, bool) {}
   __device__ __forceinline__ void chunk(const tc::ItemCtx& c, const uint32_t (&v)[32], int col0) {
     if (col0 >= c.N) return;
     const int nvalid = c.N - col0;
@@ -527,14 +533,19 @@ struct EpiGrad {
     float* dotq;  // [2][M][num_slots]
     int num_slots;
   };
+  static constexpr bool kUnrollChunks = true;  // the operand double buffer lives in registers
   const Params& p;
   float rho, c_t, gs, dotq;
   const __nv_bfloat16* qrow;
   const __nv_bfloat16* krow;
   float* grow;
+  uint4 nq[4], nk[4];  // operands of the NEXT chunk (requested one chunk ahead)
+  uint4 cq[4], ck[4];  // operands of the current chunk
+  bool cur_ok, nxt_ok;
   __device__ EpiGrad(const Params& p_, uint8_t*) : p(p_) {
     const float inv_tau = p.temp_dev ? 1.0f / __ldg(p.temp_dev) : p.inv_tau;
-    gs = inv_tau;  // scaled by 1 / (2 M) in item_begin (M comes with the item)
+    gs = inv_tau;  // scaled by 1 / (2 M) per chunk (M comes with the item)
+    cur_ok = nxt_ok = false;
   }
   __device__ __forceinline__ void item_begin(const tc::ItemCtx& c) {
     const int row = c.row_valid ? c.row : 0;
@@ -547,16 +558,41 @@ struct EpiGrad {
     krow = prow + (c.prob == 0 ? 0 : p.D);  // the positive row of the gathered side
     grow = (c.prob == 0 ? p.grad_cond : p.grad_t) + static_cast<int64_t>(row) * p.D;
   }
+  __device__ __forceinline__ void request(const tc::ItemCtx& c, int col0) {
+    nxt_ok = c.row_valid && col0 + 32 <= c.N;
+    if (nxt_ok) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        nq[i] = *reinterpret_cast<const uint4*>(qrow + col0 + 8 * i);
+        nk[i] = *reinterpret_cast<const uint4*>(krow + col0 + 8 * i);
+      }
+    }
+  }
+  __device__ __forceinline__ void prefetch(const tc::ItemCtx& c, int col0) { request(c, col0); }
+  // called between the TMEM load of a chunk and its wait: what was requested becomes current, the next
+  // chunk's operands (if there is one in this tile) are requested
+  __device__ __forceinline__ void advance(const tc::ItemCtx& c, int next_col0, bool has_next) {
+    cur_ok = nxt_ok;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      cq[i] = nq[i];
+      ck[i] = nk[i];
+    }
+    if (has_next)
+      request(c, next_col0);
+    else
+      nxt_ok = false;
+  }
   __device__ __forceinline__ void chunk(const tc::ItemCtx& c, const uint32_t (&v)[32], int col0) {
     if (!c.row_valid || col0 >= c.N) return;
     const float g1 = gs / (2.0f * c.M);
     const float* ks = p.ksum + c.prob * p.D + col0;
-    if (col0 + 32 <= c.N) {
+    if (cur_ok) {
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
         float q[8], k[8];
-        bf16x8_to_f32(*reinterpret_cast<const uint4*>(qrow + col0 + i), q);
-        bf16x8_to_f32(*reinterpret_cast<const uint4*>(krow + col0 + i), k);
+        bf16x8_to_f32(cq[i >> 3], q);
+        bf16x8_to_f32(ck[i >> 3], k);
         const float4 s0 = __ldg(reinterpret_cast<const float4*>(ks + i)), s1 = __ldg(reinterpret_cast<const float4*>(ks + i + 4));
         const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
         float g[8];
@@ -729,14 +765,15 @@ struct OmcPlan {
 
 static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, bool need_p, bool need_grad) {
   const int sms = device_sm_count();
-  tc::fill_shape(&pl->g_s, 2, (int)bs, (int)n_total, (int)dim, 256, 1);
+  const int cl = tc::pick_cluster((int)bs);
+  tc::fill_shape(&pl->g_s, 2, (int)bs, (int)n_total, (int)dim, 256, 1, 1, false, cl);
   tc::choose_splits(&pl->g_s, sms, 32, 1);
   pl->slots = pl->g_s.n_splits * 2;  // NE = 8 -> two column halves per split
   pl->npad = static_cast<int64_t>(align_up(static_cast<size_t>(n_total), 8));
   pl->nslab = ceil_div((int)n_total, PREP_ROWS);
   pl->ncs = pl->nslab * ceil_div(2 * (int)dim, 256);
   pl->bn_dq = dim > 128 ? 256 : 128;
-  tc::fill_shape(&pl->g_dq, 2, (int)bs, (int)dim, (int)n_total, pl->bn_dq, /*a: fp16*/ 0, /*b: fp16*/ 0, /*b_mn*/ true);
+  tc::fill_shape(&pl->g_dq, 2, (int)bs, (int)dim, (int)n_total, pl->bn_dq, /*a: fp16*/ 0, /*b: fp16*/ 0, /*b_mn*/ true, cl);
   tc::choose_splits(&pl->g_dq, sms, 64, 4);
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -752,7 +789,7 @@ static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, bool
   pl->off_rowce = take(sizeof(float) * 2 * bs);
   pl->off_rowstat = take(sizeof(float4) * 2 * bs);
   pl->off_blockpart = take(sizeof(float2) * ceil_div64(2 * bs, 256));
-  pl->dslots = pl->g_dq.k_splits == 1 ? pl->g_dq.n_splits : 1;
+  pl->dslots = pl->g_dq.k_splits == 1 ? pl->g_dq.n_splits * 2 : 1;  // EpiGrad runs with two column halves per tile
   pl->off_dotq = take(sizeof(float) * 2 * bs * pl->dslots);
   pl->off_ksump = take(sizeof(float) * 2 * dim * pl->nslab);
   pl->off_ksum = take(sizeof(float) * 2 * dim);
@@ -832,11 +869,11 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
   CUtensorMap tmA[2], tmB[2];
   rc = tc::make_tmap_2d(&tmA[0], pk + row_offset * 2 * dim + dim, VAST_BF16, bs, dim, 2 * dim, tc::BM);  // local cond
   if (rc) return rc;
-  rc = tc::make_tmap_2d(&tmB[0], pk, VAST_BF16, n_total, dim, 2 * dim, 256);  // all t
+  rc = tc::make_tmap_2d(&tmB[0], pk, VAST_BF16, n_total, dim, 2 * dim, 256 / pl.g_s.cl);  // all t
   if (rc) return rc;
   rc = tc::make_tmap_2d(&tmA[1], pk + row_offset * 2 * dim, VAST_BF16, bs, dim, 2 * dim, tc::BM);  // local t
   if (rc) return rc;
-  rc = tc::make_tmap_2d(&tmB[1], pk + dim, VAST_BF16, n_total, dim, 2 * dim, 256);  // all cond
+  rc = tc::make_tmap_2d(&tmB[1], pk + dim, VAST_BF16, n_total, dim, 2 * dim, 256 / pl.g_s.cl);  // all cond
   if (rc) return rc;
 
   auto run_stats = [&](const int* gate) -> int {
@@ -961,8 +998,8 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
         P.tmB[i] = tmKb[i];
       }
       P.epi = {rowstat, ksum, pk, static_cast<int>(row_offset), D, inv_tau, contra_temp_dev, c_sm, grad_cond, grad_t, dotq, pl.dslots};
-      rc = pl.bn_dq == 256 ? tc::launch_gemm<EpiGrad, 256, 4, 4, true>(P, stream, "omc_dq_gemm")
-                           : tc::launch_gemm<EpiGrad, 128, 4, 4, true>(P, stream, "omc_dq_gemm");
+      rc = pl.bn_dq == 256 ? tc::launch_gemm<EpiGrad, 256, 4, 8, true>(P, stream, "omc_dq_gemm")
+                           : tc::launch_gemm<EpiGrad, 128, 4, 8, true>(P, stream, "omc_dq_gemm");
       if (rc) return rc;
     } else {  // split-K partials, summed in a fixed order by the reduce kernel
       tc::KernelParams<tc::EpiStore::Params> P;

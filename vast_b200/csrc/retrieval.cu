@@ -53,6 +53,7 @@ struct EpiTopK {
     uint32_t col_offset;
   };
   static size_t smem_bytes(int cap) { return static_cast<size_t>(cap + 1) * tc::BM * sizeof(uint64_t); }
+  static constexpr bool kUnrollChunks = false;
   const Params& p;
   uint32_t lists;  // shared-space address of this warp's 32 rows: [32][cap + 1] keys
   uint32_t my;     // this lane's row
@@ -72,6 +73,8 @@ struct EpiTopK {
     thr = -INFINITY;
     cnt = 0;
   }
+  __device__ __forceinline__ void prefetch(const tc::ItemCtx&, int) {}
+  __device__ __forceinline__ void advance(const tc::ItemCtx&, int, bool) {}
 
   // Sort 32*E keys (register e of lane l holds element e*32 + l) in descending order (bitonic network).
   __device__ __forceinline__ static void sort_desc(uint64_t (&key)[E], int lane) {
@@ -624,7 +627,7 @@ struct TopkPlan {
   int cap;  // candidate buffer capacity per row
 };
 static void topk_plan(TopkPlan* pl, int64_t n_q, int64_t n_k, int64_t cols, int64_t k) {
-  tc::fill_shape(&pl->g, 1, (int)n_q, (int)n_k, (int)cols, 256, 1);
+  tc::fill_shape(&pl->g, 1, (int)n_q, (int)n_k, (int)cols, 256, 1, 1, false, tc::pick_cluster((int)n_q));
   int max_splits = static_cast<int>(MERGE_CAP * 32 / (k > 0 ? k : 1));
   if (max_splits > 64) max_splits = 64;
   if (max_splits < 1) max_splits = 1;
@@ -698,7 +701,7 @@ extern "C" int vast_sim_topk(const void* q_op, const void* k_op, int64_t n_q, in
     P.g = pl.g;
     int r = tc::make_tmap_2d(&P.tmA[0], q_op, VAST_BF16, n_q, cols, cols, tc::BM);
     if (r) return r;
-    r = tc::make_tmap_2d(&P.tmB[0], k_op, VAST_BF16, n_k, cols, cols, 256);
+    r = tc::make_tmap_2d(&P.tmB[0], k_op, VAST_BF16, n_k, cols, cols, 256 / pl.g.cl);
     if (r) return r;
     P.epi = {part, static_cast<int>(k), pl.cap, pl.g.n_splits, static_cast<uint32_t>(col_offset)};
     return tc::launch_gemm<Epi, 256, STAGES, 4>(P, stream, "sim_topk_gemm", Epi::smem_bytes(pl.cap));

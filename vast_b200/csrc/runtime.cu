@@ -93,7 +93,8 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, int64_t rows, int
 }
 
 void choose_splits(GemmShape* g, int sm_count, int max_n_splits, int max_k_splits) {
-  const int row_blocks = g->num_problems * g->m_blocks;
+  const int row_blocks = g->num_problems * g->m_groups;
+  sm_count = sm_count / (g->cl > 0 ? g->cl : 1);  // persistent grid = one cluster per `cl` SMs
   // cost model: waves * (work per item) with a small per-item flush overhead (in k-block units)
   double best = 1e300;
   int best_ns = 1, best_ks = 1;
