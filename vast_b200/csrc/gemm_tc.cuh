@@ -327,7 +327,9 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, int64_t rows, int
 
 // Pick how many N-splits (and K-splits) to cut each 128-row block into so the persistent grid
 // is evenly loaded.  row_blocks = problems * m_blocks.
-void choose_splits(GemmShape* g, int sm_count, int max_n_splits, int max_k_splits);
+// item_overhead: fixed cost of one work item in units of one k-block's MMA time (pipeline fill, partial flush,
+// and for the top-k epilogue the burst of list compactions after every restart).
+void choose_splits(GemmShape* g, int sm_count, int max_n_splits, int max_k_splits, double item_overhead = 2.0);
 
 // a_fmt / b_fmt: 0 = fp16, 1 = bf16 (may differ); b_mn: B operand is MN-major (see gemm_tc_kernel).
 inline void fill_shape(GemmShape* g, int problems, int M, int N, int K, int BN, int a_fmt, int b_fmt = -1,

@@ -46,13 +46,15 @@ __device__ __forceinline__ uint64_t lds_u64(uint32_t addr) {
 template <int E>
 struct EpiTopK {
   struct Params {
-    uint64_t* out;  // [M][n_splits][k], each list sorted best-first, 0 = empty
+    uint64_t* out;  // [M][num_slots][k], each list sorted best-first, 0 = empty
     int k;
-    int cap;  // buffer capacity per row, k < cap <= 32 * E
-    int n_splits;
+    int cap;     // buffer capacity per row, k < cap <= 32 * E
+    int stride;  // row stride of the buffers in keys (>= cap)
+    int num_slots;  // lists per row = N-splits x column halves (8 epilogue warps: two warps share a row, each
+                    // scanning one half of every tile's columns into its own list)
     uint32_t col_offset;
   };
-  static size_t smem_bytes(int cap) { return static_cast<size_t>(cap + 1) * tc::BM * sizeof(uint64_t); }
+  static size_t smem_bytes(int stride, int ne) { return static_cast<size_t>(stride) * 32 * ne * sizeof(uint64_t); }
   static constexpr bool kUnrollChunks = false;
   const Params& p;
   uint32_t lists;  // shared-space address of this warp's 32 rows: [32][cap + 1] keys
@@ -61,10 +63,9 @@ struct EpiTopK {
   float thr;
   int cnt;
   __device__ EpiTopK(const Params& p_, uint8_t* smem) : p(p_) {
-    // odd row stride (in 8-byte words): simultaneous appends of different rows spread over the banks
-    stride_b = static_cast<uint32_t>(p.cap + 1) * 8u;
-    const uint32_t q = (threadIdx.x >> 5) & 3;  // one epilogue warp per TMEM lane quadrant (NE == 4)
-    lists = ptx::smem_u32(smem) + q * 32u * stride_b;
+    stride_b = static_cast<uint32_t>(p.stride) * 8u;
+    const uint32_t ew = (threadIdx.x >> 5) - 2;  // epilogue warp index: every warp owns 32 private lists
+    lists = ptx::smem_u32(smem) + ew * 32u * stride_b;
     my = lists + (threadIdx.x & 31) * stride_b;
     thr = -INFINITY;
     cnt = 0;
@@ -110,14 +111,16 @@ struct EpiTopK {
     }
   }
 
-  // Warp-collective: every row of the warp holding more than k candidates (or any, if `all`) is sorted,
-  // cut to its best k, and gets its threshold refreshed.
-  __device__ __forceinline__ void compact(int lane, bool all, int& n_mine, float& thr_mine) const {
+  // Warp-collective: every row of the warp named in `rows` is sorted, cut to its best k, and gets its
+  // threshold refreshed.  Only the rows whose buffer is full are compacted (not the whole warp's): the cost
+  // per tile stays even across the 16 epilogue warps of a CTA pair, which all have to hand the accumulator
+  // back before the next MMA can start.
+  __device__ __forceinline__ void compact(int lane, unsigned rows, int& n_mine, float& thr_mine) const {
     __syncwarp();
 #pragma unroll 1
-    for (int r = 0; r < 32; ++r) {
+    for (; rows != 0; rows &= rows - 1) {
+      const int r = __ffs(rows) - 1;
       const int n = __shfl_sync(0xffffffffu, n_mine, r);
-      if (!(n > p.k || (all && n > 0))) continue;
       const uint32_t row = lists + static_cast<uint32_t>(r) * stride_b;
       const int keep = n < p.k ? n : p.k;
       uint64_t kth = 0;
@@ -163,29 +166,51 @@ struct EpiTopK {
     const int cap = p.cap;
     float t = thr;
     int n = cnt;
-    int resume = 32;  // first column of this chunk that could not be appended (buffer full)
+    float s[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float s = __uint_as_float(v[i]);
-      if (i < nvalid && s > t) {
-        if (n < cap) {
-          sts_u64(my + n * 8, make_key(s, gcol + i));
-          ++n;
-        } else if (resume == 32) {
-          resume = i;
+    for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(v[i]);
+    if (nvalid < 32) {  // last chunk of the score matrix: columns past the end can never be candidates
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i >= nvalid) s[i] = -INFINITY;
+    }
+    // Branch-free filter: maxima of the four 8-column groups, then of the chunk.  In the steady state nearly
+    // every chunk ends here (one compare); otherwise only the groups that hold a candidate are scanned.
+    float gm[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      gm[g] = fmaxf(fmaxf(fmaxf(s[8 * g], s[8 * g + 1]), fmaxf(s[8 * g + 2], s[8 * g + 3])),
+                    fmaxf(fmaxf(s[8 * g + 4], s[8 * g + 5]), fmaxf(s[8 * g + 6], s[8 * g + 7])));
+    const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+    int resume = 32;  // first column of this chunk that could not be appended (buffer full)
+    if (mx > t) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (gm[g] > t) {
+#pragma unroll
+          for (int i = 8 * g; i < 8 * g + 8; ++i) {
+            if (s[i] > t) {
+              if (n < cap) {
+                sts_u64(my + n * 8, make_key(s[i], gcol + i));
+                ++n;
+              } else if (resume == 32) {
+                resume = i;
+              }
+            }
+          }
         }
       }
     }
-    while (__any_sync(0xffffffffu, resume < 32)) {
-      compact(c.lane, false, n, t);
+    unsigned full_rows;
+    while ((full_rows = __ballot_sync(0xffffffffu, resume < 32)) != 0) {
+      compact(c.lane, full_rows, n, t);
       const int from = resume;
       resume = 32;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float s = __uint_as_float(v[i]);
-        if (i >= from && i < nvalid && s > t) {
+        if (i >= from && s[i] > t) {
           if (n < cap) {
-            sts_u64(my + n * 8, make_key(s, gcol + i));
+            sts_u64(my + n * 8, make_key(s[i], gcol + i));
             ++n;
           } else if (resume == 32) {
             resume = i;
@@ -200,7 +225,7 @@ struct EpiTopK {
   __device__ __forceinline__ void item_end(const tc::ItemCtx& c) {
     float t = thr;
     int n_mine = cnt;
-    compact(c.lane, true, n_mine, t);
+    compact(c.lane, __ballot_sync(0xffffffffu, n_mine > 0), n_mine, t);
     const int row0 = c.row - c.lane;  // first row of this warp
 #pragma unroll 1
     for (int r = 0; r < 32; ++r) {
@@ -208,7 +233,7 @@ struct EpiTopK {
       if (row >= c.M) break;
       const int n = __shfl_sync(0xffffffffu, n_mine, r);
       const uint32_t src = lists + static_cast<uint32_t>(r) * stride_b;
-      uint64_t* dst = p.out + (static_cast<int64_t>(row) * p.n_splits + c.n_split) * p.k;
+      uint64_t* dst = p.out + (static_cast<int64_t>(row) * p.num_slots + c.slot) * p.k;
       for (int i = c.lane; i < p.k; i += 32) dst[i] = i < n ? lds_u64(src + i * 8) : 0ull;
     }
     __syncwarp();
@@ -614,36 +639,50 @@ __global__ void scatter_scores_kernel(const int32_t* __restrict__ text_idx, cons
 
 static inline unsigned blocks_for(int64_t n, int per_block) { return static_cast<unsigned>(ceil_div64(n, per_block)); }
 
-template <class T, int S>
+template <class T, int S, int S2, int NE_>
 struct TopkTag {
   using type = T;
   static constexpr int stages = S;
+  static constexpr int stages2 = S2;
+  static constexpr int ne = NE_;
 };
 
 struct TopkPlan {
   tc::GemmShape g;
   size_t ws_bytes;
-  int e;    // key registers per lane in the epilogue sort
-  int cap;  // candidate buffer capacity per row
+  int e;       // key registers per lane in the epilogue sort
+  int cap;     // candidate buffer capacity per list
+  int stride;  // list stride in keys
+  int ne;      // epilogue warps (8: two lists per row and N-split)
+  int slots;   // lists per row
 };
 static void topk_plan(TopkPlan* pl, int64_t n_q, int64_t n_k, int64_t cols, int64_t k) {
   tc::fill_shape(&pl->g, 1, (int)n_q, (int)n_k, (int)cols, 256, 1, 1, false, tc::pick_cluster((int)n_q));
-  int max_splits = static_cast<int>(MERGE_CAP * 32 / (k > 0 ? k : 1));
-  if (max_splits > 64) max_splits = 64;
-  if (max_splits < 1) max_splits = 1;
-  tc::choose_splits(&pl->g, device_sm_count(), max_splits, 1);
-  pl->ws_bytes = pl->g.n_splits > 1 ? align_up(sizeof(uint64_t) * n_q * pl->g.n_splits * k, 256) : 0;
   // k <= 16: 32 slots (>= 16 spare); k <= 48: 64 slots; k <= 64: 80 slots (shared memory bound), sorted as 128
   if (k <= 16) {
     pl->e = 1;
     pl->cap = 32;
+    pl->stride = 32;
+    pl->ne = 8;
   } else if (k <= 48) {
     pl->e = 2;
     pl->cap = 64;
+    pl->stride = 64;
+    pl->ne = 8;
   } else {
     pl->e = 4;
     pl->cap = 80;
+    pl->stride = 81;
+    pl->ne = 4;
   }
+  const int halves = pl->ne / 4;
+  int max_splits = static_cast<int>(MERGE_CAP * 32 / (k > 0 ? k : 1)) / halves;
+  if (max_splits > 64) max_splits = 64;
+  if (max_splits < 1) max_splits = 1;
+  // every N-split restarts its lists from an empty threshold (a burst of compactions): weigh that against wave balance
+  tc::choose_splits(&pl->g, device_sm_count(), max_splits, 1, 96.0);
+  pl->slots = pl->g.n_splits * halves;
+  pl->ws_bytes = pl->slots > 1 ? align_up(sizeof(uint64_t) * n_q * pl->slots * k, 256) : 0;
 }
 
 }  // namespace vast
@@ -691,11 +730,13 @@ extern "C" int vast_sim_topk(const void* q_op, const void* k_op, int64_t n_q, in
   topk_plan(&pl, n_q, n_k, cols, k);
   VAST_REQUIRE(workspace_bytes >= pl.ws_bytes && (pl.ws_bytes == 0 || workspace), VAST_ERR_WORKSPACE,
                "sim_topk: workspace %zu < required %zu", workspace_bytes, pl.ws_bytes);
-  uint64_t* part = pl.g.n_splits > 1 ? static_cast<uint64_t*>(workspace) : out_keys;
+  uint64_t* part = pl.slots > 1 ? static_cast<uint64_t*>(workspace) : out_keys;
   int rc;
   auto run = [&](auto tag) -> int {
     using Epi = typename decltype(tag)::type;
     constexpr int STAGES = decltype(tag)::stages;
+    constexpr int STAGES2 = decltype(tag)::stages2;
+    constexpr int NE = decltype(tag)::ne;
     tc::KernelParams<typename Epi::Params> P;
     memset(&P, 0, sizeof(P));
     P.g = pl.g;
@@ -703,18 +744,19 @@ extern "C" int vast_sim_topk(const void* q_op, const void* k_op, int64_t n_q, in
     if (r) return r;
     r = tc::make_tmap_2d(&P.tmB[0], k_op, VAST_BF16, n_k, cols, cols, 256 / pl.g.cl);
     if (r) return r;
-    P.epi = {part, static_cast<int>(k), pl.cap, pl.g.n_splits, static_cast<uint32_t>(col_offset)};
-    return tc::launch_gemm<Epi, 256, STAGES, 4>(P, stream, "sim_topk_gemm", Epi::smem_bytes(pl.cap));
+    P.epi = {part, static_cast<int>(k), pl.cap, pl.stride, pl.slots, static_cast<uint32_t>(col_offset)};
+    return tc::launch_gemm<Epi, 256, STAGES, NE, false, STAGES2>(P, stream, "sim_topk_gemm", Epi::smem_bytes(pl.stride, NE));
   };
+  // <epilogue, ring depth of a lone CTA (48 KB stages), ring depth of a CTA pair (32 KB stages), epilogue warps>
   if (pl.e == 1)
-    rc = run(TopkTag<EpiTopK<1>, 4>{});
+    rc = run(TopkTag<EpiTopK<1>, 3, 5, 8>{});
   else if (pl.e == 2)
-    rc = run(TopkTag<EpiTopK<2>, 3>{});
+    rc = run(TopkTag<EpiTopK<2>, 2, 3, 8>{});
   else
-    rc = run(TopkTag<EpiTopK<4>, 3>{});
+    rc = run(TopkTag<EpiTopK<4>, 3, 4, 4>{});
   if (rc) return rc;
-  if (pl.g.n_splits > 1) {
-    topk_merge_kernel<<<blocks_for(n_q, 4), 128, 0, stream>>>(part, k, pl.g.n_splits * k, pl.g.n_splits, (int)k, n_q, (int)k, out_keys);
+  if (pl.slots > 1) {
+    topk_merge_kernel<<<blocks_for(n_q, 4), 128, 0, stream>>>(part, k, pl.slots * k, pl.slots, (int)k, n_q, (int)k, out_keys);
     VAST_LAUNCH_OK("topk_merge(splits)");
   }
   return VAST_OK;

@@ -92,7 +92,7 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, int64_t rows, int
   return VAST_OK;
 }
 
-void choose_splits(GemmShape* g, int sm_count, int max_n_splits, int max_k_splits) {
+void choose_splits(GemmShape* g, int sm_count, int max_n_splits, int max_k_splits, double item_overhead) {
   const int row_blocks = g->num_problems * g->m_groups;
   sm_count = sm_count / (g->cl > 0 ? g->cl : 1);  // persistent grid = one cluster per `cl` SMs
   // cost model: waves * (work per item) with a small per-item flush overhead (in k-block units)
@@ -110,7 +110,7 @@ void choose_splits(GemmShape* g, int sm_count, int max_n_splits, int max_k_split
       if (ns_eff != ns) continue;
       const long long items = 1LL * row_blocks * ns * ks;
       const long long waves = (items + sm_count - 1) / sm_count;
-      const double per_item = static_cast<double>(tps) * kbps + 2.0 + (ks > 1 ? 4.0 : 0.0);
+      const double per_item = static_cast<double>(tps) * kbps + item_overhead + (ks > 1 ? 4.0 : 0.0);
       const double cost = waves * per_item;
       if (cost < best * 0.999) {
         best = cost;
