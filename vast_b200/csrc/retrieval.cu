@@ -53,6 +53,13 @@ struct EpiTopK {
     int num_slots;  // lists per row = N-splits x column halves (8 epilogue warps: two warps share a row, each
                     // scanning one half of every tile's columns into its own list)
     uint32_t col_offset;
+    // [M] zero-initialised: orderable bits of a PROVEN lower bound of each row's final k-th best score.  Every
+    // list that holds k candidates publishes its k-th score (atomic max); every list re-reads the bound once
+    // per tile.  Lists of the same row (the other column half, other N-splits, earlier items) thereby share
+    // their progress, so a list that starts late admits almost nothing it does not need.  A score that TIES
+    // the shared bound must still be admitted (it may carry the lower column index), hence the bound is used
+    // one ulp lower; ties against the list's own k-th lose as before (its columns arrive in increasing order).
+    uint32_t* thr_shared;
   };
   static size_t smem_bytes(int stride, int ne) { return static_cast<size_t>(stride) * 32 * ne * sizeof(uint64_t); }
   static constexpr bool kUnrollChunks = false;
@@ -62,6 +69,7 @@ struct EpiTopK {
   uint32_t stride_b;
   float thr;
   int cnt;
+  int grow;  // this lane's row (or -1)
   __device__ EpiTopK(const Params& p_, uint8_t* smem) : p(p_) {
     stride_b = static_cast<uint32_t>(p.stride) * 8u;
     const uint32_t ew = (threadIdx.x >> 5) - 2;  // epilogue warp index: every warp owns 32 private lists
@@ -70,11 +78,22 @@ struct EpiTopK {
     thr = -INFINITY;
     cnt = 0;
   }
-  __device__ __forceinline__ void item_begin(const tc::ItemCtx&) {
+  __device__ __forceinline__ void item_begin(const tc::ItemCtx& c) {
     thr = -INFINITY;
     cnt = 0;
+    grow = c.row_valid ? c.row : -1;
   }
-  __device__ __forceinline__ void prefetch(const tc::ItemCtx&, int) {}
+  // once per tile: pick up the bound other lists of this row have proven meanwhile
+  __device__ __forceinline__ void prefetch(const tc::ItemCtx&, int) {
+    if (p.thr_shared != nullptr && grow >= 0) {
+      const uint32_t o = *reinterpret_cast<const volatile uint32_t*>(p.thr_shared + grow);
+      if (o != 0) {
+        float b = f32_from_orderable(o - 1);  // one ulp below the bound: "s > b" admits ties with the bound
+        if (b == 0.f) b = __uint_as_float(0x80000001u);  // bound +0.0: -0.0 would compare equal, step to -denorm_min
+        if (b > thr) thr = b;                            // (a NaN bound is never published)
+      }
+    }
+  }
   __device__ __forceinline__ void advance(const tc::ItemCtx&, int, bool) {}
 
   // Sort 32*E keys (register e of lane l holds element e*32 + l) in descending order (bitonic network).
@@ -125,16 +144,13 @@ struct EpiTopK {
       const int keep = n < p.k ? n : p.k;
       uint64_t kth = 0;
       if constexpr (E == 1) {
-        // <= 32 candidates: rank each key by counting the larger ones (32 independent broadcast loads, no
-        // dependent shuffle chain), then write the best `keep` to their sorted positions.
-        const uint64_t key = lane < n ? lds_u64(row + lane * 8) : 0ull;
-        int rank = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) rank += (lds_u64(row + j * 8) > key && j < n) ? 1 : 0;
-        __syncwarp();
-        if (lane < n && rank < keep) sts_u64(row + rank * 8, key);
-        const unsigned m = __ballot_sync(0xffffffffu, lane < n && rank == p.k - 1);
-        if (m) kth = __shfl_sync(0xffffffffu, key, __ffs(m) - 1);
+        // <= 32 candidates, one per lane: 15-stage bitonic network over warp shuffles (about half the
+        // instructions of ranking every key against the other 31)
+        uint64_t key[1];
+        key[0] = lane < n ? lds_u64(row + lane * 8) : 0ull;
+        sort_desc(key, lane);
+        if (lane < keep) sts_u64(row + lane * 8, key[0]);
+        kth = __shfl_sync(0xffffffffu, key[0], (p.k - 1) & 31);
       } else {
         uint64_t key[E];
 #pragma unroll
@@ -153,7 +169,12 @@ struct EpiTopK {
       }
       if (lane == r) {
         n_mine = keep;
-        if (keep == p.k) thr_mine = f32_from_orderable(static_cast<uint32_t>(kth >> 32));
+        if (keep == p.k) {
+          const uint32_t ko = static_cast<uint32_t>(kth >> 32);
+          const float kf = f32_from_orderable(ko);
+          if (kf > thr_mine) thr_mine = kf;
+          if (p.thr_shared != nullptr && grow >= 0 && kf == kf) atomicMax(p.thr_shared + grow, ko);
+        }
       }
     }
     __syncwarp();
@@ -206,14 +227,21 @@ struct EpiTopK {
       compact(c.lane, full_rows, n, t);
       const int from = resume;
       resume = 32;
+      if (from < 32) {  // lanes whose buffer was full: the rest of the chunk against the refreshed threshold
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (i >= from && s[i] > t) {
-          if (n < cap) {
-            sts_u64(my + n * 8, make_key(s[i], gcol + i));
-            ++n;
-          } else if (resume == 32) {
-            resume = i;
+        for (int g = 0; g < 4; ++g) {
+          if (8 * g + 7 >= from && gm[g] > t) {
+#pragma unroll
+            for (int i = 8 * g; i < 8 * g + 8; ++i) {
+              if (i >= from && s[i] > t) {
+                if (n < cap) {
+                  sts_u64(my + n * 8, make_key(s[i], gcol + i));
+                  ++n;
+                } else if (resume == 32) {
+                  resume = i;
+                }
+              }
+            }
           }
         }
       }
@@ -650,6 +678,7 @@ struct TopkTag {
 struct TopkPlan {
   tc::GemmShape g;
   size_t ws_bytes;
+  size_t thr_bytes;  // shared per-row bounds at the start of the workspace
   int e;       // key registers per lane in the epilogue sort
   int cap;     // candidate buffer capacity per list
   int stride;  // list stride in keys
@@ -680,9 +709,11 @@ static void topk_plan(TopkPlan* pl, int64_t n_q, int64_t n_k, int64_t cols, int6
   if (max_splits > 64) max_splits = 64;
   if (max_splits < 1) max_splits = 1;
   // every N-split restarts its lists from an empty threshold (a burst of compactions): weigh that against wave balance
-  tc::choose_splits(&pl->g, device_sm_count(), max_splits, 1, 96.0);
+  // lists share their thresholds (EpiTopK::Params::thr_shared), so a fresh N-split costs little: balance the waves
+  tc::choose_splits(&pl->g, device_sm_count(), max_splits, 1, 16.0);
   pl->slots = pl->g.n_splits * halves;
-  pl->ws_bytes = pl->slots > 1 ? align_up(sizeof(uint64_t) * n_q * pl->slots * k, 256) : 0;
+  pl->thr_bytes = align_up(sizeof(uint32_t) * n_q, 256);
+  pl->ws_bytes = pl->thr_bytes + (pl->slots > 1 ? align_up(sizeof(uint64_t) * n_q * pl->slots * k, 256) : 0);
 }
 
 }  // namespace vast
@@ -728,9 +759,11 @@ extern "C" int vast_sim_topk(const void* q_op, const void* k_op, int64_t n_q, in
   VAST_REQUIRE(col_offset >= 0 && col_offset + n_k < 0xFFFFFFFFll, VAST_ERR_INVALID, "sim_topk: col_offset out of range");
   TopkPlan pl;
   topk_plan(&pl, n_q, n_k, cols, k);
-  VAST_REQUIRE(workspace_bytes >= pl.ws_bytes && (pl.ws_bytes == 0 || workspace), VAST_ERR_WORKSPACE,
-               "sim_topk: workspace %zu < required %zu", workspace_bytes, pl.ws_bytes);
-  uint64_t* part = pl.slots > 1 ? static_cast<uint64_t*>(workspace) : out_keys;
+  VAST_REQUIRE(workspace_bytes >= pl.ws_bytes && workspace, VAST_ERR_WORKSPACE, "sim_topk: workspace %zu < required %zu",
+               workspace_bytes, pl.ws_bytes);
+  uint32_t* thr_shared = static_cast<uint32_t*>(workspace);
+  VAST_CUDA_OK(cudaMemsetAsync(thr_shared, 0, pl.thr_bytes, stream));
+  uint64_t* part = pl.slots > 1 ? reinterpret_cast<uint64_t*>(static_cast<char*>(workspace) + pl.thr_bytes) : out_keys;
   int rc;
   auto run = [&](auto tag) -> int {
     using Epi = typename decltype(tag)::type;
@@ -744,7 +777,7 @@ extern "C" int vast_sim_topk(const void* q_op, const void* k_op, int64_t n_q, in
     if (r) return r;
     r = tc::make_tmap_2d(&P.tmB[0], k_op, VAST_BF16, n_k, cols, cols, 256 / pl.g.cl);
     if (r) return r;
-    P.epi = {part, static_cast<int>(k), pl.cap, pl.stride, pl.slots, static_cast<uint32_t>(col_offset)};
+    P.epi = {part, static_cast<int>(k), pl.cap, pl.stride, pl.slots, static_cast<uint32_t>(col_offset), thr_shared};
     return tc::launch_gemm<Epi, 256, STAGES, NE, false, STAGES2>(P, stream, "sim_topk_gemm", Epi::smem_bytes(pl.stride, NE));
   };
   // <epilogue, ring depth of a lone CTA (48 KB stages), ring depth of a CTA pair (32 KB stages), epilogue warps>
