@@ -39,6 +39,10 @@ struct GemmShape {
   int n_tiles, n_splits, tiles_per_split;
   int k_blocks, k_splits, kb_per_split;
   int num_items;
+  // Optional two-class schedule (streaming top-k): the first m_groups - tail_groups row-block groups are one
+  // work item each (all N-tiles: a list that is never restarted), the last tail_groups are cut into
+  // tail_splits column ranges of tail_tps tiles so that the final wave still fills the machine.
+  int tail_groups, tail_splits, tail_tps;
   uint32_t idesc;
 };
 
@@ -70,6 +74,26 @@ struct WorkItem {
 // is its rank in the cluster.
 __device__ __forceinline__ WorkItem decode_item(const GemmShape& g, int idx, int cta_rank) {
   WorkItem w;
+  if (g.tail_groups > 0) {
+    const int full = g.m_groups - g.tail_groups;
+    int grp = idx, split = 0;
+    w.tile_begin = 0;
+    w.tile_end = g.n_tiles;
+    if (idx >= full) {
+      const int j = idx - full;
+      grp = full + j / g.tail_splits;
+      split = j - (j / g.tail_splits) * g.tail_splits;
+      w.tile_begin = split * g.tail_tps;
+      w.tile_end = min(w.tile_begin + g.tail_tps, g.n_tiles);
+    }
+    w.prob = 0;
+    w.m_blk = grp * g.cl + cta_rank;
+    w.n_split = split;
+    w.k_split = 0;
+    w.kb_begin = 0;
+    w.kb_end = g.k_blocks;
+    return w;
+  }
   w.k_split = idx % g.k_splits;
   idx /= g.k_splits;
   w.n_split = idx % g.n_splits;
@@ -112,7 +136,7 @@ struct SmemLayout {
 //         (stage free) and `tfull` (accumulator ready) barriers; both CTAs' epilogue warps arrive on the
 //         leader's `tempty` barrier (accumulator drained).
 template <class Epi, int BN, int STAGES, int NE, bool B_MN, int CL>
-__global__ void __launch_bounds__(64 + 32 * NE, 1)
+__global__ void __launch_bounds__(64 + 32 * NE + 32 * Epi::kAuxWarps, 1)
 gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
   static_assert(NE == 4 || NE == 8, "4 or 8 epilogue warps");
   static_assert(BN == 128 || BN == 256, "BN");
@@ -256,6 +280,10 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
         }
       }
     }
+  } else if (warp >= 2 + NE) {
+    // ------------------------------------------------------------ auxiliary warps of the epilogue (every CTA)
+    // (EpiTopK: list-maintenance warps fed by the filter warps through shared-memory queues)
+    if constexpr (Epi::kAuxWarps > 0) Epi::aux_main(P.epi, epi_smem, g, cluster_id, num_clusters, cta_rank, warp - 2 - NE, lane);
   } else {
     // ------------------------------------------------------------ epilogue warps (every CTA)
     const int ew = warp - 2;
@@ -349,6 +377,7 @@ inline void fill_shape(GemmShape* g, int problems, int M, int N, int K, int BN, 
   g->k_splits = 1;
   g->kb_per_split = g->k_blocks;
   g->num_items = problems * g->m_groups;
+  g->tail_groups = g->tail_splits = g->tail_tps = 0;
   g->idesc = ptx::umma_idesc_f16(static_cast<uint32_t>(a_fmt), static_cast<uint32_t>(b_fmt), b_mn ? 1u : 0u,
                                  static_cast<uint32_t>(BM * cl), static_cast<uint32_t>(BN));
 }
@@ -372,12 +401,12 @@ int launch_gemm_cl(const KernelParams<typename Epi::Params>& P, cudaStream_t str
   const int clusters = P.g.num_items < clusters_max ? P.g.num_items : clusters_max;
   if (clusters <= 0) return VAST_OK;
   if constexpr (CL == 1) {
-    VAST_TIMED(stream, name, (kern<<<clusters, 64 + 32 * NE, smem, stream>>>(P)));
+    VAST_TIMED(stream, name, (kern<<<clusters, 64 + 32 * NE + 32 * Epi::kAuxWarps, smem, stream>>>(P)));
   } else {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(static_cast<unsigned>(clusters * CL), 1, 1);
-    cfg.blockDim = dim3(64 + 32 * NE, 1, 1);
+    cfg.blockDim = dim3(64 + 32 * NE + 32 * Epi::kAuxWarps, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -414,6 +443,7 @@ struct EpiStore {
     float alpha;
   };
   static constexpr bool kUnrollChunks = false;
+  static constexpr int kAuxWarps = 0;
   const Params& p;
   __device__ EpiStore(const Params& p_, uint8_t*) : p(p_) {}
   __device__ __forceinline__ void item_begin(const ItemCtx&) {}

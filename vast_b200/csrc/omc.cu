@@ -84,6 +84,7 @@ struct EpiStats {
     const float* temp_dev;
   };
   static constexpr bool kUnrollChunks = false;
+  static constexpr int kAuxWarps = 0;
   const Params& p;
   float m2, l, scale2;
   __device__ EpiStats(const Params& p_, uint8_t*) : p(p_) { scale2 = p.temp_dev ? kLog2e / __ldg(p.temp_dev) : p.scale2; }
@@ -144,6 +145,7 @@ struct EpiSoft {
     int* ovf;  // raised when a chunk sum leaves the fp16 range (single-pass form) or nullptr
   };
   static constexpr bool kUnrollChunks = false;
+  static constexpr int kAuxWarps = 0;
   const Params& p;
   float ref, l, bw, be, scale2;
   int bidx, tcol;
@@ -534,6 +536,7 @@ struct EpiGrad {
     int num_slots;
   };
   static constexpr bool kUnrollChunks = true;  // the operand double buffer lives in registers
+  static constexpr int kAuxWarps = 0;
   const Params& p;
   float rho, c_t, gs, dotq;
   const __nv_bfloat16* qrow;

@@ -4,6 +4,8 @@
 // the candidate bookkeeping of the ITM re-rank (bucket by video, scatter scores).
 //
 // Ordering rule everywhere: score descending, index ascending (torch leaves ties unspecified).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
@@ -25,15 +27,27 @@ __device__ __forceinline__ uint64_t make_key(float s, uint32_t idx) {
 constexpr int TOPK_MAX = 64;  // largest k of the GEMM-epilogue selection
 
 // ------------------------------------------------------------------ GEMM epilogue: running top-k
-// One thread owns one query row (TMEM lane) and sees that row's scores in increasing column order.
-// Steady state is ONE compare per score against the row's current k-th best (a register).  Scores that
-// pass are appended to the row's candidate buffer in shared memory ([row][pos], capacity CAP > k); when
-// a buffer of the warp is full the warp compacts all 32 of its rows together: each row's candidates are
-// bitonic-sorted across the lanes (keys are unique, so (score desc, index asc) is a strict order), the
-// best k stay, and the k-th becomes the new threshold.  Compactions are rare (the number of candidates
-// that beat the running k-th grows only logarithmically with the columns seen) and warp-converged, so
-// the epilogue stays hidden behind the MMAs of the next accumulator tile.
-//   E = 32-bit... number of key registers per lane in the sort: CAP <= 32 * E.
+// Two warp roles share the work, decoupled by shared-memory queues:
+//
+//  * FILTER warps (the 8 epilogue warps: TMEM lane quadrant x column half).  One thread owns one query row and
+//    sees that row's scores of the current accumulator tile.  Steady state per 32 scores: a max tree and ONE
+//    compare against the row's admission threshold; only 8-column groups that hold a score above it are looked
+//    at, and such a score is pushed as (row, key) into the quadrant's queue.  This work is uniform, so the 16
+//    filter warps of a CTA pair hand the accumulator back at the same pace and the MMAs never wait for one
+//    slow warp.
+//  * LIST warps (4 auxiliary warps, one per quadrant of 32 rows).  They pop candidates and insert them into the
+//    row's sorted top-k list (<= 64 keys = 2 registers per lane: position by ballot + popc, shift by shuffle),
+//    then raise the row's admission threshold to the new k-th score.  Irregular work, off the critical
+//    path; a full queue back-pressures the filters.
+//
+// Keys (score, ~index) are unique, so (score desc, index asc) is a strict order and the result does not depend
+// on arrival order.  Thresholds are kept ONE ULP BELOW the k-th score: a score that ties the k-th is admitted
+// and the exact key comparison in the list warp decides (it wins iff its column index is lower).
+// Every list publishes its k-th score as a proven lower bound of the row's final k-th score (thr_shared, atomic
+// max in global memory); lists of the same row in other N-splits / CTAs start from that bound.
+constexpr int TOPK_QCAP = 128;            // queue entries per quadrant
+constexpr uint32_t TOPK_END = 0xFFFFFFFFu;  // row field of the end-of-item marker
+
 __device__ __forceinline__ void sts_u64(uint32_t addr, uint64_t v) {
   asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
 }
@@ -42,151 +56,127 @@ __device__ __forceinline__ uint64_t lds_u64(uint32_t addr) {
   asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4_volatile(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.volatile.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32_volatile(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u32_volatile(uint32_t addr, uint32_t v) {
+  asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32_volatile(uint32_t addr) { return __uint_as_float(lds_u32_volatile(addr)); }
+__device__ __forceinline__ uint32_t atoms_add(uint32_t addr, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void named_barrier(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+// largest float strictly below the float whose orderable bits are o (o != 0); never returns -0.0
+__device__ __forceinline__ float f32_below_orderable(uint32_t o) {
+  float b = f32_from_orderable(o - 1);
+  if (b == 0.f) b = __uint_as_float(0x80000001u);  // bound +0.0: -0.0 would compare equal, step to -denorm_min
+  return b;
+}
 
+// Sort 32*E keys (register e of lane l holds element e*32 + l) in descending order (bitonic network over shuffles).
 template <int E>
+__device__ __forceinline__ void sort_desc(uint64_t (&key)[E], int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32 * E; size <<= 1) {
+#pragma unroll
+    for (int st = size >> 1; st > 0; st >>= 1) {
+      if (st >= 32) {  // partner lives in another register of the same lane
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int pe = e ^ (st >> 5);
+          if (pe > e) {
+            const bool desc = (((e << 5) & size) == 0);
+            const uint64_t a = key[e], b = key[pe];
+            const bool sw = desc ? (a < b) : (a > b);
+            key[e] = sw ? b : a;
+            key[pe] = sw ? a : b;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int idx = (e << 5) | lane;
+          const uint64_t other = __shfl_xor_sync(0xffffffffu, key[e], st);
+          const bool desc = ((idx & size) == 0);
+          const bool lower = ((lane & st) == 0);  // this lane holds the lower index of the pair
+          const bool keep_max = (desc == lower);  // descending run: the lower index keeps the larger key
+          const bool gt = key[e] > other;
+          key[e] = (gt == keep_max) ? key[e] : other;
+        }
+      }
+    }
+  }
+}
+
+template <int E>  // key registers per lane of a list warp: lists hold up to 32 * E keys (k <= 32 * E)
 struct EpiTopK {
   struct Params {
-    uint64_t* out;  // [M][num_slots][k], each list sorted best-first, 0 = empty
+    uint64_t* out;  // [M][n_splits][k], each list sorted best-first, 0 = empty
     int k;
-    int cap;     // buffer capacity per row, k < cap <= 32 * E
-    int stride;  // row stride of the buffers in keys (>= cap)
-    int num_slots;  // lists per row = N-splits x column halves (8 epilogue warps: two warps share a row, each
-                    // scanning one half of every tile's columns into its own list)
+    int n_splits;
+    int halves;  // filter warps per quadrant (column halves of a tile) = end markers per item
     uint32_t col_offset;
-    // [M] zero-initialised: orderable bits of a PROVEN lower bound of each row's final k-th best score.  Every
-    // list that holds k candidates publishes its k-th score (atomic max); every list re-reads the bound once
-    // per tile.  Lists of the same row (the other column half, other N-splits, earlier items) thereby share
-    // their progress, so a list that starts late admits almost nothing it does not need.  A score that TIES
-    // the shared bound must still be admitted (it may carry the lower column index), hence the bound is used
-    // one ulp lower; ties against the list's own k-th lose as before (its columns arrive in increasing order).
-    uint32_t* thr_shared;
+    uint32_t* thr_shared;  // [M] zero-initialised orderable bits of a proven lower bound of the final k-th score
   };
-  static size_t smem_bytes(int stride, int ne) { return static_cast<size_t>(stride) * 32 * ne * sizeof(uint64_t); }
   static constexpr bool kUnrollChunks = false;
+  static constexpr int kAuxWarps = 4;
+  static constexpr int LSTRIDE = 32 * E + 1;  // keys per list row; odd: lanes walking 32 different rows hit different banks
+  static constexpr uint32_t LIST_BYTES = tc::BM * LSTRIDE * 8;
+  static constexpr uint32_t THR_OFF = LIST_BYTES;                  // [128] float admission thresholds
+  static constexpr uint32_t CNT_OFF = THR_OFF + tc::BM * 4;        // [128] keys held per list
+  static constexpr uint32_t RING_OFF = CNT_OFF + tc::BM * 4;       // [4][QCAP] uint4 (key lo, key hi, row, sequence)
+  static constexpr uint32_t CTRL_OFF = RING_OFF + 4 * TOPK_QCAP * 16;  // [4] {tail (reserved), head (consumed)}
+  static size_t smem_bytes() { return CTRL_OFF + 4 * 8; }
+
   const Params& p;
-  uint32_t lists;  // shared-space address of this warp's 32 rows: [32][cap + 1] keys
-  uint32_t my;     // this lane's row
-  uint32_t stride_b;
+  uint32_t base, thr_addr, ring, ctrl;
+  int quad, row_valid;
   float thr;
-  int cnt;
-  int grow;  // this lane's row (or -1)
   __device__ EpiTopK(const Params& p_, uint8_t* smem) : p(p_) {
-    stride_b = static_cast<uint32_t>(p.stride) * 8u;
-    const uint32_t ew = (threadIdx.x >> 5) - 2;  // epilogue warp index: every warp owns 32 private lists
-    lists = ptx::smem_u32(smem) + ew * 32u * stride_b;
-    my = lists + (threadIdx.x & 31) * stride_b;
+    base = ptx::smem_u32(smem);
+    quad = (threadIdx.x >> 5) & 3;
+    thr_addr = base + THR_OFF + (quad * 32 + (threadIdx.x & 31)) * 4;
+    ring = base + RING_OFF + quad * TOPK_QCAP * 16;
+    ctrl = base + CTRL_OFF + quad * 8;
     thr = -INFINITY;
-    cnt = 0;
+    row_valid = 0;
   }
+  // ---------------------------------------------------------------- filter warps
   __device__ __forceinline__ void item_begin(const tc::ItemCtx& c) {
-    thr = -INFINITY;
-    cnt = 0;
-    grow = c.row_valid ? c.row : -1;
+    row_valid = c.row_valid;
+    named_barrier(1 + quad, 32 * (p.halves + 1));  // the list warp has reset lists and thresholds for this item
+    thr = lds_f32_volatile(thr_addr);
   }
-  // once per tile: pick up the bound other lists of this row have proven meanwhile
-  __device__ __forceinline__ void prefetch(const tc::ItemCtx&, int) {
-    if (p.thr_shared != nullptr && grow >= 0) {
-      const uint32_t o = *reinterpret_cast<const volatile uint32_t*>(p.thr_shared + grow);
-      if (o != 0) {
-        float b = f32_from_orderable(o - 1);  // one ulp below the bound: "s > b" admits ties with the bound
-        if (b == 0.f) b = __uint_as_float(0x80000001u);  // bound +0.0: -0.0 would compare equal, step to -denorm_min
-        if (b > thr) thr = b;                            // (a NaN bound is never published)
-      }
-    }
-  }
+  __device__ __forceinline__ void prefetch(const tc::ItemCtx&, int) {}
   __device__ __forceinline__ void advance(const tc::ItemCtx&, int, bool) {}
-
-  // Sort 32*E keys (register e of lane l holds element e*32 + l) in descending order (bitonic network).
-  __device__ __forceinline__ static void sort_desc(uint64_t (&key)[E], int lane) {
-#pragma unroll
-    for (int size = 2; size <= 32 * E; size <<= 1) {
-#pragma unroll
-      for (int st = size >> 1; st > 0; st >>= 1) {
-        if (st >= 32) {  // partner lives in another register of the same lane
-#pragma unroll
-          for (int e = 0; e < E; ++e) {
-            const int pe = e ^ (st >> 5);
-            if (pe > e) {
-              const bool desc = (((e << 5) & size) == 0);
-              const uint64_t a = key[e], b = key[pe];
-              const bool sw = desc ? (a < b) : (a > b);
-              key[e] = sw ? b : a;
-              key[pe] = sw ? a : b;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < E; ++e) {
-            const int idx = (e << 5) | lane;
-            const uint64_t other = __shfl_xor_sync(0xffffffffu, key[e], st);
-            const bool desc = ((idx & size) == 0);
-            const bool lower = ((lane & st) == 0);  // this lane holds the lower index of the pair
-            const bool keep_max = (desc == lower);  // descending run: the lower index keeps the larger key
-            const bool gt = key[e] > other;
-            key[e] = (gt == keep_max) ? key[e] : other;
-          }
-        }
-      }
+  __device__ __forceinline__ void push(uint64_t key, uint32_t row) {
+    const uint32_t slot = atoms_add(ctrl, 1);
+    if (slot - lds_u32_volatile(ctrl + 4) >= TOPK_QCAP) {  // queue full: wait for the list warp (watchdog: trap, never hang)
+      const long long t0 = clock64();
+      while (slot - lds_u32_volatile(ctrl + 4) >= TOPK_QCAP)
+        if (clock64() - t0 > 6000000000LL) __trap();
     }
+    sts_v4(ring + (slot % TOPK_QCAP) * 16, make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), row, slot + 1));
   }
-
-  // Warp-collective: every row of the warp named in `rows` is sorted, cut to its best k, and gets its
-  // threshold refreshed.  Only the rows whose buffer is full are compacted (not the whole warp's): the cost
-  // per tile stays even across the 16 epilogue warps of a CTA pair, which all have to hand the accumulator
-  // back before the next MMA can start.
-  __device__ __forceinline__ void compact(int lane, unsigned rows, int& n_mine, float& thr_mine) const {
-    __syncwarp();
-#pragma unroll 1
-    for (; rows != 0; rows &= rows - 1) {
-      const int r = __ffs(rows) - 1;
-      const int n = __shfl_sync(0xffffffffu, n_mine, r);
-      const uint32_t row = lists + static_cast<uint32_t>(r) * stride_b;
-      const int keep = n < p.k ? n : p.k;
-      uint64_t kth = 0;
-      if constexpr (E == 1) {
-        // <= 32 candidates, one per lane: 15-stage bitonic network over warp shuffles (about half the
-        // instructions of ranking every key against the other 31)
-        uint64_t key[1];
-        key[0] = lane < n ? lds_u64(row + lane * 8) : 0ull;
-        sort_desc(key, lane);
-        if (lane < keep) sts_u64(row + lane * 8, key[0]);
-        kth = __shfl_sync(0xffffffffu, key[0], (p.k - 1) & 31);
-      } else {
-        uint64_t key[E];
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          const int pos = e * 32 + lane;
-          key[e] = pos < n ? lds_u64(row + pos * 8) : 0ull;
-        }
-        sort_desc(key, lane);
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          const int pos = e * 32 + lane;
-          if (pos < keep) sts_u64(row + pos * 8, key[e]);
-          const uint64_t cand = __shfl_sync(0xffffffffu, key[e], (p.k - 1) & 31);
-          if (e == ((p.k - 1) >> 5)) kth = cand;
-        }
-      }
-      if (lane == r) {
-        n_mine = keep;
-        if (keep == p.k) {
-          const uint32_t ko = static_cast<uint32_t>(kth >> 32);
-          const float kf = f32_from_orderable(ko);
-          if (kf > thr_mine) thr_mine = kf;
-          if (p.thr_shared != nullptr && grow >= 0 && kf == kf) atomicMax(p.thr_shared + grow, ko);
-        }
-      }
-    }
-    __syncwarp();
-  }
-
   __device__ __forceinline__ void chunk(const tc::ItemCtx& c, const uint32_t (&v)[32], int col0) {
     if (col0 >= c.N) return;
     const int nvalid = c.N - col0;
     const uint32_t gcol = p.col_offset + static_cast<uint32_t>(col0);
-    const int cap = p.cap;
-    float t = thr;
-    int n = cnt;
     float s[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(v[i]);
@@ -195,76 +185,215 @@ struct EpiTopK {
       for (int i = 0; i < 32; ++i)
         if (i >= nvalid) s[i] = -INFINITY;
     }
-    // Branch-free filter: maxima of the four 8-column groups, then of the chunk.  In the steady state nearly
-    // every chunk ends here (one compare); otherwise only the groups that hold a candidate are scanned.
+    const float t = row_valid ? fmaxf(thr, lds_f32_volatile(thr_addr)) : INFINITY;  // thresholds only rise
+    thr = t;
     float gm[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g)
       gm[g] = fmaxf(fmaxf(fmaxf(s[8 * g], s[8 * g + 1]), fmaxf(s[8 * g + 2], s[8 * g + 3])),
                     fmaxf(fmaxf(s[8 * g + 4], s[8 * g + 5]), fmaxf(s[8 * g + 6], s[8 * g + 7])));
     const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-    int resume = 32;  // first column of this chunk that could not be appended (buffer full)
     if (mx > t) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         if (gm[g] > t) {
 #pragma unroll
-          for (int i = 8 * g; i < 8 * g + 8; ++i) {
-            if (s[i] > t) {
-              if (n < cap) {
-                sts_u64(my + n * 8, make_key(s[i], gcol + i));
-                ++n;
-              } else if (resume == 32) {
-                resume = i;
-              }
-            }
-          }
+          for (int i = 8 * g; i < 8 * g + 8; ++i)
+            if (s[i] > t) push(make_key(s[i], gcol + i), static_cast<uint32_t>(c.lane));
         }
       }
     }
-    unsigned full_rows;
-    while ((full_rows = __ballot_sync(0xffffffffu, resume < 32)) != 0) {
-      compact(c.lane, full_rows, n, t);
-      const int from = resume;
-      resume = 32;
-      if (from < 32) {  // lanes whose buffer was full: the rest of the chunk against the refreshed threshold
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (8 * g + 7 >= from && gm[g] > t) {
-#pragma unroll
-            for (int i = 8 * g; i < 8 * g + 8; ++i) {
-              if (i >= from && s[i] > t) {
-                if (n < cap) {
-                  sts_u64(my + n * 8, make_key(s[i], gcol + i));
-                  ++n;
-                } else if (resume == 32) {
-                  resume = i;
-                }
-              }
-            }
-          }
-        }
-      }
-    }
-    thr = t;
-    cnt = n;
+  }
+  __device__ __forceinline__ void item_end(const tc::ItemCtx& c) {
+    __syncwarp();
+    if (c.lane == 0) push(0ull, TOPK_END);
   }
 
-  __device__ __forceinline__ void item_end(const tc::ItemCtx& c) {
-    float t = thr;
-    int n_mine = cnt;
-    compact(c.lane, __ballot_sync(0xffffffffu, n_mine > 0), n_mine, t);
-    const int row0 = c.row - c.lane;  // first row of this warp
-#pragma unroll 1
-    for (int r = 0; r < 32; ++r) {
-      const int row = row0 + r;
-      if (row >= c.M) break;
-      const int n = __shfl_sync(0xffffffffu, n_mine, r);
-      const uint32_t src = lists + static_cast<uint32_t>(r) * stride_b;
-      uint64_t* dst = p.out + (static_cast<int64_t>(row) * p.num_slots + c.slot) * p.k;
-      for (int i = c.lane; i < p.k; i += 32) dst[i] = i < n ? lds_u64(src + i * 8) : 0ull;
+  // ---------------------------------------------------------------- list warps
+  // A list is UNSORTED while it holds fewer than k keys (appends only, no threshold yet) and sorted best-first
+  // from the moment it is full (one bitonic sort), after which every insert keeps it sorted.
+  struct ListCtx {
+    const Params& p;
+    uint32_t lists, thr0, cnt0;
+    int k, lane, row_base, M;
+  };
+  // warp-collective: sort list r (c keys), store it, and if it is full set the row's admission threshold
+  __device__ __forceinline__ static void sort_list(const ListCtx& L, int r, int c) {
+    const uint32_t la = L.lists + (r * LSTRIDE + L.lane) * 8;
+    uint64_t key[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) key[e] = (e * 32 + L.lane) < c ? lds_u64(la + e * 32 * 8) : 0ull;
+    sort_desc<E>(key, L.lane);
+    uint64_t kth = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      if (e * 32 + L.lane < L.k) sts_u64(la + e * 32 * 8, key[e]);
+      const uint64_t cand = __shfl_sync(0xffffffffu, key[e], (L.k - 1) & 31);
+      if (e == ((L.k - 1) >> 5)) kth = cand;
     }
+    if (c >= L.k && L.lane == 0) raise(L, r, kth);
     __syncwarp();
+  }
+  __device__ __forceinline__ static void raise(const ListCtx& L, int r, uint64_t kth) {
+    const uint32_t ko = static_cast<uint32_t>(kth >> 32);
+    sts_u32_volatile(L.thr0 + r * 4, __float_as_uint(f32_below_orderable(ko)));
+    const int grow = L.row_base + r;
+    if (L.p.thr_shared != nullptr && grow < L.M) atomicMax(L.p.thr_shared + grow, ko);
+  }
+
+  __device__ static void aux_main(const Params& p, uint8_t* smem, const tc::GemmShape& g, int cluster_id, int num_clusters,
+                                  int cta_rank, int quad, int lane) {
+    const uint32_t base = ptx::smem_u32(smem);
+    const uint32_t ring = base + RING_OFF + quad * TOPK_QCAP * 16;
+    const uint32_t ctrl = base + CTRL_OFF + quad * 8;
+    ListCtx L{p, base + quad * 32 * (LSTRIDE * 8), base + THR_OFF + quad * 32 * 4, base + CNT_OFF + quad * 32 * 4, p.k, lane, 0, g.M};
+    if (lane == 0) {
+      sts_u32_volatile(ctrl, 0);
+      sts_u32_volatile(ctrl + 4, 0);
+    }
+    for (int i = lane; i < TOPK_QCAP; i += 32) sts_v4(ring + i * 16, make_uint4(0, 0, 0, 0));  // sequence 0 = never written
+    uint32_t head = 0;
+    const int k = p.k;
+    for (int item = cluster_id; item < g.num_items; item += num_clusters) {
+      const tc::WorkItem w = tc::decode_item(g, item, cta_rank);
+      L.row_base = w.m_blk * tc::BM + quad * 32;
+      const int row = L.row_base + lane;  // lane <-> row for resets / thresholds
+      // ---- empty lists; admission threshold = the row's proven bound so far
+      float t0 = -INFINITY;
+      if (row < g.M && p.thr_shared != nullptr) {
+        const uint32_t o = *reinterpret_cast<const volatile uint32_t*>(p.thr_shared + row);
+        if (o != 0) t0 = f32_below_orderable(o);
+      }
+      sts_u32_volatile(L.thr0 + lane * 4, __float_as_uint(t0));
+      sts_u32_volatile(L.cnt0 + lane * 4, 0);
+      __syncwarp();
+      named_barrier(1 + quad, 32 * (p.halves + 1));  // release the filter warps into this item
+      // ---- consume until every filter warp of the quadrant has sent its end marker
+      int ends = 0;
+      long long idle_since = 0;
+      while (ends < p.halves) {
+        // the contiguous prefix of written entries among the next (up to) 32 reserved slots, one per lane
+        const uint32_t pending = lds_u32_volatile(ctrl) - head;
+        const uint32_t mine = head + lane;
+        uint4 ent = make_uint4(0, 0, 0, 0);
+        bool ready = false;
+        if (static_cast<uint32_t>(lane) < pending) {
+          ent = lds_v4_volatile(ring + (mine % TOPK_QCAP) * 16);
+          ready = ent.w == mine + 1;
+        }
+        const unsigned rb = __ballot_sync(0xffffffffu, ready);
+        const int ntake = rb == 0xffffffffu ? 32 : __ffs(~rb) - 1;  // leading ready entries
+        if (ntake == 0) {  // nothing yet (watchdog: a broken pipeline traps instead of hanging)
+          if (idle_since == 0) idle_since = clock64();
+          else if (clock64() - idle_since > 6000000000LL) __trap();
+          continue;
+        }
+        idle_since = 0;
+        const bool have = lane < ntake;
+        const bool is_end = have && ent.z == TOPK_END;
+        ends += __popc(__ballot_sync(0xffffffffu, is_end));
+        head += ntake;
+        if (lane == 0) sts_u32_volatile(ctrl + 4, head);  // the slots are free again (entries live in registers now)
+        const uint64_t key = (static_cast<uint64_t>(ent.y) << 32) | ent.x;
+        bool todo = have && !is_end;
+        if (ntake >= 4) {
+          // ---- burst (cold lists: every score is a candidate): one lane per entry; entries of one row take turns
+          unsigned m;
+          while ((m = __ballot_sync(0xffffffffu, todo)) != 0) {
+            bool filled = false;  // this lane's append completed its list: sort it
+            if (todo) {
+              const unsigned peers = __match_any_sync(m, ent.z);
+              if (__ffs(peers) - 1 == lane) {
+                const uint32_t ra = L.lists + ent.z * (LSTRIDE * 8);
+                const int c = static_cast<int>(lds_u32_volatile(L.cnt0 + ent.z * 4));
+                if (c < k) {
+                  sts_u64(ra + c * 8, key);
+                  sts_u32_volatile(L.cnt0 + ent.z * 4, c + 1);
+                  filled = c + 1 == k;
+                } else if (key > lds_u64(ra + (k - 1) * 8)) {
+                  int pos = k - 1;
+                  while (pos > 0) {
+                    const uint64_t prev = lds_u64(ra + (pos - 1) * 8);
+                    if (prev >= key) break;
+                    sts_u64(ra + pos * 8, prev);
+                    --pos;
+                  }
+                  sts_u64(ra + pos * 8, key);
+                  raise(L, static_cast<int>(ent.z), lds_u64(ra + (k - 1) * 8));
+                }
+                todo = false;
+              }
+            }
+            __syncwarp();
+            unsigned fm = __ballot_sync(0xffffffffu, filled);
+            for (; fm != 0; fm &= fm - 1) sort_list(L, static_cast<int>(__shfl_sync(0xffffffffu, ent.z, __ffs(fm) - 1)), k);
+          }
+        } else {
+          // ---- trickle (steady state): the whole warp inserts one entry at a time: position by ballot + popc,
+          //      shift by shuffle
+#pragma unroll 1
+          for (int j = 0; j < ntake; ++j) {
+            if (__shfl_sync(0xffffffffu, todo ? 1 : 0, j) == 0) continue;
+            const uint64_t kj = __shfl_sync(0xffffffffu, key, j);
+            const int r = static_cast<int>(__shfl_sync(0xffffffffu, ent.z, j));
+            const int c = static_cast<int>(lds_u32_volatile(L.cnt0 + r * 4));
+            const uint32_t la = L.lists + (r * LSTRIDE + lane) * 8;
+            if (c < k) {
+              if (lane == 0) {
+                sts_u64(L.lists + (r * LSTRIDE + c) * 8, kj);
+                sts_u32_volatile(L.cnt0 + r * 4, c + 1);
+              }
+              __syncwarp();
+              if (c + 1 == k) sort_list(L, r, k);
+              continue;
+            }
+            uint64_t lk[E];
+            int above = 0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+              lk[e] = (e * 32 + lane) < k ? lds_u64(la + e * 32 * 8) : 0ull;
+              above += __popc(__ballot_sync(0xffffffffu, lk[e] > kj));
+            }
+            if (above >= k) continue;  // not among the row's k best any more (the threshold rose after it was pushed)
+            uint64_t kth = 0;
+            uint64_t carry = 0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+              uint64_t up = __shfl_up_sync(0xffffffffu, lk[e], 1);
+              if (lane == 0) up = carry;
+              carry = __shfl_sync(0xffffffffu, lk[e], 31);
+              const int idx = e * 32 + lane;
+              const uint64_t nk = idx < above ? lk[e] : (idx == above ? kj : up);
+              if (idx < k) sts_u64(la + e * 32 * 8, nk);
+              const uint64_t cand = __shfl_sync(0xffffffffu, nk, (k - 1) & 31);
+              if (e == ((k - 1) >> 5)) kth = cand;
+            }
+            if (lane == 0) raise(L, r, kth);
+            __syncwarp();
+          }
+        }
+        __syncwarp();
+      }
+      // ---- write the 32 lists of this item (sorting the ones that never filled up); a whole-row item also clears
+      //      the row's unused split slots
+      const bool whole = w.tile_begin == 0 && w.tile_end == g.n_tiles;
+#pragma unroll 1
+      for (int r = 0; r < 32; ++r) {
+        const int grow = L.row_base + r;
+        if (grow >= g.M) break;
+        const int c = static_cast<int>(lds_u32_volatile(L.cnt0 + r * 4));
+        if (c < k && c > 1) sort_list(L, r, c);
+        uint64_t* dst = p.out + (static_cast<int64_t>(grow) * p.n_splits + w.n_split) * k;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int idx = e * 32 + lane;
+          if (idx < k) dst[idx] = idx < c ? lds_u64(L.lists + (r * LSTRIDE + idx) * 8) : 0ull;
+        }
+        if (whole)
+          for (int i = k + lane; i < p.n_splits * k; i += 32) dst[i] = 0ull;
+      }
+      __syncwarp();
+    }
   }
 };
 
@@ -679,41 +808,33 @@ struct TopkPlan {
   tc::GemmShape g;
   size_t ws_bytes;
   size_t thr_bytes;  // shared per-row bounds at the start of the workspace
-  int e;       // key registers per lane in the epilogue sort
-  int cap;     // candidate buffer capacity per list
-  int stride;  // list stride in keys
-  int ne;      // epilogue warps (8: two lists per row and N-split)
-  int slots;   // lists per row
+  int e;             // key registers per lane of the list warps (lists of up to 32 * e keys)
 };
 static void topk_plan(TopkPlan* pl, int64_t n_q, int64_t n_k, int64_t cols, int64_t k) {
   tc::fill_shape(&pl->g, 1, (int)n_q, (int)n_k, (int)cols, 256, 1, 1, false, tc::pick_cluster((int)n_q));
-  // k <= 16: 32 slots (>= 16 spare); k <= 48: 64 slots; k <= 64: 80 slots (shared memory bound), sorted as 128
-  if (k <= 16) {
-    pl->e = 1;
-    pl->cap = 32;
-    pl->stride = 32;
-    pl->ne = 8;
-  } else if (k <= 48) {
-    pl->e = 2;
-    pl->cap = 64;
-    pl->stride = 64;
-    pl->ne = 8;
-  } else {
-    pl->e = 4;
-    pl->cap = 80;
-    pl->stride = 81;
-    pl->ne = 4;
-  }
-  const int halves = pl->ne / 4;
-  int max_splits = static_cast<int>(MERGE_CAP * 32 / (k > 0 ? k : 1)) / halves;
+  pl->e = k <= 32 ? 1 : 2;
+  int max_splits = static_cast<int>(MERGE_CAP * 32 / (k > 0 ? k : 1));
   if (max_splits > 64) max_splits = 64;
   if (max_splits < 1) max_splits = 1;
-  // every N-split restarts its lists from an empty threshold (a burst of compactions): weigh that against wave balance
-  // lists share their thresholds (EpiTopK::Params::thr_shared), so a fresh N-split costs little: balance the waves
-  tc::choose_splits(&pl->g, device_sm_count(), max_splits, 1, 16.0);
-  pl->slots = pl->g.n_splits * halves;
+  // Two-class schedule: as many whole row-block groups as fill complete waves (their lists are never restarted);
+  // the groups of the last, partial wave are cut into column ranges so that it fills the machine as well.
+  tc::GemmShape& g = pl->g;
+  const int clusters = device_sm_count() / g.cl;
+  const int tail = g.m_groups % clusters;
+  int splits = tail > 0 ? clusters / tail : 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits > g.n_tiles) splits = g.n_tiles;
+  // (with three or more complete waves the imbalance is small and a restarted list costs more than it saves)
+  if (tail > 0 && splits > 1 && g.m_groups / clusters < 3) {
+    g.tail_groups = tail;
+    g.tail_tps = ceil_div(g.n_tiles, splits);
+    g.tail_splits = ceil_div(g.n_tiles, g.tail_tps);
+    g.n_splits = g.tail_splits;  // split slots per row in the candidate buffer
+    g.tiles_per_split = g.tail_tps;
+    g.num_items = (g.m_groups - tail) + tail * g.tail_splits;
+  }
   pl->thr_bytes = align_up(sizeof(uint32_t) * n_q, 256);
-  pl->ws_bytes = pl->thr_bytes + (pl->slots > 1 ? align_up(sizeof(uint64_t) * n_q * pl->slots * k, 256) : 0);
+  pl->ws_bytes = pl->thr_bytes + (pl->g.n_splits > 1 ? align_up(sizeof(uint64_t) * n_q * pl->g.n_splits * k, 256) : 0);
 }
 
 }  // namespace vast
@@ -763,7 +884,7 @@ extern "C" int vast_sim_topk(const void* q_op, const void* k_op, int64_t n_q, in
                workspace_bytes, pl.ws_bytes);
   uint32_t* thr_shared = static_cast<uint32_t*>(workspace);
   VAST_CUDA_OK(cudaMemsetAsync(thr_shared, 0, pl.thr_bytes, stream));
-  uint64_t* part = pl.slots > 1 ? reinterpret_cast<uint64_t*>(static_cast<char*>(workspace) + pl.thr_bytes) : out_keys;
+  uint64_t* part = pl.g.n_splits > 1 ? reinterpret_cast<uint64_t*>(static_cast<char*>(workspace) + pl.thr_bytes) : out_keys;
   int rc;
   auto run = [&](auto tag) -> int {
     using Epi = typename decltype(tag)::type;
@@ -777,19 +898,17 @@ extern "C" int vast_sim_topk(const void* q_op, const void* k_op, int64_t n_q, in
     if (r) return r;
     r = tc::make_tmap_2d(&P.tmB[0], k_op, VAST_BF16, n_k, cols, cols, 256 / pl.g.cl);
     if (r) return r;
-    P.epi = {part, static_cast<int>(k), pl.cap, pl.stride, pl.slots, static_cast<uint32_t>(col_offset), thr_shared};
-    return tc::launch_gemm<Epi, 256, STAGES, NE, false, STAGES2>(P, stream, "sim_topk_gemm", Epi::smem_bytes(pl.stride, NE));
+    P.epi = {part, static_cast<int>(k), pl.g.n_splits, NE / 4, static_cast<uint32_t>(col_offset), thr_shared};
+    return tc::launch_gemm<Epi, 256, STAGES, NE, false, STAGES2>(P, stream, "sim_topk_gemm", Epi::smem_bytes());
   };
-  // <epilogue, ring depth of a lone CTA (48 KB stages), ring depth of a CTA pair (32 KB stages), epilogue warps>
+  // <epilogue, ring depth of a lone CTA (48 KB stages), ring depth of a CTA pair (32 KB stages), filter warps>
   if (pl.e == 1)
     rc = run(TopkTag<EpiTopK<1>, 3, 5, 8>{});
-  else if (pl.e == 2)
-    rc = run(TopkTag<EpiTopK<2>, 2, 3, 8>{});
   else
-    rc = run(TopkTag<EpiTopK<4>, 3, 4, 4>{});
+    rc = run(TopkTag<EpiTopK<2>, 3, 4, 8>{});
   if (rc) return rc;
-  if (pl.slots > 1) {
-    topk_merge_kernel<<<blocks_for(n_q, 4), 128, 0, stream>>>(part, k, pl.slots * k, pl.slots, (int)k, n_q, (int)k, out_keys);
+  if (pl.g.n_splits > 1) {
+    topk_merge_kernel<<<blocks_for(n_q, 4), 128, 0, stream>>>(part, k, pl.g.n_splits * k, pl.g.n_splits, (int)k, n_q, (int)k, out_keys);
     VAST_LAUNCH_OK("topk_merge(splits)");
   }
   return VAST_OK;
