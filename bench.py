@@ -80,7 +80,7 @@ class ClockSampler:
                 for bit, nm in names.items():
                     if bit and (r & bit) == bit and bit & (bit - 1) == 0:
                         self.reasons.add(nm)
-                time.sleep(0.02)
+                time.sleep(0.002)
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"sampler_error:{type(e).__name__}")
 
@@ -145,19 +145,43 @@ def run_ours(args):
     pack_all = torch.empty(N_GLOBAL, 2 * DIM, dtype=torch.bfloat16, device=dev) if world > 1 else local_pack
     state = {"buf": None}
 
+    step_ctr = torch.zeros(1, dtype=torch.int64, device=dev)   # device-side Philox offset: graph replays draw fresh noise
+
     def step_dev(i):
         ft, fc = dev_sets[i % R]
         ops.pack_pair(ft, fc, out=local_pack)
         if world > 1:
             dist.all_gather_into_tensor(pack_all, local_pack)
-        state["buf"] = ops.omc_step(pack_all, bs, rank * bs, temp, 0.1, 1e-4, seed=1234, offset=i, need_sample=True,
-                                    need_grad=True, buffers=state["buf"])
+        state["buf"] = ops.omc_step(pack_all, bs, rank * bs, temp, 0.1, 1e-4, seed=1234, offset=0, need_sample=True,
+                                    need_grad=True, buffers=state["buf"], step_counter=step_ctr)
 
     for i in range(W):
         step_dev(i)
+    # The step is a fixed sequence of enqueue-only launches: capture it once per input set in a CUDA graph
+    # (the all-gather included when N > 1) and time graph replays; falls back to eager launches if capture fails.
+    run_step, mode = step_dev, "eager launches"
+    if not args.no_graph:
+        try:
+            gstream = torch.cuda.Stream()
+            graphs = []
+            gstream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(gstream):
+                for i in range(R):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=gstream):
+                        step_dev(i)
+                    graphs.append(g)
+            torch.cuda.current_stream().wait_stream(gstream)
+            torch.cuda.synchronize()
+            run_step, mode = (lambda i: graphs[i % R].replay()), f"CUDA-graph replay ({R} graphs, one per input set)"
+        except Exception as e:  # pragma: no cover
+            torch.cuda.synchronize()
+            mode = f"eager launches (graph capture failed: {type(e).__name__})"
+    for i in range(W):
+        run_step(i)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms = timed_loop(torch, dist, world, step_dev, K)
+    ms = timed_loop(torch, dist, world, run_step, K)
     clocks = sampler.stop()
     loss_val = state["buf"]["loss"].item()
     value = N_GLOBAL * K / (ms * 1e-3)
@@ -193,31 +217,50 @@ def run_ours(args):
                 "step_algorithmic_tflops": round(8.0 * bs * N_GLOBAL * DIM * world / (ms / K * 1e-3) / 1e12 / world, 1),
                 "step_frac": round(8.0 * bs * N_GLOBAL * DIM / (ms / K * 1e-3) / 1e12 / peaks["tf_sustained"], 4)}
 
-    # ---- e2e: public API, pinned host inputs (bf16), H2D + D2H inside the timed region
+    # ---- e2e: public API, pinned host inputs (bf16), H2D + D2H inside the timed region.  Like the reference's
+    # PrefetchLoader (data/loader.py:90-125) the next step's inputs are copied on a side stream while the current
+    # step computes; every timed step issues one H2D of a full input set and reads its loss back (a host sync).
     pin = [(t.bfloat16().pin_memory(), c.bfloat16().pin_memory()) for t, c in host_sets]
-    d_t = torch.empty(bs, DIM, dtype=torch.bfloat16, device=dev)
-    d_c = torch.empty(bs, DIM, dtype=torch.bfloat16, device=dev)
+    dbuf = [(torch.empty(bs, DIM, dtype=torch.bfloat16, device=dev), torch.empty(bs, DIM, dtype=torch.bfloat16, device=dev))
+            for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    ev_in = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_free = [torch.cuda.Event(), torch.cuda.Event()]
     temp_param = torch.nn.Parameter(torch.tensor(TEMP, device=dev))
     sink = {"loss": 0.0}
 
+    def prefetch(i):
+        b = i % 2
+        copy_stream.wait_event(ev_free[b])
+        with torch.cuda.stream(copy_stream):
+            dbuf[b][0].copy_(pin[i % R][0], non_blocking=True)
+            dbuf[b][1].copy_(pin[i % R][1], non_blocking=True)
+            ev_in[b].record(copy_stream)
+
     def step_e2e(i):
-        ht, hc = pin[i % R]
-        d_t.copy_(ht, non_blocking=True)
-        d_c.copy_(hc, non_blocking=True)
-        ft = d_t.detach().requires_grad_()
-        fc = d_c.detach().requires_grad_()
+        b = i % 2
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev_in[b])
+        ft = dbuf[b][0].detach().requires_grad_()
+        fc = dbuf[b][1].detach().requires_grad_()
         temp_param.grad = None
         loss, neg_text, neg_cond = vast_b200.omc_loss_and_negatives(fc, ft, temp_param, rank=rank, world_size=world)
         loss.backward()
-        sink["loss"] = loss.item()  # D2H read of the step's result
+        ev_free[b].record(cur)
+        prefetch(i + 1)              # H2D of the next step's inputs overlaps this step's kernels
+        sink["loss"] = loss.item()   # D2H read of the step's result
 
+    for e in ev_free:
+        e.record(torch.cuda.current_stream())
+    prefetch(0)
     for i in range(W):
         step_e2e(i)
     Ke = min(K, 200)
-    ms_e = timed_loop(torch, dist, world, step_e2e, Ke)
+    ms_e = timed_loop(torch, dist, world, lambda i: step_e2e(i + W), Ke)
     e2e = {"value": N_GLOBAL * Ke / (ms_e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": 2 * bs * DIM * 2,
            "d2h_bytes_per_step": 4, "ms_per_step": ms_e / Ke, "steps": Ke,
-           "api": "vast_b200.omc_loss_and_negatives(...) + loss.backward() + loss.item()"}
+           "api": "vast_b200.omc_loss_and_negatives(...) + loss.backward() + loss.item(); next step's H2D prefetched on a "
+                  "side stream (pinned host memory)"}
 
     # ---- retrieval (config 5): streaming similarity + top-16, columns sharded over the ranks
     ret = None
@@ -264,6 +307,7 @@ def run_ours(args):
                                    f"{N_GLOBAL}, D={DIM}, tau={TEMP}, label smoothing 0.1, bf16-in/fp32-accumulate, "
                                    f"{world} rank(s) x {bs} rows, one packed NCCL all-gather per step",
                        "l2": f"inputs rotate over {R} distinct sets ({R * per_set >> 20} MiB > 126 MB L2)",
+                       "launch": mode,
                        "loss_last_step": loss_val},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * K, "roofline": roofline,
             "cpu_baseline": cpu, "retrieval": ret,
@@ -343,6 +387,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-retrieval", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

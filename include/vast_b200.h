@@ -122,6 +122,9 @@ VAST_API size_t vast_omc_workspace_bytes(int64_t bs, int64_t n_total, int64_t di
  *               chunk is drawn by inverse CDF, and the constant floor is the uniform component of a
  *               two-part mixture; all randomness is Philox4x32-10(seed, offset), restated by
  *               oracle/spec.py::hardneg_hier_sample.
+ *   step_counter optional DEVICE uint64: the Philox offset actually used is offset + *step_counter, and the
+ *               library adds 1 to *step_counter at the end of the step (stream-ordered).  A step captured
+ *               in a CUDA graph therefore draws fresh noise on every replay.
  *   debug_noise [2, bs, n_total] f32 or NULL: caller-supplied Exp(1) variates; the draw is then
  *               literally argmax_j w_j / debug_noise_j (index 0 = cond2t) -- index-exact parity tests
  *               against the reference's own draws.  Implies VAST_OMC_TWO_PASS.
@@ -134,7 +137,7 @@ VAST_API size_t vast_omc_workspace_bytes(int64_t bs, int64_t n_total, int64_t di
  * The [bs, n_total] logit matrices are never written to HBM. */
 VAST_API int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int64_t dim, int64_t row_offset,
                   float contra_temp, const float* contra_temp_dev, float label_smoothing, float weight_floor,
-                  uint64_t seed, uint64_t offset, const float* debug_noise, int flags,
+                  uint64_t seed, uint64_t offset, uint64_t* step_counter, const float* debug_noise, int flags,
                   float* loss, int64_t* neg_idx, float* grad_cond, float* grad_t, float* grad_temp,
                   float* lse, void* workspace, size_t workspace_bytes, vast_stream_t stream);
 

@@ -226,3 +226,37 @@ def test_loss_only_and_errors():
         ops.omc_step(pack, 40, 8, 0.07)  # local rows outside [0, n_total)
     with pytest.raises(RuntimeError):
         ops.omc_step(pack, 40, 0, -1.0)
+
+
+def test_step_counter_advances_the_philox_offset():
+    """A device-side step counter makes the step replayable (CUDA graphs) with fresh noise: call i with counter c
+    draws exactly what a call with offset + c draws, and the library increments the counter."""
+    from vast_b200 import ops
+    gen = torch.Generator().manual_seed(21)
+    n, d = 160, 64
+    t = torch.nn.functional.normalize(torch.randn(n, d, generator=gen), dim=-1)
+    c = torch.nn.functional.normalize(t + 0.8 * torch.randn(n, d, generator=gen), dim=-1)
+    pack = ops.pack_pair(t.cuda(), c.cuda())
+    ctr = torch.zeros(1, dtype=torch.int64, device="cuda")
+    a0 = ops.omc_step(pack, n, 0, 0.07, seed=5, offset=40, step_counter=ctr)["neg_idx"].clone()
+    a1 = ops.omc_step(pack, n, 0, 0.07, seed=5, offset=40, step_counter=ctr)["neg_idx"].clone()
+    assert ctr.item() == 2
+    b0 = ops.omc_step(pack, n, 0, 0.07, seed=5, offset=40)["neg_idx"]
+    b1 = ops.omc_step(pack, n, 0, 0.07, seed=5, offset=41)["neg_idx"]
+    assert torch.equal(a0, b0) and torch.equal(a1, b1) and not torch.equal(a0, a1)
+    # and the same through a captured graph
+    g = torch.cuda.CUDAGraph()
+    buf = ops.omc_step(pack, n, 0, 0.07, seed=5, offset=40, step_counter=ctr)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            buf = ops.omc_step(pack, n, 0, 0.07, seed=5, offset=40, step_counter=ctr, buffers=buf)
+    torch.cuda.current_stream().wait_stream(s)
+    ctr.zero_()
+    g.replay()
+    r0 = buf["neg_idx"].clone()
+    g.replay()
+    r1 = buf["neg_idx"].clone()
+    torch.cuda.synchronize()
+    assert torch.equal(r0, b0) and torch.equal(r1, b1) and ctr.item() == 2

@@ -139,6 +139,7 @@ struct EpiSoft {
     int tgt_offset;
     int row_offset;  // global row of local row 0 (decorrelates ranks that share a seed)
     uint32_t seed_lo, seed_hi, off_lo, off_hi;
+    const unsigned long long* step_ctr;  // optional device counter added to the Philox offset
     const float* noise;  // ELEM only: [2][M][N] caller-supplied Exp(1) noise
     int64_t noise_ld;
     int do_sample;
@@ -149,8 +150,15 @@ struct EpiSoft {
   const Params& p;
   float ref, l, bw, be, scale2;
   int bidx, tcol;
+  uint32_t off_lo, off_hi;
   uint4 rnd;
-  __device__ EpiSoft(const Params& p_, uint8_t*) : p(p_) { scale2 = p.temp_dev ? kLog2e / __ldg(p.temp_dev) : p.scale2; }
+  __device__ EpiSoft(const Params& p_, uint8_t*) : p(p_) {
+    scale2 = p.temp_dev ? kLog2e / __ldg(p.temp_dev) : p.scale2;
+    unsigned long long off = (static_cast<unsigned long long>(p.off_hi) << 32) | p.off_lo;
+    if (p.step_ctr != nullptr) off += *p.step_ctr;
+    off_lo = static_cast<uint32_t>(off);
+    off_hi = static_cast<uint32_t>(off >> 32);
+  }
   __device__ __forceinline__ void item_begin(const tc::ItemCtx& c) {
     ref = c.row_valid ? p.ref2[static_cast<int64_t>(c.prob) * c.M + c.row] : 0.f;
     l = 0.f;
@@ -224,8 +232,8 @@ struct EpiSoft {
       const int gc = col0 >> 5;  // global chunk index
       // one Philox call serves four chunks; a warp's column ranges start at multiples of 128 columns
       if ((gc & 3) == 0)
-        rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(gc >> 2), static_cast<uint32_t>(p.row_offset + c.row), p.off_lo,
-                                       (p.off_hi << 1) | static_cast<uint32_t>(c.prob)),
+        rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(gc >> 2), static_cast<uint32_t>(p.row_offset + c.row), off_lo,
+                                       (off_hi << 1) | static_cast<uint32_t>(c.prob)),
                             make_uint2(p.seed_lo, p.seed_hi));
       const uint32_t w = (gc & 3) == 0 ? rnd.x : (gc & 3) == 1 ? rnd.y : (gc & 3) == 2 ? rnd.z : rnd.w;
       const float e = expo_from_bits(w);
@@ -394,6 +402,7 @@ struct RowStatParams {
   const __half* P;
   int64_t ldp;
   uint32_t seed_lo, seed_hi, off_lo, off_hi;
+  const unsigned long long* step_ctr;
   const float* ksum;  // [2][D]
   const __nv_bfloat16* pack;
   float4* rowstat;  // [2][M]
@@ -475,8 +484,10 @@ __global__ void __launch_bounds__(256) omc_row_stats_kernel(const RowStatParams 
     if (p.elem_mode) {
       pick = bidx;
     } else if (p.N > 1) {
-      const uint4 rnd = philox4x32_10(make_uint4(0xFFFFFFFFu, static_cast<uint32_t>(p.row_offset + row), p.off_lo,
-                                                 (p.off_hi << 1) | static_cast<uint32_t>(prob)),
+      unsigned long long off = (static_cast<unsigned long long>(p.off_hi) << 32) | p.off_lo;
+      if (p.step_ctr != nullptr) off += *p.step_ctr;
+      const uint4 rnd = philox4x32_10(make_uint4(0xFFFFFFFFu, static_cast<uint32_t>(p.row_offset + row), static_cast<uint32_t>(off),
+                                                 (static_cast<uint32_t>(off >> 32) << 1) | static_cast<uint32_t>(prob)),
                                       make_uint2(p.seed_lo, p.seed_hi));
       const float u_in = unit_from_bits(rnd.x), u_mix = unit_from_bits(rnd.y), u_uni = unit_from_bits(rnd.z);
       // mixture: softmax part (mass l, column drawn in proportion to Pt) vs floor part (uniform, mass floor*ltot*(N-1))
@@ -692,7 +703,8 @@ __global__ void __launch_bounds__(256) omc_final_kernel(const float* __restrict_
                                                        int dslots, int rows2, int M, float inv_tau,
                                                        const float* __restrict__ temp_dev, float eps_ls, float c_sm,
                                                        float2* __restrict__ blockpart, int* __restrict__ ticket,
-                                                       float* __restrict__ loss, float* __restrict__ grad_temp) {
+                                                       float* __restrict__ loss, float* __restrict__ grad_temp,
+                                                       unsigned long long* __restrict__ step_ctr) {
   __shared__ float red[2][256];
   __shared__ int is_last;
   const int r = blockIdx.x * 256 + threadIdx.x;
@@ -749,6 +761,7 @@ __global__ void __launch_bounds__(256) omc_final_kernel(const float* __restrict_
     const float scale = 1.0f / (2.0f * M);
     loss[0] = red[0][0] * scale;
     if (grad_temp) grad_temp[0] = red[1][0] * scale;
+    if (step_ctr) *step_ctr += 1;  // the next step (e.g. the next replay of a captured graph) draws fresh noise
   }
 }
 
@@ -819,7 +832,8 @@ extern "C" size_t vast_omc_workspace_bytes(int64_t bs, int64_t n_total, int64_t 
 
 extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int64_t dim, int64_t row_offset,
                              float contra_temp, const float* contra_temp_dev, float label_smoothing,
-                             float weight_floor, uint64_t seed, uint64_t offset, const float* debug_noise, int flags,
+                             float weight_floor, uint64_t seed, uint64_t offset, uint64_t* step_counter,
+                             const float* debug_noise, int flags,
                              float* loss, int64_t* neg_idx, float* grad_cond, float* grad_t, float* grad_temp, float* lse,
                              void* workspace, size_t workspace_bytes, vast_stream_t stream) {
   VAST_REQUIRE(pack && loss && workspace, VAST_ERR_INVALID, "omc_step: null pointer");
@@ -919,6 +933,7 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
     P.epi.seed_hi = static_cast<uint32_t>(seed >> 32);
     P.epi.off_lo = static_cast<uint32_t>(offset);
     P.epi.off_hi = static_cast<uint32_t>(offset >> 32);
+    P.epi.step_ctr = reinterpret_cast<const unsigned long long*>(step_counter);
     P.epi.noise = debug_noise;
     P.epi.noise_ld = n_total;
     P.epi.do_sample = need_sample ? 1 : 0;
@@ -973,6 +988,7 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
     R.seed_hi = static_cast<uint32_t>(seed >> 32);
     R.off_lo = static_cast<uint32_t>(offset);
     R.off_hi = static_cast<uint32_t>(offset >> 32);
+    R.step_ctr = reinterpret_cast<const unsigned long long*>(step_counter);
     R.ksum = ksum;
     R.pack = pk;
     R.rowstat = rowstat;
@@ -1042,7 +1058,8 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
   VAST_TIMED(stream, "omc_final",
              (omc_final_kernel<<<ceil_div(2 * M, 256), 256, 0, stream>>>(rowce, rowstat, zt, need_grad ? dotq : nullptr, pl.dslots,
                                                                         2 * M, M, inv_tau, contra_temp_dev, label_smoothing, c_sm,
-                                                                        blockpart, &wflags[1], loss, need_grad ? grad_temp : nullptr)));
+                                                                        blockpart, &wflags[1], loss, need_grad ? grad_temp : nullptr,
+                                                                        reinterpret_cast<unsigned long long*>(step_counter))));
   VAST_LAUNCH_OK("omc_final");
   return VAST_OK;
 }

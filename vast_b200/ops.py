@@ -146,13 +146,15 @@ OMC_TWO_PASS = 1
 def omc_step(pack: torch.Tensor, bs: int, row_offset: int, contra_temp, label_smoothing: float = 0.1,
              weight_floor: float = 1e-4, seed: int = 0, offset: int = 0, need_sample: bool = True,
              need_grad: bool = True, debug_noise: torch.Tensor | None = None, want_lse: bool = False,
-             buffers: dict | None = None, two_pass: bool = False):
+             buffers: dict | None = None, two_pass: bool = False, step_counter: torch.Tensor | None = None):
     """Fused OMC step (vast.py:405-440 + backward) on the packed, gathered features.
     Returns dict(loss[1], neg_idx[2,bs] | None, grad_cond, grad_t, grad_temp | None, lse | None).
     `buffers` (a dict returned by an earlier call with the same shapes/flags) re-uses outputs + workspace.
     two_pass: evaluate the logits twice (VAST_OMC_TWO_PASS) instead of the default single pass with the
     on-device fallback; debug_noise [2, bs, n_total] (Exp(1) variates) switches to the reference-literal
-    per-element race argmax_j w_j / E_j for index-exact tests."""
+    per-element race argmax_j w_j / E_j for index-exact tests.
+    step_counter: optional device int64[1]; the Philox offset used is offset + step_counter[0] and the step
+    increments it (so a CUDA-graph replay of the step draws fresh noise)."""
     require_cuda(pack)
     assert pack.dtype == torch.bfloat16 and pack.is_contiguous() and pack.dim() == 2 and pack.shape[1] % 2 == 0
     n_total, dim = pack.shape[0], pack.shape[1] // 2
@@ -179,7 +181,7 @@ def omc_step(pack: torch.Tensor, bs: int, row_offset: int, contra_temp, label_sm
         contra_temp = 0.0
     check(lib().vast_omc_step(ptr(pack), bs, n_total, dim, row_offset, float(contra_temp), ptr(temp_dev), float(label_smoothing),
                               float(weight_floor), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1),
-                              ptr(debug_noise), OMC_TWO_PASS if two_pass else 0, ptr(loss), ptr(neg), ptr(gc), ptr(gt),
+                              ptr(step_counter), ptr(debug_noise), OMC_TWO_PASS if two_pass else 0, ptr(loss), ptr(neg), ptr(gc), ptr(gt),
                               ptr(gtemp), ptr(lse),
                               ptr(ws), ws.numel(), stream_ptr()), "omc_step")
     return dict(loss=loss, neg_idx=neg, grad_cond=gc, grad_t=gt, grad_temp=gtemp, lse=lse, _ws=(ws, temp_dev))
