@@ -313,9 +313,17 @@ def run_ours(args):
             "cpu_baseline": cpu, "retrieval": ret,
         }
         print(json.dumps(line), flush=True)
+    # teardown: captured graphs hold NCCL kernels; drop them before the process group goes away, and leave
+    # without waiting for communicator destruction (it can block after graph-captured collectives)
+    run_step = None
+    graphs = None
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def cpu_contrastive(sample_steps=3, budget_s=None, steps=None, warmup=1):

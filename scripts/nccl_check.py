@@ -1,0 +1,50 @@
+"""Multi-GPU correctness check (run under torchrun, one rank per GPU, NCCL):
+  * omc_loss_and_negatives with the packed all-gather == the oracle evaluated on the gathered features
+  * column-sharded retrieval_topk + candidate all-gather + merge == the single-GPU result
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 scripts/nccl_check.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+import vast_b200
+from oracle import spec
+
+bs, d, temp = 192, 256, 0.07
+n = bs * world
+g = torch.Generator().manual_seed(7)
+t = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=-1)
+c = torch.nn.functional.normalize(t + 0.8 * torch.randn(n, d, generator=g), dim=-1)
+sl = slice(rank * bs, (rank + 1) * bs)
+ft = t[sl].cuda().requires_grad_()
+fc = c[sl].cuda().requires_grad_()
+tau = torch.nn.Parameter(torch.tensor(temp, device="cuda"))
+loss, neg_text, neg_cond = vast_b200.omc_loss_and_negatives(fc, ft, tau)      # rank / world from the process group
+loss.backward()
+tb, cb = t.bfloat16().float().numpy(), c.bfloat16().float().numpy()
+o = spec.omc_loss(cb[sl], tb[sl], tb, cb, temp, rank=rank)
+ok = abs(loss.item() - o["loss"]) < 1e-3 * abs(o["loss"])
+for got, want in ((ft.grad, o["grad_t"]), (fc.grad, o["grad_cond"])):
+    ok &= np.linalg.norm(got.cpu().numpy() - want) < 1e-3 * np.linalg.norm(want)
+ok &= abs(tau.grad.item() - o["grad_temp"]) < 1e-3 * abs(o["grad_temp"])
+tgt = torch.arange(rank * bs, (rank + 1) * bs)
+ok &= bool((neg_text.cpu() != tgt).all() and (neg_cond.cpu() != tgt).all() and (neg_text.cpu() < n).all())
+
+# retrieval: sharded == single
+nt, nv, k = 700, 3001, 16
+q = torch.nn.functional.normalize(torch.randn(nt, d, generator=g), dim=-1).cuda()
+v = torch.nn.functional.normalize(torch.randn(nv, d, generator=g), dim=-1).cuda()
+for mode in ("bf16", "fp32"):
+    v1, i1 = vast_b200.retrieval_topk(q, v, k, mode=mode)
+    v2, i2 = vast_b200.retrieval_topk(q, v, k, mode=mode, shard=(rank, world))
+    ok &= bool(torch.equal(i1, i2))
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("nccl_check", "OK" if flag.item() == 1 else "FAILED", "world", world, "loss", loss.item(), flush=True)
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1 else 1)
