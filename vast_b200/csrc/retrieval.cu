@@ -147,6 +147,13 @@ struct EpiTopK {
   uint32_t base, thr_addr, ring, ctrl;
   int quad, row_valid;
   float thr;
+  // Cold start (rows without a threshold, k <= 16): the first tile of an item is NOT pushed score by score -- each
+  // lane runs its 128 scores through a 16-deep sorted register network (uniform, branch-free) and pushes only the
+  // survivors, with their k-th as the first threshold.  Pushing everything until the list warp has caught up costs
+  // ~0.2-0.4 ms per item (measured); the network costs ~5 us.
+  float ts[16];
+  uint32_t ti[16];
+  int prime_left;  // chunks of the cold tile still to absorb (0 = normal operation)
   __device__ EpiTopK(const Params& p_, uint8_t* smem) : p(p_) {
     base = ptx::smem_u32(smem);
     quad = (threadIdx.x >> 5) & 3;
@@ -155,12 +162,37 @@ struct EpiTopK {
     ctrl = base + CTRL_OFF + quad * 8;
     thr = -INFINITY;
     row_valid = 0;
+    prime_left = 0;
   }
   // ---------------------------------------------------------------- filter warps
   __device__ __forceinline__ void item_begin(const tc::ItemCtx& c) {
     row_valid = c.row_valid;
     named_barrier(1 + quad, 32 * (p.halves + 1));  // the list warp has reset lists and thresholds for this item
     thr = lds_f32_volatile(thr_addr);
+    const bool cold = __any_sync(0xffffffffu, row_valid && thr == -INFINITY);
+    prime_left = (cold && p.k <= 16) ? 256 / (32 * p.halves) : 0;  // the chunks of one tile seen by this warp
+    if (prime_left > 0) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        ts[q] = -INFINITY;
+        ti[q] = 0;
+      }
+    }
+  }
+  // push what the register network kept (scores above the row's bound), its k-th becomes the threshold
+  __device__ __forceinline__ void prime_flush(int lane) {
+    prime_left = 0;
+    if (!row_valid) return;
+    float kth = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      if (ts[q] > thr) push(make_key(ts[q], ti[q]), static_cast<uint32_t>(lane));
+      if (q == p.k - 1) kth = ts[q];
+    }
+    if (kth > -INFINITY) {  // k scores of this row's columns are >= kth: ties must stay admissible
+      const float b = f32_below_orderable(f32_orderable(kth));
+      if (b > thr) thr = b;
+    }
   }
   __device__ __forceinline__ void prefetch(const tc::ItemCtx&, int) {}
   __device__ __forceinline__ void advance(const tc::ItemCtx&, int, bool) {}
@@ -185,6 +217,27 @@ struct EpiTopK {
       for (int i = 0; i < 32; ++i)
         if (i >= nvalid) s[i] = -INFINITY;
     }
+    if (prime_left > 0) {  // warp-uniform
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float x = s[i];
+        uint32_t xi = gcol + i;
+        bool ins = false;  // once x has found its place everything behind it moves down one position
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {  // strict >: of equal scores the earlier column stays in front
+          const bool sw = ins || x > ts[q];
+          ins = sw;
+          const float tv = ts[q];
+          const uint32_t tx = ti[q];
+          ts[q] = sw ? x : tv;
+          ti[q] = sw ? xi : tx;
+          x = sw ? tv : x;
+          xi = sw ? tx : xi;
+        }
+      }
+      if (--prime_left == 0) prime_flush(c.lane);
+      return;
+    }
     const float t = row_valid ? fmaxf(thr, lds_f32_volatile(thr_addr)) : INFINITY;  // thresholds only rise
     thr = t;
     float gm[4];
@@ -205,6 +258,7 @@ struct EpiTopK {
     }
   }
   __device__ __forceinline__ void item_end(const tc::ItemCtx& c) {
+    if (prime_left > 0) prime_flush(c.lane);  // the item ended inside its first tile
     __syncwarp();
     if (c.lane == 0) push(0ull, TOPK_END);
   }
@@ -239,6 +293,30 @@ struct EpiTopK {
     sts_u32_volatile(L.thr0 + r * 4, __float_as_uint(f32_below_orderable(ko)));
     const int grow = L.row_base + r;
     if (L.p.thr_shared != nullptr && grow < L.M) atomicMax(L.p.thr_shared + grow, ko);
+  }
+
+  // One lane inserts `key` into its row's FULL sorted list of k <= KL keys: all keys to registers (independent loads),
+  // the insert position from KL compares, only the shifted tail is written back.  No dependent load/store chain and no
+  // divergence between the lanes of a burst (a walk from the list's end costs ~60 cycles per shifted key).
+  template <int KL>
+  __device__ __forceinline__ static uint64_t insert_regs(uint32_t ra, int k, uint64_t key, uint64_t* dropped = nullptr) {
+    uint64_t a[KL];
+#pragma unroll
+    for (int i = 0; i < KL; ++i) a[i] = i < k ? lds_u64(ra + i * 8) : 0ull;
+    uint64_t kth = 0;
+    bool prev_gt = true;  // a[-1] > key by convention
+#pragma unroll
+    for (int i = 0; i < KL; ++i) {
+      const bool gt = a[i] > key;
+      const uint64_t nv = gt ? a[i] : (prev_gt ? key : a[i > 0 ? i - 1 : 0]);
+      if (!gt && i < k) sts_u64(ra + i * 8, nv);
+      if (i == k - 1) {
+        kth = nv;
+        if (dropped != nullptr) *dropped = gt ? key : a[i];  // what no longer fits into these k slots
+      }
+      prev_gt = gt;
+    }
+    return kth;
   }
 
   __device__ static void aux_main(const Params& p, uint8_t* smem, const tc::GemmShape& g, int cluster_id, int num_clusters,
@@ -296,8 +374,9 @@ struct EpiTopK {
         if (lane == 0) sts_u32_volatile(ctrl + 4, head);  // the slots are free again (entries live in registers now)
         const uint64_t key = (static_cast<uint64_t>(ent.y) << 32) | ent.x;
         bool todo = have && !is_end;
-        if (ntake >= 4) {
-          // ---- burst (cold lists: every score is a candidate): one lane per entry; entries of one row take turns
+        {
+          // ---- one lane per entry; entries of one row take turns.  (Cold lists -- every score is a candidate -- arrive
+          //      32 at a time, the steady state delivers one or two; the same code serves both.)
           unsigned m;
           while ((m = __ballot_sync(0xffffffffu, todo)) != 0) {
             bool filled = false;  // this lane's append completed its list: sort it
@@ -311,15 +390,17 @@ struct EpiTopK {
                   sts_u32_volatile(L.cnt0 + ent.z * 4, c + 1);
                   filled = c + 1 == k;
                 } else if (key > lds_u64(ra + (k - 1) * 8)) {
-                  int pos = k - 1;
-                  while (pos > 0) {
-                    const uint64_t prev = lds_u64(ra + (pos - 1) * 8);
-                    if (prev >= key) break;
-                    sts_u64(ra + pos * 8, prev);
-                    --pos;
+                  uint64_t kth;
+                  if (k <= 16) {
+                    kth = insert_regs<16>(ra, k, key);
+                  } else if (k <= 32) {
+                    kth = insert_regs<32>(ra, k, key);
+                  } else {  // 33..64 keys: two segments of <= 32; what drops out of the first heads the second
+                    uint64_t second = key;
+                    if (key > lds_u64(ra + 31 * 8)) insert_regs<32>(ra, 32, key, &second);
+                    kth = insert_regs<32>(ra + 32 * 8, k - 32, second);
                   }
-                  sts_u64(ra + pos * 8, key);
-                  raise(L, static_cast<int>(ent.z), lds_u64(ra + (k - 1) * 8));
+                  raise(L, static_cast<int>(ent.z), kth);
                 }
                 todo = false;
               }
@@ -327,49 +408,6 @@ struct EpiTopK {
             __syncwarp();
             unsigned fm = __ballot_sync(0xffffffffu, filled);
             for (; fm != 0; fm &= fm - 1) sort_list(L, static_cast<int>(__shfl_sync(0xffffffffu, ent.z, __ffs(fm) - 1)), k);
-          }
-        } else {
-          // ---- trickle (steady state): the whole warp inserts one entry at a time: position by ballot + popc,
-          //      shift by shuffle
-#pragma unroll 1
-          for (int j = 0; j < ntake; ++j) {
-            if (__shfl_sync(0xffffffffu, todo ? 1 : 0, j) == 0) continue;
-            const uint64_t kj = __shfl_sync(0xffffffffu, key, j);
-            const int r = static_cast<int>(__shfl_sync(0xffffffffu, ent.z, j));
-            const int c = static_cast<int>(lds_u32_volatile(L.cnt0 + r * 4));
-            const uint32_t la = L.lists + (r * LSTRIDE + lane) * 8;
-            if (c < k) {
-              if (lane == 0) {
-                sts_u64(L.lists + (r * LSTRIDE + c) * 8, kj);
-                sts_u32_volatile(L.cnt0 + r * 4, c + 1);
-              }
-              __syncwarp();
-              if (c + 1 == k) sort_list(L, r, k);
-              continue;
-            }
-            uint64_t lk[E];
-            int above = 0;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-              lk[e] = (e * 32 + lane) < k ? lds_u64(la + e * 32 * 8) : 0ull;
-              above += __popc(__ballot_sync(0xffffffffu, lk[e] > kj));
-            }
-            if (above >= k) continue;  // not among the row's k best any more (the threshold rose after it was pushed)
-            uint64_t kth = 0;
-            uint64_t carry = 0;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-              uint64_t up = __shfl_up_sync(0xffffffffu, lk[e], 1);
-              if (lane == 0) up = carry;
-              carry = __shfl_sync(0xffffffffu, lk[e], 31);
-              const int idx = e * 32 + lane;
-              const uint64_t nk = idx < above ? lk[e] : (idx == above ? kj : up);
-              if (idx < k) sts_u64(la + e * 32 * 8, nk);
-              const uint64_t cand = __shfl_sync(0xffffffffu, nk, (k - 1) & 31);
-              if (e == ((k - 1) >> 5)) kth = cand;
-            }
-            if (lane == 0) raise(L, r, kth);
-            __syncwarp();
           }
         }
         __syncwarp();
@@ -438,6 +476,45 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const uint64_t* __restr
     }
     if (lane == 0) out[row * k_out + r] = wbest;
   }
+}
+
+// Small merges (parts * k_in <= 32 * E keys, the common case: a few N-splits or GPUs): one bitonic sort per row.
+template <int E>
+__global__ void __launch_bounds__(128) topk_merge_sort_kernel(const uint64_t* __restrict__ in, int64_t part_stride,
+                                                             int64_t row_stride, int parts, int k_in, int64_t n_rows,
+                                                             int k_out, uint64_t* __restrict__ out) {
+  const int64_t row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const int total = parts * k_in;
+  uint64_t key[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int idx = e * 32 + lane;
+    key[e] = idx < total ? in[(idx / k_in) * part_stride + row * row_stride + (idx % k_in)] : 0ull;
+  }
+  sort_desc<E>(key, lane);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int idx = e * 32 + lane;
+    if (idx < k_out) out[row * k_out + idx] = key[e];
+  }
+}
+
+static int launch_topk_merge(const uint64_t* in, int64_t part_stride, int64_t row_stride, int parts, int k_in, int64_t n_rows,
+                             int k_out, uint64_t* out, cudaStream_t stream) {
+  const unsigned blocks = static_cast<unsigned>(ceil_div64(n_rows, 4));
+  const int total = parts * k_in;
+  if (total <= 32 && k_out <= 32)
+    topk_merge_sort_kernel<1><<<blocks, 128, 0, stream>>>(in, part_stride, row_stride, parts, k_in, n_rows, k_out, out);
+  else if (total <= 64 && k_out <= 64)
+    topk_merge_sort_kernel<2><<<blocks, 128, 0, stream>>>(in, part_stride, row_stride, parts, k_in, n_rows, k_out, out);
+  else if (total <= 128 && k_out <= 128)
+    topk_merge_sort_kernel<4><<<blocks, 128, 0, stream>>>(in, part_stride, row_stride, parts, k_in, n_rows, k_out, out);
+  else
+    topk_merge_kernel<<<blocks, 128, 0, stream>>>(in, part_stride, row_stride, parts, k_in, n_rows, k_out, out);
+  VAST_LAUNCH_OK("topk_merge");
+  return VAST_OK;
 }
 
 __global__ void topk_unpack_kernel(const uint64_t* __restrict__ keys, int64_t count, float* __restrict__ vals,
@@ -824,8 +901,7 @@ static void topk_plan(TopkPlan* pl, int64_t n_q, int64_t n_k, int64_t cols, int6
   int splits = tail > 0 ? clusters / tail : 1;
   if (splits > max_splits) splits = max_splits;
   if (splits > g.n_tiles) splits = g.n_tiles;
-  // (with three or more complete waves the imbalance is small and a restarted list costs more than it saves)
-  if (tail > 0 && splits > 1 && g.m_groups / clusters < 3) {
+  if (tail > 0 && splits > 1) {
     g.tail_groups = tail;
     g.tail_tps = ceil_div(g.n_tiles, splits);
     g.tail_splits = ceil_div(g.n_tiles, g.tail_tps);
@@ -908,8 +984,8 @@ extern "C" int vast_sim_topk(const void* q_op, const void* k_op, int64_t n_q, in
     rc = run(TopkTag<EpiTopK<2>, 3, 4, 8>{});
   if (rc) return rc;
   if (pl.g.n_splits > 1) {
-    topk_merge_kernel<<<blocks_for(n_q, 4), 128, 0, stream>>>(part, k, pl.g.n_splits * k, pl.g.n_splits, (int)k, n_q, (int)k, out_keys);
-    VAST_LAUNCH_OK("topk_merge(splits)");
+    rc = launch_topk_merge(part, k, pl.g.n_splits * k, pl.g.n_splits, (int)k, n_q, (int)k, out_keys, stream);
+    if (rc) return rc;
   }
   return VAST_OK;
 }
@@ -919,9 +995,7 @@ extern "C" int vast_topk_merge(const uint64_t* keys_in, int64_t parts, int64_t n
   VAST_REQUIRE(keys_in && keys_out && parts > 0 && n_q >= 0 && k_in > 0 && k_out > 0, VAST_ERR_INVALID, "topk_merge: bad arguments");
   VAST_REQUIRE(parts * k_in <= MERGE_CAP * 32, VAST_ERR_UNSUPPORTED, "topk_merge: parts*k_in must be <= %d", MERGE_CAP * 32);
   if (n_q == 0) return VAST_OK;
-  topk_merge_kernel<<<blocks_for(n_q, 4), 128, 0, stream>>>(keys_in, n_q * k_in, k_in, (int)parts, (int)k_in, n_q, (int)k_out, keys_out);
-  VAST_LAUNCH_OK("topk_merge");
-  return VAST_OK;
+  return launch_topk_merge(keys_in, n_q * k_in, k_in, (int)parts, (int)k_in, n_q, (int)k_out, keys_out, stream);
 }
 
 extern "C" int vast_topk_unpack(const uint64_t* keys, int64_t count, float* values, int32_t* indices, vast_stream_t stream) {
