@@ -141,7 +141,11 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
   static_assert(NE == 4 || NE == 8, "4 or 8 epilogue warps");
   static_assert(BN == 128 || BN == 256, "BN");
   static_assert(CL == 1 || CL == 2, "single CTA or CTA pair");
-  if (P.gate != nullptr && *reinterpret_cast<const volatile int*>(P.gate) == 0) return;
+  pdl_trigger();
+  if (P.gate != nullptr) {  // the flag is written by a predecessor
+    pdl_wait();
+    if (*reinterpret_cast<const volatile int*>(P.gate) == 0) return;
+  }
   using L = SmemLayout<BN, STAGES, CL>;
   constexpr int HALVES = NE / 4;
   constexpr int COLS_PER_WARP = BN / HALVES;
@@ -194,6 +198,7 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
     __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the predecessor's tail; operands and epilogue inputs are read below
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (every CTA)
@@ -400,24 +405,8 @@ int launch_gemm_cl(const KernelParams<typename Epi::Params>& P, cudaStream_t str
   const int clusters_max = device_sm_count() / CL;
   const int clusters = P.g.num_items < clusters_max ? P.g.num_items : clusters_max;
   if (clusters <= 0) return VAST_OK;
-  if constexpr (CL == 1) {
-    VAST_TIMED(stream, name, (kern<<<clusters, 64 + 32 * NE + 32 * Epi::kAuxWarps, smem, stream>>>(P)));
-  } else {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(static_cast<unsigned>(clusters * CL), 1, 1);
-    cfg.blockDim = dim3(64 + 32 * NE + 32 * Epi::kAuxWarps, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    VAST_TIMED(stream, name, (cudaLaunchKernelEx(&cfg, kern, P)));
-  }
+  VAST_TIMED(stream, name,
+             (launch_ex(kern, static_cast<unsigned>(clusters * CL), 64 + 32 * NE + 32 * Epi::kAuxWarps, smem, stream, CL, P)));
   VAST_LAUNCH_OK(name);
   return VAST_OK;
 }

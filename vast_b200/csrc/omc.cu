@@ -267,6 +267,8 @@ __global__ void __launch_bounds__(256) omc_prep_kernel(const __nv_bfloat16* __re
                                                       float* __restrict__ zt, float* __restrict__ ref2, float scale2,
                                                       const float* __restrict__ temp_dev, int* __restrict__ flags,
                                                       __half* __restrict__ pack16) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][264];
   __shared__ int is_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -369,6 +371,8 @@ __global__ void __launch_bounds__(256) omc_prep_kernel(const __nv_bfloat16* __re
 // ------------------------------------------------------------------ two-pass form: merge pass-1 partials
 __global__ void __launch_bounds__(128) omc_stats_finalize_kernel(const float2* __restrict__ partial, int slots, int rows2,
                                                                 float* __restrict__ ref2, const int* __restrict__ gate) {
+  pdl_trigger();
+  pdl_wait();
   if (gate != nullptr && *gate == 0) return;
   const int r = blockIdx.x * 128 + threadIdx.x;
   if (r >= rows2) return;
@@ -420,6 +424,8 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
 }
 
 __global__ void __launch_bounds__(256) omc_row_stats_kernel(const RowStatParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;
   if (r >= 2 * p.M) return;
@@ -654,6 +660,8 @@ struct GradReduceParams {
   float* dotq;  // [2][M]
 };
 __global__ void __launch_bounds__(256) omc_grad_reduce_kernel(const GradReduceParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;
   if (r >= 2 * p.M) return;
@@ -705,6 +713,8 @@ __global__ void __launch_bounds__(256) omc_final_kernel(const float* __restrict_
                                                        float2* __restrict__ blockpart, int* __restrict__ ticket,
                                                        float* __restrict__ loss, float* __restrict__ grad_temp,
                                                        unsigned long long* __restrict__ step_ctr) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[2][256];
   __shared__ int is_last;
   const int r = blockIdx.x * 256 + threadIdx.x;
@@ -877,9 +887,8 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
   VAST_CUDA_OK(cudaMemsetAsync(wflags, 0, sizeof(int) * FLAG_INTS, stream));
   // K1
   VAST_TIMED(stream, "omc_prep",
-             (omc_prep_kernel<<<pl.ncs + ceil_div(M, 8), 256, 0, stream>>>(pk, N, D, M, static_cast<int>(row_offset), pl.ncs, pl.nslab,
-                                                                            ksump, ksum, zt, two_pass ? nullptr : ref2,
-                                                                            kLog2e * inv_tau, contra_temp_dev, wflags, pack16)));
+             (launch_ex(omc_prep_kernel, pl.ncs + ceil_div(M, 8), 256, 0, stream, 1, pk, N, D, M, static_cast<int>(row_offset), pl.ncs,
+                        pl.nslab, ksump, ksum, zt, two_pass ? nullptr : ref2, kLog2e * inv_tau, contra_temp_dev, wflags, pack16)));
   VAST_LAUNCH_OK("omc_prep");
 
   // tensor maps of the S GEMMs: A = local rows, B = all rows, both strided views of `pack`
@@ -906,8 +915,8 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
     int r = tc::launch_gemm<EpiStats, 256, 4, 8>(P, stream, gate ? "omc_stats_gemm_gated" : "omc_stats_gemm");
     if (r) return r;
     VAST_TIMED(stream, gate ? "omc_stats_finalize_gated" : "omc_stats_finalize",
-               (omc_stats_finalize_kernel<<<ceil_div(2 * M, 128), 128, 0, stream>>>(reinterpret_cast<const float2*>(partial), pl.slots,
-                                                                                    2 * M, ref2, gate)));
+               (launch_ex(omc_stats_finalize_kernel, ceil_div(2 * M, 128), 128, 0, stream, 1, reinterpret_cast<const float2*>(partial),
+                          pl.slots, 2 * M, ref2, gate)));
     VAST_LAUNCH_OK("omc_stats_finalize");
     return VAST_OK;
   };
@@ -994,7 +1003,7 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
     R.rowstat = rowstat;
     R.rowce = rowce;
     R.lse_out = lse;
-    VAST_TIMED(stream, "omc_row_stats", (omc_row_stats_kernel<<<ceil_div(2 * M, 8), 256, 0, stream>>>(R)));
+    VAST_TIMED(stream, "omc_row_stats", (launch_ex(omc_row_stats_kernel, ceil_div(2 * M, 8), 256, 0, stream, 1, R)));
     VAST_LAUNCH_OK("omc_row_stats");
   }
 
@@ -1049,17 +1058,16 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
       G.grad_cond = grad_cond;
       G.grad_t = grad_t;
       G.dotq = dotq;
-      VAST_TIMED(stream, "omc_grad_reduce", (omc_grad_reduce_kernel<<<ceil_div(2 * M, 8), 256, 0, stream>>>(G)));
+      VAST_TIMED(stream, "omc_grad_reduce", (launch_ex(omc_grad_reduce_kernel, ceil_div(2 * M, 8), 256, 0, stream, 1, G)));
       VAST_LAUNCH_OK("omc_grad_reduce");
     }
   }
 
   // K5
   VAST_TIMED(stream, "omc_final",
-             (omc_final_kernel<<<ceil_div(2 * M, 256), 256, 0, stream>>>(rowce, rowstat, zt, need_grad ? dotq : nullptr, pl.dslots,
-                                                                        2 * M, M, inv_tau, contra_temp_dev, label_smoothing, c_sm,
-                                                                        blockpart, &wflags[1], loss, need_grad ? grad_temp : nullptr,
-                                                                        reinterpret_cast<unsigned long long*>(step_counter))));
+             (launch_ex(omc_final_kernel, ceil_div(2 * M, 256), 256, 0, stream, 1, rowce, rowstat, zt, need_grad ? dotq : nullptr,
+                        pl.dslots, 2 * M, M, inv_tau, contra_temp_dev, label_smoothing, c_sm, blockpart, &wflags[1], loss,
+                        need_grad ? grad_temp : nullptr, reinterpret_cast<unsigned long long*>(step_counter))));
   VAST_LAUNCH_OK("omc_final");
   return VAST_OK;
 }

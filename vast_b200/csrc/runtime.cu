@@ -2,6 +2,7 @@
 // encoding (driver entry point fetched through the runtime, no link-time libcuda dependency),
 // work-split heuristics.
 #include <cstdarg>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -28,6 +29,15 @@ int device_sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VAST_NO_PDL");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 struct KTimer {
