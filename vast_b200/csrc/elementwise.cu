@@ -131,13 +131,22 @@ __global__ void __launch_bounds__(POOL_THREADS) pool_concat_kernel(const PoolPar
 #pragma unroll
       for (int i = 0; i < V; ++i) acc[i] = 0.f;
       if (tl < lanes) {
-#pragma unroll 4
-        for (int64_t j = tl; j < count; j += lanes) {
-          const int64_t f = j / used, t = j - f * used;
+        // (frame, token) advance incrementally: a 64-bit division per 16-byte load made this loop ALU-bound
+        const int iused = static_cast<int>(used), icount = static_cast<int>(count);
+        int f = tl / iused, t = tl - f * iused;
+        const TI* col = base + static_cast<int64_t>(v0 + vc) * V;
+        const int64_t tok_stride = s.c, frame_stride = s.tok * s.c;
+#pragma unroll 8
+        for (int j = tl; j < icount; j += lanes) {
           float x[V];
-          Vec<TI>::load(base + (f * s.tok + t) * s.c + static_cast<int64_t>(v0 + vc) * V, x);
+          Vec<TI>::load(col + f * frame_stride + t * tok_stride, x);
 #pragma unroll
           for (int i = 0; i < V; ++i) acc[i] += x[i];
+          t += lanes;
+          while (t >= iused) {
+            t -= iused;
+            ++f;
+          }
         }
       }
 #pragma unroll
@@ -204,6 +213,71 @@ __global__ void __launch_bounds__(128) l2norm_kernel(const TI* __restrict__ x, i
     const float v = to_f<TI>(xr[c]) / denom;
     if (y32) y32[row * ldy + c] = v;
     if (y16) y16[row * ld16 + c] = __float2bfloat16_rn(v);
+  }
+}
+
+// Vectorised variant (dim, ldx multiples of the 16-byte vector; outputs 16-byte aligned): 128-bit loads, float4 /
+// 16-byte bf16 stores; the second pass re-reads the row from L1.
+template <class TI>
+__global__ void __launch_bounds__(128) l2norm_vec_kernel(const TI* __restrict__ x, int64_t rows, int dim, int64_t ldx, float eps,
+                                                         float* __restrict__ y32, int64_t ldy,
+                                                         __nv_bfloat16* __restrict__ y16, int64_t ld16,
+                                                         float* __restrict__ inv_norm) {
+  constexpr int V = Vec<TI>::N;
+  const int64_t row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const TI* xr = x + row * ldx;
+  float ss = 0.f;
+#pragma unroll 4
+  for (int c = lane * V; c < dim; c += 32 * V) {
+    float v[V];
+    const uint4 u = *reinterpret_cast<const uint4*>(xr + c);  // cached: read again below
+    if constexpr (sizeof(TI) == 4) {
+      v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+    } else {
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if constexpr (std::is_same<TI, __nv_bfloat16>::value) {
+          v[2 * i] = __uint_as_float(w[i] << 16);
+          v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        } else {
+          const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+          v[2 * i] = t.x;
+          v[2 * i + 1] = t.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) ss = fmaf(v[i], v[i], ss);
+  }
+  ss = warp_sum(ss);
+  const float denom = fmaxf(sqrtf(ss), eps);
+  if (lane == 0 && inv_norm) inv_norm[row] = 1.0f / denom;
+#pragma unroll 4
+  for (int c = lane * V; c < dim; c += 32 * V) {
+    float v[V];
+    Vec<TI>::load(xr + c, v);
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = v[i] / denom;
+    if (y32) {
+#pragma unroll
+      for (int i = 0; i < V; i += 4)
+        *reinterpret_cast<float4*>(y32 + row * ldy + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+    if (y16) {
+      uint32_t w[V / 2];
+#pragma unroll
+      for (int i = 0; i < V / 2; ++i) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      if constexpr (V == 8)
+        *reinterpret_cast<uint4*>(y16 + row * ld16 + c) = make_uint4(w[0], w[1], w[2], w[3]);
+      else
+        *reinterpret_cast<uint2*>(y16 + row * ld16 + c) = make_uint2(w[0], w[1]);
+    }
   }
 }
 
@@ -451,6 +525,21 @@ extern "C" int vast_l2norm(const void* x, int x_dtype, int64_t rows, int64_t dim
   if (rows == 0) return VAST_OK;
   const unsigned grid = static_cast<unsigned>(ceil_div64(rows, 4));
   auto* y16 = static_cast<__nv_bfloat16*>(y_16);
+  const int64_t vin = x_dtype == VAST_F32 ? 4 : 8;  // elements per 16-byte input vector
+  const bool vec = dim % vin == 0 && ldx % vin == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && dim < (1ll << 30) &&
+                   (!y_f32 || (ldy % 4 == 0 && (reinterpret_cast<uintptr_t>(y_f32) & 15) == 0)) &&
+                   (!y_16 || (ld16 % vin == 0 && (reinterpret_cast<uintptr_t>(y_16) & (vin == 8 ? 15 : 7)) == 0));
+  if (vec && (x_dtype == VAST_F32 || x_dtype == VAST_BF16 || x_dtype == VAST_F16)) {
+    const int d = static_cast<int>(dim);
+    if (x_dtype == VAST_F32)
+      l2norm_vec_kernel<float><<<grid, 128, 0, stream>>>(static_cast<const float*>(x), rows, d, ldx, eps, y_f32, ldy, y16, ld16, inv_norm);
+    else if (x_dtype == VAST_BF16)
+      l2norm_vec_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), rows, d, ldx, eps, y_f32, ldy, y16, ld16, inv_norm);
+    else
+      l2norm_vec_kernel<__half><<<grid, 128, 0, stream>>>(static_cast<const __half*>(x), rows, d, ldx, eps, y_f32, ldy, y16, ld16, inv_norm);
+    VAST_LAUNCH_OK("l2norm");
+    return VAST_OK;
+  }
   if (x_dtype == VAST_F32)
     l2norm_kernel<float><<<grid, 128, 0, stream>>>(static_cast<const float*>(x), rows, dim, ldx, eps, y_f32, ldy, y16, ld16, inv_norm);
   else if (x_dtype == VAST_BF16)
