@@ -42,6 +42,17 @@ for mode in ("bf16", "fp32"):
     v1, i1 = vast_b200.retrieval_topk(q, v, k, mode=mode)
     v2, i2 = vast_b200.retrieval_topk(q, v, k, mode=mode, shard=(rank, world))
     ok &= bool(torch.equal(i1, i2))
+# negative-row exchange == all_gather_with_grad(x)[idx], values and gradients (NCCL all_to_all)
+xg = torch.randn(bs, 7, 16, generator=g).cuda()
+idx = torch.randint(0, n, (bs,), generator=g).cuda()
+wgt = torch.randn(bs, 7, 16, generator=g).cuda()
+xa = xg.clone().requires_grad_()
+ref = vast_b200.all_gather_with_grad(xa)[idx]
+(ref * wgt).sum().backward()
+xb = xg.clone().requires_grad_()
+got = vast_b200.exchange_rows(xb, idx)
+(got * wgt).sum().backward()
+ok &= bool(torch.equal(got, ref)) and bool(torch.allclose(xb.grad, xa.grad, atol=1e-5))
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:

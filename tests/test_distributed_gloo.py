@@ -73,3 +73,53 @@ def test_metric_helpers_host_logic():
     assert rows == [0, 1, 2] and cols == [0, 0, 1]
     assert _format("forward", 0.365, 0.635, 0.75) == {"forward_r1": 36.5, "forward_recall": "36.5/63.5/75.0",
                                                        "forward_ravg": 58.3}
+
+
+def _exchange_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vast_b200 import distributed as D
+    bs = 5
+    g = torch.Generator().manual_seed(100 + rank)
+    x = torch.randn(bs, 3, 4, generator=g)
+    idx = torch.randint(0, world * bs, (bs,), generator=g)
+    wgt = torch.randn(bs, 3, 4, generator=g)
+    # reference path (model/vast.py:422 + indexing): gather everything with gradient, then index
+    xa = x.clone().requires_grad_()
+    ref = D.all_gather_with_grad(xa)[idx]
+    (ref * wgt).sum().backward()
+    # exchange path: only the requested rows travel
+    xb = x.clone().requires_grad_()
+    got = D.exchange_rows(xb, idx)
+    (got * wgt).sum().backward()
+    q.put((rank, bool(torch.equal(got, ref)), bool(torch.allclose(xb.grad, xa.grad, atol=1e-6)), float(xa.grad.abs().sum())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("world", [2, 3])
+def test_exchange_rows_equals_gather_with_grad_then_index(world):
+    """negative-row exchange == all_gather_with_grad(condition_feats)[neg_idx], values and gradients."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, 29750 + world, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=100) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+    assert all(r[1] and r[2] for r in res), res
+    assert any(r[3] > 0 for r in res)
+
+
+def test_exchange_rows_single_process():
+    from vast_b200 import distributed as D
+    x = torch.randn(6, 2, requires_grad=True)
+    idx = torch.tensor([5, 0, 0, 3, 2, 5])
+    y = D.exchange_rows(x, idx)
+    assert torch.equal(y, x[idx])
+    y.sum().backward()
+    assert torch.equal(x.grad[:, 0], torch.tensor([2., 0., 1., 1., 0., 2.]))

@@ -12,7 +12,11 @@ import torch.distributed as dist
 import torch.nn.functional as F
 
 from . import ops
-from .distributed import _rank, _world, all_gather_with_grad, concat_all_gather
+from .distributed import _rank, _world, all_gather_with_grad, concat_all_gather, exchange_rows
+
+# fetch only the sampled negative rows of `condition_feats` from their owner ranks instead of
+# all-gathering the whole [N, S, 768] tensor with gradient (model/vast.py:422).  Same values, same gradients.
+NEGATIVE_ROW_EXCHANGE = True
 
 _call_counter = itertools.count()
 
@@ -133,10 +137,17 @@ def forward_ret(self, batch, task, compute_loss=True):
         loss, neg_text, neg_cond = omc_loss_and_negatives(feat_cond, feat_t, self.contra_temp)
         loss_itc.append(loss)
         condition_feats = self.batch_get(batch, f'condition_feats_{t[1:]}')
-        condition_feats_collate = all_gather_with_grad(condition_feats)
-        input_ids_1, attention_mask_1, condition_feats_3 = gather_negatives(
-            condition_feats, condition_feats_collate, input_ids, attention_mask, input_ids_collate,
-            attention_mask_collate, neg_text, neg_cond)
+        if NEGATIVE_ROW_EXCHANGE and _world() > 1:
+            cond_neg = exchange_rows(condition_feats, neg_cond)          # [bs, S, H]: only the sampled rows travel
+            own = torch.arange(cond_neg.shape[0], dtype=torch.int64, device=cond_neg.device)
+            input_ids_1, attention_mask_1, condition_feats_3 = gather_negatives(
+                condition_feats, cond_neg, input_ids, attention_mask, input_ids_collate, attention_mask_collate,
+                neg_text, own)
+        else:
+            condition_feats_collate = all_gather_with_grad(condition_feats)
+            input_ids_1, attention_mask_1, condition_feats_3 = gather_negatives(
+                condition_feats, condition_feats_collate, input_ids, attention_mask, input_ids_collate,
+                attention_mask_collate, neg_text, neg_cond)
         output = self.multimodal_encoder.bert(input_ids=input_ids_1, attention_mask=attention_mask_1,
                                               encoder_hidden_states=condition_feats_3).last_hidden_state
         batch_size = neg_cond.shape[0]

@@ -63,6 +63,72 @@ def all_gather_with_grad(tensors: torch.Tensor) -> torch.Tensor:
     return _GatherWithGrad.apply(tensors)
 
 
+class _ExchangeRows(torch.autograd.Function):
+    """rows = all_gather(x)[idx] WITHOUT gathering x: every rank receives only the bs rows it asked for.
+
+    SURVEY 8(f-1): the reference all-gathers the whole `condition_feats` [N, S, 768] with gradient
+    (model/vast.py:422, utils/distributed.py:12-47) just to index bs sampled negatives out of it, and its
+    backward all-reduces a [W, bs, S, 768] gradient to keep one slice.  Here the sampled indices are
+    all-gathered (W*bs int64), owners send the requested rows (one all_to_all), and the backward returns the
+    row gradients to their owners the same way (scatter-add) -- W x less traffic in both directions, the
+    same values and gradients."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        w, r = _world(), _rank()
+        bs = x.shape[0]
+        idx = idx.to(torch.int64)
+        if w == 1:
+            ctx.single = True
+            ctx.save_for_backward(idx)
+            ctx.bs = bs
+            return x.index_select(0, idx)
+        ctx.single = False
+        idx_all = torch.empty(w * bs, dtype=torch.int64, device=idx.device)
+        dist.all_gather_into_tensor(idx_all, idx.contiguous())
+        table = idx_all.view(w, bs).cpu()                      # the one host read: W*bs indices -> split sizes
+        owner, local = table // bs, table % bs
+        send_rows = [local[p][owner[p] == r] for p in range(w)]   # what rank p wants from me, in its request order
+        send_splits = [int(s.numel()) for s in send_rows]
+        my_owner = owner[r]
+        order = torch.argsort(my_owner, stable=True)          # my requests grouped by owner, request order kept
+        recv_splits = [int((my_owner == p).sum()) for p in range(w)]
+        send_index = torch.cat(send_rows).to(x.device)
+        order_dev = order.to(x.device)
+        send_buf = x.index_select(0, send_index).contiguous()
+        recv_buf = torch.empty((bs,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_to_all_single(recv_buf, send_buf, recv_splits, send_splits)
+        out = torch.empty_like(recv_buf)
+        out.index_copy_(0, order_dev, recv_buf)
+        ctx.save_for_backward(send_index, order_dev)
+        ctx.splits = (send_splits, recv_splits)
+        ctx.bs = bs
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        if ctx.single:
+            (idx,) = ctx.saved_tensors
+            gx = torch.zeros((ctx.bs,) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
+            gx.index_add_(0, idx, g)
+            return gx, None
+        send_index, order_dev = ctx.saved_tensors
+        send_splits, recv_splits = ctx.splits
+        g_sorted = g.index_select(0, order_dev).contiguous()
+        back = torch.empty((sum(send_splits),) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
+        dist.all_to_all_single(back, g_sorted, send_splits, recv_splits)
+        gx = torch.zeros((ctx.bs,) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
+        gx.index_add_(0, send_index, back)
+        return gx, None
+
+
+def exchange_rows(x: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """Differentiable `all_gather_with_grad(x)[idx]` (idx: [bs] global row indices in rank order) that moves only
+    the requested rows between ranks."""
+    return _ExchangeRows.apply(x, idx)
+
+
 def ddp_allgather(input: torch.Tensor) -> torch.Tensor:
     """utils/distributed.py:133-149: ragged all-gather along dim 0 (sizes exchanged once, pad to max,
     one all_gather_into_tensor, trim)."""
