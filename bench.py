@@ -165,6 +165,7 @@ def run_ours(args):
     # ---- inputs: R rotating sets so consecutive steps never find their inputs in the 126 MB L2
     per_set = 2 * bs * DIM * 4
     R = max(2, -(-160 * 2 ** 20 // per_set))
+    R += R % 2   # even: the peer-memory gather alternates two symmetric buffers
     host_sets = [synth(N_GLOBAL, DIM, 1234 + s, rows) for s in range(R)]
     dev_sets = [(t.to(dev), c.to(dev)) for t, c in host_sets]
     temp = torch.full((1,), TEMP, device=dev)
@@ -173,13 +174,23 @@ def run_ours(args):
     state = {"buf": None}
 
     step_ctr = torch.zeros(1, dtype=torch.int64, device=dev)   # device-side Philox offset: graph replays draw fresh noise
+    pg = None
+    if world > 1 and not args.nccl_gather:
+        from vast_b200.peer import packed_gather
+        pg = packed_gather(bs, DIM, dev)   # fused pack + all-gather over NVLink peer / multicast memory
+    gather_mode = ("one kernel: pack + all-gather by " + pg.mode) if pg is not None else \
+        ("one packed NCCL all-gather per step" if world > 1 else "single rank (no gather)")
 
     def step_dev(i):
         ft, fc = dev_sets[i % R]
-        ops.pack_pair(ft, fc, out=local_pack)
-        if world > 1:
-            dist.all_gather_into_tensor(pack_all, local_pack)
-        state["buf"] = ops.omc_step(pack_all, bs, rank * bs, temp, 0.1, 1e-4, seed=1234, offset=0, need_sample=True,
+        if pg is not None:
+            pack = pg.gather(ft, fc, slot=i % 2)
+        else:
+            ops.pack_pair(ft, fc, out=local_pack)
+            if world > 1:
+                dist.all_gather_into_tensor(pack_all, local_pack)
+            pack = pack_all
+        state["buf"] = ops.omc_step(pack, bs, rank * bs, temp, 0.1, 1e-4, seed=1234, offset=0, need_sample=True,
                                     need_grad=True, buffers=state["buf"], step_counter=step_ctr)
 
     for i in range(W):
@@ -334,7 +345,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"BASELINE cfg3: OMC contrastive loss + hard-negative sampling + backward, global batch "
                                    f"{N_GLOBAL}, D={DIM}, tau={TEMP}, label smoothing 0.1, bf16-in/fp32-accumulate, "
-                                   f"{world} rank(s) x {bs} rows, one packed NCCL all-gather per step",
+                                   f"{world} rank(s) x {bs} rows, {gather_mode}",
                        "l2": f"inputs rotate over {R} distinct sets ({R * per_set >> 20} MiB > 126 MB L2)",
                        "launch": mode,
                        "loss_last_step": loss_val},
@@ -425,6 +436,7 @@ def main():
     ap.add_argument("--no-retrieval", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--nccl-gather", action="store_true", help="N > 1: pack_pair + NCCL all-gather instead of the fused peer-memory kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

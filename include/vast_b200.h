@@ -97,6 +97,17 @@ VAST_API int vast_l2norm_bwd(const float* grad_y, int64_t ldg, const float* y, i
 VAST_API int vast_pack_pair(const void* feat_t, const void* feat_cond, int dtype, int64_t bs, int64_t dim,
                    int64_t ld_in, void* pack_bf16, vast_stream_t stream);
 
+/* Fused pack + all-gather over NVLink / NVSwitch (replaces vast_pack_pair followed by an all-gather call):
+ * every 16-byte vector of this rank's packed rows is stored into the gathered [n_total, 2*dim] bf16 buffer of EVERY
+ * rank, at rows [row_offset, row_offset + bs) -- with one multimem.st to `multicast_ptr` (the NVSwitch multicast
+ * address of the symmetric buffer) when it is non-NULL, otherwise with one store per entry of `peer_ptrs[world]`
+ * (the buffer's unicast address on each rank, this rank included).  The caller issues a cross-rank barrier on the
+ * same stream afterwards (and must not let a rank run more than one step ahead of a buffer that is still being
+ * read: alternate two buffers).  concat_all_gather semantics of utils/distributed.py:50-66. */
+VAST_API int vast_pack_pair_push(const void* feat_t, const void* feat_cond, int dtype, int64_t bs, int64_t dim,
+                        int64_t ld_in, int64_t row_offset, void* multicast_ptr, void* const* peer_ptrs, int world,
+                        vast_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * OMC / ITC contrastive loss + hard-negative sampling + backward   (model/vast.py:405-440)
  * ---------------------------------------------------------------------------------------- */

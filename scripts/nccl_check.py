@@ -34,6 +34,23 @@ ok &= abs(tau.grad.item() - o["grad_temp"]) < 1e-3 * abs(o["grad_temp"])
 tgt = torch.arange(rank * bs, (rank + 1) * bs)
 ok &= bool((neg_text.cpu() != tgt).all() and (neg_cond.cpu() != tgt).all() and (neg_text.cpu() < n).all())
 
+# fused pack + all-gather over peer memory == pack_pair + NCCL all-gather, bit for bit
+from vast_b200 import ops
+from vast_b200.peer import packed_gather
+pg = packed_gather(bs, d, "cuda")
+if pg is not None:
+    for it in range(3):
+        a = torch.randn(bs, d, generator=g).cuda() + rank
+        b = torch.randn(bs, d, generator=g).cuda()
+        got_pack = pg.gather(a, b).clone()
+        ref_pack = torch.empty(n, 2 * d, dtype=torch.bfloat16, device="cuda")
+        dist.all_gather_into_tensor(ref_pack, ops.pack_pair(a, b))
+        ok &= bool(torch.equal(got_pack, ref_pack))
+    if rank == 0:
+        print("peer gather:", pg.mode, flush=True)
+elif rank == 0:
+    print("peer gather: unavailable", flush=True)
+
 # retrieval: sharded == single
 nt, nv, k = 700, 3001, 16
 q = torch.nn.functional.normalize(torch.randn(nt, d, generator=g), dim=-1).cuda()

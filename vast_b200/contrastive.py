@@ -30,12 +30,20 @@ class _OmcFn(torch.autograd.Function):
     def forward(ctx, feat_cond, feat_t, contra_temp, rank, world_size, label_smoothing, weight_floor, seed, offset,
                 need_sample, debug_noise):
         bs, dim = feat_t.shape
-        local = ops.pack_pair(feat_t.detach(), feat_cond.detach())
-        if world_size > 1:
-            pack = torch.empty(world_size * bs, 2 * dim, dtype=torch.bfloat16, device=local.device)
-            dist.all_gather_into_tensor(pack, local)  # ONE collective for both feature blocks
+        pg = None
+        if world_size > 1 and dim % 8 == 0:
+            from .peer import packed_gather
+            pg = packed_gather(bs, dim, feat_t.device)
+        if pg is not None:
+            # pack + all-gather in ONE kernel: rows go straight into every rank's gathered buffer over NVLink
+            pack = pg.gather(feat_t.detach(), feat_cond.detach())
         else:
-            pack = local
+            local = ops.pack_pair(feat_t.detach(), feat_cond.detach())
+            if world_size > 1:
+                pack = torch.empty(world_size * bs, 2 * dim, dtype=torch.bfloat16, device=local.device)
+                dist.all_gather_into_tensor(pack, local)  # ONE collective for both feature blocks
+            else:
+                pack = local
         need_grad = any(ctx.needs_input_grad[:3])
         out = ops.omc_step(pack, bs, rank * bs, contra_temp.detach() if isinstance(contra_temp, torch.Tensor) else contra_temp,
                            label_smoothing, weight_floor, seed, offset, need_sample, need_grad, debug_noise)

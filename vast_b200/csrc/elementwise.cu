@@ -350,6 +350,63 @@ __global__ void __launch_bounds__(256) pack_pair_vec_kernel(const TI* __restrict
   }
 }
 
+// ------------------------------------------------------------------ fused pack + all-gather over NVLink
+// The all-gather of model/vast.py:395,404 done by the packing kernel itself: every 16-byte vector of this rank's
+// packed rows is stored straight into the gathered buffer of EVERY rank of the node -- one `multimem.st` to the
+// NVSwitch multicast address of the symmetric buffer (the switch replicates it), or, without multicast support,
+// one peer store per rank.  No intermediate send buffer and no NCCL call; a cross-rank barrier after the kernel
+// (issued by the host side on the same stream) publishes the buffer.
+constexpr int PUSH_MAX_PEERS = 16;
+struct PushDst {
+  void* mc;                    // multicast address of the gathered buffer, or nullptr
+  void* peer[PUSH_MAX_PEERS];  // unicast address of the gathered buffer on every rank (used when mc == nullptr)
+  int world;
+};
+__device__ __forceinline__ void multimem_st16(void* p, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+               : "memory");
+}
+template <class TI>
+__global__ void __launch_bounds__(256) pack_pair_push_kernel(const TI* __restrict__ ft, const TI* __restrict__ fc, int64_t bs,
+                                                            int dim8, int64_t ld, int64_t row_offset, const PushDst dst) {
+  const int64_t total = bs * 2 * dim8;
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int64_t b = i / (2 * dim8);
+  const int v = static_cast<int>(i - b * 2 * dim8);  // 16-byte vector inside the packed row
+  const bool second = v >= dim8;
+  const TI* src = (second ? fc : ft) + b * ld + static_cast<int64_t>(second ? v - dim8 : v) * 8;
+  uint4 o;
+  if constexpr (sizeof(TI) == 4) {
+    const float4 a = ld_stream_f4(src), c = ld_stream_f4(src + 4);
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(c.x, c.y), h3 = __floats2bfloat162_rn(c.z, c.w);
+    o.x = *reinterpret_cast<uint32_t*>(&h0);
+    o.y = *reinterpret_cast<uint32_t*>(&h1);
+    o.z = *reinterpret_cast<uint32_t*>(&h2);
+    o.w = *reinterpret_cast<uint32_t*>(&h3);
+  } else if constexpr (std::is_same<TI, __nv_bfloat16>::value) {
+    o = ld_stream16(src);
+  } else {
+    const uint4 raw = ld_stream16(src);
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+    uint32_t* ow = &o.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      __nv_bfloat162 r = __floats2bfloat162_rn(f.x, f.y);
+      ow[j] = *reinterpret_cast<uint32_t*>(&r);
+    }
+  }
+  const int64_t off = ((row_offset + b) * 2 * dim8 + v) * 16;  // byte offset inside the gathered [N, 2D] bf16 buffer
+  if (dst.mc != nullptr) {
+    multimem_st16(static_cast<char*>(dst.mc) + off, o);
+  } else {
+    for (int r = 0; r < dst.world; ++r) *reinterpret_cast<uint4*>(static_cast<char*>(dst.peer[r]) + off) = o;
+  }
+}
+
 // ------------------------------------------------------------------ negative gather + 3-way concat
 // Source row r in [0, 2bs): r < bs -> cond_local[r], written to out rows r and r + 2bs (read once,
 // written twice); r >= bs -> cond_all[neg_cond[r - bs]] written to out row r.  Compulsory traffic:
@@ -591,6 +648,42 @@ extern "C" int vast_pack_pair(const void* feat_t, const void* feat_cond, int dty
   else
     VAST_REQUIRE(false, VAST_ERR_UNSUPPORTED, "pack_pair: bad dtype");
   VAST_LAUNCH_OK("pack_pair");
+  return VAST_OK;
+}
+
+extern "C" int vast_pack_pair_push(const void* feat_t, const void* feat_cond, int dtype, int64_t bs, int64_t dim, int64_t ld_in,
+                                   int64_t row_offset, void* multicast_ptr, void* const* peer_ptrs, int world,
+                                   vast_stream_t stream) {
+  VAST_REQUIRE(feat_t && feat_cond && dim > 0 && ld_in >= dim && bs >= 0 && row_offset >= 0, VAST_ERR_INVALID,
+               "pack_pair_push: bad arguments");
+  VAST_REQUIRE(world >= 1 && world <= PUSH_MAX_PEERS && (multicast_ptr != nullptr || peer_ptrs != nullptr), VAST_ERR_INVALID,
+               "pack_pair_push: need a multicast pointer or 1..%d peer pointers", PUSH_MAX_PEERS);
+  VAST_REQUIRE(dim % 8 == 0 && ld_in % 8 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(feat_t) | reinterpret_cast<uintptr_t>(feat_cond) |
+                     reinterpret_cast<uintptr_t>(multicast_ptr)) & 15) == 0,
+               VAST_ERR_UNSUPPORTED, "pack_pair_push: dim and ld must be multiples of 8, pointers 16-byte aligned");
+  if (bs == 0) return VAST_OK;
+  PushDst dst;
+  memset(&dst, 0, sizeof(dst));
+  dst.mc = multicast_ptr;
+  dst.world = world;
+  if (multicast_ptr == nullptr)
+    for (int r = 0; r < world; ++r) {
+      VAST_REQUIRE(peer_ptrs[r] != nullptr && (reinterpret_cast<uintptr_t>(peer_ptrs[r]) & 15) == 0, VAST_ERR_INVALID,
+                   "pack_pair_push: bad peer pointer %d", r);
+      dst.peer[r] = peer_ptrs[r];
+    }
+  const int dim8 = static_cast<int>(dim / 8);
+  const unsigned g = static_cast<unsigned>(ceil_div64(bs * 2 * dim8, 256));
+  if (dtype == VAST_F32)
+    VAST_TIMED(stream, "pack_pair_push", (pack_pair_push_kernel<float><<<g, 256, 0, stream>>>(static_cast<const float*>(feat_t), static_cast<const float*>(feat_cond), bs, dim8, ld_in, row_offset, dst)));
+  else if (dtype == VAST_BF16)
+    VAST_TIMED(stream, "pack_pair_push", (pack_pair_push_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(feat_t), static_cast<const __nv_bfloat16*>(feat_cond), bs, dim8, ld_in, row_offset, dst)));
+  else if (dtype == VAST_F16)
+    VAST_TIMED(stream, "pack_pair_push", (pack_pair_push_kernel<__half><<<g, 256, 0, stream>>>(static_cast<const __half*>(feat_t), static_cast<const __half*>(feat_cond), bs, dim8, ld_in, row_offset, dst)));
+  else
+    VAST_REQUIRE(false, VAST_ERR_UNSUPPORTED, "pack_pair_push: bad dtype");
+  VAST_LAUNCH_OK("pack_pair_push");
   return VAST_OK;
 }
 

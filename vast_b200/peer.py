@@ -1,0 +1,79 @@
+"""Fused pack + all-gather over NVLink 5 / NVSwitch peer memory (replaces `vast_pack_pair` + NCCL all-gather on the
+training path, model/vast.py:395,404 / utils/distributed.py:50-66).
+
+The gathered `[N, 2D]` bf16 buffer lives in symmetric memory (`torch.distributed._symmetric_memory`: the same
+allocation mapped into every rank of the node, plus an NVSwitch multicast mapping where the driver offers one).
+`vast_pack_pair_push` converts this rank's rows and stores every 16-byte vector straight into the buffer of ALL ranks
+(one `multimem.st` to the multicast address, or one peer store per rank); a symmetric-memory barrier on the same
+stream publishes it.  Two buffers alternate so that a rank that is one step ahead never overwrites rows a slower
+rank is still reading."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+import torch.distributed as dist
+
+from ._lib import check, dtype_code, lib, ptr, require_cuda, stream_ptr
+
+
+class PackedGather:
+    def __init__(self, bs: int, dim: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.bs, self.dim = bs, dim
+        self.bufs, self.hdls = [], []
+        for _ in range(2):
+            b = symm.empty(self.world * bs, 2 * dim, dtype=torch.bfloat16, device=device)
+            self.bufs.append(b)
+            self.hdls.append(symm.rendezvous(b, self.group))
+        self.use_multicast = os.environ.get("VAST_PEER_MULTICAST", "1") == "1"
+        self.turn = 0
+
+    def _dst(self, i):
+        h = self.hdls[i]
+        mc = int(getattr(h, "multicast_ptr", 0) or 0) if self.use_multicast else 0
+        peers = (ctypes.c_void_p * self.world)(*[int(p) for p in h.buffer_ptrs])
+        return mc, peers
+
+    @property
+    def mode(self) -> str:
+        mc, _ = self._dst(0)
+        return "multimem.st to the NVSwitch multicast address" if mc else "peer stores to every rank"
+
+    @torch.no_grad()
+    def gather(self, feat_t: torch.Tensor, feat_cond: torch.Tensor, slot: int | None = None) -> torch.Tensor:
+        """[N, 2D] bf16 = rows of (feat_t | feat_cond) of all ranks in rank order (valid on the current stream)."""
+        require_cuda(feat_t, feat_cond)
+        assert feat_t.shape == feat_cond.shape == (self.bs, self.dim) and feat_t.dtype == feat_cond.dtype
+        i = self.turn if slot is None else slot
+        self.turn = i ^ 1
+        ft, fc = feat_t.contiguous(), feat_cond.contiguous()
+        mc, peers = self._dst(i)
+        check(lib().vast_pack_pair_push(ptr(ft), ptr(fc), dtype_code(ft.dtype), self.bs, self.dim, self.dim,
+                                        self.rank * self.bs, ctypes.c_void_p(mc) if mc else None, peers, self.world,
+                                        stream_ptr()), "pack_pair_push")
+        self.hdls[i].barrier(channel=0)
+        return self.bufs[i]
+
+
+_cache: dict = {}
+
+
+def packed_gather(bs: int, dim: int, device) -> PackedGather | None:
+    """Cached PackedGather for this shape, or None when symmetric memory is unavailable / disabled
+    (VAST_PEER_GATHER=0): the caller then uses vast_pack_pair + NCCL all_gather_into_tensor."""
+    if os.environ.get("VAST_PEER_GATHER", "1") != "1" or not dist.is_initialized() or dist.get_world_size() == 1:
+        return None
+    key = (bs, dim, torch.device(device).index)
+    if key not in _cache:
+        try:
+            _cache[key] = PackedGather(bs, dim, device)
+        except Exception as e:  # symmetric memory not supported on this system / build
+            import warnings
+            warnings.warn(f"vast_b200: peer-memory all-gather unavailable ({type(e).__name__}: {e}); using NCCL")
+            _cache[key] = None
+    return _cache[key]
