@@ -331,6 +331,14 @@ def run_ours(args):
                             "peak": peaks["tf_burst"], "unit": "TFLOP/s",
                             "frac": round(ach / peaks["tf_burst"], 4) if ach else None,
                             "peak_source": f"{peaks['src']} bf16 burst (kernel dominates a short step)"}}
+        if world > 1:   # the same problem with the QUERY rows sharded instead (no merge, lists built once)
+            def step_rows(i):
+                vast_b200.retrieval_topk(rt, rv, RET_K, mode="bf16", shard=shard, shard_mode="rows")
+            for i in range(2):
+                step_rows(i)
+            ms_rr = timed_loop(torch, dist, world, step_rows, Kr)
+            ret["row_sharded"] = {"value": RET_N * Kr / (ms_rr * 1e-3), "unit": "queries/s", "ms_per_step": ms_rr / Kr,
+                                  "note": "query rows sharded over the GPUs, finished lists all-gathered (identical result)"}
         del rt, rv
 
     # ---- CPU baseline: the torch port of the reference path on the host cores (rank 0, N=1 only)

@@ -22,7 +22,8 @@ def _shard_bounds(n: int, rank: int, world: int):
 
 
 @torch.no_grad()
-def retrieval_topk(feat_t: torch.Tensor, feat_cond: torch.Tensor, k: int, mode: str = "bf16", shard=None):
+def retrieval_topk(feat_t: torch.Tensor, feat_cond: torch.Tensor, k: int, mode: str = "bf16", shard=None,
+                   shard_mode: str = "cols"):
     """For every row of feat_t [Nt, D] the k best rows of feat_cond [Nv, D] by (score desc, index asc).
 
     mode "bf16": bf16 inputs, fp32 accumulate (tensor cores) -- scores are the bf16-mode similarities.
@@ -30,7 +31,10 @@ def retrieval_topk(feat_t: torch.Tensor, feat_cond: torch.Tensor, k: int, mode: 
                  fp64 re-score in a fixed summation order, proof check (shortlist cut-off + error bound below
                  the k-th exact score) and brute-force fp64 fallback for rows that cannot be proven.
     shard (rank, world): this rank scores only its slice of the columns; candidate lists are all-gathered
-                 and merged (column-sharded evaluation).  Returns (values f32, indices i32) [Nt, k]."""
+                 and merged (column-sharded evaluation).  Returns (values f32, indices i32) [Nt, k].
+    shard_mode "cols" (default, the layout of the ITM stage: every rank owns its videos) or "rows": every rank scores
+                 its slice of the QUERY rows against all columns and the finished lists are all-gathered -- no merge,
+                 and every row's list is built once instead of once per rank (W x less list work; identical result)."""
     assert feat_t.dim() == 2 and feat_cond.dim() == 2 and feat_t.shape[1] == feat_cond.shape[1]
     nt, nv = feat_t.shape[0], feat_cond.shape[0]
     rank, world = shard if shard is not None else (0, 1)
@@ -44,17 +48,32 @@ def retrieval_topk(feat_t: torch.Tensor, feat_cond: torch.Tensor, k: int, mode: 
         raise RuntimeError(f"retrieval_topk: k={k} exceeds the supported maximum {ops.TOPK_MAX}")
     ft = feat_t.float().contiguous() if exact else feat_t.contiguous()
     fc = feat_cond.float().contiguous() if exact else feat_cond.contiguous()
-    q_op = ops.sim_pack_operand(ft, sim_mode, True)
-    if hi > lo:
-        k_op = ops.sim_pack_operand(fc[lo:hi], sim_mode, False)
-        keys = ops.sim_topk(q_op, k_op, kl, col_offset=lo)
-    else:
-        keys = torch.zeros(nt, kl, dtype=torch.int64, device=ft.device)
-    if world > 1:
+    if shard_mode == "rows" and world > 1:
         import torch.distributed as dist
-        allk = torch.empty(world, nt, kl, dtype=torch.int64, device=keys.device)
-        dist.all_gather_into_tensor(allk, keys)
-        keys = ops.topk_merge(allk, kl)
+        per = (nt + world - 1) // world
+        rlo, rhi = min(rank * per, nt), min((rank + 1) * per, nt)
+        mine = torch.zeros(per, kl, dtype=torch.int64, device=ft.device)
+        if rhi > rlo:
+            q_op = ops.sim_pack_operand(ft[rlo:rhi], sim_mode, True)
+            k_op = ops.sim_pack_operand(fc, sim_mode, False)
+            mine[:rhi - rlo] = ops.sim_topk(q_op, k_op, kl)
+        allk = torch.empty(world * per, kl, dtype=torch.int64, device=ft.device)
+        dist.all_gather_into_tensor(allk, mine)
+        keys = allk[:nt].contiguous()
+    else:
+        if shard_mode not in ("cols", "rows"):
+            raise ValueError(shard_mode)
+        q_op = ops.sim_pack_operand(ft, sim_mode, True)
+        if hi > lo:
+            k_op = ops.sim_pack_operand(fc[lo:hi], sim_mode, False)
+            keys = ops.sim_topk(q_op, k_op, kl, col_offset=lo)
+        else:
+            keys = torch.zeros(nt, kl, dtype=torch.int64, device=ft.device)
+        if world > 1:
+            import torch.distributed as dist
+            allk = torch.empty(world, nt, kl, dtype=torch.int64, device=keys.device)
+            dist.all_gather_into_tensor(allk, keys)
+            keys = ops.topk_merge(allk, kl)
     vals, idx = ops.topk_unpack(keys)
     if not exact:
         return vals, idx
