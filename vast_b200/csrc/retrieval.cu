@@ -132,6 +132,7 @@ struct EpiTopK {
     int halves;  // filter warps per quadrant (column halves of a tile) = end markers per item
     uint32_t col_offset;
     uint32_t* thr_shared;  // [M] zero-initialised orderable bits of a proven lower bound of the final k-th score
+    int debug;             // experiment switches (VAST_TOPK_DEBUG): 1 no priming, 2 list warps drop entries, 4 filters never push
   };
   static constexpr bool kUnrollChunks = false;
   static constexpr int kAuxWarps = 4;
@@ -170,7 +171,7 @@ struct EpiTopK {
     named_barrier(1 + quad, 32 * (p.halves + 1));  // the list warp has reset lists and thresholds for this item
     thr = lds_f32_volatile(thr_addr);
     const bool cold = __any_sync(0xffffffffu, row_valid && thr == -INFINITY);
-    prime_left = (cold && p.k <= 16) ? 256 / (32 * p.halves) : 0;  // the chunks of one tile seen by this warp
+    prime_left = (cold && p.k <= 16 && !(p.debug & 1)) ? 256 / (32 * p.halves) : 0;  // the chunks of one tile seen by this warp
     if (prime_left > 0) {
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
@@ -180,16 +181,15 @@ struct EpiTopK {
     }
   }
   // push what the register network kept (scores above the row's bound), its k-th becomes the threshold
-  __device__ __forceinline__ void prime_flush(int lane) {
+  __device__ __forceinline__ void prime_flush(int lane) {  // warp-converged
     prime_left = 0;
-    if (!row_valid) return;
     float kth = -INFINITY;
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
-      if (ts[q] > thr) push(make_key(ts[q], ti[q]), static_cast<uint32_t>(lane));
+      push_agg(row_valid && ts[q] > thr, make_key(ts[q], ti[q]), lane);
       if (q == p.k - 1) kth = ts[q];
     }
-    if (kth > -INFINITY) {  // k scores of this row's columns are >= kth: ties must stay admissible
+    if (row_valid && kth > -INFINITY) {  // k scores of this row's columns are >= kth: ties must stay admissible
       const float b = f32_below_orderable(f32_orderable(kth));
       if (b > thr) thr = b;
     }
@@ -197,6 +197,7 @@ struct EpiTopK {
   __device__ __forceinline__ void prefetch(const tc::ItemCtx&, int) {}
   __device__ __forceinline__ void advance(const tc::ItemCtx&, int, bool) {}
   __device__ __forceinline__ void push(uint64_t key, uint32_t row) {
+    if ((p.debug & 4) && row != TOPK_END) return;
     const uint32_t slot = atoms_add(ctrl, 1);
     if (slot - lds_u32_volatile(ctrl + 4) >= TOPK_QCAP) {  // queue full: wait for the list warp (watchdog: trap, never hang)
       const long long t0 = clock64();
@@ -204,6 +205,28 @@ struct EpiTopK {
         if (clock64() - t0 > 6000000000LL) __trap();
     }
     sts_v4(ring + (slot % TOPK_QCAP) * 16, make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), row, slot + 1));
+  }
+  // Warp-converged push: every lane with `has` enqueues (its row = its lane, key); ONE shared-memory atomic per call
+  // reserves the slots of all of them (a push from inside divergent code costs an atomic and a round trip per lane).
+  __device__ __forceinline__ void push_agg(bool has, uint64_t key, int lane) {
+    if ((p.debug & 4)) return;
+    const unsigned act = __ballot_sync(0xffffffffu, has);
+    if (act == 0) return;
+    const int leader = __ffs(act) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atoms_add(ctrl, __popc(act));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (has) {
+      const uint32_t slot = base + __popc(act & ((1u << lane) - 1u));
+      if (slot - lds_u32_volatile(ctrl + 4) >= TOPK_QCAP) {  // queue full: wait for the list warp (watchdog: trap, never hang)
+        const long long t0 = clock64();
+        while (slot - lds_u32_volatile(ctrl + 4) >= TOPK_QCAP)
+          if (clock64() - t0 > 6000000000LL) __trap();
+      }
+      sts_v4(ring + (slot % TOPK_QCAP) * 16,
+             make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), static_cast<uint32_t>(lane), slot + 1));
+    }
+    __syncwarp();
   }
   __device__ __forceinline__ void chunk(const tc::ItemCtx& c, const uint32_t (&v)[32], int col0) {
     if (col0 >= c.N) return;
@@ -246,13 +269,21 @@ struct EpiTopK {
       gm[g] = fmaxf(fmaxf(fmaxf(s[8 * g], s[8 * g + 1]), fmaxf(s[8 * g + 2], s[8 * g + 3])),
                     fmaxf(fmaxf(s[8 * g + 4], s[8 * g + 5]), fmaxf(s[8 * g + 6], s[8 * g + 7])));
     const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-    if (mx > t) {
+    if (__any_sync(0xffffffffu, mx > t)) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        if (gm[g] > t) {
+        if (__any_sync(0xffffffffu, gm[g] > t)) {  // warp-uniform: the candidates of this 8-column group, all rows at once
+          unsigned m8 = 0;
 #pragma unroll
-          for (int i = 8 * g; i < 8 * g + 8; ++i)
-            if (s[i] > t) push(make_key(s[i], gcol + i), static_cast<uint32_t>(c.lane));
+          for (int j = 0; j < 8; ++j) m8 |= (s[8 * g + j] > t) ? (1u << j) : 0u;
+          while (__any_sync(0xffffffffu, m8 != 0)) {
+            const int j = __ffs(m8) - 1;  // this lane's next candidate column inside the group (-1: none)
+            float sv = s[8 * g];
+#pragma unroll
+            for (int jj = 1; jj < 8; ++jj) sv = (j == jj) ? s[8 * g + jj] : sv;
+            push_agg(m8 != 0, make_key(sv, gcol + 8 * g + (j < 0 ? 0 : j)), c.lane);
+            m8 &= m8 - 1;
+          }
         }
       }
     }
@@ -366,14 +397,15 @@ struct EpiTopK {
           else if (clock64() - idle_since > 6000000000LL) __trap();
           continue;
         }
-        idle_since = 0;
         const bool have = lane < ntake;
         const bool is_end = have && ent.z == TOPK_END;
-        ends += __popc(__ballot_sync(0xffffffffu, is_end));
+        const unsigned end_mask = __ballot_sync(0xffffffffu, is_end);
+        idle_since = 0;
+        ends += __popc(end_mask);
         head += ntake;
         if (lane == 0) sts_u32_volatile(ctrl + 4, head);  // the slots are free again (entries live in registers now)
         const uint64_t key = (static_cast<uint64_t>(ent.y) << 32) | ent.x;
-        bool todo = have && !is_end;
+        bool todo = have && !is_end && !(p.debug & 2);
         {
           // ---- one lane per entry; entries of one row take turns.  (Cold lists -- every score is a candidate -- arrive
           //      32 at a time, the steady state delivers one or two; the same code serves both.)
@@ -974,7 +1006,8 @@ extern "C" int vast_sim_topk(const void* q_op, const void* k_op, int64_t n_q, in
     if (r) return r;
     r = tc::make_tmap_2d(&P.tmB[0], k_op, VAST_BF16, n_k, cols, cols, 256 / pl.g.cl);
     if (r) return r;
-    P.epi = {part, static_cast<int>(k), pl.g.n_splits, NE / 4, static_cast<uint32_t>(col_offset), thr_shared};
+    const char* dbg = getenv("VAST_TOPK_DEBUG");
+    P.epi = {part, static_cast<int>(k), pl.g.n_splits, NE / 4, static_cast<uint32_t>(col_offset), thr_shared, dbg ? atoi(dbg) : 0};
     return tc::launch_gemm<Epi, 256, STAGES, NE, false, STAGES2>(P, stream, "sim_topk_gemm", Epi::smem_bytes());
   };
   // <epilogue, ring depth of a lone CTA (48 KB stages), ring depth of a CTA pair (32 KB stages), filter warps>
