@@ -51,6 +51,26 @@ if pg is not None:
 elif rank == 0:
     print("peer gather: unavailable", flush=True)
 
+# the same step as one CUDA-graph launch (vast_b200.OmcGraphStep): same loss / gradients, three steps in a row
+gstep = vast_b200.OmcGraphStep(bs, d, tau)
+prev = None
+for it in range(3):
+    ft2 = t[sl].cuda().requires_grad_()
+    fc2 = c[sl].cuda().requires_grad_()
+    tau.grad = None
+    l2, nt2, nc2 = gstep(fc2, ft2)
+    l2.backward()
+    ok &= abs(l2.item() - o["loss"]) < 1e-3 * abs(o["loss"])
+    for got, want in ((ft2.grad, o["grad_t"]), (fc2.grad, o["grad_cond"])):
+        ok &= np.linalg.norm(got.cpu().numpy() - want) < 1e-3 * np.linalg.norm(want)
+    ok &= abs(tau.grad.item() - o["grad_temp"]) < 1e-3 * abs(o["grad_temp"])
+    ok &= bool((nt2.cpu() != tgt).all() and (nc2.cpu() != tgt).all() and (nt2.cpu() < n).all())
+    if prev is not None:
+        ok &= not torch.equal(prev, nt2)      # fresh Philox noise on every replay
+    prev = nt2.clone()
+if rank == 0:
+    print("graphed step ok:", bool(ok), flush=True)
+
 # retrieval: sharded == single
 nt, nv, k = 700, 3001, 16
 q = torch.nn.functional.normalize(torch.randn(nt, d, generator=g), dim=-1).cuda()

@@ -38,6 +38,49 @@ def test_omc_autograd_matches_oracle(golden):
     assert (neg_text.cpu() != torch.arange(64)).all() and (neg_cond.cpu() != torch.arange(64)).all()
 
 
+def test_graphed_step_matches_eager_and_oracle(golden):
+    """vast_b200.OmcGraphStep: the fused step as one CUDA-graph launch -- same loss / gradients as the oracle, fresh
+    negatives every replay, live temperature parameter, and a loud error for gradients that were overwritten."""
+    import vast_b200
+    g = golden("omc_w1")
+    temp = nn.Parameter(torch.tensor(0.07, device="cuda"))
+    step = vast_b200.OmcGraphStep(64, g["feat_t"].shape[1], temp, rank=0, world_size=1)
+    tb, cb = bf16_round(g["feat_t"]), bf16_round(g["feat_cond"])
+    negs = []
+    for it, tau in enumerate((0.07, 0.07, 0.05)):
+        with torch.no_grad():
+            temp.fill_(tau)                      # in-place update (what an optimizer does) is seen by the graph
+        temp.grad = None
+        ft = torch.from_numpy(g["feat_t"]).cuda().requires_grad_()
+        fc = torch.from_numpy(g["feat_cond"]).cuda().requires_grad_()
+        loss, neg_text, neg_cond = step(fc, ft)
+        (2.0 * loss).backward()
+        o = spec.omc_loss(cb, tb, tb, cb, tau, grad_out=2.0)
+        assert abs(loss.item() - o["loss"]) < 1e-3 * o["loss"]
+        assert rel(ft.grad.cpu().numpy(), o["grad_t"]) < 1e-3
+        assert rel(fc.grad.cpu().numpy(), o["grad_cond"]) < 1e-3
+        assert abs(temp.grad.item() - o["grad_temp"]) < 1e-3 * abs(o["grad_temp"])
+        assert (neg_text.cpu() != torch.arange(64)).all() and (neg_cond.cpu() != torch.arange(64)).all()
+        negs.append(neg_text.clone())
+    assert not torch.equal(negs[0], negs[1])
+    # a loader may fill the step's own input buffers (no device-to-device copy in the call)
+    fc_in, ft_in = step.inputs()
+    ft_in.copy_(torch.from_numpy(g["feat_t"]))
+    fc_in.copy_(torch.from_numpy(g["feat_cond"]))
+    loss_in, _, _ = step(fc_in, ft_in)
+    assert abs(loss_in.item() - o["loss"]) < 1e-3 * o["loss"]
+    # outputs of call i are overwritten by call i+2: backward of the stale loss must raise
+    ft = torch.from_numpy(g["feat_t"]).cuda().requires_grad_()
+    fc = torch.from_numpy(g["feat_cond"]).cuda().requires_grad_()
+    stale, _, _ = step(fc, ft)
+    step(fc, ft)
+    step(fc, ft)
+    with pytest.raises(RuntimeError):
+        stale.backward()
+    with pytest.raises(RuntimeError):
+        step(fc[:10], ft[:10])
+
+
 class _Stub(nn.Module):
     """Stand-in for the VAST module: what forward_ret touches (model/vast.py:383-464)."""
 

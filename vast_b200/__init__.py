@@ -7,6 +7,7 @@ from . import ops  # noqa: F401
 from .contrastive import forward_ret, gather_negatives, omc_loss_and_negatives  # noqa: F401
 from .distributed import (all_gather_list, all_gather_with_grad, any_broadcast, concat_all_gather,  # noqa: F401
                           ddp_allgather, exchange_rows)
+from .graphed import OmcGraphStep  # noqa: F401
 from .features import build_feature, l2_normalize, pool_concat  # noqa: F401
 from .retrieval import (compute_metric_ret, evaluate_ret, recall_from_feats, refine_score_matrix,  # noqa: F401
                         retrieval_topk)

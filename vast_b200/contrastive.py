@@ -60,11 +60,14 @@ class _OmcFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, _a, _b):
-        gc, gt, gtemp = ctx.saved_tensors
-        d_temp = (g * gtemp).reshape(ctx.temp_shape) if ctx.temp_shape is not None and ctx.needs_input_grad[2] else None
-        return ((g * gc).to(ctx.dtypes[0]) if ctx.needs_input_grad[0] else None,
-                (g * gt).to(ctx.dtypes[1]) if ctx.needs_input_grad[1] else None,
-                d_temp, None, None, None, None, None, None, None, None)
+        need = ctx.needs_input_grad
+        want_temp = ctx.temp_shape is not None and need[2]
+        src = [t for t, w in zip(ctx.saved_tensors, (need[0], need[1], want_temp)) if w]
+        scaled = iter(torch._foreach_mul(src, g) if src else ())       # one launch for all three products
+        d_cond = next(scaled).to(ctx.dtypes[0]) if need[0] else None
+        d_t = next(scaled).to(ctx.dtypes[1]) if need[1] else None
+        d_temp = next(scaled).reshape(ctx.temp_shape) if want_temp else None
+        return d_cond, d_t, d_temp, None, None, None, None, None, None, None, None
 
 
 def omc_loss_and_negatives(feat_cond, feat_t, contra_temp, *, rank=None, world_size=None, label_smoothing=0.1,
