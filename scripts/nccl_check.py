@@ -77,8 +77,8 @@ q = torch.nn.functional.normalize(torch.randn(nt, d, generator=g), dim=-1).cuda(
 v = torch.nn.functional.normalize(torch.randn(nv, d, generator=g), dim=-1).cuda()
 for mode in ("bf16", "fp32"):
     v1, i1 = vast_b200.retrieval_topk(q, v, k, mode=mode)
-    v2, i2 = vast_b200.retrieval_topk(q, v, k, mode=mode, shard=(rank, world))
-    v3, i3 = vast_b200.retrieval_topk(q, v, k, mode=mode, shard=(rank, world), shard_mode="rows")
+    v2, i2 = vast_b200.retrieval_topk(q, v, k, mode=mode, shard=(rank, world), shard_mode="cols")
+    v3, i3 = vast_b200.retrieval_topk(q, v, k, mode=mode, shard=(rank, world))          # default: query rows sharded
     ok &= bool(torch.equal(i1, i2)) and bool(torch.equal(i1, i3)) and bool(torch.equal(v1, v3))
 # negative-row exchange == all_gather_with_grad(x)[idx], values and gradients (NCCL all_to_all)
 xg = torch.randn(bs, 7, 16, generator=g).cuda()
