@@ -1,7 +1,7 @@
 """Multi-GPU correctness check (run under torchrun, one rank per GPU, NCCL):
   * omc_loss_and_negatives with the packed all-gather == the oracle evaluated on the gathered features
   * column-sharded retrieval_topk + candidate all-gather + merge == the single-GPU result
-    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 scripts/nccl_check.py"""
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np

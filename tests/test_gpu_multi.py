@@ -1,5 +1,5 @@
 """Multi-GPU (NCCL, one process per GPU) checks; skipped unless the box has at least two GPUs.  The same checks
-run stand-alone under torchrun as scripts/nccl_check.py (validated at 2 and 8 B200s)."""
+run stand-alone under torchrun as tests/multi_gpu_check.py (validated at 2 and 8 B200s)."""
 import os
 import subprocess
 import sys
@@ -18,6 +18,6 @@ def test_nccl_check_two_ranks():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(ROOT, "scripts", "nccl_check.py")]
+           "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=500, cwd=ROOT)
     assert r.returncode == 0 and "nccl_check OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
