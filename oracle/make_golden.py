@@ -11,6 +11,7 @@ What is driven (reference file:line):
   evaluation_mm.compute_metric_ret evaluation/evaluation_mm.py:326-380
   evaluation_mm.refine_score_matrix evaluation/evaluation_mm.py:253-319
   concat_all_gather / ddp_allgather / all_gather_with_grad   utils/distributed.py:33-66,133-149
+  evaluation_mm.evaluate_ret       evaluation/evaluation_mm.py:171-251   (val_log of a stubbed two-task evaluation)
 """
 from __future__ import annotations
 
@@ -268,6 +269,58 @@ def golden_features():
     print("features: feat_vas", tuple(feat.shape))
 
 
+def golden_evaluate_ret():
+    """evaluation_mm.evaluate_ret (evaluation/evaluation_mm.py:171-251) end to end: a stub model that returns
+    pre-seeded evaluation dicts per batch (what VAST.forward_ret(compute_loss=False) returns, model/vast.py:468-483),
+    two sub-tasks, multi-caption ids (5 texts per video, flattened at :195-201), bidirectional metrics, ITM re-rank
+    with k=16 (>= 10, so R@10 is independent of torch's tie order among the zeros of the refined matrix)."""
+    import json
+    from easydict import EasyDict as edict
+    ns = R.load()
+    nv, per, d, s, h, l, nb = 24, 5, 64, 4, 16, 6, 3
+    nt = nv * per
+    g = torch.Generator().manual_seed(77)
+    conds, feats_v = {}, {}
+    for i, task in enumerate(("tv", "tvas")):
+        _, feats_v[task] = synth_feats(nv, d, 3030 + i)
+        conds[task] = torch.randn(nv, s, h, generator=g)
+    base = 0.5 * (feats_v["tv"] + feats_v["tvas"])
+    feat_t = F.normalize(base.repeat_interleave(per, dim=0) + 1.0 * torch.randn(nt, d, generator=g), dim=-1)
+    tids = torch.randint(0, 30522, (nt, l), generator=g)
+    tmask = (torch.rand(nt, l, generator=g) > 0.1).long()
+    ids = [f"vid{i}" for i in range(nv)]
+    stub = R.make_stub_model(hidden=h)
+    stub.config.itm_rerank_num = 16
+    stub.config.ret_bidirection_evaluation = True
+
+    class Model:
+        config = stub.config
+        compute_slice_scores = stub.compute_slice_scores
+
+        def __call__(self, batch, tasks, compute_loss=False):
+            assert compute_loss is False
+            return batch["ev"]
+
+    loader = []
+    vb = nv // nb
+    for b in range(nb):
+        vs = slice(b * vb, (b + 1) * vb)
+        ts = slice(b * vb * per, (b + 1) * vb * per)
+        ev = {"feat_t": feat_t[ts], "input_ids": tids[ts], "attention_mask": tmask[ts]}
+        for task in ("tv", "tvas"):
+            ev[f"feat_cond_{task}"] = feats_v[task][vs]
+            ev[f"condition_feats_{task}"] = conds[task][vs]
+        loader.append({"ids": ids[vs], "ids_txt": [[v] * per for v in ids[vs]], "ev": ev})
+    log = ns.E.evaluate_ret(Model(), "ret%tv%tvas", loader, 0)
+    out = dict(feat_t=feat_t.numpy(), ids_tok=tids.numpy(), mask=tmask.numpy(), per=np.int64(per), nb=np.int64(nb),
+               log_json=np.array(json.dumps(log, sort_keys=True)))
+    for task in ("tv", "tvas"):
+        out[f"feat_v_{task}"] = feats_v[task].numpy()
+        out[f"cond_{task}"] = conds[task].numpy()
+    np.savez_compressed(os.path.join(GOLD, "evaluate_ret.npz"), **out)
+    print("evaluate_ret:", json.dumps(log, sort_keys=True)[:300])
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     golden_w2()          # spawns its own process group first (port separate from the W=1 group)
@@ -275,4 +328,5 @@ if __name__ == "__main__":
     golden_omc_w1()
     golden_retrieval()
     golden_features()
+    golden_evaluate_ret()
     print("golden vectors written to", GOLD)

@@ -383,6 +383,32 @@ def refine_score_matrix(condition_feats_per_rank, input_ids, attention_mask, sco
     return out
 
 
+def evaluate_ret(feat_t, input_ids, attention_mask, feat_cond, condition_feats_per_rank, ids, ids_txt,
+                 slice_scorer, itm_rerank_num, bidirection=False):
+    """evaluation/evaluation_mm.py:171-251 after the per-batch collection: per sub-task the ITC metrics on
+    feat_t @ feat_cond.T (:223-232, keys renamed forward->video, backward->txt :226,229) and the ITM metrics on the
+    re-ranked matrix (:236-249).  feat_cond / condition_feats_per_rank: dicts keyed by sub-task."""
+    val_log = {}
+    scores = {}
+    for task, fc in feat_cond.items():
+        scores[task] = score_matrix(feat_t, fc)
+        log = {k.replace("forward", "video"): v for k, v in compute_metric_ret(scores[task], ids, ids_txt, "forward").items()}
+        if bidirection:
+            log.update({k.replace("backward", "txt"): v
+                        for k, v in compute_metric_ret(scores[task], ids, ids_txt, "backward").items()})
+        val_log[f"ret_itc_{task}"] = log
+    for task in feat_cond:
+        r = refine_score_matrix(condition_feats_per_rank[task], input_ids, attention_mask, scores[task], slice_scorer,
+                                itm_rerank_num, "forward")
+        log = {k.replace("forward", "video"): v for k, v in compute_metric_ret(r, ids, ids_txt, "forward").items()}
+        if bidirection:
+            r = refine_score_matrix(condition_feats_per_rank[task], input_ids, attention_mask, scores[task],
+                                    slice_scorer, itm_rerank_num, "backward")
+            log.update({k.replace("backward", "txt"): v for k, v in compute_metric_ret(r, ids, ids_txt, "backward").items()})
+        val_log[f"ret_itm_{task}"] = log
+    return val_log
+
+
 # ----------------------------------------------------------------------------
 # collectives (semantics only)
 # ----------------------------------------------------------------------------

@@ -168,6 +168,38 @@ def test_refine_score_matrix_golden(golden, direction, k):
     assert log[f"{direction}_recall"] == str(g[f"c_recall_{direction}"])
 
 
+def test_evaluate_ret_dropin_golden(golden):
+    """vast_b200.evaluate_ret == the reference's evaluate_ret (evaluation_mm.py:171-251) on the same stubbed
+    two-task evaluation: 3 loader batches, 5 captions per video (list-of-lists ids_txt), both directions, ITM k=16."""
+    import json
+    import types
+    import vast_b200
+    g = golden("evaluate_ret")
+    per, nb = int(g["per"]), int(g["nb"])
+    nv = g["feat_v_tv"].shape[0]
+    ids = [f"vid{i}" for i in range(nv)]
+    m = _StubModel()
+
+    class Model:
+        config = types.SimpleNamespace(itm_rerank_num=16, ret_bidirection_evaluation=True)
+        compute_slice_scores = staticmethod(m.compute_slice_scores)
+
+        def __call__(self, batch, tasks, compute_loss=False):
+            assert compute_loss is False and tasks == "ret%tv%tvas"
+            return batch["ev"]
+
+    loader, vb = [], nv // nb
+    for b in range(nb):
+        vs, ts = slice(b * vb, (b + 1) * vb), slice(b * vb * per, (b + 1) * vb * per)
+        ev = {"feat_t": cu(g["feat_t"][ts]), "input_ids": cu(g["ids_tok"][ts]), "attention_mask": cu(g["mask"][ts])}
+        for t in ("tv", "tvas"):
+            ev[f"feat_cond_{t}"] = cu(g[f"feat_v_{t}"][vs])
+            ev[f"condition_feats_{t}"] = cu(g[f"cond_{t}"][vs])
+        loader.append({"ids": ids[vs], "ids_txt": [[v] * per for v in ids[vs]], "ev": ev})
+    log = vast_b200.evaluate_ret(Model(), "ret%tv%tvas", loader, 0)
+    assert log == json.loads(str(g["log_json"]))
+
+
 def test_bucket_and_scatter():
     from vast_b200 import ops
     g = torch.Generator().manual_seed(2)
