@@ -293,6 +293,9 @@ def run_ours(args):
         def step_e2e(i):
             b = i % 2
             cur = torch.cuda.current_stream()
+            # like PrefetchLoader.__next__ (data/loader.py:104-125): start the NEXT step's H2D before computing this
+            # one -- its buffer was last read by step i-1, whose loss has already been read back
+            prefetch(i + 1, call)
             cur.wait_event(ev_in[b])
             block = bufs(i, call)
             ft = block[0].detach().requires_grad_()
@@ -301,7 +304,6 @@ def run_ours(args):
             loss, neg_text, neg_cond = call(fc, ft)
             loss.backward()              # gradients w.r.t. both feature blocks and the temperature
             ev_free[b].record(cur)
-            prefetch(i + 1, call)        # H2D of the next step's inputs overlaps this step's kernels
             sink["loss"] = loss.item()   # D2H read of the step's result (synchronous, like utils/pipeline.py:47)
         return step_e2e
 
