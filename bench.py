@@ -6,7 +6,8 @@
 
 Primary line (one JSON object on stdout, rank 0):
   metric  contrastive_fwd_bwd_pairs_per_sec on BASELINE config 3 (global batch 4096, 1024-d, tau .07):
-          a "step" = pack -> all-gather (N > 1) -> fused OMC loss + hard-negative sampling + backward.
+          a "step" = pack -> all-gather (N > 1) -> fused OMC loss + hard-negative sampling + backward
+          (N = 1: packing is fused into the step's first kernel, vast_omc_step_local).
   value   device-timed throughput with the fp32 features already resident in HBM.
   e2e     the same step through the public API (vast_b200.omc_loss_and_negatives + .backward()) with
           pinned HOST feature buffers: H2D of the step's inputs and D2H of the loss inside the timed region.
@@ -183,6 +184,11 @@ def run_ours(args):
 
     def step_dev(i):
         ft, fc = dev_sets[i % R]
+        if world == 1 and not args.separate_pack:
+            # one rank: packing is part of the step's first kernel (vast_omc_step_local)
+            state["buf"] = ops.omc_step_local(ft, fc, temp, 0.1, 1e-4, seed=1234, offset=0, need_sample=True,
+                                              need_grad=True, buffers=state["buf"], step_counter=step_ctr)
+            return
         if pg is not None:
             pack = pg.gather(ft, fc, slot=i % 2)
         else:
@@ -482,6 +488,7 @@ def main():
     ap.add_argument("--no-retrieval", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--separate-pack", action="store_true", help="N = 1: vast_pack_pair + vast_omc_step instead of vast_omc_step_local")
     ap.add_argument("--nccl-gather", action="store_true", help="N > 1: pack_pair + NCCL all-gather instead of the fused peer-memory kernel")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -116,6 +116,8 @@ VAST_API size_t vast_omc_workspace_bytes(int64_t bs, int64_t n_total, int64_t di
 
 /* vast_omc_step flags */
 #define VAST_OMC_TWO_PASS 1 /* evaluate the logits twice (row max / sum-exp pass first) instead of once */
+#define VAST_OMC_SEPARATE_ROW_STATS 2 /* run the row statistics + hard-negative draw as their own kernel instead of
+                                         inside the dQ GEMM's epilogue (same results bit for bit; A/B aid) */
 
 /* One fused contrastive step on this rank's rows.
  *   pack        [n_total, 2*dim] bf16, row n = (feat_t_all[n] | feat_cond_all[n]) in rank order
@@ -151,6 +153,19 @@ VAST_API int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int64_
                   uint64_t seed, uint64_t offset, uint64_t* step_counter, const float* debug_noise, int flags,
                   float* loss, int64_t* neg_idx, float* grad_cond, float* grad_t, float* grad_temp,
                   float* lse, void* workspace, size_t workspace_bytes, vast_stream_t stream);
+
+/* The same step for a single rank (world_size 1: n_total = bs, row_offset 0) straight from the two feature
+ * blocks feat_t / feat_cond [bs, dim] (dtype f32 / bf16 / f16, row stride ld_in elements, 16-byte aligned,
+ * ld_in % 8 == 0): vast_pack_pair and the step's first kernel run as ONE pass over the features -- with no
+ * all-gather between them there is nothing to wait for.  pack_bf16 [bs, 2*dim] is written (the operand of the
+ * similarity GEMMs; same contents as vast_pack_pair's output).  All other arguments as vast_omc_step; results
+ * agree with vast_pack_pair + vast_omc_step up to the summation order of the target logits (fp32 rounding). */
+VAST_API int vast_omc_step_local(const void* feat_t, const void* feat_cond, int dtype, int64_t ld_in, void* pack_bf16,
+                        int64_t bs, int64_t dim, float contra_temp, const float* contra_temp_dev,
+                        float label_smoothing, float weight_floor, uint64_t seed, uint64_t offset,
+                        uint64_t* step_counter, const float* debug_noise, int flags, float* loss, int64_t* neg_idx,
+                        float* grad_cond, float* grad_t, float* grad_temp, float* lse, void* workspace,
+                        size_t workspace_bytes, vast_stream_t stream);
 
 /* Negative gather + 3-way concat (model/vast.py:432-448):
  *   ids_out  [3bs, L]  = cat(ids_local, ids_local, ids_all[neg_text])          (int64)

@@ -260,3 +260,67 @@ def test_step_counter_advances_the_philox_offset():
     r1 = buf["neg_idx"].clone()
     torch.cuda.synchronize()
     assert torch.equal(r0, b0) and torch.equal(r1, b1) and ctr.item() == 2
+
+
+@pytest.mark.parametrize("bs,world,rank,dim,noise", [(4096, 1, 0, 1024, False), (2048, 2, 1, 1024, False), (1024, 1, 0, 512, False),
+                                                      (300, 1, 0, 520, False), (512, 4, 2, 256, False), (64, 1, 0, 512, True),
+                                                      (640, 1, 0, 384, True)])
+def test_fused_row_stats_equal_separate_kernel(bs, world, rank, dim, noise):
+    """The row statistics + hard-negative draw run inside the dQ GEMM's epilogue by default; the stand-alone kernel
+    (VAST_OMC_SEPARATE_ROW_STATS) must give the same bits: gradients, negatives, lse (the loss and d tau sum <q, sum K>
+    in a different order: 1e-6)."""
+    n = bs * world
+    gen = torch.Generator().manual_seed(3 * bs + dim)
+    t = torch.nn.functional.normalize(torch.randn(n, dim, generator=gen), dim=-1)
+    c = torch.nn.functional.normalize(t + 0.8 * torch.randn(n, dim, generator=gen), dim=-1)
+    kw = dict(seed=77, offset=5, want_lse=True)
+    if noise:
+        kw["debug_noise"] = torch.empty(2, bs, n).exponential_(generator=gen).cuda()
+    a = run_step(t.numpy(), c.numpy(), bs, rank, 0.07, separate_row_stats=False, **kw)
+    b = run_step(t.numpy(), c.numpy(), bs, rank, 0.07, separate_row_stats=True, **kw)
+    for k in ("grad_t", "grad_cond", "neg_idx", "lse"):
+        assert torch.equal(a[k], b[k]), k
+    assert abs(a["loss"].item() - b["loss"].item()) <= 2e-6 * abs(b["loss"].item())
+    assert abs(a["grad_temp"].item() - b["grad_temp"].item()) <= 1e-5 * abs(b["grad_temp"].item()) + 1e-7
+    o = oracle(t.numpy(), c.numpy(), bs, rank, 0.07)
+    check_against_oracle(a, o, bs)
+
+
+@pytest.mark.parametrize("two_pass", [False, True])
+@pytest.mark.parametrize("n,dim,dtype", [(4096, 1024, torch.float32), (100, 72, torch.float32), (1, 8, torch.float32),
+                                         (130, 264, torch.bfloat16), (333, 136, torch.float16), (64, 128, torch.bfloat16),
+                                         (65, 1032, torch.float32)])
+def test_single_rank_step_from_features(n, dim, dtype, two_pass):
+    """vast_omc_step_local (one rank: packing fused into the step's first kernel) vs the oracle, its `pack` output
+    bit-identical to vast_pack_pair, negatives vs the sampler's restatement."""
+    from vast_b200 import ops
+    gen = torch.Generator().manual_seed(n + dim)
+    t = torch.nn.functional.normalize(torch.randn(n, dim, generator=gen), dim=-1)
+    c = torch.nn.functional.normalize(t + 0.8 * torch.randn(n, dim, generator=gen), dim=-1)
+    td, cd = t.to(dtype).cuda(), c.to(dtype).cuda()
+    seed, offset = 4242, 11
+    out = ops.omc_step_local(td, cd, 0.07, seed=seed, offset=offset, want_lse=True, two_pass=two_pass)
+    torch.cuda.synchronize()
+    assert torch.equal(out["pack"], ops.pack_pair(td, cd))
+    tn, cn = td.float().cpu().numpy(), cd.float().cpu().numpy()
+    o = oracle(tn, cn, n, 0, 0.07)
+    check_against_oracle(out, o, n)
+    check_negatives_hier(out["neg_idx"], o, seed, offset, 0, n, n)
+    # against the two-kernel form: same operands, z_t summed in another order -> agreement far inside the tolerance
+    ref = ops.omc_step(ops.pack_pair(td, cd), n, 0, 0.07, seed=seed, offset=offset, want_lse=True, two_pass=two_pass)
+    assert rel(out["grad_t"].cpu().numpy(), ref["grad_t"].cpu().numpy()) < 1e-4
+    assert abs(out["loss"].item() - ref["loss"].item()) <= 1e-5 * abs(ref["loss"].item())
+    assert (out["neg_idx"] == ref["neg_idx"]).float().mean().item() >= 0.97 or n < 8
+    # loss-only / no sampling, and reuse of the returned buffers
+    lo = ops.omc_step_local(td, cd, 0.07, need_sample=False, need_grad=False)
+    assert abs(lo["loss"].item() - o["loss"]) <= RTOL * abs(o["loss"]) + 1e-6
+    again = ops.omc_step_local(td, cd, 0.07, seed=seed, offset=offset, want_lse=True, two_pass=two_pass, buffers=out)
+    torch.cuda.synchronize()
+    assert again["loss"] is out["loss"]
+
+
+def test_single_rank_step_rejects_unaligned():
+    from vast_b200 import ops
+    x = torch.randn(16, 12).cuda()
+    with pytest.raises(RuntimeError):
+        ops.omc_step_local(x, x, 0.07)     # D % 8 != 0

@@ -34,7 +34,14 @@ class _OmcFn(torch.autograd.Function):
         if world_size > 1 and dim % 8 == 0:
             from .peer import packed_gather
             pg = packed_gather(bs, dim, feat_t.device)
-        if pg is not None:
+        need_grad = any(ctx.needs_input_grad[:3])
+        temp = contra_temp.detach() if isinstance(contra_temp, torch.Tensor) else contra_temp
+        out = None
+        if world_size == 1 and ops.local_step_ok(feat_t) and ops.local_step_ok(feat_cond):
+            # one rank: nothing to gather, so packing is fused into the step's first kernel
+            out = ops.omc_step_local(feat_t.detach(), feat_cond.detach(), temp, label_smoothing, weight_floor, seed, offset,
+                                     need_sample, need_grad, debug_noise)
+        elif pg is not None:
             # pack + all-gather in ONE kernel: rows go straight into every rank's gathered buffer over NVLink
             pack = pg.gather(feat_t.detach(), feat_cond.detach())
         else:
@@ -44,9 +51,9 @@ class _OmcFn(torch.autograd.Function):
                 dist.all_gather_into_tensor(pack, local)  # ONE collective for both feature blocks
             else:
                 pack = local
-        need_grad = any(ctx.needs_input_grad[:3])
-        out = ops.omc_step(pack, bs, rank * bs, contra_temp.detach() if isinstance(contra_temp, torch.Tensor) else contra_temp,
-                           label_smoothing, weight_floor, seed, offset, need_sample, need_grad, debug_noise)
+        if out is None:
+            out = ops.omc_step(pack, bs, rank * bs, temp, label_smoothing, weight_floor, seed, offset, need_sample, need_grad,
+                               debug_noise)
         if need_grad:
             ctx.save_for_backward(out["grad_cond"], out["grad_t"], out["grad_temp"])
         ctx.temp_shape = contra_temp.shape if isinstance(contra_temp, torch.Tensor) else None

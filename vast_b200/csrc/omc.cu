@@ -28,6 +28,8 @@
 // 128 x D fp32; at D = 1024 that is 512 KB, twice the 256 KB of TMEM (512 columns x 128 lanes).
 // Staging Pt in fp16 through L2 (32 MB per direction at bs = N = 4096; the L2 holds 126 MB) keeps S at
 // one evaluation; fp32 logits / log-softmax / gradient matrices are never materialised.
+#include <type_traits>
+
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
@@ -368,6 +370,150 @@ __global__ void __launch_bounds__(256) omc_prep_kernel(const __nv_bfloat16* __re
   }
 }
 
+// ------------------------------------------------------------------ K0 + K1 fused (single rank)
+// With one rank there is no all-gather between the packing kernel (vast_pack_pair) and K1, so both run as ONE pass
+// over the fp features: every element is read once and leaves as the bf16 operand (pack), its fp16 copy (pack16),
+// a column-sum contribution and a term of the target logit.  A block owns PP_ROWS rows x 128 columns of BOTH
+// halves of the packed row (lanes 0-15: feat_t columns, lanes 16-31: the same columns of feat_cond), so
+// <t_i, c_i> is a shuffle away.  Two tickets keep every reduction in a fixed order: the last block of a column
+// tile sums that tile's slab partials into ksum, the last block of a slab sums its rows' per-tile dot products
+// into z_t (and the exponent reference).
+constexpr int PP_ROWS = 64;
+template <class TI>
+__device__ __forceinline__ uint4 load8_as_bf16(const TI* src) {
+  uint4 o;
+  if constexpr (sizeof(TI) == 4) {
+    const float4 a = ld_stream_f4(src), c = ld_stream_f4(src + 4);
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(c.x, c.y), h3 = __floats2bfloat162_rn(c.z, c.w);
+    o.x = *reinterpret_cast<const uint32_t*>(&h0);
+    o.y = *reinterpret_cast<const uint32_t*>(&h1);
+    o.z = *reinterpret_cast<const uint32_t*>(&h2);
+    o.w = *reinterpret_cast<const uint32_t*>(&h3);
+  } else if constexpr (std::is_same<TI, __nv_bfloat16>::value) {
+    o = ld_stream16(src);
+  } else {
+    const uint4 raw = ld_stream16(src);
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+    uint32_t* ow = &o.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      const __nv_bfloat162 r = __floats2bfloat162_rn(f.x, f.y);
+      ow[j] = *reinterpret_cast<const uint32_t*>(&r);
+    }
+  }
+  return o;
+}
+
+template <class TI>
+__global__ void __launch_bounds__(256) omc_pack_prep_kernel(const TI* __restrict__ ft, const TI* __restrict__ fc, int64_t ld,
+                                                           int n, int dim, int nslab, int ctiles,
+                                                           __nv_bfloat16* __restrict__ pack, __half* __restrict__ pack16,
+                                                           float* __restrict__ ksum_partial, float* __restrict__ ksum,
+                                                           float* __restrict__ zt_part, float* __restrict__ zt,
+                                                           float* __restrict__ ref2, float scale2,
+                                                           const float* __restrict__ temp_dev, int* __restrict__ flags,
+                                                           int* __restrict__ slab_tickets) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float red[8][264];
+  __shared__ int last_of_tile, last_of_slab;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slab = blockIdx.x / ctiles, ct = blockIdx.x - slab * ctiles;
+  const int second = lane >> 4;                   // 0: feat_t half, 1: feat_cond half
+  const int col = ct * 128 + (lane & 15) * 8;     // column inside the half
+  const bool cvalid = col < dim;
+  const int cols = 2 * dim;
+  const int r0 = slab * PP_ROWS + warp * (PP_ROWS / 8);
+  const TI* src = (second ? fc : ft) + col;
+  uint4 raw[PP_ROWS / 8];
+#pragma unroll
+  for (int i = 0; i < PP_ROWS / 8; ++i) {
+    const int r = r0 + i;
+    raw[i] = (cvalid && r < n) ? load8_as_bf16<TI>(src + static_cast<int64_t>(r) * ld) : make_uint4(0, 0, 0, 0);
+  }
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < PP_ROWS / 8; ++i) {
+    const int r = r0 + i;
+    const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+    uint4 h16;
+    uint32_t* hw = &h16.x;
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xffff0000u);
+      acc[2 * j] += lo;
+      acc[2 * j + 1] += hi;
+      const __half2 h = __floats2half2_rn(lo, hi);
+      hw[j] = *reinterpret_cast<const uint32_t*>(&h);
+      const uint32_t ow = __shfl_xor_sync(0xffffffffu, w[j], 16);  // the same columns of the other half
+      dot = fmaf(lo, __uint_as_float(ow << 16), dot);
+      dot = fmaf(hi, __uint_as_float(ow & 0xffff0000u), dot);
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (r < n) {
+      if (cvalid) {
+        const int64_t at = static_cast<int64_t>(r) * cols + second * dim + col;
+        *reinterpret_cast<uint4*>(pack + at) = raw[i];
+        if (pack16 != nullptr) *reinterpret_cast<uint4*>(pack16 + at) = h16;
+      }
+      if (lane == 0) zt_part[static_cast<int64_t>(r) * ctiles + ct] = dot;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  // thread x owns the block's column x: half = x / 128, column inside the half = ct * 128 + x % 128
+  const int my_col = ct * 128 + (threadIdx.x & 127);
+  const int64_t my_gc = static_cast<int64_t>(threadIdx.x >> 7) * dim + my_col;
+  if (my_col < dim) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w][threadIdx.x];
+    ksum_partial[static_cast<int64_t>(slab) * cols + my_gc] = sum;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    last_of_tile = (atomicAdd(&flags[8 + ct], 1) == nslab - 1);
+    last_of_slab = (atomicAdd(&slab_tickets[slab], 1) == ctiles - 1);
+  }
+  __syncthreads();
+  if (last_of_tile) {
+    __threadfence();
+    if (my_col < dim) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int b = 0;
+      for (; b + 4 <= nslab; b += 4) {
+        a0 += __ldcg(ksum_partial + static_cast<int64_t>(b) * cols + my_gc);
+        a1 += __ldcg(ksum_partial + static_cast<int64_t>(b + 1) * cols + my_gc);
+        a2 += __ldcg(ksum_partial + static_cast<int64_t>(b + 2) * cols + my_gc);
+        a3 += __ldcg(ksum_partial + static_cast<int64_t>(b + 3) * cols + my_gc);
+      }
+      for (; b < nslab; ++b) a0 += __ldcg(ksum_partial + static_cast<int64_t>(b) * cols + my_gc);
+      ksum[my_gc] = (a0 + a1) + (a2 + a3);
+    }
+  }
+  if (last_of_slab) {
+    __threadfence();
+    const int r = slab * PP_ROWS + threadIdx.x;
+    if (static_cast<int>(threadIdx.x) < PP_ROWS && r < n) {
+      float z = 0.f;
+      for (int t = 0; t < ctiles; ++t) z += __ldcg(zt_part + static_cast<int64_t>(r) * ctiles + t);
+      zt[r] = z;
+      zt[n + r] = z;
+      if (ref2 != nullptr) {
+        if (temp_dev) scale2 = kLog2e / __ldg(temp_dev);
+        ref2[r] = z * scale2;
+        ref2[n + r] = z * scale2;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ two-pass form: merge pass-1 partials
 __global__ void __launch_bounds__(128) omc_stats_finalize_kernel(const float2* __restrict__ partial, int slots, int rows2,
                                                                 float* __restrict__ ref2, const int* __restrict__ gate) {
@@ -551,11 +697,31 @@ struct EpiGrad {
     float* grad_t;
     float* dotq;  // [2][M][num_slots]
     int num_slots;
+    // ---- fused row statistics (K3 folded into this epilogue; `partial` == nullptr: K3 ran as its own kernel and
+    // `rowstat` holds its results).  Every epilogue thread merges the soft epilogue's partials of its own row while
+    // the first accumulator tile is still being multiplied; the threads of the first column range also draw the
+    // hard negative and publish (rho, c_t, p_target, lse) for the final reduction.  Bit-identical to K3: the
+    // lane-strided butterfly sums of the warp-per-row kernel are replayed as the same binary trees.
+    const float4* partial;  // [2][M][sslots] from EpiSoft
+    int sslots;             // <= 32
+    const float* ref2;
+    const float* zt;
+    float eps_ls, floor;
+    int n_total;
+    int64_t* neg_idx;  // [2][M] or nullptr
+    int elem_mode;
+    const __half* Pm;  // Pt
+    int64_t ldp;
+    uint32_t seed_lo, seed_hi, off_lo, off_hi;
+    const unsigned long long* step_ctr;
+    float4* rowstat_out;  // [2][M] (rho, c_t, p_target, lse)
+    float* lse_out;       // [2][M] or nullptr
+    float* dots;          // [2][M][num_slots] partials of <q, sum_j K_j>
   };
   static constexpr bool kUnrollChunks = true;  // the operand double buffer lives in registers
   static constexpr int kAuxWarps = 0;
   const Params& p;
-  float rho, c_t, gs, dotq;
+  float rho, c_t, gs, dotq, dots;
   const __nv_bfloat16* qrow;
   const __nv_bfloat16* krow;
   float* grow;
@@ -567,12 +733,127 @@ struct EpiGrad {
     gs = inv_tau;  // scaled by 1 / (2 M) per chunk (M comes with the item)
     cur_ok = nxt_ok = false;
   }
+  // K3 for one row on one thread (see omc_row_stats_kernel, whose arithmetic this replays operation for operation).
+  // A free-standing function (no `this`): the epilogue object, with its operand double buffer, must stay in registers.
+  static __device__ __noinline__ float2 fused_row_stats(const Params& p, int prob, int M, int row, float gs, bool publish) {
+    float rho, c_t;
+    const int r = prob * M + row;
+    const float4* pp = p.partial + static_cast<int64_t>(r) * p.sslots;
+    float lv[32];
+    float bw = p.elem_mode ? -1.f : 0.f, be = 1.f;
+    int bidx = -1;
+#pragma unroll
+    for (int s = 0; s < 32; ++s) {
+      lv[s] = 0.f;
+      if (s < p.sslots) {
+        const float4 q = pp[s];
+        lv[s] = q.x;
+        const int idx = __float_as_int(q.w);
+        if (idx >= 0) {
+          const float lhs = q.y * be, rhs = bw * q.z;
+          if (bidx < 0 || lhs > rhs || (lhs == rhs && idx < bidx)) {
+            bw = q.y;
+            be = q.z;
+            bidx = idx;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {  // the xor-butterfly of warp_sum as a tree
+#pragma unroll
+      for (int i = 0; i < o; ++i) lv[i] += lv[i + o];
+    }
+    const float l = lv[0];
+    const float ref = p.ref2[r], zt = p.zt[r];
+    const float scale2 = kLog2e * gs;
+    const float pt_un = exp2f(fmaf(zt, scale2, -ref));
+    const float ltot = l + pt_un;
+    rho = 1.0f / ltot;
+    const float pt = pt_un * rho;
+    c_t = pt - (1.f - p.eps_ls);
+    if (!publish) return make_float2(rho, c_t);
+    // ---- publisher: hard negative + what the final reduction needs
+    const float lse = (ref + log2f(ltot)) * kLn2;
+    if (p.neg_idx != nullptr) {
+      const int N = p.n_total;
+      const int tcol = p.row_offset + row;
+      int pick = -1;
+      if (p.elem_mode) {
+        pick = bidx;
+      } else if (N > 1) {
+        unsigned long long off = (static_cast<unsigned long long>(p.off_hi) << 32) | p.off_lo;
+        if (p.step_ctr != nullptr) off += *p.step_ctr;
+        const uint4 rnd = philox4x32_10(make_uint4(0xFFFFFFFFu, static_cast<uint32_t>(p.row_offset + row), static_cast<uint32_t>(off),
+                                                   (static_cast<uint32_t>(off >> 32) << 1) | static_cast<uint32_t>(prob)),
+                                        make_uint2(p.seed_lo, p.seed_hi));
+        const float u_in = unit_from_bits(rnd.x), u_mix = unit_from_bits(rnd.y), u_uni = unit_from_bits(rnd.z);
+        const float w_a = l, w_b = p.floor * ltot * static_cast<float>(N - 1);
+        const bool take_a = bidx >= 0 && u_mix * (w_a + w_b) < w_a;
+        if (take_a) {
+          const __half* src = p.Pm + static_cast<int64_t>(r) * p.ldp + bidx * 32;
+          float v[32], pre[32];
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            uint4 u = make_uint4(0, 0, 0, 0);
+            if (bidx * 32 + 8 * g8 < N) u = *reinterpret_cast<const uint4*>(src + 8 * g8);  // ldp is a multiple of 8 >= N
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __half22float2(h[j]);
+              v[8 * g8 + 2 * j] = f.x;
+              v[8 * g8 + 2 * j + 1] = f.y;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (bidx * 32 + i >= N) v[i] = 0.f;
+            pre[i] = v[i];
+          }
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {  // Kogge-Stone inclusive prefix, the same additions as the warp version
+#pragma unroll
+            for (int i = 31; i >= o; --i) pre[i] += pre[i - o];
+          }
+          const float target = u_in * pre[31];
+          int hit = -1, last = -1;
+#pragma unroll
+          for (int i = 31; i >= 0; --i) {
+            if (v[i] > 0.f) {
+              if (last < 0) last = i;
+              if (pre[i] >= target) hit = i;
+            }
+          }
+          if (hit >= 0)
+            pick = bidx * 32 + hit;
+          else if (last >= 0)
+            pick = bidx * 32 + last;
+        }
+        if (pick < 0) {  // uniform over the N - 1 non-target columns
+          int j = static_cast<int>(u_uni * static_cast<float>(N - 1));
+          j = j > N - 2 ? N - 2 : j;
+          pick = j >= tcol ? j + 1 : j;
+        }
+      }
+      p.neg_idx[r] = pick;
+    }
+    p.rowstat_out[r] = make_float4(rho, c_t, pt, lse);
+    if (p.lse_out) p.lse_out[r] = lse;
+    return make_float2(rho, c_t);
+  }
   __device__ __forceinline__ void item_begin(const tc::ItemCtx& c) {
     const int row = c.row_valid ? c.row : 0;
-    const float4 st = p.rowstat[static_cast<int64_t>(c.prob) * c.M + row];
-    rho = st.x;
-    c_t = st.y;
+    if (p.partial != nullptr) {
+      const float2 st = fused_row_stats(p, c.prob, c.M, row, gs, c.n_split == 0 && c.k_split == 0 && c.half == 0 && c.row_valid);
+      rho = st.x;
+      c_t = st.y;
+    } else {
+      const float4 st = p.rowstat[static_cast<int64_t>(c.prob) * c.M + row];
+      rho = st.x;
+      c_t = st.y;
+    }
     dotq = 0.f;
+    dots = 0.f;
     const __nv_bfloat16* prow = p.pack + static_cast<int64_t>(p.row_offset + row) * 2 * p.D;
     qrow = prow + (c.prob == 0 ? p.D : 0);  // this direction's query row
     krow = prow + (c.prob == 0 ? 0 : p.D);  // the positive row of the gathered side
@@ -620,6 +901,7 @@ struct EpiGrad {
         for (int j = 0; j < 8; ++j) {
           const float a = __uint_as_float(v[i + j]);
           dotq = fmaf(q[j], a, dotq);
+          dots = fmaf(q[j], sv[j], dots);
           g[j] = g1 * (fmaf(rho, a, c_t * k[j]) - p.c_sm * sv[j]);
         }
         *reinterpret_cast<float4*>(grow + col0 + i) = make_float4(g[0], g[1], g[2], g[3]);
@@ -632,13 +914,18 @@ struct EpiGrad {
           const float a = __uint_as_float(v[i]);
           const float q = __bfloat162float(qrow[col0 + i]), k = __bfloat162float(krow[col0 + i]);
           dotq = fmaf(q, a, dotq);
+          dots = fmaf(q, ks[i], dots);
           grow[col0 + i] = g1 * (fmaf(rho, a, c_t * k) - p.c_sm * ks[i]);
         }
       }
     }
   }
   __device__ __forceinline__ void item_end(const tc::ItemCtx& c) {
-    if (c.row_valid) p.dotq[(static_cast<int64_t>(c.prob) * c.M + c.row) * p.num_slots + c.slot] = dotq;
+    if (c.row_valid) {
+      const int64_t at = (static_cast<int64_t>(c.prob) * c.M + c.row) * p.num_slots + c.slot;
+      p.dotq[at] = dotq;
+      if (p.dots != nullptr) p.dots[at] = dots;
+    }
   }
 };
 
@@ -708,7 +995,8 @@ __global__ void __launch_bounds__(256) omc_grad_reduce_kernel(const GradReducePa
 // One thread per (direction, row); per-block sums in a fixed order, the last block (ticket) adds the block sums.
 __global__ void __launch_bounds__(256) omc_final_kernel(const float* __restrict__ rowce, const float4* __restrict__ rowstat,
                                                        const float* __restrict__ zt, const float* __restrict__ dotq,
-                                                       int dslots, int rows2, int M, float inv_tau,
+                                                       const float* __restrict__ dots, int dslots, int rows2, int M,
+                                                       float inv_tau,
                                                        const float* __restrict__ temp_dev, float eps_ls, float c_sm,
                                                        float2* __restrict__ blockpart, int* __restrict__ ticket,
                                                        float* __restrict__ loss, float* __restrict__ grad_temp,
@@ -720,16 +1008,30 @@ __global__ void __launch_bounds__(256) omc_final_kernel(const float* __restrict_
   const int r = blockIdx.x * 256 + threadIdx.x;
   float a = 0.f, b = 0.f;
   if (r < rows2) {
-    a = rowce[r];
-    if (dotq != nullptr) {
-      if (temp_dev) inv_tau = 1.0f / __ldg(temp_dev);
-      const float4 st = rowstat[r];  // (rho, c_t, p_target, <q, ksum>)
-      float dq = 0.f;
-      for (int s = 0; s < dslots; ++s) dq += dotq[static_cast<int64_t>(r) * dslots + s];
+    if (temp_dev) inv_tau = 1.0f / __ldg(temp_dev);
+    if (dots != nullptr) {
+      // statistics fused into the dQ epilogue: rowstat = (rho, c_t, p_target, lse), <q, sum_j K_j> arrives as partials
+      const float4 st = rowstat[r];
+      float dq = 0.f, ds = 0.f;
+      for (int s = 0; s < dslots; ++s) {
+        dq += dotq[static_cast<int64_t>(r) * dslots + s];
+        ds += dots[static_cast<int64_t>(r) * dslots + s];
+      }
       const float z = zt[r];
-      const float pz = st.x * dq + st.z * z;  // sum_j p_ij s_ij
-      // d loss / d tau row term: -(1/tau) sum_j (p_ij - y_ij) z_ij
-      b = -inv_tau * inv_tau * (pz - (1.f - eps_ls) * z - c_sm * st.w);
+      a = st.w - (1.f - eps_ls) * inv_tau * z - c_sm * inv_tau * ds;
+      const float pz = st.x * dq + st.z * z;
+      b = -inv_tau * inv_tau * (pz - (1.f - eps_ls) * z - c_sm * ds);
+    } else {
+      a = rowce[r];
+      if (dotq != nullptr) {
+        const float4 st = rowstat[r];  // (rho, c_t, p_target, <q, ksum>)
+        float dq = 0.f;
+        for (int s = 0; s < dslots; ++s) dq += dotq[static_cast<int64_t>(r) * dslots + s];
+        const float z = zt[r];
+        const float pz = st.x * dq + st.z * z;  // sum_j p_ij s_ij
+        // d loss / d tau row term: -(1/tau) sum_j (p_ij - y_ij) z_ij
+        b = -inv_tau * inv_tau * (pz - (1.f - eps_ls) * z - c_sm * st.w);
+      }
     }
   }
   red[0][threadIdx.x] = a;
@@ -782,10 +1084,12 @@ struct OmcPlan {
   int bn_dq;
   int slots;
   int nslab, ncs;
+  int nslab_pp, ctiles_pp;  // fused pack + prep (single rank): PP_ROWS-row slabs x 128-column tiles
   int64_t npad;
   // workspace offsets (bytes)
   int dslots;  // <q, dQraw> partials per row
-  size_t off_flags, off_partial, off_ref2, off_zt, off_rowce, off_rowstat, off_blockpart, off_dotq, off_ksump, off_ksum, off_P,
+  size_t off_ztpart;
+  size_t off_flags, off_partial, off_ref2, off_zt, off_rowce, off_rowstat, off_blockpart, off_dotq, off_dots, off_ksump, off_ksum, off_P,
       off_dq, off_k16, total;
 };
 
@@ -808,7 +1112,10 @@ static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, bool
     off += bytes;
     return r;
   };
-  pl->off_flags = take(sizeof(int) * FLAG_INTS);
+  pl->nslab_pp = ceil_div((int)n_total, PP_ROWS);
+  pl->ctiles_pp = ceil_div((int)dim, 128);
+  pl->off_flags = take(sizeof(int) * (FLAG_INTS + pl->nslab_pp));  // flags, then one ticket per pack+prep slab
+  pl->off_ztpart = take(sizeof(float) * n_total * pl->ctiles_pp);
   pl->off_partial = take(sizeof(float4) * 2 * bs * pl->slots);
   pl->off_ref2 = take(sizeof(float) * 2 * bs);
   pl->off_zt = take(sizeof(float) * 2 * bs);
@@ -817,7 +1124,8 @@ static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, bool
   pl->off_blockpart = take(sizeof(float2) * ceil_div64(2 * bs, 256));
   pl->dslots = pl->g_dq.k_splits == 1 ? pl->g_dq.n_splits * 2 : 1;  // EpiGrad runs with two column halves per tile
   pl->off_dotq = take(sizeof(float) * 2 * bs * pl->dslots);
-  pl->off_ksump = take(sizeof(float) * 2 * dim * pl->nslab);
+  pl->off_dots = take(sizeof(float) * 2 * bs * pl->dslots);
+  pl->off_ksump = take(sizeof(float) * 2 * dim * pl->nslab_pp);  // nslab_pp >= nslab
   pl->off_ksum = take(sizeof(float) * 2 * dim);
   pl->off_P = pl->off_dq = 0;
   if (need_p) pl->off_P = take(sizeof(__half) * 2 * bs * pl->npad);
@@ -840,12 +1148,14 @@ extern "C" size_t vast_omc_workspace_bytes(int64_t bs, int64_t n_total, int64_t 
   return pl.total;
 }
 
-extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int64_t dim, int64_t row_offset,
-                             float contra_temp, const float* contra_temp_dev, float label_smoothing,
-                             float weight_floor, uint64_t seed, uint64_t offset, uint64_t* step_counter,
-                             const float* debug_noise, int flags,
-                             float* loss, int64_t* neg_idx, float* grad_cond, float* grad_t, float* grad_temp, float* lse,
-                             void* workspace, size_t workspace_bytes, vast_stream_t stream) {
+// feat_t_in / feat_cond_in non-null (single rank only): `pack` is an OUTPUT written by the fused pack + prep kernel.
+static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in_dtype, int64_t ld_in,
+                         const void* pack, int64_t bs, int64_t n_total, int64_t dim, int64_t row_offset,
+                         float contra_temp, const float* contra_temp_dev, float label_smoothing,
+                         float weight_floor, uint64_t seed, uint64_t offset, uint64_t* step_counter,
+                         const float* debug_noise, int flags,
+                         float* loss, int64_t* neg_idx, float* grad_cond, float* grad_t, float* grad_temp, float* lse,
+                         void* workspace, size_t workspace_bytes, vast_stream_t stream) {
   VAST_REQUIRE(pack && loss && workspace, VAST_ERR_INVALID, "omc_step: null pointer");
   VAST_REQUIRE(bs > 0 && n_total >= bs && dim > 0, VAST_ERR_INVALID, "omc_step: bad sizes");
   VAST_REQUIRE(bs < (1 << 24) && n_total < (1 << 30) && dim <= 16384, VAST_ERR_UNSUPPORTED, "omc_step: sizes too large");
@@ -877,6 +1187,9 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
   float4* rowstat = reinterpret_cast<float4*>(ws + pl.off_rowstat);
   float2* blockpart = reinterpret_cast<float2*>(ws + pl.off_blockpart);
   float* dotq = reinterpret_cast<float*>(ws + pl.off_dotq);
+  float* dots = reinterpret_cast<float*>(ws + pl.off_dots);
+  // K3 folded into the dQ GEMM's epilogue whenever that GEMM assembles the gradient itself (no split-K)
+  const bool fused_stats = need_grad && pl.g_dq.k_splits == 1 && pl.slots <= 32 && (flags & VAST_OMC_SEPARATE_ROW_STATS) == 0;
   __half* pack16 = need_grad ? reinterpret_cast<__half*>(ws + pl.off_k16) : nullptr;
 
   const auto* pk = static_cast<const __nv_bfloat16*>(pack);
@@ -884,12 +1197,34 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
   const int M = static_cast<int>(bs), N = static_cast<int>(n_total), D = static_cast<int>(dim);
   int rc;
 
-  VAST_CUDA_OK(cudaMemsetAsync(wflags, 0, sizeof(int) * FLAG_INTS, stream));
-  // K1
-  VAST_TIMED(stream, "omc_prep",
-             (launch_ex(omc_prep_kernel, pl.ncs + ceil_div(M, 8), 256, 0, stream, 1, pk, N, D, M, static_cast<int>(row_offset), pl.ncs,
-                        pl.nslab, ksump, ksum, zt, two_pass ? nullptr : ref2, kLog2e * inv_tau, contra_temp_dev, wflags, pack16)));
-  VAST_LAUNCH_OK("omc_prep");
+  if (feat_t_in != nullptr) {
+    // K0 + K1 in one pass over the fp features (single rank: nothing to gather in between)
+    VAST_CUDA_OK(cudaMemsetAsync(wflags, 0, sizeof(int) * (FLAG_INTS + pl.nslab_pp), stream));
+    float* ztpart = reinterpret_cast<float*>(ws + pl.off_ztpart);
+    auto* pko = const_cast<__nv_bfloat16*>(pk);
+    float* ref2_or_null = two_pass ? nullptr : ref2;
+    const unsigned grid = static_cast<unsigned>(pl.nslab_pp * pl.ctiles_pp);
+#define VAST_PACK_PREP(T)                                                                                                       \
+  VAST_TIMED(stream, "omc_pack_prep",                                                                                           \
+             (launch_ex(omc_pack_prep_kernel<T>, grid, 256, 0, stream, 1, static_cast<const T*>(feat_t_in),                     \
+                        static_cast<const T*>(feat_cond_in), ld_in, N, D, pl.nslab_pp, pl.ctiles_pp, pko, pack16, ksump, ksum, \
+                        ztpart, zt, ref2_or_null, kLog2e * inv_tau, contra_temp_dev, wflags, wflags + FLAG_INTS)))
+    if (in_dtype == VAST_F32)
+      VAST_PACK_PREP(float);
+    else if (in_dtype == VAST_BF16)
+      VAST_PACK_PREP(__nv_bfloat16);
+    else
+      VAST_PACK_PREP(__half);
+#undef VAST_PACK_PREP
+    VAST_LAUNCH_OK("omc_pack_prep");
+  } else {
+    VAST_CUDA_OK(cudaMemsetAsync(wflags, 0, sizeof(int) * FLAG_INTS, stream));
+    // K1
+    VAST_TIMED(stream, "omc_prep",
+               (launch_ex(omc_prep_kernel, pl.ncs + ceil_div(M, 8), 256, 0, stream, 1, pk, N, D, M, static_cast<int>(row_offset), pl.ncs,
+                          pl.nslab, ksump, ksum, zt, two_pass ? nullptr : ref2, kLog2e * inv_tau, contra_temp_dev, wflags, pack16)));
+    VAST_LAUNCH_OK("omc_prep");
+  }
 
   // tensor maps of the S GEMMs: A = local rows, B = all rows, both strided views of `pack`
   CUtensorMap tmA[2], tmB[2];
@@ -973,8 +1308,8 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
     if (rc) return rc;
   }
 
-  // K3: row statistics + hard negatives
-  {
+  // K3: row statistics + hard negatives (its own kernel unless the dQ epilogue does it)
+  if (!fused_stats) {
     RowStatParams R;
     memset(&R, 0, sizeof(R));
     R.partial = partial;
@@ -1025,7 +1360,39 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
         P.tmA[i] = tmPa[i];
         P.tmB[i] = tmKb[i];
       }
-      P.epi = {rowstat, ksum, pk, static_cast<int>(row_offset), D, inv_tau, contra_temp_dev, c_sm, grad_cond, grad_t, dotq, pl.dslots};
+      P.epi.rowstat = rowstat;
+      P.epi.ksum = ksum;
+      P.epi.pack = pk;
+      P.epi.row_offset = static_cast<int>(row_offset);
+      P.epi.D = D;
+      P.epi.inv_tau = inv_tau;
+      P.epi.temp_dev = contra_temp_dev;
+      P.epi.c_sm = c_sm;
+      P.epi.grad_cond = grad_cond;
+      P.epi.grad_t = grad_t;
+      P.epi.dotq = dotq;
+      P.epi.num_slots = pl.dslots;
+      if (fused_stats) {
+        P.epi.partial = partial;
+        P.epi.sslots = pl.slots;
+        P.epi.ref2 = ref2;
+        P.epi.zt = zt;
+        P.epi.eps_ls = label_smoothing;
+        P.epi.floor = weight_floor;
+        P.epi.n_total = N;
+        P.epi.neg_idx = neg_idx;
+        P.epi.elem_mode = elem ? 1 : 0;
+        P.epi.Pm = Pbuf;
+        P.epi.ldp = pl.npad;
+        P.epi.seed_lo = static_cast<uint32_t>(seed);
+        P.epi.seed_hi = static_cast<uint32_t>(seed >> 32);
+        P.epi.off_lo = static_cast<uint32_t>(offset);
+        P.epi.off_hi = static_cast<uint32_t>(offset >> 32);
+        P.epi.step_ctr = reinterpret_cast<const unsigned long long*>(step_counter);
+        P.epi.rowstat_out = rowstat;
+        P.epi.lse_out = lse;
+        P.epi.dots = dots;
+      }
       rc = pl.bn_dq == 256 ? tc::launch_gemm<EpiGrad, 256, 4, 8, true>(P, stream, "omc_dq_gemm")
                            : tc::launch_gemm<EpiGrad, 128, 4, 8, true>(P, stream, "omc_dq_gemm");
       if (rc) return rc;
@@ -1066,8 +1433,35 @@ extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int6
   // K5
   VAST_TIMED(stream, "omc_final",
              (launch_ex(omc_final_kernel, ceil_div(2 * M, 256), 256, 0, stream, 1, rowce, rowstat, zt, need_grad ? dotq : nullptr,
-                        pl.dslots, 2 * M, M, inv_tau, contra_temp_dev, label_smoothing, c_sm, blockpart, &wflags[1], loss,
+                        fused_stats ? dots : nullptr, pl.dslots, 2 * M, M, inv_tau, contra_temp_dev, label_smoothing, c_sm, blockpart, &wflags[1], loss,
                         need_grad ? grad_temp : nullptr, reinterpret_cast<unsigned long long*>(step_counter))));
   VAST_LAUNCH_OK("omc_final");
   return VAST_OK;
+}
+
+extern "C" int vast_omc_step(const void* pack, int64_t bs, int64_t n_total, int64_t dim, int64_t row_offset,
+                             float contra_temp, const float* contra_temp_dev, float label_smoothing,
+                             float weight_floor, uint64_t seed, uint64_t offset, uint64_t* step_counter,
+                             const float* debug_noise, int flags,
+                             float* loss, int64_t* neg_idx, float* grad_cond, float* grad_t, float* grad_temp, float* lse,
+                             void* workspace, size_t workspace_bytes, vast_stream_t stream) {
+  return omc_step_impl(nullptr, nullptr, 0, 0, pack, bs, n_total, dim, row_offset, contra_temp, contra_temp_dev, label_smoothing,
+                       weight_floor, seed, offset, step_counter, debug_noise, flags, loss, neg_idx, grad_cond, grad_t, grad_temp,
+                       lse, workspace, workspace_bytes, stream);
+}
+
+extern "C" int vast_omc_step_local(const void* feat_t, const void* feat_cond, int dtype, int64_t ld_in, void* pack_bf16,
+                                   int64_t bs, int64_t dim, float contra_temp, const float* contra_temp_dev,
+                                   float label_smoothing, float weight_floor, uint64_t seed, uint64_t offset,
+                                   uint64_t* step_counter, const float* debug_noise, int flags, float* loss, int64_t* neg_idx,
+                                   float* grad_cond, float* grad_t, float* grad_temp, float* lse, void* workspace,
+                                   size_t workspace_bytes, vast_stream_t stream) {
+  VAST_REQUIRE(feat_t && feat_cond && pack_bf16, VAST_ERR_INVALID, "omc_step_local: null pointer");
+  VAST_REQUIRE(dtype == VAST_F32 || dtype == VAST_BF16 || dtype == VAST_F16, VAST_ERR_UNSUPPORTED, "omc_step_local: bad dtype");
+  VAST_REQUIRE(ld_in >= dim && ld_in % 8 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(feat_t) | reinterpret_cast<uintptr_t>(feat_cond)) & 15) == 0,
+               VAST_ERR_UNSUPPORTED, "omc_step_local: ld_in must be a multiple of 8 and the features 16-byte aligned");
+  return omc_step_impl(feat_t, feat_cond, dtype, ld_in, pack_bf16, bs, bs, dim, 0, contra_temp, contra_temp_dev, label_smoothing,
+                       weight_floor, seed, offset, step_counter, debug_noise, flags, loss, neg_idx, grad_cond, grad_t, grad_temp,
+                       lse, workspace, workspace_bytes, stream);
 }

@@ -103,6 +103,11 @@ class OmcGraphStep:
     # the launches of one step on the current stream, static buffers only
     def _enqueue(self, s: int):
         ft, fc = self.feat_t_in[s], self.feat_cond_in[s]
+        if self.world == 1 and ops.local_step_ok(ft):
+            self._out[s] = ops.omc_step_local(ft, fc, self._temp, self.ls, self.wf, seed=self.seed, offset=0,
+                                              need_sample=self.need_negatives, need_grad=True, buffers=self._out[s],
+                                              step_counter=self._ctr)
+            return
         if self.pg is not None:
             pack = self.pg.gather(ft, fc, slot=s)
         else:

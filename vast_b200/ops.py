@@ -141,12 +141,21 @@ def pack_pair(feat_t: torch.Tensor, feat_cond: torch.Tensor, out: torch.Tensor |
 
 # ------------------------------------------------------------------ contrastive step
 OMC_TWO_PASS = 1
+OMC_SEPARATE_ROW_STATS = 2
+
+
+def _omc_flags(two_pass: bool, separate_row_stats: bool | None) -> int:
+    import os
+    if separate_row_stats is None:
+        separate_row_stats = os.environ.get("VAST_OMC_SEPARATE_ROW_STATS", "0") == "1"
+    return (OMC_TWO_PASS if two_pass else 0) | (OMC_SEPARATE_ROW_STATS if separate_row_stats else 0)
 
 
 def omc_step(pack: torch.Tensor, bs: int, row_offset: int, contra_temp, label_smoothing: float = 0.1,
              weight_floor: float = 1e-4, seed: int = 0, offset: int = 0, need_sample: bool = True,
              need_grad: bool = True, debug_noise: torch.Tensor | None = None, want_lse: bool = False,
-             buffers: dict | None = None, two_pass: bool = False, step_counter: torch.Tensor | None = None):
+             buffers: dict | None = None, two_pass: bool = False, step_counter: torch.Tensor | None = None,
+             separate_row_stats: bool | None = None):
     """Fused OMC step (vast.py:405-440 + backward) on the packed, gathered features.
     Returns dict(loss[1], neg_idx[2,bs] | None, grad_cond, grad_t, grad_temp | None, lse | None).
     `buffers` (a dict returned by an earlier call with the same shapes/flags) re-uses outputs + workspace.
@@ -154,7 +163,9 @@ def omc_step(pack: torch.Tensor, bs: int, row_offset: int, contra_temp, label_sm
     on-device fallback; debug_noise [2, bs, n_total] (Exp(1) variates) switches to the reference-literal
     per-element race argmax_j w_j / E_j for index-exact tests.
     step_counter: optional device int64[1]; the Philox offset used is offset + step_counter[0] and the step
-    increments it (so a CUDA-graph replay of the step draws fresh noise)."""
+    increments it (so a CUDA-graph replay of the step draws fresh noise).
+    separate_row_stats: run the row statistics / hard-negative draw as their own kernel instead of inside the dQ
+    GEMM's epilogue (identical results; default from VAST_OMC_SEPARATE_ROW_STATS, off)."""
     require_cuda(pack)
     assert pack.dtype == torch.bfloat16 and pack.is_contiguous() and pack.dim() == 2 and pack.shape[1] % 2 == 0
     n_total, dim = pack.shape[0], pack.shape[1] // 2
@@ -181,10 +192,58 @@ def omc_step(pack: torch.Tensor, bs: int, row_offset: int, contra_temp, label_sm
         contra_temp = 0.0
     check(lib().vast_omc_step(ptr(pack), bs, n_total, dim, row_offset, float(contra_temp), ptr(temp_dev), float(label_smoothing),
                               float(weight_floor), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1),
-                              ptr(step_counter), ptr(debug_noise), OMC_TWO_PASS if two_pass else 0, ptr(loss), ptr(neg), ptr(gc), ptr(gt),
+                              ptr(step_counter), ptr(debug_noise), _omc_flags(two_pass, separate_row_stats), ptr(loss), ptr(neg), ptr(gc), ptr(gt),
                               ptr(gtemp), ptr(lse),
                               ptr(ws), ws.numel(), stream_ptr()), "omc_step")
     return dict(loss=loss, neg_idx=neg, grad_cond=gc, grad_t=gt, grad_temp=gtemp, lse=lse, _ws=(ws, temp_dev))
+
+
+def omc_step_local(feat_t: torch.Tensor, feat_cond: torch.Tensor, contra_temp, label_smoothing: float = 0.1,
+                   weight_floor: float = 1e-4, seed: int = 0, offset: int = 0, need_sample: bool = True,
+                   need_grad: bool = True, debug_noise: torch.Tensor | None = None, want_lse: bool = False,
+                   buffers: dict | None = None, two_pass: bool = False, step_counter: torch.Tensor | None = None,
+                   separate_row_stats: bool | None = None):
+    """The fused OMC step for ONE rank straight from the feature blocks feat_t / feat_cond [bs, D] (fp32 / bf16 /
+    fp16): packing and the step's first kernel are a single pass over the features (vast_omc_step_local).
+    Same returns as `omc_step` plus "pack" (the [bs, 2D] bf16 operand it wrote)."""
+    require_cuda(feat_t, feat_cond)
+    assert feat_t.shape == feat_cond.shape and feat_t.dtype == feat_cond.dtype and feat_t.dim() == 2
+    ft, fc = feat_t.contiguous(), feat_cond.contiguous()
+    bs, dim = ft.shape
+    dev = ft.device
+    if debug_noise is not None:
+        assert debug_noise.shape == (2, bs, bs) and debug_noise.dtype == torch.float32 and debug_noise.is_contiguous()
+    if buffers is not None:
+        loss, neg, gc, gt, gtemp, lse, pack = (buffers[k] for k in ("loss", "neg_idx", "grad_cond", "grad_t", "grad_temp",
+                                                                   "lse", "pack"))
+        ws = buffers["_ws"][0]
+        assert (neg is not None) == need_sample and (gc is not None) == need_grad and (lse is not None) == want_lse
+        assert pack.shape == (bs, 2 * dim)
+    else:
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        neg = torch.empty(2, bs, dtype=torch.int64, device=dev) if need_sample else None
+        gc = torch.empty(bs, dim, dtype=torch.float32, device=dev) if need_grad else None
+        gt = torch.empty(bs, dim, dtype=torch.float32, device=dev) if need_grad else None
+        gtemp = torch.empty(1, dtype=torch.float32, device=dev) if need_grad else None
+        lse = torch.empty(2, bs, dtype=torch.float32, device=dev) if want_lse else None
+        pack = torch.empty(bs, 2 * dim, dtype=torch.bfloat16, device=dev)
+        ws = _ws(lib().vast_omc_workspace_bytes(bs, bs, dim, int(need_sample), int(need_grad)), dev)
+    temp_dev = None
+    if isinstance(contra_temp, torch.Tensor):
+        require_cuda(contra_temp)
+        temp_dev = contra_temp.detach().reshape(1).float()
+        contra_temp = 0.0
+    check(lib().vast_omc_step_local(ptr(ft), ptr(fc), dtype_code(ft.dtype), ft.stride(0), ptr(pack), bs, dim,
+                                    float(contra_temp), ptr(temp_dev), float(label_smoothing), float(weight_floor),
+                                    int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), ptr(step_counter),
+                                    ptr(debug_noise), _omc_flags(two_pass, separate_row_stats), ptr(loss), ptr(neg), ptr(gc),
+                                    ptr(gt), ptr(gtemp), ptr(lse), ptr(ws), ws.numel(), stream_ptr()), "omc_step_local")
+    return dict(loss=loss, neg_idx=neg, grad_cond=gc, grad_t=gt, grad_temp=gtemp, lse=lse, pack=pack, _ws=(ws, temp_dev, ft, fc))
+
+
+def local_step_ok(feat_t: torch.Tensor) -> bool:
+    """vast_omc_step_local needs 16-byte vectors: D a multiple of 8 (contiguous rows are then 16-byte aligned)."""
+    return feat_t.dim() == 2 and feat_t.shape[1] % 8 == 0 and feat_t.data_ptr() % 16 == 0
 
 
 def gather_rows_concat3(ids_local, mask_local, ids_all, mask_all, cond_local, cond_all, neg_text, neg_cond):
