@@ -299,22 +299,23 @@ def test_single_rank_step_from_features(n, dim, dtype, two_pass):
     c = torch.nn.functional.normalize(t + 0.8 * torch.randn(n, dim, generator=gen), dim=-1)
     td, cd = t.to(dtype).cuda(), c.to(dtype).cuda()
     seed, offset = 4242, 11
-    out = ops.omc_step_local(td, cd, 0.07, seed=seed, offset=offset, want_lse=True, two_pass=two_pass)
+    temp = 0.5 if n == 1 else 0.07   # n = 1: loss and gradients are exactly 0, only fp32 rounding times 1 / tau^2 remains
+    out = ops.omc_step_local(td, cd, temp, seed=seed, offset=offset, want_lse=True, two_pass=two_pass)
     torch.cuda.synchronize()
     assert torch.equal(out["pack"], ops.pack_pair(td, cd))
     tn, cn = td.float().cpu().numpy(), cd.float().cpu().numpy()
-    o = oracle(tn, cn, n, 0, 0.07)
+    o = oracle(tn, cn, n, 0, temp)
     check_against_oracle(out, o, n)
     check_negatives_hier(out["neg_idx"], o, seed, offset, 0, n, n)
     # against the two-kernel form: same operands, z_t summed in another order -> agreement far inside the tolerance
-    ref = ops.omc_step(ops.pack_pair(td, cd), n, 0, 0.07, seed=seed, offset=offset, want_lse=True, two_pass=two_pass)
+    ref = ops.omc_step(ops.pack_pair(td, cd), n, 0, temp, seed=seed, offset=offset, want_lse=True, two_pass=two_pass)
     assert rel(out["grad_t"].cpu().numpy(), ref["grad_t"].cpu().numpy()) < 1e-4
-    assert abs(out["loss"].item() - ref["loss"].item()) <= 1e-5 * abs(ref["loss"].item())
+    assert abs(out["loss"].item() - ref["loss"].item()) <= 1e-5 * abs(ref["loss"].item()) + 1e-6
     assert (out["neg_idx"] == ref["neg_idx"]).float().mean().item() >= 0.97 or n < 8
     # loss-only / no sampling, and reuse of the returned buffers
-    lo = ops.omc_step_local(td, cd, 0.07, need_sample=False, need_grad=False)
+    lo = ops.omc_step_local(td, cd, temp, need_sample=False, need_grad=False)
     assert abs(lo["loss"].item() - o["loss"]) <= RTOL * abs(o["loss"]) + 1e-6
-    again = ops.omc_step_local(td, cd, 0.07, seed=seed, offset=offset, want_lse=True, two_pass=two_pass, buffers=out)
+    again = ops.omc_step_local(td, cd, temp, seed=seed, offset=offset, want_lse=True, two_pass=two_pass, buffers=out)
     torch.cuda.synchronize()
     assert again["loss"] is out["loss"]
 

@@ -168,9 +168,12 @@ def test_refine_score_matrix_golden(golden, direction, k):
     assert log[f"{direction}_recall"] == str(g[f"c_recall_{direction}"])
 
 
-def test_evaluate_ret_dropin_golden(golden):
+@pytest.mark.parametrize("streaming", [False, True])
+def test_evaluate_ret_dropin_golden(golden, streaming):
     """vast_b200.evaluate_ret == the reference's evaluate_ret (evaluation_mm.py:171-251) on the same stubbed
-    two-task evaluation: 3 loader batches, 5 captions per video (list-of-lists ids_txt), both directions, ITM k=16."""
+    two-task evaluation: 3 loader batches, 5 captions per video (list-of-lists ids_txt), both directions, ITM k=16.
+    streaming=True never builds the [Nt, Nv] matrix (exact-mode streaming top-k + list-layout re-rank) and must
+    reproduce the reference's val_log as well."""
     import json
     import types
     import vast_b200
@@ -196,8 +199,41 @@ def test_evaluate_ret_dropin_golden(golden):
             ev[f"feat_cond_{t}"] = cu(g[f"feat_v_{t}"][vs])
             ev[f"condition_feats_{t}"] = cu(g[f"cond_{t}"][vs])
         loader.append({"ids": ids[vs], "ids_txt": [[v] * per for v in ids[vs]], "ev": ev})
-    log = vast_b200.evaluate_ret(Model(), "ret%tv%tvas", loader, 0)
+    log = vast_b200.evaluate_ret(Model(), "ret%tv%tvas", loader, 0, streaming=streaming)
     assert log == json.loads(str(g["log_json"]))
+
+
+@pytest.mark.parametrize("direction", ["forward", "backward"])
+@pytest.mark.parametrize("nt,nv,k,per", [(600, 120, 16, 5), (300, 300, 4, 1), (40, 9, 12, 4), (257, 257, 50, 1)])
+def test_streaming_rerank_equals_dense(direction, nt, nv, k, per):
+    """refine_candidates + recall_from_candidates (no score matrix) == refine_score_matrix + compute_metric_ret on
+    the materialised matrix: same candidates, same ITM scores at the same positions, same metrics -- including
+    k < 10 (ties among the zeros of the refined matrix decide R@10) and multi-caption ids."""
+    import vast_b200
+    from vast_b200 import ops, retrieval
+    t, v = feats(nt, nv, 64, 100 + nt + k, noise=3.0)
+    g = torch.Generator().manual_seed(nt)
+    ids_tok = torch.randint(0, 30522, (nt, 12), generator=g).cuda()
+    mask = torch.ones(nt, 12, dtype=torch.int64).cuda()
+    cond = torch.randn(nv, 5, 16, generator=g).cuda()
+    m = _StubModel()
+    tc, vc = t.cuda(), v.cuda()
+    score = ops.gemm_nt_f32(tc, vc)
+    dense = vast_b200.refine_score_matrix(cond, ids_tok, mask, score, m, k, direction)
+    idx, itm = retrieval.refine_candidates(cond, ids_tok, mask, tc, vc, m, k, direction)
+    rows = torch.arange(idx.shape[0], device="cuda")[:, None].expand_as(idx)
+    ok = idx >= 0
+    rebuilt = torch.zeros_like(dense)
+    if direction == "forward":
+        rebuilt[rows[ok], idx[ok].long()] = itm[ok]
+    else:
+        rebuilt[idx[ok].long(), rows[ok]] = itm[ok]
+    assert torch.equal(rebuilt != 0, dense != 0)
+    assert torch.allclose(rebuilt, dense, rtol=1e-5, atol=1e-7)
+    ids = [f"v{i}" for i in range(nv)]
+    ids_txt = [f"v{(i // per) % nv}" for i in range(nt)]
+    assert retrieval.recall_from_candidates(idx, itm, ids, ids_txt, direction) == \
+        vast_b200.compute_metric_ret(dense, ids, ids_txt, direction)
 
 
 def test_bucket_and_scatter():

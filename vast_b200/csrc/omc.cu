@@ -326,19 +326,40 @@ __global__ void __launch_bounds__(256) omc_prep_kernel(const __nv_bfloat16* __re
     if (threadIdx.x == 0) is_last = (atomicAdd(&flags[8 + ctile], 1) == nslab - 1);
     __syncthreads();
     if (is_last) {
+      // This block is the tail of the kernel: warp w sums every 8th slab starting at w with 8 independent 16-byte
+      // loads per lane and round trip (lane = 8 consecutive columns); the 8 warp sums are added in warp order.
       __threadfence();
+      const int c8 = ctile * 256 + lane * 8;
+      float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (c8 < cols) {
+        for (int b0 = warp; b0 < nslab; b0 += 32) {
+          float4 v[4][2];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int b = b0 + 8 * u;
+            const float* src = ksum_partial + static_cast<int64_t>(b < nslab ? b : b0) * cols + c8;
+            v[u][0] = __ldcg(reinterpret_cast<const float4*>(src));
+            v[u][1] = __ldcg(reinterpret_cast<const float4*>(src + 4));
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (b0 + 8 * u < nslab) {
+              a[0] += v[u][0].x; a[1] += v[u][0].y; a[2] += v[u][0].z; a[3] += v[u][0].w;
+              a[4] += v[u][1].x; a[5] += v[u][1].y; a[6] += v[u][1].z; a[7] += v[u][1].w;
+            }
+          }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = a[j];
+      __syncthreads();
       const int c = ctile * 256 + threadIdx.x;
       if (c < cols) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        int b = 0;
-        for (; b + 4 <= nslab; b += 4) {
-          a0 += __ldcg(ksum_partial + static_cast<int64_t>(b) * cols + c);
-          a1 += __ldcg(ksum_partial + static_cast<int64_t>(b + 1) * cols + c);
-          a2 += __ldcg(ksum_partial + static_cast<int64_t>(b + 2) * cols + c);
-          a3 += __ldcg(ksum_partial + static_cast<int64_t>(b + 3) * cols + c);
-        }
-        for (; b < nslab; ++b) a0 += __ldcg(ksum_partial + static_cast<int64_t>(b) * cols + c);
-        ksum[c] = (a0 + a1) + (a2 + a3);
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += red[w][threadIdx.x];
+        ksum[c] = sum;
       }
     }
   } else {
@@ -483,18 +504,41 @@ __global__ void __launch_bounds__(256) omc_pack_prep_kernel(const TI* __restrict
   }
   __syncthreads();
   if (last_of_tile) {
+    // ksum of this tile's 256 columns = sum over slabs, fixed order.  This block is the tail of the kernel, so the
+    // loads must not queue up behind each other: warp w sums every 8th slab starting at w, 8 independent 16-byte
+    // loads per lane and round trip (lane = 8 consecutive columns), then the 8 warp sums are added in warp order.
     __threadfence();
-    if (my_col < dim) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      int b = 0;
-      for (; b + 4 <= nslab; b += 4) {
-        a0 += __ldcg(ksum_partial + static_cast<int64_t>(b) * cols + my_gc);
-        a1 += __ldcg(ksum_partial + static_cast<int64_t>(b + 1) * cols + my_gc);
-        a2 += __ldcg(ksum_partial + static_cast<int64_t>(b + 2) * cols + my_gc);
-        a3 += __ldcg(ksum_partial + static_cast<int64_t>(b + 3) * cols + my_gc);
+    const int half = lane >> 4, c8 = ct * 128 + (lane & 15) * 8;
+    const int64_t gc8 = static_cast<int64_t>(half) * dim + c8;
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (c8 < dim) {
+      for (int b0 = warp; b0 < nslab; b0 += 32) {
+        float4 v[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int b = b0 + 8 * u;
+          const float* src = ksum_partial + static_cast<int64_t>(b < nslab ? b : b0) * cols + gc8;
+          v[u][0] = __ldcg(reinterpret_cast<const float4*>(src));
+          v[u][1] = __ldcg(reinterpret_cast<const float4*>(src + 4));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (b0 + 8 * u < nslab) {
+            a[0] += v[u][0].x; a[1] += v[u][0].y; a[2] += v[u][0].z; a[3] += v[u][0].w;
+            a[4] += v[u][1].x; a[5] += v[u][1].y; a[6] += v[u][1].z; a[7] += v[u][1].w;
+          }
+        }
       }
-      for (; b < nslab; ++b) a0 += __ldcg(ksum_partial + static_cast<int64_t>(b) * cols + my_gc);
-      ksum[my_gc] = (a0 + a1) + (a2 + a3);
+    }
+    __syncthreads();  // `red` was read by every thread above (before the tickets); safe to reuse
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = a[j];
+    __syncthreads();
+    if (my_col < dim) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sum += red[w][threadIdx.x];
+      ksum[my_gc] = sum;
     }
   }
   if (last_of_slab) {
@@ -502,6 +546,7 @@ __global__ void __launch_bounds__(256) omc_pack_prep_kernel(const TI* __restrict
     const int r = slab * PP_ROWS + threadIdx.x;
     if (static_cast<int>(threadIdx.x) < PP_ROWS && r < n) {
       float z = 0.f;
+#pragma unroll 8
       for (int t = 0; t < ctiles; ++t) z += __ldcg(zt_part + static_cast<int64_t>(r) * ctiles + t);
       zt[r] = z;
       zt[n + r] = z;
@@ -992,8 +1037,27 @@ __global__ void __launch_bounds__(256) omc_grad_reduce_kernel(const GradReducePa
 }
 
 // ------------------------------------------------------------------ K5: loss and d tau
-// One thread per (direction, row); per-block sums in a fixed order, the last block (ticket) adds the block sums.
-__global__ void __launch_bounds__(256) omc_final_kernel(const float* __restrict__ rowce, const float4* __restrict__ rowstat,
+// Latency-bound tail of the step: FINAL_ROWS rows per 1024-thread block (8 per thread, all loads independent), so the
+// headline shape (2 x 4096 rows) is ONE block with no ticket; larger problems add a last-block pass over the block
+// sums.  Every sum runs in a fixed order (thread-sequential, xor butterfly, warp order) -> deterministic.
+constexpr int FINAL_THREADS = 1024;
+constexpr int FINAL_RPT = 8;
+constexpr int FINAL_ROWS = FINAL_THREADS * FINAL_RPT;
+__device__ __forceinline__ float2 block_sum2_1024(float a, float b, float (*red)[32]) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) {
+    red[0][warp] = a;
+    red[1][warp] = b;
+  }
+  __syncthreads();
+  a = red[0][lane];
+  b = red[1][lane];
+  return make_float2(warp_sum(a), warp_sum(b));  // every warp computes the same totals
+}
+__global__ void __launch_bounds__(FINAL_THREADS) omc_final_kernel(const float* __restrict__ rowce, const float4* __restrict__ rowstat,
                                                        const float* __restrict__ zt, const float* __restrict__ dotq,
                                                        const float* __restrict__ dots, int dslots, int rows2, int M,
                                                        float inv_tau,
@@ -1003,76 +1067,65 @@ __global__ void __launch_bounds__(256) omc_final_kernel(const float* __restrict_
                                                        unsigned long long* __restrict__ step_ctr) {
   pdl_trigger();
   pdl_wait();
-  __shared__ float red[2][256];
+  __shared__ float red[2][32];
   __shared__ int is_last;
-  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (temp_dev) inv_tau = 1.0f / __ldg(temp_dev);
   float a = 0.f, b = 0.f;
-  if (r < rows2) {
-    if (temp_dev) inv_tau = 1.0f / __ldg(temp_dev);
-    if (dots != nullptr) {
-      // statistics fused into the dQ epilogue: rowstat = (rho, c_t, p_target, lse), <q, sum_j K_j> arrives as partials
-      const float4 st = rowstat[r];
-      float dq = 0.f, ds = 0.f;
-      for (int s = 0; s < dslots; ++s) {
-        dq += dotq[static_cast<int64_t>(r) * dslots + s];
-        ds += dots[static_cast<int64_t>(r) * dslots + s];
-      }
-      const float z = zt[r];
-      a = st.w - (1.f - eps_ls) * inv_tau * z - c_sm * inv_tau * ds;
-      const float pz = st.x * dq + st.z * z;
-      b = -inv_tau * inv_tau * (pz - (1.f - eps_ls) * z - c_sm * ds);
-    } else {
-      a = rowce[r];
-      if (dotq != nullptr) {
-        const float4 st = rowstat[r];  // (rho, c_t, p_target, <q, ksum>)
-        float dq = 0.f;
-        for (int s = 0; s < dslots; ++s) dq += dotq[static_cast<int64_t>(r) * dslots + s];
+#pragma unroll
+  for (int i = 0; i < FINAL_RPT; ++i) {
+    const int r = blockIdx.x * FINAL_ROWS + i * FINAL_THREADS + threadIdx.x;
+    if (r < rows2) {
+      if (dots != nullptr) {
+        // statistics fused into the dQ epilogue: rowstat = (rho, c_t, p_target, lse), <q, sum_j K_j> arrives as partials
+        const float4 st = rowstat[r];
+        float dq = 0.f, ds = 0.f;
+#pragma unroll 4
+        for (int s = 0; s < dslots; ++s) {
+          dq += dotq[static_cast<int64_t>(r) * dslots + s];
+          ds += dots[static_cast<int64_t>(r) * dslots + s];
+        }
         const float z = zt[r];
-        const float pz = st.x * dq + st.z * z;  // sum_j p_ij s_ij
-        // d loss / d tau row term: -(1/tau) sum_j (p_ij - y_ij) z_ij
-        b = -inv_tau * inv_tau * (pz - (1.f - eps_ls) * z - c_sm * st.w);
+        a += st.w - (1.f - eps_ls) * inv_tau * z - c_sm * inv_tau * ds;
+        const float pz = st.x * dq + st.z * z;
+        b += -inv_tau * inv_tau * (pz - (1.f - eps_ls) * z - c_sm * ds);
+      } else {
+        a += rowce[r];
+        if (dotq != nullptr) {
+          const float4 st = rowstat[r];  // (rho, c_t, p_target, <q, ksum>)
+          float dq = 0.f;
+#pragma unroll 4
+          for (int s = 0; s < dslots; ++s) dq += dotq[static_cast<int64_t>(r) * dslots + s];
+          const float z = zt[r];
+          const float pz = st.x * dq + st.z * z;  // sum_j p_ij s_ij
+          // d loss / d tau row term: -(1/tau) sum_j (p_ij - y_ij) z_ij
+          b += -inv_tau * inv_tau * (pz - (1.f - eps_ls) * z - c_sm * st.w);
+        }
       }
     }
   }
-  red[0][threadIdx.x] = a;
-  red[1][threadIdx.x] = b;
-  __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if (static_cast<int>(threadIdx.x) < s) {
-      red[0][threadIdx.x] += red[0][threadIdx.x + s];
-      red[1][threadIdx.x] += red[1][threadIdx.x + s];
+  float2 tot = block_sum2_1024(a, b, red);
+  if (gridDim.x > 1) {
+    if (threadIdx.x == 0) {
+      blockpart[blockIdx.x] = tot;
+      __threadfence();
+      is_last = (atomicAdd(ticket, 1) == static_cast<int>(gridDim.x) - 1);
     }
     __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    blockpart[blockIdx.x] = make_float2(red[0][0], red[1][0]);
+    if (!is_last) return;
     __threadfence();
-    is_last = (atomicAdd(ticket, 1) == static_cast<int>(gridDim.x) - 1);
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  a = 0.f;
-  b = 0.f;
-  for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += 256) {
-    const float2 v = __ldcg(blockpart + i);
-    a += v.x;
-    b += v.y;
-  }
-  red[0][threadIdx.x] = a;
-  red[1][threadIdx.x] = b;
-  __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if (static_cast<int>(threadIdx.x) < s) {
-      red[0][threadIdx.x] += red[0][threadIdx.x + s];
-      red[1][threadIdx.x] += red[1][threadIdx.x + s];
+    a = 0.f;
+    b = 0.f;
+    for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += FINAL_THREADS) {
+      const float2 v = __ldcg(blockpart + i);
+      a += v.x;
+      b += v.y;
     }
-    __syncthreads();
+    tot = block_sum2_1024(a, b, red);
   }
   if (threadIdx.x == 0) {
     const float scale = 1.0f / (2.0f * M);
-    loss[0] = red[0][0] * scale;
-    if (grad_temp) grad_temp[0] = red[1][0] * scale;
+    loss[0] = tot.x * scale;
+    if (grad_temp) grad_temp[0] = tot.y * scale;
     if (step_ctr) *step_ctr += 1;  // the next step (e.g. the next replay of a captured graph) draws fresh noise
   }
 }
@@ -1432,7 +1485,7 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
 
   // K5
   VAST_TIMED(stream, "omc_final",
-             (launch_ex(omc_final_kernel, ceil_div(2 * M, 256), 256, 0, stream, 1, rowce, rowstat, zt, need_grad ? dotq : nullptr,
+             (launch_ex(omc_final_kernel, ceil_div(2 * M, FINAL_ROWS), FINAL_THREADS, 0, stream, 1, rowce, rowstat, zt, need_grad ? dotq : nullptr,
                         fused_stats ? dots : nullptr, pl.dslots, 2 * M, M, inv_tau, contra_temp_dev, label_smoothing, c_sm, blockpart, &wflags[1], loss,
                         need_grad ? grad_temp : nullptr, reinterpret_cast<unsigned long long*>(step_counter))));
   VAST_LAUNCH_OK("omc_final");

@@ -225,9 +225,103 @@ def refine_score_matrix(condition_feats, input_ids, attention_mask, score_matrix
     return out.to(score_matrix_t_cond.dtype)
 
 
+# ------------------------------------------------------------------ streaming re-rank (no [Nt, Nv] matrix anywhere)
 @torch.no_grad()
-def evaluate_ret(model, tasks, val_loader, global_step):
-    """Drop-in for evaluation_mm.py:171-251 (same val_log keys: ret_itc_{task}, ret_itm_{task})."""
+def refine_candidates(condition_feats, input_ids, attention_mask, feat_t, feat_cond, model, itm_rerank_num,
+                      direction='forward', mode='fp32', small_batch=25):
+    """`refine_score_matrix` (evaluation_mm.py:253-319) without the score matrix: candidates come from the streaming
+    top-k over the FEATURES, the refined scores stay in the [rows, k] layout of the candidate lists.
+
+    condition_feats [Nv_local, S, H] are this rank's videos (rank order = column order, as in the reference);
+    input_ids / attention_mask [Nt, L], feat_t [Nt, D], feat_cond [Nv, D] are the gathered, full tensors.
+    Returns (idx int32 [rows, k], itm f32 [rows, k]), identical on every rank:
+      forward : rows = texts,  idx[t] = the k best videos of text t (score desc, index asc), itm = P(match)
+      backward: rows = videos, idx[v] = the k best texts of video v
+    Empty slots (fewer than k columns) have idx = -1 and itm = 0.  The dense matrix of the reference is
+    `zeros(Nt, Nv)` with itm scattered at (t, idx[t, j]) / (idx[v, j], v): `recall_from_candidates` evaluates
+    R@K on exactly that matrix without building it.  Every rank re-ranks the pairs whose video it owns, in the
+    reference's per-video mini-batches; the [rows, k] score blocks are summed across ranks (each slot is written
+    by exactly one rank) instead of the dense transposed all-gather of evaluation_mm.py:317."""
+    k = itm_rerank_num
+    nt, nv = feat_t.shape[0], feat_cond.shape[0]
+    dev = feat_t.device
+    rank, world = _rank(), _world()
+    shard = (rank, world) if world > 1 else None
+    if direction == 'forward':
+        _, idx = retrieval_topk(feat_t, feat_cond, min(k, nv), mode, shard)            # [nt, k] video per text
+        t_idx = torch.arange(nt, dtype=torch.int32, device=dev)[:, None].expand_as(idx).reshape(-1)
+        v_idx = idx.reshape(-1)
+    else:
+        _, idx = retrieval_topk(feat_cond, feat_t, min(k, nt), mode, shard)            # [nv, k] text per video
+        v_idx = torch.arange(nv, dtype=torch.int32, device=dev)[:, None].expand_as(idx).reshape(-1)
+        t_idx = idx.reshape(-1)
+    cur_length = condition_feats.shape[0]
+    length_ls = all_gather_list(cur_length)
+    start = sum(length_ls[:rank])
+    local = (v_idx >= start) & (v_idx < start + cur_length) & (t_idx >= 0)
+    v_local = torch.where(local, v_idx - start, torch.full_like(v_idx, -1))
+    texts, vids, scores = _rerank_pairs(condition_feats, input_ids, attention_mask, t_idx, v_local, model, small_batch)
+    # back into the list layout: both sides hold the same set of unique (text, video) pairs -> sort both by the pair key
+    itm = torch.zeros(idx.numel(), dtype=torch.float32, device=dev)
+    slots = local.nonzero().flatten()
+    if slots.numel() > 0:
+        key_slot = t_idx[slots].long() * nv + v_idx[slots].long()
+        key_pair = texts.long() * nv + (vids.long() + start)
+        itm[slots[torch.argsort(key_slot)]] = scores[torch.argsort(key_pair)]
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(itm)
+    return idx, itm.view_as(idx)
+
+
+def _rank_in_sparse_row(idx, itm, gt):
+    """Rank of column gt[r] in row r of the matrix that is zero except itm[r, j] at column idx[r, j] (ties -> lower
+    index first, like the dense kernel).  idx/itm [R, k], gt [R] -> int64 [R]."""
+    gtc = gt[:, None].to(idx.dtype)
+    valid = idx >= 0
+    at_gt = valid & (idx == gtc)
+    s_gt = (itm * at_gt).sum(dim=1, keepdim=True)                       # 0 when gt is not a candidate
+    ahead = valid & ~at_gt & ((itm > s_gt) | ((itm == s_gt) & (idx < gtc)))
+    r = ahead.sum(dim=1)
+    # columns outside the list hold 0: they tie with gt only if s_gt == 0, and then the lower indices come first
+    listed_below = (valid & (idx < gtc)).sum(dim=1)
+    return r + torch.where(s_gt[:, 0] == 0, gt.long() - listed_below, torch.zeros_like(r))
+
+
+@torch.no_grad()
+def recall_from_candidates(idx, itm, ids, ids_txt, direction='forward'):
+    """`compute_metric_ret` (evaluation_mm.py:326-380) on the refined matrix given as candidate lists
+    (`refine_candidates`): same dict, no [Nt, Nv] matrix."""
+    dev = idx.device
+    if direction == 'forward':
+        first = _first_index(ids)
+        gt = torch.tensor([first[t] for t in ids_txt], dtype=torch.int64, device=dev)
+        rank = _rank_in_sparse_row(idx, itm, gt)
+        n = len(ids_txt)
+    else:
+        rows, cols = _backward_pairs(ids, ids_txt)                      # (text, video) ground-truth pairs
+        cols_t = torch.tensor(cols, dtype=torch.int64, device=dev)
+        r = _rank_in_sparse_row(idx[cols_t], itm[cols_t], torch.tensor(rows, dtype=torch.int64, device=dev))
+        rank = torch.full((len(ids),), 2 ** 40, dtype=torch.int64, device=dev)
+        rank = rank.scatter_reduce(0, cols_t, r, reduce='amin')
+        n = len(ids)
+    counts = torch.stack([(rank < 1).sum(), (rank < 5).sum(), (rank < 10).sum()]).tolist()  # one host read
+    return _format(direction, counts[0] / n, counts[1] / n, counts[2] / n)
+
+
+# above this many score-matrix entries evaluate_ret switches to the streaming path on its own (1 GiB of fp32)
+STREAMING_THRESHOLD = 1 << 28
+
+
+@torch.no_grad()
+def evaluate_ret(model, tasks, val_loader, global_step, streaming=None):
+    """Drop-in for evaluation_mm.py:171-251 (same val_log keys: ret_itc_{task}, ret_itm_{task}).
+
+    streaming=False: the reference's flow on a materialised [Nt, Nv] fp32 matrix (drop-in `refine_score_matrix` /
+    `compute_metric_ret`).  streaming=True: the matrix is never built -- exact-mode streaming top-k for the ITC
+    metrics (`recall_from_feats`), candidate lists + ITM scores in list layout for the re-rank (`refine_candidates`,
+    `recall_from_candidates`); the work is sharded over the ranks instead of repeated on each.  Default (None):
+    streaming once Nt * Nv exceeds STREAMING_THRESHOLD (cfg5 would need 40 GB)."""
     val_log = {}
     ids, ids_txt, input_ids, attention_mask, feat_t = [], [], [], [], []
     subtasks = tasks.split('%')[1:]
@@ -255,6 +349,28 @@ def evaluate_ret(model, tasks, val_loader, global_step):
     input_ids = ddp_allgather(torch.cat(input_ids, dim=0))
     attention_mask = ddp_allgather(torch.cat(attention_mask, dim=0))
     bidir = bool(getattr(model.config, 'ret_bidirection_evaluation', False))
+    if streaming is None:
+        streaming = feat_t.shape[0] * len(ids) > STREAMING_THRESHOLD
+    if streaming:
+        shard = (_rank(), _world()) if _world() > 1 else None
+        dirs = (('forward', 'video'),) + ((('backward', 'txt'),) if bidir else ())
+        feat_cond = {}
+        for t in subtasks:
+            feat_cond[t] = ddp_allgather(torch.cat(store[f'feat_cond_{t}'], dim=0)).float()
+            log = {}
+            for d, name in dirs:
+                log.update({k_.replace(d, name): v for k_, v in
+                            recall_from_feats(feat_t.float(), feat_cond[t], ids, ids_txt, d, mode='fp32', shard=shard).items()})
+            val_log[f'ret_itc_{t}'] = log
+        for t in subtasks:
+            cond = torch.cat(store[f'condition_feats_{t}'], dim=0)
+            log = {}
+            for d, name in dirs:
+                idx, itm = refine_candidates(cond, input_ids, attention_mask, feat_t.float(), feat_cond[t], model,
+                                             model.config.itm_rerank_num, direction=d, mode='fp32')
+                log.update({k_.replace(d, name): v for k_, v in recall_from_candidates(idx, itm, ids, ids_txt, d).items()})
+            val_log[f'ret_itm_{t}'] = log
+        return val_log
     scores = {}
     for t in subtasks:
         fc = ddp_allgather(torch.cat(store[f'feat_cond_{t}'], dim=0))
