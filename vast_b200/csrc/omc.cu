@@ -428,7 +428,7 @@ __device__ __forceinline__ uint4 load8_as_bf16(const TI* src) {
 }
 
 template <class TI>
-__global__ void __launch_bounds__(256) omc_pack_prep_kernel(const TI* __restrict__ ft, const TI* __restrict__ fc, int64_t ld,
+__global__ void __launch_bounds__(256, 4) omc_pack_prep_kernel(const TI* __restrict__ ft, const TI* __restrict__ fc, int64_t ld,
                                                            int n, int dim, int nslab, int ctiles,
                                                            __nv_bfloat16* __restrict__ pack, __half* __restrict__ pack16,
                                                            float* __restrict__ ksum_partial, float* __restrict__ ksum,
@@ -614,12 +614,8 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
   }
 }
 
-__global__ void __launch_bounds__(256) omc_row_stats_kernel(const RowStatParams p) {
-  pdl_trigger();
-  pdl_wait();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * 8 + warp;
-  if (r >= 2 * p.M) return;
+// The statistics of row r = (direction, local row) by one warp; returns (rho, c_t) to every lane.
+__device__ __forceinline__ float2 row_stats_warp(const RowStatParams& p, int r, int lane) {
   const float inv_tau = p.temp_dev ? 1.0f / __ldg(p.temp_dev) : p.inv_tau;
   const int prob = r / p.M, row = r - prob * p.M;
   const int tcol = p.row_offset + row;
@@ -723,6 +719,16 @@ __global__ void __launch_bounds__(256) omc_row_stats_kernel(const RowStatParams 
     p.rowce[r] = lse - (1.f - p.eps_ls) * inv_tau * zt - c_sm * inv_tau * dot_s;
     if (p.lse_out) p.lse_out[r] = lse;
   }
+  return make_float2(rho, pt - (1.f - p.eps_ls));
+}
+
+__global__ void __launch_bounds__(256) omc_row_stats_kernel(const RowStatParams p) {
+  pdl_trigger();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= 2 * p.M) return;
+  row_stats_warp(p, r, lane);
 }
 
 // ------------------------------------------------------------------ K4 epilogue: gradient assembly in the dQ GEMM
@@ -990,6 +996,8 @@ struct GradReduceParams {
   float* grad_cond;
   float* grad_t;
   float* dotq;  // [2][M]
+  int fused_stats;  // the warp computes the row's statistics itself (K3 folded in; same warp-per-row layout)
+  RowStatParams rs;
 };
 __global__ void __launch_bounds__(256) omc_grad_reduce_kernel(const GradReduceParams p) {
   pdl_trigger();
@@ -999,8 +1007,16 @@ __global__ void __launch_bounds__(256) omc_grad_reduce_kernel(const GradReducePa
   if (r >= 2 * p.M) return;
   const float inv_tau = p.temp_dev ? 1.0f / __ldg(p.temp_dev) : p.inv_tau;
   const int prob = r / p.M, row = r - prob * p.M;
-  const float4 st = p.rowstat[r];
-  const float rho = st.x, c_t = st.y;
+  float rho, c_t;
+  if (p.fused_stats) {
+    const float2 st = row_stats_warp(p.rs, r, lane);
+    rho = st.x;
+    c_t = st.y;
+  } else {
+    const float4 st = p.rowstat[r];
+    rho = st.x;
+    c_t = st.y;
+  }
   const float g1 = inv_tau / (2.0f * p.M);
   const __nv_bfloat16* prow = p.pack + static_cast<int64_t>(p.row_offset + row) * 2 * p.D;
   const __nv_bfloat16* qv = prow + (prob == 0 ? p.D : 0);
@@ -1037,13 +1053,13 @@ __global__ void __launch_bounds__(256) omc_grad_reduce_kernel(const GradReducePa
 }
 
 // ------------------------------------------------------------------ K5: loss and d tau
-// Latency-bound tail of the step: FINAL_ROWS rows per 1024-thread block (8 per thread, all loads independent), so the
-// headline shape (2 x 4096 rows) is ONE block with no ticket; larger problems add a last-block pass over the block
-// sums.  Every sum runs in a fixed order (thread-sequential, xor butterfly, warp order) -> deterministic.
-constexpr int FINAL_THREADS = 1024;
-constexpr int FINAL_RPT = 8;
+// Latency-bound tail of the step: one thread per (direction, row), block sums, the last block (ticket) adds the block
+// sums.  Every sum runs in a fixed order (xor butterfly, warp order, block order) -> deterministic.  (One 1024-thread
+// block for the whole headline shape was tried: a single SM pulling 0.7 MB out of L2 takes 2x longer.)
+constexpr int FINAL_THREADS = 256;
+constexpr int FINAL_RPT = 1;
 constexpr int FINAL_ROWS = FINAL_THREADS * FINAL_RPT;
-__device__ __forceinline__ float2 block_sum2_1024(float a, float b, float (*red)[32]) {
+__device__ __forceinline__ float2 block_sum2(float a, float b, float (*red)[32]) {
   a = warp_sum(a);
   b = warp_sum(b);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1053,8 +1069,9 @@ __device__ __forceinline__ float2 block_sum2_1024(float a, float b, float (*red)
     red[1][warp] = b;
   }
   __syncthreads();
-  a = red[0][lane];
-  b = red[1][lane];
+  const bool live = lane < FINAL_THREADS / 32;
+  a = live ? red[0][lane] : 0.f;
+  b = live ? red[1][lane] : 0.f;
   return make_float2(warp_sum(a), warp_sum(b));  // every warp computes the same totals
 }
 __global__ void __launch_bounds__(FINAL_THREADS) omc_final_kernel(const float* __restrict__ rowce, const float4* __restrict__ rowstat,
@@ -1064,7 +1081,8 @@ __global__ void __launch_bounds__(FINAL_THREADS) omc_final_kernel(const float* _
                                                        const float* __restrict__ temp_dev, float eps_ls, float c_sm,
                                                        float2* __restrict__ blockpart, int* __restrict__ ticket,
                                                        float* __restrict__ loss, float* __restrict__ grad_temp,
-                                                       unsigned long long* __restrict__ step_ctr) {
+                                                       unsigned long long* __restrict__ step_ctr,
+                                                       const int* __restrict__ poison) {
   pdl_trigger();
   pdl_wait();
   __shared__ float red[2][32];
@@ -1103,7 +1121,7 @@ __global__ void __launch_bounds__(FINAL_THREADS) omc_final_kernel(const float* _
       }
     }
   }
-  float2 tot = block_sum2_1024(a, b, red);
+  float2 tot = block_sum2(a, b, red);
   if (gridDim.x > 1) {
     if (threadIdx.x == 0) {
       blockpart[blockIdx.x] = tot;
@@ -1120,10 +1138,13 @@ __global__ void __launch_bounds__(FINAL_THREADS) omc_final_kernel(const float* _
       a += v.x;
       b += v.y;
     }
-    tot = block_sum2_1024(a, b, red);
+    tot = block_sum2(a, b, red);
   }
   if (threadIdx.x == 0) {
-    const float scale = 1.0f / (2.0f * M);
+    float scale = 1.0f / (2.0f * M);
+    // VAST_OMC_ASSUME_IN_RANGE: the fallback launches were skipped; if the range was exceeded after all the step's
+    // numbers are meaningless -> fail loudly with a NaN loss / d tau
+    if (poison != nullptr && *reinterpret_cast<const volatile int*>(poison) != 0) scale = __int_as_float(0x7fc00000);
     loss[0] = tot.x * scale;
     if (grad_temp) grad_temp[0] = tot.y * scale;
     if (step_ctr) *step_ctr += 1;  // the next step (e.g. the next replay of a captured graph) draws fresh noise
@@ -1222,6 +1243,7 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
   const bool need_sample = neg_idx != nullptr;
   const bool elem = debug_noise != nullptr;                         // reference-literal per-element race
   const bool two_pass = elem || (flags & VAST_OMC_TWO_PASS) != 0;  // otherwise: single pass + gated fallback
+  const bool assume_in_range = !two_pass && (flags & VAST_OMC_ASSUME_IN_RANGE) != 0;
   OmcPlan pl;
   omc_plan(&pl, bs, n_total, dim, need_sample || need_grad, need_grad);
   VAST_REQUIRE(workspace_bytes >= pl.total, VAST_ERR_WORKSPACE, "omc_step: workspace %zu < required %zu", workspace_bytes, pl.total);
@@ -1355,15 +1377,20 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
   } else {
     rc = run_soft(nullptr, &wflags[0]);  // K2: exponent reference = the positive pair's logit
     if (rc) return rc;
-    rc = run_stats(&wflags[0]);          // the next three launches are no-ops unless the fp16 range overflowed
-    if (rc) return rc;
-    rc = run_soft(&wflags[0], nullptr);
-    if (rc) return rc;
+    if (!assume_in_range) {
+      rc = run_stats(&wflags[0]);        // the next three launches are no-ops unless the fp16 range overflowed
+      if (rc) return rc;
+      rc = run_soft(&wflags[0], nullptr);
+      if (rc) return rc;
+    }
   }
 
-  // K3: row statistics + hard negatives (its own kernel unless the dQ epilogue does it)
-  if (!fused_stats) {
-    RowStatParams R;
+  // K3: row statistics + hard negatives.  Its own kernel only when nothing downstream can host it: with a
+  // gradient it runs inside the dQ GEMM's epilogue (fused_stats) or inside the split-K reduce kernel (same
+  // warp-per-row layout), both of which are the first consumers of its results.
+  const bool stats_in_reduce = need_grad && pl.g_dq.k_splits > 1 && (flags & VAST_OMC_SEPARATE_ROW_STATS) == 0;
+  RowStatParams R;
+  {
     memset(&R, 0, sizeof(R));
     R.partial = partial;
     R.slots = pl.slots;
@@ -1391,6 +1418,8 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
     R.rowstat = rowstat;
     R.rowce = rowce;
     R.lse_out = lse;
+  }
+  if (!fused_stats && !stats_in_reduce) {
     VAST_TIMED(stream, "omc_row_stats", (launch_ex(omc_row_stats_kernel, ceil_div(2 * M, 8), 256, 0, stream, 1, R)));
     VAST_LAUNCH_OK("omc_row_stats");
   }
@@ -1478,6 +1507,8 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
       G.grad_cond = grad_cond;
       G.grad_t = grad_t;
       G.dotq = dotq;
+      G.fused_stats = stats_in_reduce ? 1 : 0;
+      G.rs = R;
       VAST_TIMED(stream, "omc_grad_reduce", (launch_ex(omc_grad_reduce_kernel, ceil_div(2 * M, 8), 256, 0, stream, 1, G)));
       VAST_LAUNCH_OK("omc_grad_reduce");
     }
@@ -1487,7 +1518,8 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
   VAST_TIMED(stream, "omc_final",
              (launch_ex(omc_final_kernel, ceil_div(2 * M, FINAL_ROWS), FINAL_THREADS, 0, stream, 1, rowce, rowstat, zt, need_grad ? dotq : nullptr,
                         fused_stats ? dots : nullptr, pl.dslots, 2 * M, M, inv_tau, contra_temp_dev, label_smoothing, c_sm, blockpart, &wflags[1], loss,
-                        need_grad ? grad_temp : nullptr, reinterpret_cast<unsigned long long*>(step_counter))));
+                        need_grad ? grad_temp : nullptr, reinterpret_cast<unsigned long long*>(step_counter),
+                        assume_in_range ? &wflags[0] : nullptr)));
   VAST_LAUNCH_OK("omc_final");
   return VAST_OK;
 }

@@ -142,13 +142,16 @@ def pack_pair(feat_t: torch.Tensor, feat_cond: torch.Tensor, out: torch.Tensor |
 # ------------------------------------------------------------------ contrastive step
 OMC_TWO_PASS = 1
 OMC_SEPARATE_ROW_STATS = 2
+OMC_ASSUME_IN_RANGE = 4
 
 
 def _omc_flags(two_pass: bool, separate_row_stats: bool | None) -> int:
     import os
     if separate_row_stats is None:
         separate_row_stats = os.environ.get("VAST_OMC_SEPARATE_ROW_STATS", "0") == "1"
-    return (OMC_TWO_PASS if two_pass else 0) | (OMC_SEPARATE_ROW_STATS if separate_row_stats else 0)
+    assume = os.environ.get("VAST_OMC_ASSUME_IN_RANGE", "0") == "1"
+    return (OMC_TWO_PASS if two_pass else 0) | (OMC_SEPARATE_ROW_STATS if separate_row_stats else 0) | \
+        (OMC_ASSUME_IN_RANGE if assume else 0)
 
 
 def omc_step(pack: torch.Tensor, bs: int, row_offset: int, contra_temp, label_smoothing: float = 0.1,
