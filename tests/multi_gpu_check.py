@@ -80,6 +80,46 @@ for mode in ("bf16", "fp32"):
     v2, i2 = vast_b200.retrieval_topk(q, v, k, mode=mode, shard=(rank, world), shard_mode="cols")
     v3, i3 = vast_b200.retrieval_topk(q, v, k, mode=mode, shard=(rank, world))          # default: query rows sharded
     ok &= bool(torch.equal(i1, i2)) and bool(torch.equal(i1, i3)) and bool(torch.equal(v1, v3))
+# streaming re-rank (refine_candidates): every rank owns a slice of the videos' condition tokens; lists and ITM scores
+# must equal the unsharded ones (ITM stub scores each pair independently of its mini-batch)
+from vast_b200 import retrieval
+
+
+class _Stub:
+    def __init__(self):
+        gg = torch.Generator().manual_seed(3)
+        self.emb = (torch.randn(1000, 16, generator=gg) * 0.1).cuda()
+        self.w = torch.randn(16, 2, generator=gg).cuda()
+
+    def compute_slice_scores(self, cond, ids, mask):
+        h = torch.tanh(self.emb[ids[:, 0]] + cond.float().mean(dim=1)[:, :16])
+        return torch.softmax(h @ self.w, dim=1)[:, 1]
+
+
+stub = _Stub()
+nt2, nv2, k2 = 301, 8 * world + 3, 6
+q2 = torch.nn.functional.normalize(torch.randn(nt2, d, generator=g), dim=-1).cuda()
+v2f = torch.nn.functional.normalize(torch.randn(nv2, d, generator=g), dim=-1).cuda()
+ids2 = torch.randint(0, 1000, (nt2, 5), generator=g).cuda()
+mask2 = torch.ones(nt2, 5, dtype=torch.int64).cuda()
+cond2 = torch.randn(nv2, 4, 16, generator=g).cuda()
+per = -(-nv2 // world)
+mine = slice(min(rank * per, nv2), min((rank + 1) * per, nv2))      # ragged: the last rank holds fewer videos
+for direction in ("forward", "backward"):
+    idx_s, itm_s = retrieval.refine_candidates(cond2[mine], ids2, mask2, q2, v2f, stub, k2, direction)
+    if direction == "forward":
+        _, idx_1 = vast_b200.retrieval_topk(q2, v2f, k2, mode="fp32")
+        tt = torch.arange(nt2, device="cuda")[:, None].expand_as(idx_1).reshape(-1)
+        vv = idx_1.reshape(-1).long()
+    else:
+        _, idx_1 = vast_b200.retrieval_topk(v2f, q2, k2, mode="fp32")
+        vv = torch.arange(nv2, device="cuda")[:, None].expand_as(idx_1).reshape(-1)
+        tt = idx_1.reshape(-1).long()
+    want = stub.compute_slice_scores(cond2[vv], ids2[tt], mask2[tt]).view_as(idx_1)
+    ok &= bool(torch.equal(idx_s, idx_1)) and bool(torch.allclose(itm_s, want, rtol=1e-5, atol=1e-7))
+if rank == 0:
+    print("streaming re-rank ok:", bool(ok), flush=True)
+
 # negative-row exchange == all_gather_with_grad(x)[idx], values and gradients (NCCL all_to_all)
 xg = torch.randn(bs, 7, 16, generator=g).cuda()
 idx = torch.randint(0, n, (bs,), generator=g).cuda()

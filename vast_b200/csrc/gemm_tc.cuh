@@ -20,6 +20,8 @@
 // Epilogue state (row statistics, top-k lists, ...) persists across the N-tiles of one item and is
 // flushed as a partial ("slot") at the end of the item; a small finalize kernel merges slots.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -118,6 +120,13 @@ struct SmemLayout {
   static constexpr uint32_t ALIGN_SLACK = 1024;
   static_assert(2 * STAGES * 8 + 4 * 8 + 8 <= BAR_BYTES, "barrier block too small");
 };
+
+// Epilogues that declare `static constexpr bool kHasFinish` get finish(epilogue warp, lane, NE) called by every epilogue
+// thread after the CTA's last work item (EpiGrad: the step's final loss / d tau reduction rides on the GEMM's tail).
+template <class E, class = void>
+struct HasFinish : std::false_type {};
+template <class E>
+struct HasFinish<E, std::void_t<decltype(E::kHasFinish)>> : std::true_type {};
 
 // B_MN = false: B is [N rows, K cols] K-major (an "NT" GEMM, S = A . B^T with B given row-wise).
 // B_MN = true : B is [K rows, N cols] row-major, i.e. the MN-major UMMA operand: each pipeline stage holds
@@ -344,6 +353,7 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
       }
       epi.item_end(ctx);
     }
+    if constexpr (HasFinish<Epi>::value) epi.finish(ew, lane, NE);
   }
 
   ptx::tc_fence_before_sync();

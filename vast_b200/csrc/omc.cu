@@ -768,25 +768,40 @@ struct EpiGrad {
     float4* rowstat_out;  // [2][M] (rho, c_t, p_target, lse)
     float* lse_out;       // [2][M] or nullptr
     float* dots;          // [2][M][num_slots] partials of <q, sum_j K_j>
+    // ---- fused final reduction (K5 folded in as well; needs the fused statistics).  The loss and d tau are LINEAR in
+    // the per-(row, column range) partials <q, acc> and <q, sum K>, so every epilogue thread just adds up its own
+    // terms; a CTA publishes one (loss, d tau) pair when it runs out of work and the last CTA (ticket) adds the
+    // pairs in CTA order: fixed order everywhere -> deterministic, and no separate kernel at the end of the step.
+    float2* cta_part;  // [grid] or nullptr
+    int* ticket;
+    float* loss;
+    float* grad_temp;
+    unsigned long long* step_ctr_rw;
+    const int* poison;
+    int M_rows;
   };
   static constexpr bool kUnrollChunks = true;  // the operand double buffer lives in registers
   static constexpr int kAuxWarps = 0;
+  static constexpr bool kHasFinish = true;
   const Params& p;
+  float* red;  // shared scratch of the final reduction
   float rho, c_t, gs, dotq, dots;
+  float fin_a, fin_b;  // this thread's share of sum_r CE_r and sum_r d CE_r / d tau
   const __nv_bfloat16* qrow;
   const __nv_bfloat16* krow;
   float* grow;
   uint4 nq[4], nk[4];  // operands of the NEXT chunk (requested one chunk ahead)
   uint4 cq[4], ck[4];  // operands of the current chunk
   bool cur_ok, nxt_ok;
-  __device__ EpiGrad(const Params& p_, uint8_t*) : p(p_) {
+  __device__ EpiGrad(const Params& p_, uint8_t* smem) : p(p_), red(reinterpret_cast<float*>(smem)) {
     const float inv_tau = p.temp_dev ? 1.0f / __ldg(p.temp_dev) : p.inv_tau;
     gs = inv_tau;  // scaled by 1 / (2 M) per chunk (M comes with the item)
     cur_ok = nxt_ok = false;
+    fin_a = fin_b = 0.f;
   }
   // K3 for one row on one thread (see omc_row_stats_kernel, whose arithmetic this replays operation for operation).
   // A free-standing function (no `this`): the epilogue object, with its operand double buffer, must stay in registers.
-  static __device__ __noinline__ float2 fused_row_stats(const Params& p, int prob, int M, int row, float gs, bool publish) {
+  static __device__ __noinline__ float4 fused_row_stats(const Params& p, int prob, int M, int row, float gs, bool publish) {
     float rho, c_t;
     const int r = prob * M + row;
     const float4* pp = p.partial + static_cast<int64_t>(r) * p.sslots;
@@ -823,7 +838,7 @@ struct EpiGrad {
     rho = 1.0f / ltot;
     const float pt = pt_un * rho;
     c_t = pt - (1.f - p.eps_ls);
-    if (!publish) return make_float2(rho, c_t);
+    if (!publish) return make_float4(rho, c_t, 0.f, 0.f);
     // ---- publisher: hard negative + what the final reduction needs
     const float lse = (ref + log2f(ltot)) * kLn2;
     if (p.neg_idx != nullptr) {
@@ -890,14 +905,17 @@ struct EpiGrad {
     }
     p.rowstat_out[r] = make_float4(rho, c_t, pt, lse);
     if (p.lse_out) p.lse_out[r] = lse;
-    return make_float2(rho, c_t);
+    // the row's terms of the loss and of d tau that do not involve the accumulator (see omc_final_kernel)
+    return make_float4(rho, c_t, lse - (1.f - p.eps_ls) * gs * zt, -gs * gs * (pt * zt - (1.f - p.eps_ls) * zt));
   }
   __device__ __forceinline__ void item_begin(const tc::ItemCtx& c) {
     const int row = c.row_valid ? c.row : 0;
     if (p.partial != nullptr) {
-      const float2 st = fused_row_stats(p, c.prob, c.M, row, gs, c.n_split == 0 && c.k_split == 0 && c.half == 0 && c.row_valid);
+      const float4 st = fused_row_stats(p, c.prob, c.M, row, gs, c.n_split == 0 && c.k_split == 0 && c.half == 0 && c.row_valid);
       rho = st.x;
       c_t = st.y;
+      fin_a += st.z;
+      fin_b += st.w;
     } else {
       const float4 st = p.rowstat[static_cast<int64_t>(c.prob) * c.M + row];
       rho = st.x;
@@ -972,10 +990,54 @@ struct EpiGrad {
     }
   }
   __device__ __forceinline__ void item_end(const tc::ItemCtx& c) {
-    if (c.row_valid) {
-      const int64_t at = (static_cast<int64_t>(c.prob) * c.M + c.row) * p.num_slots + c.slot;
-      p.dotq[at] = dotq;
-      if (p.dots != nullptr) p.dots[at] = dots;
+    if (!c.row_valid) return;
+    if (p.cta_part != nullptr) {
+      fin_a -= p.c_sm * gs * dots;
+      fin_b -= gs * gs * (rho * dotq - p.c_sm * dots);
+      return;
+    }
+    const int64_t at = (static_cast<int64_t>(c.prob) * c.M + c.row) * p.num_slots + c.slot;
+    p.dotq[at] = dotq;
+    if (p.dots != nullptr) p.dots[at] = dots;
+  }
+  // after the CTA's last item (every epilogue thread): CTA sum -> cta_part, the last CTA finishes the step
+  __device__ __forceinline__ void finish(int ew, int lane, int ne) {
+    if (p.cta_part == nullptr) return;
+    const float a = warp_sum(fin_a), b = warp_sum(fin_b);
+    if (lane == 0) {
+      red[2 * ew] = a;
+      red[2 * ew + 1] = b;
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(ne * 32) : "memory");  // the epilogue warps only
+    if (ew != 0) return;
+    int last = 0;
+    if (lane == 0) {
+      float sa = 0.f, sb = 0.f;
+      for (int w = 0; w < ne; ++w) {
+        sa += red[2 * w];
+        sb += red[2 * w + 1];
+      }
+      p.cta_part[blockIdx.x] = make_float2(sa, sb);
+      __threadfence();
+      last = atomicAdd(p.ticket, 1) == static_cast<int>(gridDim.x) - 1;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();
+    float sa = 0.f, sb = 0.f;
+    for (int i = lane; i < static_cast<int>(gridDim.x); i += 32) {
+      const float2 v = __ldcg(p.cta_part + i);
+      sa += v.x;
+      sb += v.y;
+    }
+    sa = warp_sum(sa);
+    sb = warp_sum(sb);
+    if (lane == 0) {
+      float scale = 1.0f / (2.0f * p.M_rows);
+      if (p.poison != nullptr && *reinterpret_cast<const volatile int*>(p.poison) != 0) scale = __int_as_float(0x7fc00000);
+      p.loss[0] = sa * scale;
+      p.grad_temp[0] = sb * scale;
+      if (p.step_ctr_rw) *p.step_ctr_rw += 1;
     }
   }
 };
@@ -1195,7 +1257,7 @@ static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, bool
   pl->off_zt = take(sizeof(float) * 2 * bs);
   pl->off_rowce = take(sizeof(float) * 2 * bs);
   pl->off_rowstat = take(sizeof(float4) * 2 * bs);
-  pl->off_blockpart = take(sizeof(float2) * ceil_div64(2 * bs, 256));
+  pl->off_blockpart = take(sizeof(float2) * (ceil_div64(2 * bs, 256) + 1024));  // block sums of K5, or one pair per GEMM CTA
   pl->dslots = pl->g_dq.k_splits == 1 ? pl->g_dq.n_splits * 2 : 1;  // EpiGrad runs with two column halves per tile
   pl->off_dotq = take(sizeof(float) * 2 * bs * pl->dslots);
   pl->off_dots = take(sizeof(float) * 2 * bs * pl->dslots);
@@ -1474,9 +1536,17 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
         P.epi.rowstat_out = rowstat;
         P.epi.lse_out = lse;
         P.epi.dots = dots;
+        // K5 rides on the GEMM's tail as well
+        P.epi.cta_part = blockpart;
+        P.epi.ticket = &wflags[1];
+        P.epi.loss = loss;
+        P.epi.grad_temp = grad_temp;
+        P.epi.step_ctr_rw = reinterpret_cast<unsigned long long*>(step_counter);
+        P.epi.poison = assume_in_range ? &wflags[0] : nullptr;
+        P.epi.M_rows = M;
       }
-      rc = pl.bn_dq == 256 ? tc::launch_gemm<EpiGrad, 256, 4, 8, true>(P, stream, "omc_dq_gemm")
-                           : tc::launch_gemm<EpiGrad, 128, 4, 8, true>(P, stream, "omc_dq_gemm");
+      rc = pl.bn_dq == 256 ? tc::launch_gemm<EpiGrad, 256, 4, 8, true>(P, stream, "omc_dq_gemm", 128)
+                           : tc::launch_gemm<EpiGrad, 128, 4, 8, true>(P, stream, "omc_dq_gemm", 128);
       if (rc) return rc;
     } else {  // split-K partials, summed in a fixed order by the reduce kernel
       tc::KernelParams<tc::EpiStore::Params> P;
@@ -1514,13 +1584,14 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
     }
   }
 
-  // K5
+  // K5 (unless the dQ GEMM's epilogue already finished the step)
+  if (!fused_stats)
   VAST_TIMED(stream, "omc_final",
              (launch_ex(omc_final_kernel, ceil_div(2 * M, FINAL_ROWS), FINAL_THREADS, 0, stream, 1, rowce, rowstat, zt, need_grad ? dotq : nullptr,
                         fused_stats ? dots : nullptr, pl.dslots, 2 * M, M, inv_tau, contra_temp_dev, label_smoothing, c_sm, blockpart, &wflags[1], loss,
                         need_grad ? grad_temp : nullptr, reinterpret_cast<unsigned long long*>(step_counter),
                         assume_in_range ? &wflags[0] : nullptr)));
-  VAST_LAUNCH_OK("omc_final");
+  if (!fused_stats) VAST_LAUNCH_OK("omc_final");
   return VAST_OK;
 }
 
