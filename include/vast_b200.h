@@ -118,9 +118,13 @@ VAST_API size_t vast_omc_workspace_bytes(int64_t bs, int64_t n_total, int64_t di
 #define VAST_OMC_TWO_PASS 1 /* evaluate the logits twice (row max / sum-exp pass first) instead of once */
 #define VAST_OMC_ASSUME_IN_RANGE 4 /* the caller guarantees that no negative beats its positive by more than
                                       16 ln2 = 11.09 nats of logit (always true for unit-norm features with
-                                      contra_temp >= 0.181, since |s| <= 1): the three flag-gated fallback launches
+                                      contra_temp >= 0.181, since |s| <= 1): the two flag-gated fallback launches
                                       are not enqueued.  If the range is exceeded after all, loss and grad_temp are
                                       NaN (never silently wrong). */
+#define VAST_OMC_WORKSPACE_CLEAN 8 /* the workspace was last used by a COMPLETED vast_omc_step / vast_omc_step_local
+                                      call of the same shape (every step leaves its flag / ticket block zeroed), so
+                                      the step does not clear it again: one launch less.  Never pass it for a fresh
+                                      or recycled allocation. */
 #define VAST_OMC_SEPARATE_ROW_STATS 2 /* run the row statistics + hard-negative draw as their own kernel instead of
                                          inside the dQ GEMM's epilogue (same results bit for bit; A/B aid) */
 

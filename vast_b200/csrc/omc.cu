@@ -19,9 +19,9 @@
 //   K5 final         : loss and d tau, block sums + last-block ticket (fixed order -> deterministic)
 // The [bs, N] logits are evaluated exactly ONCE.  Pt needs the fp16 range: an entry overflows only if
 // some negative beats its positive by more than 16 ln2 = 11.09 nats ((s_ij - s_ii) > 0.78 at tau = 0.07).
-// The soft epilogue detects that (chunk sum >= 65504) and raises a device flag; three flag-gated
+// The soft epilogue detects that (chunk sum >= 65504) and raises a device flag; two flag-gated
 // launches then redo the step in the two-pass form (K2a stats GEMM: online row max / sum-exp; K2b
-// finalize: ref_i = lse_i; K2c soft GEMM again, now Pt = softmax <= 1).  No host synchronisation
+// soft GEMM again with ref_i = lse_i merged from K2a's partials, so Pt = softmax <= 1).  No host synchronisation
 // either way.  VAST_OMC_TWO_PASS / debug noise select the two-pass form directly.
 //
 // Why dQ is not fused FlashAttention-style into K2: the dQ accumulator of a 128-row block is
@@ -146,6 +146,12 @@ struct EpiSoft {
     int64_t noise_ld;
     int do_sample;
     int* ovf;  // raised when a chunk sum leaves the fp16 range (single-pass form) or nullptr
+    // two-pass form: the row-statistics pass's (max2, sum exp2) partials.  When non-null the exponent reference is
+    // the row's log2-domain log-sum-exp merged from them right here (Pt becomes the softmax probability), and the
+    // threads of the first column range publish it to ref2_out for the kernels downstream.
+    const float2* stats_partial;  // [2][M][stats_slots]
+    int stats_slots;
+    float* ref2_out;
   };
   static constexpr bool kUnrollChunks = false;
   static constexpr int kAuxWarps = 0;
@@ -162,7 +168,24 @@ struct EpiSoft {
     off_hi = static_cast<uint32_t>(off >> 32);
   }
   __device__ __forceinline__ void item_begin(const tc::ItemCtx& c) {
-    ref = c.row_valid ? p.ref2[static_cast<int64_t>(c.prob) * c.M + c.row] : 0.f;
+    const int64_t r = static_cast<int64_t>(c.prob) * c.M + c.row;
+    if (p.stats_partial != nullptr) {
+      ref = 0.f;
+      if (c.row_valid) {
+        const float2* pp = p.stats_partial + r * p.stats_slots;
+        float mm = -INFINITY;
+        for (int s = 0; s < p.stats_slots; ++s) mm = fmaxf(mm, pp[s].x);
+        float ls = 0.f;
+        for (int s = 0; s < p.stats_slots; ++s) {
+          const float2 q = pp[s];
+          if (q.y > 0.f) ls += q.y * exp2f(q.x - mm);
+        }
+        ref = mm + log2f(ls);
+        if (c.n_split == 0 && c.half == 0) p.ref2_out[r] = ref;
+      }
+    } else {
+      ref = c.row_valid ? p.ref2[r] : 0.f;
+    }
     l = 0.f;
     bw = ELEM ? -1.f : 0.f;
     be = 1.f;
@@ -361,6 +384,7 @@ __global__ void __launch_bounds__(256) omc_prep_kernel(const __nv_bfloat16* __re
         for (int w = 0; w < 8; ++w) sum += red[w][threadIdx.x];
         ksum[c] = sum;
       }
+      if (threadIdx.x == 0) flags[8 + ctile] = 0;  // every other block of the tile has taken its ticket: leave it clean
     }
   } else {
     const int i = (blockIdx.x - ncs) * 8 + warp;
@@ -540,8 +564,10 @@ __global__ void __launch_bounds__(256, 4) omc_pack_prep_kernel(const TI* __restr
       for (int w = 0; w < 8; ++w) sum += red[w][threadIdx.x];
       ksum[my_gc] = sum;
     }
+    if (threadIdx.x == 0) flags[8 + ct] = 0;  // every other block of the tile has taken its ticket: leave it clean
   }
   if (last_of_slab) {
+    if (threadIdx.x == 0) slab_tickets[slab] = 0;
     __threadfence();
     const int r = slab * PP_ROWS + threadIdx.x;
     if (static_cast<int>(threadIdx.x) < PP_ROWS && r < n) {
@@ -557,25 +583,6 @@ __global__ void __launch_bounds__(256, 4) omc_pack_prep_kernel(const TI* __restr
       }
     }
   }
-}
-
-// ------------------------------------------------------------------ two-pass form: merge pass-1 partials
-__global__ void __launch_bounds__(128) omc_stats_finalize_kernel(const float2* __restrict__ partial, int slots, int rows2,
-                                                                float* __restrict__ ref2, const int* __restrict__ gate) {
-  pdl_trigger();
-  pdl_wait();
-  if (gate != nullptr && *gate == 0) return;
-  const int r = blockIdx.x * 128 + threadIdx.x;
-  if (r >= rows2) return;
-  const float2* pp = partial + static_cast<int64_t>(r) * slots;
-  float mm = -INFINITY;
-  for (int s = 0; s < slots; ++s) mm = fmaxf(mm, pp[s].x);
-  float l = 0.f;
-  for (int s = 0; s < slots; ++s) {
-    const float2 q = pp[s];
-    if (q.y > 0.f) l += q.y * exp2f(q.x - mm);
-  }
-  ref2[r] = mm + log2f(l);  // log2-domain log-sum-exp: Pt becomes the softmax probability
 }
 
 // ------------------------------------------------------------------ K3: row statistics + hard negatives
@@ -779,6 +786,7 @@ struct EpiGrad {
     unsigned long long* step_ctr_rw;
     const int* poison;
     int M_rows;
+    int* ovf_reset;
   };
   static constexpr bool kUnrollChunks = true;  // the operand double buffer lives in registers
   static constexpr int kAuxWarps = 0;
@@ -1038,6 +1046,8 @@ struct EpiGrad {
       p.loss[0] = sa * scale;
       p.grad_temp[0] = sb * scale;
       if (p.step_ctr_rw) *p.step_ctr_rw += 1;
+      *p.ticket = 0;  // the step leaves its flag block as it found it (all zero): see VAST_OMC_WORKSPACE_CLEAN
+      *p.ovf_reset = 0;
     }
   }
 };
@@ -1144,7 +1154,7 @@ __global__ void __launch_bounds__(FINAL_THREADS) omc_final_kernel(const float* _
                                                        float2* __restrict__ blockpart, int* __restrict__ ticket,
                                                        float* __restrict__ loss, float* __restrict__ grad_temp,
                                                        unsigned long long* __restrict__ step_ctr,
-                                                       const int* __restrict__ poison) {
+                                                       const int* __restrict__ poison, int* __restrict__ ovf_reset) {
   pdl_trigger();
   pdl_wait();
   __shared__ float red[2][32];
@@ -1210,6 +1220,8 @@ __global__ void __launch_bounds__(FINAL_THREADS) omc_final_kernel(const float* _
     loss[0] = tot.x * scale;
     if (grad_temp) grad_temp[0] = tot.y * scale;
     if (step_ctr) *step_ctr += 1;  // the next step (e.g. the next replay of a captured graph) draws fresh noise
+    *ticket = 0;                   // leave the flag block all zero (VAST_OMC_WORKSPACE_CLEAN)
+    *ovf_reset = 0;
   }
 }
 
@@ -1224,7 +1236,7 @@ struct OmcPlan {
   int64_t npad;
   // workspace offsets (bytes)
   int dslots;  // <q, dQraw> partials per row
-  size_t off_ztpart;
+  size_t off_ztpart, off_spartial;
   size_t off_flags, off_partial, off_ref2, off_zt, off_rowce, off_rowstat, off_blockpart, off_dotq, off_dots, off_ksump, off_ksum, off_P,
       off_dq, off_k16, total;
 };
@@ -1253,6 +1265,7 @@ static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, bool
   pl->off_flags = take(sizeof(int) * (FLAG_INTS + pl->nslab_pp));  // flags, then one ticket per pack+prep slab
   pl->off_ztpart = take(sizeof(float) * n_total * pl->ctiles_pp);
   pl->off_partial = take(sizeof(float4) * 2 * bs * pl->slots);
+  pl->off_spartial = take(sizeof(float2) * 2 * bs * pl->slots);  // statistics pass (its readers overlap the soft pass's writers)
   pl->off_ref2 = take(sizeof(float) * 2 * bs);
   pl->off_zt = take(sizeof(float) * 2 * bs);
   pl->off_rowce = take(sizeof(float) * 2 * bs);
@@ -1306,6 +1319,7 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
   const bool elem = debug_noise != nullptr;                         // reference-literal per-element race
   const bool two_pass = elem || (flags & VAST_OMC_TWO_PASS) != 0;  // otherwise: single pass + gated fallback
   const bool assume_in_range = !two_pass && (flags & VAST_OMC_ASSUME_IN_RANGE) != 0;
+  const bool ws_clean = (flags & VAST_OMC_WORKSPACE_CLEAN) != 0;  // flag block already zero: skip the memset node
   OmcPlan pl;
   omc_plan(&pl, bs, n_total, dim, need_sample || need_grad, need_grad);
   VAST_REQUIRE(workspace_bytes >= pl.total, VAST_ERR_WORKSPACE, "omc_step: workspace %zu < required %zu", workspace_bytes, pl.total);
@@ -1314,6 +1328,7 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
   char* ws = static_cast<char*>(workspace);
   int* wflags = reinterpret_cast<int*>(ws + pl.off_flags);  // see FLAG_INTS
   float4* partial = reinterpret_cast<float4*>(ws + pl.off_partial);
+  float2* spartial = reinterpret_cast<float2*>(ws + pl.off_spartial);
   float* ref2 = reinterpret_cast<float*>(ws + pl.off_ref2);
   float* zt = reinterpret_cast<float*>(ws + pl.off_zt);
   float* rowce = reinterpret_cast<float*>(ws + pl.off_rowce);
@@ -1336,7 +1351,7 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
 
   if (feat_t_in != nullptr) {
     // K0 + K1 in one pass over the fp features (single rank: nothing to gather in between)
-    VAST_CUDA_OK(cudaMemsetAsync(wflags, 0, sizeof(int) * (FLAG_INTS + pl.nslab_pp), stream));
+    if (!ws_clean) VAST_CUDA_OK(cudaMemsetAsync(wflags, 0, sizeof(int) * (FLAG_INTS + pl.nslab_pp), stream));
     float* ztpart = reinterpret_cast<float*>(ws + pl.off_ztpart);
     auto* pko = const_cast<__nv_bfloat16*>(pk);
     float* ref2_or_null = two_pass ? nullptr : ref2;
@@ -1355,7 +1370,7 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
 #undef VAST_PACK_PREP
     VAST_LAUNCH_OK("omc_pack_prep");
   } else {
-    VAST_CUDA_OK(cudaMemsetAsync(wflags, 0, sizeof(int) * FLAG_INTS, stream));
+    if (!ws_clean) VAST_CUDA_OK(cudaMemsetAsync(wflags, 0, sizeof(int) * FLAG_INTS, stream));
     // K1
     VAST_TIMED(stream, "omc_prep",
                (launch_ex(omc_prep_kernel, pl.ncs + ceil_div(M, 8), 256, 0, stream, 1, pk, N, D, M, static_cast<int>(row_offset), pl.ncs,
@@ -1383,17 +1398,16 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
       P.tmA[i] = tmA[i];
       P.tmB[i] = tmB[i];
     }
-    P.epi = {reinterpret_cast<float2*>(partial), pl.slots, kLog2e * inv_tau, contra_temp_dev};
-    int r = tc::launch_gemm<EpiStats, 256, 4, 8>(P, stream, gate ? "omc_stats_gemm_gated" : "omc_stats_gemm");
-    if (r) return r;
-    VAST_TIMED(stream, gate ? "omc_stats_finalize_gated" : "omc_stats_finalize",
-               (launch_ex(omc_stats_finalize_kernel, ceil_div(2 * M, 128), 128, 0, stream, 1, reinterpret_cast<const float2*>(partial),
-                          pl.slots, 2 * M, ref2, gate)));
-    VAST_LAUNCH_OK("omc_stats_finalize");
-    return VAST_OK;
+    P.epi = {spartial, pl.slots, kLog2e * inv_tau, contra_temp_dev};
+    return tc::launch_gemm<EpiStats, 256, 4, 8>(P, stream, gate ? "omc_stats_gemm_gated" : "omc_stats_gemm");
   };
-  auto fill_soft = [&](auto& P, const int* gate, int* ovf) {
+  auto fill_soft = [&](auto& P, const int* gate, int* ovf, bool after_stats) {
     memset(&P, 0, sizeof(P));
+    if (after_stats) {  // exponent reference = log-sum-exp merged from the statistics pass's partials
+      P.epi.stats_partial = spartial;
+      P.epi.stats_slots = pl.slots;
+      P.epi.ref2_out = ref2;
+    }
     P.g = pl.g_s;
     P.gate = gate;
     for (int i = 0; i < 2; ++i) {
@@ -1420,29 +1434,29 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
     P.epi.do_sample = need_sample ? 1 : 0;
     P.epi.ovf = ovf;
   };
-  auto run_soft = [&](const int* gate, int* ovf) -> int {
+  auto run_soft = [&](const int* gate, int* ovf, bool after_stats) -> int {
     if (elem) {
       tc::KernelParams<EpiSoft<true>::Params> P;
-      fill_soft(P, gate, ovf);
+      fill_soft(P, gate, ovf, after_stats);
       return tc::launch_gemm<EpiSoft<true>, 256, 4, 8>(P, stream, "omc_soft_gemm_elem");
     }
     tc::KernelParams<EpiSoft<false>::Params> P;
-    fill_soft(P, gate, ovf);
+    fill_soft(P, gate, ovf, after_stats);
     return tc::launch_gemm<EpiSoft<false>, 256, 4, 8>(P, stream, gate ? "omc_soft_gemm_gated" : "omc_soft_gemm");
   };
 
   if (two_pass) {
     rc = run_stats(nullptr);
     if (rc) return rc;
-    rc = run_soft(nullptr, nullptr);
+    rc = run_soft(nullptr, nullptr, true);
     if (rc) return rc;
   } else {
-    rc = run_soft(nullptr, &wflags[0]);  // K2: exponent reference = the positive pair's logit
+    rc = run_soft(nullptr, &wflags[0], false);  // K2: exponent reference = the positive pair's logit
     if (rc) return rc;
     if (!assume_in_range) {
-      rc = run_stats(&wflags[0]);        // the next three launches are no-ops unless the fp16 range overflowed
+      rc = run_stats(&wflags[0]);        // the next two launches are no-ops unless the fp16 range overflowed
       if (rc) return rc;
-      rc = run_soft(&wflags[0], nullptr);
+      rc = run_soft(&wflags[0], nullptr, true);
       if (rc) return rc;
     }
   }
@@ -1544,6 +1558,7 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
         P.epi.step_ctr_rw = reinterpret_cast<unsigned long long*>(step_counter);
         P.epi.poison = assume_in_range ? &wflags[0] : nullptr;
         P.epi.M_rows = M;
+        P.epi.ovf_reset = &wflags[0];
       }
       rc = pl.bn_dq == 256 ? tc::launch_gemm<EpiGrad, 256, 4, 8, true>(P, stream, "omc_dq_gemm", 128)
                            : tc::launch_gemm<EpiGrad, 128, 4, 8, true>(P, stream, "omc_dq_gemm", 128);
@@ -1590,7 +1605,7 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
              (launch_ex(omc_final_kernel, ceil_div(2 * M, FINAL_ROWS), FINAL_THREADS, 0, stream, 1, rowce, rowstat, zt, need_grad ? dotq : nullptr,
                         fused_stats ? dots : nullptr, pl.dslots, 2 * M, M, inv_tau, contra_temp_dev, label_smoothing, c_sm, blockpart, &wflags[1], loss,
                         need_grad ? grad_temp : nullptr, reinterpret_cast<unsigned long long*>(step_counter),
-                        assume_in_range ? &wflags[0] : nullptr)));
+                        assume_in_range ? &wflags[0] : nullptr, &wflags[0])));
   if (!fused_stats) VAST_LAUNCH_OK("omc_final");
   return VAST_OK;
 }

@@ -143,15 +143,18 @@ def pack_pair(feat_t: torch.Tensor, feat_cond: torch.Tensor, out: torch.Tensor |
 OMC_TWO_PASS = 1
 OMC_SEPARATE_ROW_STATS = 2
 OMC_ASSUME_IN_RANGE = 4
+OMC_WORKSPACE_CLEAN = 8
 
 
-def _omc_flags(two_pass: bool, separate_row_stats: bool | None) -> int:
+def _omc_flags(two_pass: bool, separate_row_stats: bool | None, buffers: dict | None = None) -> int:
     import os
     if separate_row_stats is None:
         separate_row_stats = os.environ.get("VAST_OMC_SEPARATE_ROW_STATS", "0") == "1"
     assume = os.environ.get("VAST_OMC_ASSUME_IN_RANGE", "0") == "1"
+    # a workspace handed back by an earlier call of the same shape was left clean by that step
+    clean = buffers is not None and buffers.get("_clean", False)
     return (OMC_TWO_PASS if two_pass else 0) | (OMC_SEPARATE_ROW_STATS if separate_row_stats else 0) | \
-        (OMC_ASSUME_IN_RANGE if assume else 0)
+        (OMC_ASSUME_IN_RANGE if assume else 0) | (OMC_WORKSPACE_CLEAN if clean else 0)
 
 
 def omc_step(pack: torch.Tensor, bs: int, row_offset: int, contra_temp, label_smoothing: float = 0.1,
@@ -195,10 +198,10 @@ def omc_step(pack: torch.Tensor, bs: int, row_offset: int, contra_temp, label_sm
         contra_temp = 0.0
     check(lib().vast_omc_step(ptr(pack), bs, n_total, dim, row_offset, float(contra_temp), ptr(temp_dev), float(label_smoothing),
                               float(weight_floor), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1),
-                              ptr(step_counter), ptr(debug_noise), _omc_flags(two_pass, separate_row_stats), ptr(loss), ptr(neg), ptr(gc), ptr(gt),
+                              ptr(step_counter), ptr(debug_noise), _omc_flags(two_pass, separate_row_stats, buffers), ptr(loss), ptr(neg), ptr(gc), ptr(gt),
                               ptr(gtemp), ptr(lse),
                               ptr(ws), ws.numel(), stream_ptr()), "omc_step")
-    return dict(loss=loss, neg_idx=neg, grad_cond=gc, grad_t=gt, grad_temp=gtemp, lse=lse, _ws=(ws, temp_dev))
+    return dict(loss=loss, neg_idx=neg, grad_cond=gc, grad_t=gt, grad_temp=gtemp, lse=lse, _ws=(ws, temp_dev), _clean=True)
 
 
 def omc_step_local(feat_t: torch.Tensor, feat_cond: torch.Tensor, contra_temp, label_smoothing: float = 0.1,
@@ -239,9 +242,10 @@ def omc_step_local(feat_t: torch.Tensor, feat_cond: torch.Tensor, contra_temp, l
     check(lib().vast_omc_step_local(ptr(ft), ptr(fc), dtype_code(ft.dtype), ft.stride(0), ptr(pack), bs, dim,
                                     float(contra_temp), ptr(temp_dev), float(label_smoothing), float(weight_floor),
                                     int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), ptr(step_counter),
-                                    ptr(debug_noise), _omc_flags(two_pass, separate_row_stats), ptr(loss), ptr(neg), ptr(gc),
+                                    ptr(debug_noise), _omc_flags(two_pass, separate_row_stats, buffers), ptr(loss), ptr(neg), ptr(gc),
                                     ptr(gt), ptr(gtemp), ptr(lse), ptr(ws), ws.numel(), stream_ptr()), "omc_step_local")
-    return dict(loss=loss, neg_idx=neg, grad_cond=gc, grad_t=gt, grad_temp=gtemp, lse=lse, pack=pack, _ws=(ws, temp_dev, ft, fc))
+    return dict(loss=loss, neg_idx=neg, grad_cond=gc, grad_t=gt, grad_temp=gtemp, lse=lse, pack=pack, _ws=(ws, temp_dev, ft, fc),
+                _clean=True)
 
 
 def local_step_ok(feat_t: torch.Tensor) -> bool:
