@@ -82,9 +82,11 @@ __device__ __forceinline__ WorkItem decode_item(const GemmShape& g, int idx, int
     w.tile_begin = 0;
     w.tile_end = g.n_tiles;
     if (idx >= full) {
+      // range-major: every tail group's first column range runs before any group's second one, so later ranges start
+      // from the bound their finished siblings proved (a list that starts warm admits far fewer candidates)
       const int j = idx - full;
-      grp = full + j / g.tail_splits;
-      split = j - (j / g.tail_splits) * g.tail_splits;
+      split = j / g.tail_groups;
+      grp = full + j - split * g.tail_groups;
       w.tile_begin = split * g.tail_tps;
       w.tile_end = min(w.tile_begin + g.tail_tps, g.n_tiles);
     }

@@ -930,9 +930,24 @@ static void topk_plan(TopkPlan* pl, int64_t n_q, int64_t n_k, int64_t cols, int6
   tc::GemmShape& g = pl->g;
   const int clusters = device_sm_count() / g.cl;
   const int tail = g.m_groups % clusters;
-  int splits = tail > 0 ? clusters / tail : 1;
-  if (splits > max_splits) splits = max_splits;
-  if (splits > g.n_tiles) splits = g.n_tiles;
+  // Column ranges per tail group: the count that minimises the tail's makespan, rounds x (tiles per range + the fixed
+  // cost of an item: pipeline fill, cold list start, its share of the merge).  (clusters / tail alone leaves a third
+  // of the machine idle when, e.g., 49 groups meet 74 clusters -- the per-rank shape of cfg5 on 8 GPUs: 3 ranges
+  // -> 147 items -> two full rounds of a third of the columns each.)
+  int splits = 1;
+  if (tail > 0) {
+    const int item_cost = 4;
+    long best = -1;
+    const int smax = max_splits < g.n_tiles ? max_splits : g.n_tiles;
+    for (int sp = 1; sp <= smax; ++sp) {
+      const long rounds = ceil_div(tail * sp, clusters);
+      const long cost = rounds * (ceil_div(g.n_tiles, sp) + (sp > 1 ? item_cost : 0));
+      if (best < 0 || cost < best) {
+        best = cost;
+        splits = sp;
+      }
+    }
+  }
   if (tail > 0 && splits > 1) {
     g.tail_groups = tail;
     g.tail_tps = ceil_div(g.n_tiles, splits);
