@@ -333,3 +333,37 @@ def test_cfg5_full_size_properties():
     merged = ops.topk_merge(torch.stack(parts), k)
     mv, mi = ops.topk_unpack(merged)
     assert torch.equal(mi, idx) and torch.equal(mv, vals)
+
+
+def test_streaming_rerank_rank_without_videos_and_tiny_k():
+    """Edge cases of the list-layout re-rank: a rank that owns no videos contributes an all-zero score block (its
+    lists are still the global ones), k = 1, and k larger than the number of videos (empty slots: idx -1, score 0)."""
+    from vast_b200 import retrieval
+    t, v = feats(50, 7, 64, 5, noise=3.0)
+    g = torch.Generator().manual_seed(1)
+    ids_tok = torch.randint(0, 30522, (50, 6), generator=g).cuda()
+    mask = torch.ones(50, 6, dtype=torch.int64).cuda()
+    cond = torch.randn(7, 3, 16, generator=g).cuda()
+    m = _StubModel()
+    tc, vc = t.cuda(), v.cuda()
+    idx0, itm0 = retrieval.refine_candidates(cond[:0], ids_tok, mask, tc, vc, m, 4, "forward")
+    assert idx0.shape == (50, 4) and (idx0 >= 0).all() and (itm0 == 0).all() and m.calls == []
+    import vast_b200
+    none = vast_b200.refine_score_matrix(cond[:0], ids_tok, mask, tc @ vc.T, m, 4, "forward")   # dense drop-in, same rank
+    assert none.shape == (50, 0) and m.calls == []
+    idx1, itm1 = retrieval.refine_candidates(cond, ids_tok, mask, tc, vc, m, 1, "forward")
+    assert idx1.shape == (50, 1) and (itm1 > 0).all()
+    idxk, itmk = retrieval.refine_candidates(cond, ids_tok, mask, tc, vc, m, 12, "forward")
+    assert idxk.shape == (50, 7) and (idxk >= 0).all()          # k is clipped to the number of videos
+    ids = [f"v{i}" for i in range(7)]
+    ids_txt = [f"v{i % 7}" for i in range(50)]
+    log = retrieval.recall_from_candidates(idxk, itmk, ids, ids_txt, "forward")
+    dense = torch.zeros(50, 7, device="cuda")
+    dense[torch.arange(50, device="cuda")[:, None].expand_as(idxk), idxk.long()] = itmk
+    import vast_b200
+    assert log == vast_b200.compute_metric_ret(dense, ids, ids_txt, "forward")
+    # R@10 with k = 1: the gt outside the single candidate ties with the other zeros, lower index first
+    log1 = retrieval.recall_from_candidates(idx1, itm1, ids, ids_txt, "forward")
+    d1 = torch.zeros(50, 7, device="cuda")
+    d1[torch.arange(50, device="cuda")[:, None], idx1.long()] = itm1
+    assert log1 == vast_b200.compute_metric_ret(d1, ids, ids_txt, "forward")

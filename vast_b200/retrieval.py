@@ -176,6 +176,10 @@ def _rerank_pairs(condition_feats, input_ids, attention_mask, text_idx, video_lo
     """Score (text, local video) candidate pairs with model.compute_slice_scores (model/vast.py:373-380),
     per video in chunks of `small_batch` like evaluation_mm.py:292-311.  Returns (texts, videos, scores)."""
     nv_local = condition_feats.shape[0]
+    if nv_local == 0 or text_idx.numel() == 0:   # a rank that owns no videos (ragged evaluation shards): nothing to score
+        dev = condition_feats.device
+        return (torch.empty(0, dtype=torch.int32, device=dev), torch.empty(0, dtype=torch.int32, device=dev),
+                torch.empty(0, dtype=torch.float32, device=dev))
     offsets, texts = ops.bucket_by_video(text_idx, video_local, nv_local)
     off = offsets.cpu().tolist()                       # one host read for the whole re-rank
     out_scores = torch.empty(off[-1], dtype=torch.float32, device=condition_feats.device)
@@ -220,7 +224,8 @@ def refine_score_matrix(condition_feats, input_ids, attention_mask, score_matrix
     v_local = torch.where(local, v_idx - start, torch.full_like(v_idx, -1))
     texts, vids, scores = _rerank_pairs(condition_feats, input_ids, attention_mask, t_idx, v_local, model, small_batch)
     cur_new = torch.zeros(nt, cur_length, dtype=torch.float32, device=dev)
-    ops.scatter_scores(texts, vids, scores, cur_new)
+    if texts.numel() > 0:
+        ops.scatter_scores(texts, vids, scores, cur_new)
     out = ddp_allgather(cur_new.T.contiguous()).T
     return out.to(score_matrix_t_cond.dtype)
 
