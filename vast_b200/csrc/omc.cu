@@ -1052,6 +1052,26 @@ struct EpiGrad {
   }
 };
 
+// block-level (sum a, sum b) in a fixed order, for 256-thread blocks
+constexpr int FINAL_THREADS = 256;
+constexpr int FINAL_RPT = 1;
+constexpr int FINAL_ROWS = FINAL_THREADS * FINAL_RPT;
+__device__ __forceinline__ float2 block_sum2(float a, float b, float (*red)[32]) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) {
+    red[0][warp] = a;
+    red[1][warp] = b;
+  }
+  __syncthreads();
+  const bool live = lane < FINAL_THREADS / 32;
+  a = live ? red[0][lane] : 0.f;
+  b = live ? red[1][lane] : 0.f;
+  return make_float2(warp_sum(a), warp_sum(b));  // every warp computes the same totals
+}
+
 // ------------------------------------------------------------------ K4': gradient from split-K partials
 // (small per-rank problems cut the dQ GEMM along K to fill the SMs; partials are summed in a fixed order)
 struct GradReduceParams {
@@ -1068,16 +1088,27 @@ struct GradReduceParams {
   float* grad_cond;
   float* grad_t;
   float* dotq;  // [2][M]
-  int fused_stats;  // the warp computes the row's statistics itself (K3 folded in; same warp-per-row layout)
+  int fused_stats;  // the warp computes the row's statistics itself (K3 folded in; same warp-per-row layout) and the
+                    // kernel finishes the step (K5 folded in: block sums, the last block adds them in block order)
   RowStatParams rs;
+  float2* blockpart;
+  int* ticket;
+  float* loss;
+  float* grad_temp;
+  unsigned long long* step_ctr;
+  const int* poison;
+  int* ovf_reset;
 };
 __global__ void __launch_bounds__(256) omc_grad_reduce_kernel(const GradReduceParams p) {
   pdl_trigger();
   pdl_wait();
+  __shared__ float red[2][32];
+  __shared__ int is_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;
-  if (r >= 2 * p.M) return;
   const float inv_tau = p.temp_dev ? 1.0f / __ldg(p.temp_dev) : p.inv_tau;
+  float fin_a = 0.f, fin_b = 0.f;  // lane 0: this row's CE term and d CE / d tau
+  if (r < 2 * p.M) {
   const int prob = r / p.M, row = r - prob * p.M;
   float rho, c_t;
   if (p.fused_stats) {
@@ -1121,31 +1152,49 @@ __global__ void __launch_bounds__(256) omc_grad_reduce_kernel(const GradReducePa
     *reinterpret_cast<float4*>(gout + d + 4) = make_float4(g[4], g[5], g[6], g[7]);
   }
   dot_q = warp_sum(dot_q);
-  if (lane == 0) p.dotq[r] = dot_q;
+  if (lane == 0) {
+    p.dotq[r] = dot_q;
+    if (p.fused_stats) {  // the row's terms of the final reduction (see omc_final_kernel); lane 0 wrote rowstat / rowce itself
+      const float4 st = p.rs.rowstat[r];
+      const float z = p.rs.zt[r];
+      fin_a = p.rs.rowce[r];
+      fin_b = -inv_tau * inv_tau * (st.x * dot_q + st.z * z - (1.f - p.rs.eps_ls) * z - p.c_sm * st.w);
+    }
+  }
+  }
+  if (!p.fused_stats) return;
+  // ---- K5: block sums (warp order), last block adds the block sums in block order
+  float2 tot = block_sum2(fin_a, fin_b, red);
+  if (threadIdx.x == 0) {
+    p.blockpart[blockIdx.x] = tot;
+    __threadfence();
+    is_last = (atomicAdd(p.ticket, 1) == static_cast<int>(gridDim.x) - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  float a = 0.f, b = 0.f;
+  for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += FINAL_THREADS) {
+    const float2 v = __ldcg(p.blockpart + i);
+    a += v.x;
+    b += v.y;
+  }
+  tot = block_sum2(a, b, red);
+  if (threadIdx.x == 0) {
+    float scale = 1.0f / (2.0f * p.M);
+    if (p.poison != nullptr && *reinterpret_cast<const volatile int*>(p.poison) != 0) scale = __int_as_float(0x7fc00000);
+    p.loss[0] = tot.x * scale;
+    p.grad_temp[0] = tot.y * scale;
+    if (p.step_ctr) *p.step_ctr += 1;
+    *p.ticket = 0;
+    *p.ovf_reset = 0;
+  }
 }
 
 // ------------------------------------------------------------------ K5: loss and d tau
 // Latency-bound tail of the step: one thread per (direction, row), block sums, the last block (ticket) adds the block
 // sums.  Every sum runs in a fixed order (xor butterfly, warp order, block order) -> deterministic.  (One 1024-thread
 // block for the whole headline shape was tried: a single SM pulling 0.7 MB out of L2 takes 2x longer.)
-constexpr int FINAL_THREADS = 256;
-constexpr int FINAL_RPT = 1;
-constexpr int FINAL_ROWS = FINAL_THREADS * FINAL_RPT;
-__device__ __forceinline__ float2 block_sum2(float a, float b, float (*red)[32]) {
-  a = warp_sum(a);
-  b = warp_sum(b);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __syncthreads();
-  if (lane == 0) {
-    red[0][warp] = a;
-    red[1][warp] = b;
-  }
-  __syncthreads();
-  const bool live = lane < FINAL_THREADS / 32;
-  a = live ? red[0][lane] : 0.f;
-  b = live ? red[1][lane] : 0.f;
-  return make_float2(warp_sum(a), warp_sum(b));  // every warp computes the same totals
-}
 __global__ void __launch_bounds__(FINAL_THREADS) omc_final_kernel(const float* __restrict__ rowce, const float4* __restrict__ rowstat,
                                                        const float* __restrict__ zt, const float* __restrict__ dotq,
                                                        const float* __restrict__ dots, int dslots, int rows2, int M,
@@ -1270,7 +1319,7 @@ static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, bool
   pl->off_zt = take(sizeof(float) * 2 * bs);
   pl->off_rowce = take(sizeof(float) * 2 * bs);
   pl->off_rowstat = take(sizeof(float4) * 2 * bs);
-  pl->off_blockpart = take(sizeof(float2) * (ceil_div64(2 * bs, 256) + 1024));  // block sums of K5, or one pair per GEMM CTA
+  pl->off_blockpart = take(sizeof(float2) * (ceil_div64(2 * bs, 8) + 1024));  // block sums of K5 / the reduce kernel, or one pair per GEMM CTA
   pl->dslots = pl->g_dq.k_splits == 1 ? pl->g_dq.n_splits * 2 : 1;  // EpiGrad runs with two column halves per tile
   pl->off_dotq = take(sizeof(float) * 2 * bs * pl->dslots);
   pl->off_dots = take(sizeof(float) * 2 * bs * pl->dslots);
@@ -1594,19 +1643,26 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
       G.dotq = dotq;
       G.fused_stats = stats_in_reduce ? 1 : 0;
       G.rs = R;
+      G.blockpart = blockpart;
+      G.ticket = &wflags[1];
+      G.loss = loss;
+      G.grad_temp = grad_temp;
+      G.step_ctr = reinterpret_cast<unsigned long long*>(step_counter);
+      G.poison = assume_in_range ? &wflags[0] : nullptr;
+      G.ovf_reset = &wflags[0];
       VAST_TIMED(stream, "omc_grad_reduce", (launch_ex(omc_grad_reduce_kernel, ceil_div(2 * M, 8), 256, 0, stream, 1, G)));
       VAST_LAUNCH_OK("omc_grad_reduce");
     }
   }
 
-  // K5 (unless the dQ GEMM's epilogue already finished the step)
-  if (!fused_stats)
+  // K5 (unless the dQ GEMM's epilogue or the split-K reduce kernel already finished the step)
+  if (!fused_stats && !stats_in_reduce)
   VAST_TIMED(stream, "omc_final",
              (launch_ex(omc_final_kernel, ceil_div(2 * M, FINAL_ROWS), FINAL_THREADS, 0, stream, 1, rowce, rowstat, zt, need_grad ? dotq : nullptr,
                         fused_stats ? dots : nullptr, pl.dslots, 2 * M, M, inv_tau, contra_temp_dev, label_smoothing, c_sm, blockpart, &wflags[1], loss,
                         need_grad ? grad_temp : nullptr, reinterpret_cast<unsigned long long*>(step_counter),
                         assume_in_range ? &wflags[0] : nullptr, &wflags[0])));
-  if (!fused_stats) VAST_LAUNCH_OK("omc_final");
+  if (!fused_stats && !stats_in_reduce) VAST_LAUNCH_OK("omc_final");
   return VAST_OK;
 }
 
