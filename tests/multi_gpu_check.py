@@ -120,6 +120,11 @@ for direction in ("forward", "backward"):
 if rank == 0:
     print("streaming re-rank ok:", bool(ok), flush=True)
 
+# id lists as sized tensor all-gathers == the reference's pickled gather, on NCCL
+my_ids = [f"vid{rank}_{i}" for i in range(rank + 1)]
+ok &= vast_b200.all_gather_ids(my_ids) == [j for i in vast_b200.all_gather_list(my_ids) for j in i]
+ok &= vast_b200.all_gather_ids([rank * 10 + i for i in range(3)]) == [r * 10 + i for r in range(world) for i in range(3)]
+
 # negative-row exchange == all_gather_with_grad(x)[idx], values and gradients (NCCL all_to_all)
 xg = torch.randn(bs, 7, 16, generator=g).cuda()
 idx = torch.randint(0, n, (bs,), generator=g).cuda()

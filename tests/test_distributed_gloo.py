@@ -123,3 +123,50 @@ def test_exchange_rows_single_process():
     assert torch.equal(y, x[idx])
     y.sum().backward()
     assert torch.equal(x.grad[:, 0], torch.tensor([2., 0., 1., 1., 0., 2.]))
+
+
+def _ids_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vast_b200 import distributed as D
+    cases = {
+        "str": [f"vidéo{rank}_{i}" for i in range(rank + 2)],              # ragged, non-ASCII
+        "int": [1000 * rank + i for i in range(3 - rank)] if rank < 3 else [],
+        "empty_on_some": ["only0"] if rank == 0 else [],
+        "mixed": [rank, f"s{rank}"],                                        # falls back to the pickled gather
+        "tuple": [(rank, 1)],
+    }
+    out = {}
+    for k, v in cases.items():
+        got = D.all_gather_ids(v)
+        want = [j for i in D.all_gather_list(v) for j in i]                 # the reference's expression
+        out[k] = (got == want, [type(x).__name__ for x in got] == [type(x).__name__ for x in want], len(got))
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("world", [2, 3])
+def test_all_gather_ids_equals_pickled_gather(world):
+    """ids gathered as sized tensor all-gathers == `[j for i in all_gather_list(ids) for j in i]`
+    (evaluation_mm.py:208-209) for string / integer / empty / mixed id lists."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ids_worker, args=(r, world, 29760 + world, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=100) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+    for rank, out in res:
+        for k, (same, same_types, n) in out.items():
+            assert same and same_types, (rank, k)
+    assert res[0][1]["str"][2] == sum(r + 2 for r in range(world))
+
+
+def test_all_gather_ids_single_process():
+    from vast_b200 import distributed as D
+    assert D.all_gather_ids(["a", "b"]) == ["a", "b"] and D.all_gather_ids([]) == [] and D.all_gather_ids((3, 4)) == [3, 4]

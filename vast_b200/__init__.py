@@ -5,8 +5,8 @@ hand-written CUDA behind the C-ABI of include/vast_b200.h (vast_b200/_C/libvast_
 ctypes).  There is no CPU or PyTorch fallback: ops raise if the library or a CUDA device is missing."""
 from . import ops  # noqa: F401
 from .contrastive import forward_ret, gather_negatives, omc_loss_and_negatives  # noqa: F401
-from .distributed import (all_gather_list, all_gather_with_grad, any_broadcast, concat_all_gather,  # noqa: F401
-                          ddp_allgather, exchange_rows)
+from .distributed import (all_gather_ids, all_gather_list, all_gather_with_grad, any_broadcast,  # noqa: F401
+                          concat_all_gather, ddp_allgather, exchange_rows)
 from .graphed import OmcGraphStep  # noqa: F401
 from .features import build_feature, l2_normalize, pool_concat  # noqa: F401
 from .retrieval import (compute_metric_ret, evaluate_ret, recall_from_candidates, recall_from_feats,  # noqa: F401

@@ -161,6 +161,38 @@ def all_gather_list(data):
     return out
 
 
+def all_gather_ids(ids, device=None):
+    """The flat id list of all ranks in rank order -- what `[j for i in all_gather_list(ids) for j in i]`
+    (evaluation_mm.py:208-209) returns -- without pickling: SURVEY 8(f-4).  Integer ids travel as one ragged int64
+    all-gather; string ids as their UTF-8 bytes plus a length table (two ragged all-gathers); anything else falls
+    back to `all_gather_list`.  `device`: where the collective's tensors live (the NCCL device on a GPU job;
+    default: CUDA if the backend is NCCL, else CPU)."""
+    ids = list(ids)
+    if _world() == 1:
+        return ids
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    # every rank must take the same branch: agree on the id kind first (0 = int, 1 = str, 2 = other, -1 = empty list)
+    kind = -1 if not ids else (0 if all(type(v) is int and -2 ** 63 <= v < 2 ** 63 for v in ids) else
+                               1 if all(type(v) is str for v in ids) else 2)
+    kinds = torch.empty(_world(), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(kinds, torch.tensor([kind], dtype=torch.int64, device=device))
+    present = {int(k) for k in kinds.tolist() if k >= 0}
+    if len(present) != 1 or present == {2}:
+        return [j for i in all_gather_list(ids) for j in i]
+    if present == {0}:
+        return ddp_allgather(torch.tensor(ids, dtype=torch.int64, device=device).reshape(-1)).tolist()
+    raw = [v.encode("utf-8") for v in ids]
+    lens = ddp_allgather(torch.tensor([len(b) for b in raw], dtype=torch.int64, device=device).reshape(-1)).tolist()
+    blob = torch.frombuffer(bytearray(b"".join(raw)), dtype=torch.uint8) if raw else torch.empty(0, dtype=torch.uint8)
+    data = ddp_allgather(blob.to(device)).cpu().numpy().tobytes()
+    out, at = [], 0
+    for n in lens:
+        out.append(data[at:at + n].decode("utf-8"))
+        at += n
+    return out
+
+
 def any_broadcast(data, root_rank):
     """utils/distributed.py:117-128."""
     if _world() == 1:

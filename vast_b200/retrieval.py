@@ -12,7 +12,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from .distributed import _rank, _world, all_gather_list, ddp_allgather
+from .distributed import _rank, _world, all_gather_ids, all_gather_list, ddp_allgather
 
 
 # ------------------------------------------------------------------ streaming similarity + top-k
@@ -348,8 +348,8 @@ def evaluate_ret(model, tasks, val_loader, global_step, streaming=None):
         for t in subtasks:
             store[f'feat_cond_{t}'].append(ev[f'feat_cond_{t}'])
             store[f'condition_feats_{t}'].append(ev[f'condition_feats_{t}'])
-    ids = [j for i in all_gather_list(ids) for j in i]
-    ids_txt = [j for i in all_gather_list(ids_txt) for j in i]
+    ids = all_gather_ids(ids)          # evaluation_mm.py:208-209 without the pickle round trip
+    ids_txt = all_gather_ids(ids_txt)
     feat_t = ddp_allgather(torch.cat(feat_t, dim=0))
     input_ids = ddp_allgather(torch.cat(input_ids, dim=0))
     attention_mask = ddp_allgather(torch.cat(attention_mask, dim=0))
