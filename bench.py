@@ -15,7 +15,8 @@ Primary line (one JSON object on stdout, rank 0):
   cpu_baseline  oracle/torch_ref.py (operation-for-operation torch CPU port of model/vast.py:405-440,
           pinned bit-for-bit to the reference by tests/golden) on the box's host cores.
   retrieval  secondary metric of the same BASELINE metric string: streaming similarity + top-16 queries/s
-          at config 5 (100k x 100k x 512), column-sharded over the N GPUs.
+          at config 5 (100k x 100k x 512), query rows sharded over the N GPUs; its own cpu_baseline is the reference's
+          dense matmul + topk on a 2000-row slice, extrapolated linearly (the reference cannot run cfg5 at all).
 Scaling is STRONG: the global batch (and the retrieval problem) is fixed, per-GPU work shrinks with N."""
 from __future__ import annotations
 
@@ -389,6 +390,8 @@ def run_ours(args):
             ret["col_sharded"] = {"value": RET_N * Kr / (ms_rc * 1e-3), "unit": "queries/s", "ms_per_step": ms_rc / Kr,
                                   "note": "video columns sharded over the GPUs, candidate lists all-gathered and merged "
                                           "(identical result; list work does not shrink with the column count)"}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            ret["cpu_baseline"] = cpu_retrieval(rt.cpu(), rv.cpu())
         del rt, rv
 
     # ---- CPU baseline: the torch port of the reference path on the host cores (rank 0, N=1 only)
@@ -453,6 +456,29 @@ def cpu_contrastive(sample_steps=3, budget_s=None, steps=None, warmup=1):
                       f"{cores} threads), median of {n}",
             "what": "oracle/torch_ref.py: torch-CPU port of model/vast.py:405-440 + autograd, bit-for-bit equal to the "
                     "reference on tests/golden/omc_w1.npz"}
+
+
+def cpu_retrieval(feat_t, feat_cond, rows=2000, repeats=3):
+    """The reference's evaluation scoring (evaluation_mm.py:223 dense fp32 scores + :257 top-k) on the host cores.  The
+    reference cannot run cfg5 at all (a 40 GB score matrix and O(N^2) Python lists), so -- as SURVEY 8d prescribes -- a
+    slice of `rows` query rows against ALL columns is timed and the rate extrapolated linearly; labelled as such."""
+    import torch
+    from oracle import torch_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    q = feat_t[:rows].float().contiguous()
+    kk = feat_cond.float().contiguous()
+    torch_ref.retrieval_step(q[:64], kk, RET_K)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        torch_ref.retrieval_step(q, kk, RET_K)
+        times.append(time.perf_counter() - t0)
+    sec = statistics.median(times)
+    return {"value": rows / sec, "unit": "queries/s", "cores": cores, "kind": "port", "extrapolated": True,
+            "sample": f"{rows} of {RET_N} query rows vs all {RET_N} columns (fp32 matmul + topk({RET_K}), torch CPU, "
+                      f"{cores} threads), median of {repeats}; rate extrapolated linearly to the full problem",
+            "ms_per_sample": sec * 1e3}
 
 
 def run_cpu_sample(torch_ref, t, c, m):

@@ -6,23 +6,30 @@
 // Single-pass flow (default):
 //   K1 prep          : column sums of the gathered features (label-smoothing term), their fp16 copy (the dQ
 //                      GEMM needs both operands in one 16-bit format), target logits z_t = <t_i, c_i> of the
-//                      local rows, per-row exponent reference ref_i = z_t / tau
+//                      local rows, per-row exponent reference ref_i = z_t / tau.  With ONE rank
+//                      (vast_omc_step_local) the same kernel also does the packing: one pass over the fp features.
 //   K2 soft GEMM     : S tile in TMEM -> Pt_ij = exp(z_ij - ref_i)  ("softmax numerators" relative to the
 //                      positive pair, so Pt_target = 1): fp16 Pt tile to the L2-resident workspace (target
 //                      column zeroed), row sums l_i, chunk-level exponential race for the hard negatives
-//   K3 row stats     : per row: l_i -> lse, CE term, 1 / l_i, p_target, and the hard-negative draw
+//   K3 row stats     : per row: l_i -> lse, CE term, 1 / l_i, p_target, and the hard-negative draw.  Runs INSIDE
+//                      K4's epilogue (each epilogue thread merges its own row's partials while the first tile is
+//                      still being multiplied), or inside the split-K reduce kernel; a kernel of its own only for
+//                      loss-only calls and VAST_OMC_SEPARATE_ROW_STATS.  All three forms give the same bits.
 //   K4 dQ GEMM       : dQraw = Pt . K, the gathered features read ROW-MAJOR as the MN-major UMMA operand
 //                      (fp16 x fp16 -> fp32; no transposed copy); the epilogue assembles the gradient in place,
 //                      dQ = (1/(2 bs tau)) (dQraw / l - (eps/N) sum_j K_j - ((1-eps) - p_target) K_target),
 //                      and <q_i, dQraw_i> for d tau.  (Small per-rank problems split K instead and a reduce
 //                      kernel sums the partials in a fixed order.)
-//   K5 final         : loss and d tau, block sums + last-block ticket (fixed order -> deterministic)
+//   K5 final         : loss and d tau.  Linear in K4's per-(row, column range) partials, so it rides on K4's tail
+//                      (per-CTA sums + last-CTA ticket, `finish` hook) or on the reduce kernel's; fixed order
+//                      everywhere -> deterministic.  A kernel of its own only where K3 is.
 // The [bs, N] logits are evaluated exactly ONCE.  Pt needs the fp16 range: an entry overflows only if
 // some negative beats its positive by more than 16 ln2 = 11.09 nats ((s_ij - s_ii) > 0.78 at tau = 0.07).
 // The soft epilogue detects that (chunk sum >= 65504) and raises a device flag; two flag-gated
 // launches then redo the step in the two-pass form (K2a stats GEMM: online row max / sum-exp; K2b
 // soft GEMM again with ref_i = lse_i merged from K2a's partials, so Pt = softmax <= 1).  No host synchronisation
 // either way.  VAST_OMC_TWO_PASS / debug noise select the two-pass form directly.
+// The flag / ticket block at the head of the workspace is self-cleaning (VAST_OMC_WORKSPACE_CLEAN skips its memset).
 //
 // Why dQ is not fused FlashAttention-style into K2: the dQ accumulator of a 128-row block is
 // 128 x D fp32; at D = 1024 that is 512 KB, twice the 256 KB of TMEM (512 columns x 128 lanes).
