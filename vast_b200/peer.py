@@ -4,8 +4,8 @@ training path, model/vast.py:395,404 / utils/distributed.py:50-66).
 The gathered `[N, 2D]` bf16 buffer lives in symmetric memory (`torch.distributed._symmetric_memory`: the same
 allocation mapped into every rank of the node, plus an NVSwitch multicast mapping where the driver offers one).
 `vast_pack_pair_push` converts this rank's rows and stores every 16-byte vector straight into the buffer of ALL ranks
-(one `multimem.st` to the multicast address, or one peer store per rank); a symmetric-memory barrier on the same
-stream publishes it.  Two buffers alternate so that a rank that is one step ahead never overwrites rows a slower
+(one `multimem.st` to the multicast address -- more than four ranks -- or one peer store per rank); a
+symmetric-memory barrier on the same stream publishes it.  Two buffers alternate so that a rank that is one step ahead never overwrites rows a slower
 rank is still reading."""
 from __future__ import annotations
 
@@ -30,7 +30,11 @@ class PackedGather:
             b = symm.empty(self.world * bs, 2 * dim, dtype=torch.bfloat16, device=device)
             self.bufs.append(b)
             self.hdls.append(symm.rendezvous(b, self.group))
-        self.use_multicast = os.environ.get("VAST_PEER_MULTICAST", "1") == "1"
+        # multimem.st pays ~20 us for the end-of-kernel flush of its replicated stores whatever the size, peer stores
+        # pay (W - 1) x the bytes: measured on B200 + NVSwitch, peer stores win at W = 2 (109 vs 120 us/step) and
+        # W = 4 (94.4 vs 96.9), multicast is what was measured at W = 8.  VAST_PEER_MULTICAST=0/1 overrides.
+        env = os.environ.get("VAST_PEER_MULTICAST")
+        self.use_multicast = (env == "1") if env in ("0", "1") else self.world > 4
         self.turn = 0
 
     def _dst(self, i):
