@@ -116,6 +116,8 @@ VAST_API size_t vast_omc_workspace_bytes(int64_t bs, int64_t n_total, int64_t di
 
 /* vast_omc_step flags */
 #define VAST_OMC_TWO_PASS 1 /* evaluate the logits twice (row max / sum-exp pass first) instead of once */
+#define VAST_OMC_SEPARATE_ROW_STATS 2 /* run the row statistics + hard-negative draw as their own kernel instead of
+                                         inside the dQ GEMM's epilogue (same results bit for bit; A/B aid) */
 #define VAST_OMC_ASSUME_IN_RANGE 4 /* the caller guarantees that no negative beats its positive by more than
                                       16 ln2 = 11.09 nats of logit (always true for unit-norm features with
                                       contra_temp >= 0.181, since |s| <= 1): the two flag-gated fallback launches
@@ -125,8 +127,6 @@ VAST_API size_t vast_omc_workspace_bytes(int64_t bs, int64_t n_total, int64_t di
                                       call of the same shape (every step leaves its flag / ticket block zeroed), so
                                       the step does not clear it again: one launch less.  Never pass it for a fresh
                                       or recycled allocation. */
-#define VAST_OMC_SEPARATE_ROW_STATS 2 /* run the row statistics + hard-negative draw as their own kernel instead of
-                                         inside the dQ GEMM's epilogue (same results bit for bit; A/B aid) */
 
 /* One fused contrastive step on this rank's rows.
  *   pack        [n_total, 2*dim] bf16, row n = (feat_t_all[n] | feat_cond_all[n]) in rank order

@@ -325,3 +325,31 @@ def test_single_rank_step_rejects_unaligned():
     x = torch.randn(16, 12).cuda()
     with pytest.raises(RuntimeError):
         ops.omc_step_local(x, x, 0.07)     # D % 8 != 0
+
+
+def test_assume_in_range_skips_fallback_and_poisons_on_violation(monkeypatch):
+    """VAST_OMC_ASSUME_IN_RANGE: without the gated fallback launches an in-range step gives the same bits as the
+    default; a step whose numerators leave the fp16 range reports NaN for the loss and d tau (never wrong numbers),
+    and the workspace is still left clean for the next step."""
+    from vast_b200 import ops
+    n, dim = 192, 128
+    gen = torch.Generator().manual_seed(5)
+    t = torch.nn.functional.normalize(torch.randn(n, dim, generator=gen), dim=-1)
+    c = torch.nn.functional.normalize(t + 0.5 * torch.randn(n, dim, generator=gen), dim=-1)
+    ref = run_step(t.numpy(), c.numpy(), n, 0, 0.07, seed=3, offset=1)
+    monkeypatch.setenv("VAST_OMC_ASSUME_IN_RANGE", "1")
+    out = run_step(t.numpy(), c.numpy(), n, 0, 0.07, seed=3, offset=1)
+    assert torch.equal(out["grad_t"], ref["grad_t"]) and torch.equal(out["neg_idx"], ref["neg_idx"])
+    assert out["loss"].item() == ref["loss"].item()
+    bad = c.clone()
+    bad[3] = -t[3]
+    bad[77] = t[3]                       # a perfect negative against an anti-correlated positive: 2 / 0.07 = 28 nats
+    pack = ops.pack_pair(t.cuda(), bad.cuda())
+    o1 = ops.omc_step(pack, n, 0, 0.07, seed=3, offset=1)
+    assert torch.isnan(o1["loss"]).item() and torch.isnan(o1["grad_temp"]).item()
+    # the poisoned step left the flag block clean: re-using its buffers for an in-range step gives the right numbers
+    o2 = ops.omc_step(ops.pack_pair(t.cuda(), c.cuda()), n, 0, 0.07, seed=3, offset=1, buffers=o1)
+    assert o2["loss"].item() == ref["loss"].item() and torch.equal(o2["grad_t"], ref["grad_t"])
+    monkeypatch.delenv("VAST_OMC_ASSUME_IN_RANGE")
+    o3 = ops.omc_step(pack, n, 0, 0.07, seed=3, offset=1)          # default: the fallback handles it
+    assert torch.isfinite(o3["loss"]).item()
