@@ -21,7 +21,7 @@ if [ $rc -eq 0 ] && [ "${SKIP_NCU:-0}" != "1" ]; then
     python bench.py --steps 6 --warmup 3 --no-cpu --no-retrieval --no-graph > gpurun_out/ncu_omc.log 2>&1
   echo "ncu omc exit $?"
   python scripts/prof_retrieval.py 100000 512 16 1 > gpurun_out/prof_ret_plain.log 2>&1 && \
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:EpiTopK -c 1 -f -o gpurun_out/prof_ret \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -c 1 -f -o gpurun_out/prof_ret \
     python scripts/prof_retrieval.py 100000 512 16 1 > gpurun_out/ncu_ret.log 2>&1
   echo "ncu ret exit $?"
 fi
