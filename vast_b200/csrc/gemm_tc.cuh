@@ -111,16 +111,22 @@ __device__ __forceinline__ WorkItem decode_item(const GemmShape& g, int idx, int
   return w;
 }
 
-template <int BN, int STAGES, int CL>
+// A_RES > 0 ("A-stationary"): the CTA's whole A row block (up to A_RES k-blocks) stays resident in shared memory for
+// all N-tiles of a work item and the ring stages carry B only.  For short K (retrieval at D = 512: 8 k-blocks) the
+// operand traffic L2 -> SM is what binds the mainloop -- every 256 x 256 x 512 tile re-fetches 256 KB of A next to
+// its 256 KB of B -- and residency halves it.
+template <int BN, int STAGES, int CL, int A_RES = 0>
 struct SmemLayout {
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = BN * BK * 2 / CL;  // a CTA pair keeps half of every B tile per CTA
-  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr uint32_t BAR_BYTES = 256;  // 2*STAGES + 4 barriers + tmem slot
+  static constexpr uint32_t A_RES_BYTES = A_RES * A_BYTES;
+  static constexpr uint32_t STAGE_BYTES = A_RES > 0 ? B_BYTES : A_BYTES + B_BYTES;
+  static constexpr uint32_t RING_OFFSET = A_RES_BYTES;
+  static constexpr uint32_t BAR_OFFSET = RING_OFFSET + STAGES * STAGE_BYTES;
+  static constexpr uint32_t BAR_BYTES = 256;  // 2*STAGES + 6 barriers + tmem slot
   static constexpr uint32_t EPI_OFFSET = BAR_OFFSET + BAR_BYTES;
   static constexpr uint32_t ALIGN_SLACK = 1024;
-  static_assert(2 * STAGES * 8 + 4 * 8 + 8 <= BAR_BYTES, "barrier block too small");
+  static_assert(2 * STAGES * 8 + 6 * 8 + 8 <= BAR_BYTES, "barrier block too small");
 };
 
 // Epilogues that declare `static constexpr bool kHasFinish` get finish(epilogue warp, lane, NE) called by every epilogue
@@ -146,18 +152,19 @@ struct HasFinish<E, std::void_t<decltype(E::kHasFinish)>> : std::true_type {};
 //         `full` barrier); only the leader issues MMAs; its tcgen05.commit is multicast to both CTAs' `empty`
 //         (stage free) and `tfull` (accumulator ready) barriers; both CTAs' epilogue warps arrive on the
 //         leader's `tempty` barrier (accumulator drained).
-template <class Epi, int BN, int STAGES, int NE, bool B_MN, int CL>
+template <class Epi, int BN, int STAGES, int NE, bool B_MN, int CL, int A_RES = 0>
 __global__ void __launch_bounds__(64 + 32 * NE + 32 * Epi::kAuxWarps, 1)
 gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
   static_assert(NE == 4 || NE == 8, "4 or 8 epilogue warps");
   static_assert(BN == 128 || BN == 256, "BN");
   static_assert(CL == 1 || CL == 2, "single CTA or CTA pair");
+  static_assert(A_RES == 0 || !B_MN, "resident A is implemented for the K-major B operand");
   pdl_trigger();
   if (P.gate != nullptr) {  // the flag is written by a predecessor
     pdl_wait();
     if (*reinterpret_cast<const volatile int*>(P.gate) == 0) return;
   }
-  using L = SmemLayout<BN, STAGES, CL>;
+  using L = SmemLayout<BN, STAGES, CL, A_RES>;
   constexpr int HALVES = NE / 4;
   constexpr int COLS_PER_WARP = BN / HALVES;
   constexpr uint32_t TMEM_COLS = 2 * BN;
@@ -172,7 +179,9 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* afull = tempty + 2;   // resident A loaded (A_RES)
+  uint64_t* aempty = afull + 1;   // every MMA of the item that read the resident A has retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 1);
   uint8_t* epi_smem = smem + L::EPI_OFFSET;
 
   const int warp = threadIdx.x >> 5;
@@ -196,6 +205,8 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
       ptx::mbar_init(&tfull[a], 1);
       ptx::mbar_init(&tempty[a], NE * CL);
     }
+    ptx::mbar_init(afull, 1);
+    ptx::mbar_init(aempty, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -216,14 +227,36 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t a_phase = 0;
       for (int item = cluster_id; item < g.num_items; item += num_clusters) {
         const WorkItem w = decode_item(g, item, cta_rank);
+        if constexpr (A_RES > 0) {
+          // the item's A row block, once: k-block kb at A_BYTES * kb (the previous item's MMAs must have retired)
+          ptx::mbar_wait(aempty, a_phase ^ 1);
+          const int nkb = w.kb_end - w.kb_begin;
+          if (!PAIR || leader) ptx::mbar_arrive_expect_tx(afull, static_cast<uint32_t>(CL * nkb) * L::A_BYTES);
+          for (int kb = w.kb_begin; kb < w.kb_end; ++kb) {
+            uint8_t* sa = smem + (kb - w.kb_begin) * L::A_BYTES;
+            if constexpr (PAIR)
+              ptx::tma_load_2d_pair(sa, &P.tmA[w.prob], afull, kb * BK, w.m_blk * BM);
+            else
+              ptx::tma_load_2d(sa, &P.tmA[w.prob], afull, kb * BK, w.m_blk * BM);
+          }
+          a_phase ^= 1;
+        }
         for (int t = w.tile_begin; t < w.tile_end; ++t) {
           for (int kb = w.kb_begin; kb < w.kb_end; ++kb) {
             ptx::mbar_wait(&empty[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * L::STAGE_BYTES;
-            uint8_t* sb = sa + L::A_BYTES;
-            if constexpr (!PAIR) {
+            uint8_t* sa = smem + L::RING_OFFSET + stage * L::STAGE_BYTES;
+            uint8_t* sb = A_RES > 0 ? sa : sa + L::A_BYTES;
+            if constexpr (A_RES > 0) {
+              constexpr int HALF_N = BN / CL;
+              if (!PAIR || leader) ptx::mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(CL) * L::B_BYTES);
+              if constexpr (PAIR)
+                ptx::tma_load_2d_pair(sb, &P.tmB[w.prob], &full[stage], kb * BK, t * BN + cta_rank * HALF_N);
+              else
+                ptx::tma_load_2d(sb, &P.tmB[w.prob], &full[stage], kb * BK, t * BN);
+            } else if constexpr (!PAIR) {
               ptx::mbar_arrive_expect_tx(&full[stage], L::STAGE_BYTES);
               ptx::tma_load_2d(sa, &P.tmA[w.prob], &full[stage], kb * BK, w.m_blk * BM);
               if constexpr (B_MN) {
@@ -262,8 +295,14 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      uint32_t a_phase = 0;
       for (int item = cluster_id; item < g.num_items; item += num_clusters) {
         const WorkItem w = decode_item(g, item, cta_rank);
+        if constexpr (A_RES > 0) {
+          ptx::mbar_wait(afull, a_phase);
+          ptx::tc_fence_after_sync();
+          a_phase ^= 1;
+        }
         for (int t = w.tile_begin; t < w.tile_end; ++t) {
           ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
           ptx::tc_fence_after_sync();
@@ -271,10 +310,12 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
           for (int kb = w.kb_begin; kb < w.kb_end; ++kb) {
             ptx::mbar_wait(&full[stage], phase);
             ptx::tc_fence_after_sync();
-            const uint32_t sa = ptx::smem_u32(smem + stage * L::STAGE_BYTES);
+            const uint32_t sst = ptx::smem_u32(smem + L::RING_OFFSET + stage * L::STAGE_BYTES);
+            const uint32_t sa = A_RES > 0 ? ptx::smem_u32(smem + (kb - w.kb_begin) * L::A_BYTES) : sst;
+            const uint32_t sbb = A_RES > 0 ? sst : sst + L::A_BYTES;
             const uint64_t da = ptx::umma_desc_sw128_kmajor(sa);
-            const uint64_t db = B_MN ? ptx::umma_desc_sw128_mnmajor(sa + L::A_BYTES, BK * 128)
-                                     : ptx::umma_desc_sw128_kmajor(sa + L::A_BYTES);
+            const uint64_t db = B_MN ? ptx::umma_desc_sw128_mnmajor(sbb, BK * 128)
+                                     : ptx::umma_desc_sw128_kmajor(sbb);
             // K-major: advance 16 elements (32 bytes) along K inside the swizzle span: +2 in 16-byte units.
             // MN-major: 16 K-rows of 128 bytes = 2048 bytes: +128.
             constexpr uint64_t B_KSTEP = B_MN ? 128 : 2;
@@ -294,6 +335,7 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
             acc_phase ^= 1;
           }
         }
+        if constexpr (A_RES > 0) ptx::umma_commit<CL>(aempty);  // the resident A may be replaced (in both CTAs)
       }
     }
   } else if (warp >= 2 + NE) {
@@ -402,13 +444,15 @@ inline void fill_shape(GemmShape* g, int problems, int M, int N, int K, int BN, 
 // CTA pairs (cta_group::2) as soon as there are two 128-row blocks to pair.
 inline int pick_cluster(int M) { return ceil_div(M, BM) >= 2 ? 2 : 1; }
 
-template <class Epi, int BN, int STAGES, int NE, bool B_MN, int CL>
+template <class Epi, int BN, int STAGES, int NE, bool B_MN, int CL, int A_RES = 0>
 int launch_gemm_cl(const KernelParams<typename Epi::Params>& P, cudaStream_t stream, const char* name, size_t epi_smem_bytes) {
-  using L = SmemLayout<BN, STAGES, CL>;
+  using L = SmemLayout<BN, STAGES, CL, A_RES>;
   const size_t smem = L::EPI_OFFSET + L::ALIGN_SLACK + epi_smem_bytes;
   VAST_REQUIRE(smem <= 232448, VAST_ERR_UNSUPPORTED, "%s: %zu bytes of shared memory exceed the 227 KB limit", name, smem);
   VAST_REQUIRE(P.g.cl == CL, VAST_ERR_INVALID, "%s: shape planned for clusters of %d, launched with %d", name, P.g.cl, CL);
-  auto kern = gemm_tc_kernel<Epi, BN, STAGES, NE, B_MN, CL>;
+  VAST_REQUIRE(A_RES == 0 || (P.g.k_blocks <= A_RES && P.g.k_splits == 1), VAST_ERR_INVALID,
+               "%s: %d k-blocks do not fit the %d resident ones", name, P.g.k_blocks, A_RES);
+  auto kern = gemm_tc_kernel<Epi, BN, STAGES, NE, B_MN, CL, A_RES>;
   static size_t attr_smem = 0;  // per instantiation; grows monotonically
   if (smem > attr_smem) {
     VAST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

@@ -1025,6 +1025,24 @@ extern "C" int vast_sim_topk(const void* q_op, const void* k_op, int64_t n_q, in
     P.epi = {part, static_cast<int>(k), pl.g.n_splits, NE / 4, static_cast<uint32_t>(col_offset), thr_shared, dbg ? atoi(dbg) : 0};
     return tc::launch_gemm<Epi, 256, STAGES, NE, false, STAGES2>(P, stream, "sim_topk_gemm", Epi::smem_bytes());
   };
+  // A-stationary mainloop (the CTA's query rows resident in shared memory, the ring carries keys only) for short
+  // operands: halves the L2 -> SM operand traffic that binds the mainloop at D = 512
+  // (measured at cfg5: 8.66 -> 8.33 ms; VAST_TOPK_ARES=0 selects the streaming-A ring of the first version)
+  static const int ares_mode = [] {
+    const char* e = getenv("VAST_TOPK_ARES");
+    return e ? atoi(e) : 1;
+  }();
+  if (ares_mode && pl.e == 1 && pl.g.cl == 2 && pl.g.k_blocks <= 8) {
+    tc::KernelParams<typename EpiTopK<1>::Params> P;
+    memset(&P, 0, sizeof(P));
+    P.g = pl.g;
+    rc = tc::make_tmap_2d(&P.tmA[0], q_op, VAST_BF16, n_q, cols, cols, tc::BM);
+    if (rc) return rc;
+    rc = tc::make_tmap_2d(&P.tmB[0], k_op, VAST_BF16, n_k, cols, cols, 256 / pl.g.cl);
+    if (rc) return rc;
+    P.epi = {part, static_cast<int>(k), pl.g.n_splits, 2, static_cast<uint32_t>(col_offset), thr_shared, 0};
+    rc = tc::launch_gemm_cl<EpiTopK<1>, 256, 3, 8, false, 2, 8>(P, stream, "sim_topk_gemm", EpiTopK<1>::smem_bytes());
+  } else
   // <epilogue, ring depth of a lone CTA (48 KB stages), ring depth of a CTA pair (32 KB stages), filter warps>
   if (pl.e == 1)
     rc = run(TopkTag<EpiTopK<1>, 3, 5, 8>{});
