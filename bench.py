@@ -381,6 +381,9 @@ def run_ours(args):
                             "peak": peaks["tf_burst"], "unit": "TFLOP/s",
                             "frac": round(ach / peaks["tf_burst"], 4) if ach else None,
                             "peak_source": f"{peaks['src']} bf16 burst (kernel dominates a short step)"}}
+        tr_r = ncu_traffic("sim_topk_gemm") if world == 1 else None
+        ret["roofline"]["traffic"] = tr_r["bytes"] if tr_r else None
+        ret["roofline"]["traffic_source"] = tr_r["source"] if tr_r else None
         if world > 1:   # the same problem with the video COLUMNS sharded instead (candidate all-gather + merge)
             def step_cols(i):
                 vast_b200.retrieval_topk(rt, rv, RET_K, mode="bf16", shard=shard, shard_mode="cols")
