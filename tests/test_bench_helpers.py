@@ -1,8 +1,6 @@
 """bench.py host-side helpers (no GPU): the peak table, the ncu-summary parser behind `roofline.traffic`, the synthetic
 inputs of SURVEY 8d, and the reference arm's JSON line shape (the contract keys the driver reads)."""
-import json
 import os
-import subprocess
 import sys
 
 import pytest
