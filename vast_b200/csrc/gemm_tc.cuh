@@ -31,6 +31,7 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 16-bit = one 128-byte swizzle span
 constexpr int MAX_PROBLEMS = 2;
+constexpr int MAX_SCHED = 192;  // entries of an explicit work-item table (two rounds of <= 96 clusters)
 
 struct GemmShape {
   int num_problems;
@@ -46,6 +47,12 @@ struct GemmShape {
   // tail_splits column ranges of tail_tps tiles so that the final wave still fills the machine.
   int tail_groups, tail_splits, tail_tps;
   uint32_t idesc;
+  // Optional explicit schedule (epilogues with kCustomTiles, MN-major B): work item idx is the single tile
+  // sched[idx] = width64 | col64 << 3 | group << 11  -- `width64` 64-column units wide (0 = empty slot, 1..BN/64),
+  // starting at column 64 * col64 of row-block group `group` (= prob * m_groups + group inside the problem).
+  // Tiles narrower than BN let a static schedule balance a grid the regular tiling leaves 1.73 waves deep.
+  int n_sched;
+  uint32_t sched[MAX_SCHED];
 };
 
 template <class EpiParams>
@@ -70,12 +77,33 @@ struct ItemCtx {
 struct WorkItem {
   int prob, m_blk, n_split, k_split;
   int tile_begin, tile_end, kb_begin, kb_end;
+  int col_base, width;  // tile t covers columns [col_base + t * BN, +width)   (regular items: 0, BN)
 };
 
 // idx enumerates (problem, row-block group, N-split, K-split); the CTA's own row block inside the group
 // is its rank in the cluster.
+template <int BN, bool CUSTOM = false>
 __device__ __forceinline__ WorkItem decode_item(const GemmShape& g, int idx, int cta_rank) {
   WorkItem w;
+  w.col_base = 0;
+  w.width = BN;
+  if constexpr (CUSTOM) {
+    if (g.n_sched > 0) {
+      const uint32_t e = g.sched[idx];
+      const int wu = static_cast<int>(e & 7u), cu = static_cast<int>((e >> 3) & 0xFFu), gg = static_cast<int>(e >> 11);
+      w.prob = gg / g.m_groups;
+      w.m_blk = (gg - w.prob * g.m_groups) * g.cl + cta_rank;
+      w.n_split = cu;  // 0 <=> the tile that starts at column 0 (the row's publisher in EpiGrad)
+      w.k_split = 0;
+      w.tile_begin = 0;
+      w.tile_end = wu ? 1 : 0;
+      w.kb_begin = 0;
+      w.kb_end = g.k_blocks;
+      w.col_base = cu * 64;
+      w.width = wu * 64;
+      return w;
+    }
+  }
   if (g.tail_groups > 0) {
     const int full = g.m_groups - g.tail_groups;
     int grp = idx, split = 0;
@@ -132,6 +160,10 @@ struct SmemLayout {
 // Epilogues that declare `static constexpr bool kHasFinish` get finish(epilogue warp, lane, NE) called by every epilogue
 // thread after the CTA's last work item (EpiGrad: the step's final loss / d tau reduction rides on the GEMM's tail).
 template <class E, class = void>
+struct HasCustomTiles : std::false_type {};
+template <class E>
+struct HasCustomTiles<E, std::void_t<decltype(E::kCustomTiles)>> : std::true_type {};
+template <class E, class = void>
 struct HasFinish : std::false_type {};
 template <class E>
 struct HasFinish<E, std::void_t<decltype(E::kHasFinish)>> : std::true_type {};
@@ -169,6 +201,7 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
   constexpr int COLS_PER_WARP = BN / HALVES;
   constexpr uint32_t TMEM_COLS = 2 * BN;
   constexpr bool PAIR = CL == 2;
+  constexpr bool CUSTOM = HasCustomTiles<Epi>::value && B_MN;  // explicit single-tile work items of any width <= BN
 
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte aligned bases (in the shared address space).
@@ -229,7 +262,7 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
       uint32_t phase = 0;
       uint32_t a_phase = 0;
       for (int item = cluster_id; item < g.num_items; item += num_clusters) {
-        const WorkItem w = decode_item(g, item, cta_rank);
+        const WorkItem w = decode_item<BN, CUSTOM>(g, item, cta_rank);
         if constexpr (A_RES > 0) {
           // the item's A row block, once: k-block kb at A_BYTES * kb (the previous item's MMAs must have retired)
           ptx::mbar_wait(aempty, a_phase ^ 1);
@@ -257,26 +290,37 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
               else
                 ptx::tma_load_2d(sb, &P.tmB[w.prob], &full[stage], kb * BK, t * BN);
             } else if constexpr (!PAIR) {
-              ptx::mbar_arrive_expect_tx(&full[stage], L::STAGE_BYTES);
-              ptx::tma_load_2d(sa, &P.tmA[w.prob], &full[stage], kb * BK, w.m_blk * BM);
               if constexpr (B_MN) {
+                const int nboxes = CUSTOM ? (w.width + 63) >> 6 : BN / 64;  // 64 K-rows x 64 columns each
+                ptx::mbar_arrive_expect_tx(&full[stage], L::A_BYTES + static_cast<uint32_t>(nboxes) * (BK * 128));
+                ptx::tma_load_2d(sa, &P.tmA[w.prob], &full[stage], kb * BK, w.m_blk * BM);
 #pragma unroll
                 for (int nb = 0; nb < BN / 64; ++nb)
-                  ptx::tma_load_2d(sb + nb * (BK * 128), &P.tmB[w.prob], &full[stage], t * BN + nb * 64, kb * BK);
+                  if (nb < nboxes)
+                    ptx::tma_load_2d(sb + nb * (BK * 128), &P.tmB[w.prob], &full[stage], w.col_base + t * BN + nb * 64, kb * BK);
               } else {
+                ptx::mbar_arrive_expect_tx(&full[stage], L::STAGE_BYTES);
+                ptx::tma_load_2d(sa, &P.tmA[w.prob], &full[stage], kb * BK, w.m_blk * BM);
                 ptx::tma_load_2d(sb, &P.tmB[w.prob], &full[stage], kb * BK, t * BN);
               }
             } else {
               // the leader's barrier collects the bytes of BOTH CTAs' loads
-              if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * L::STAGE_BYTES);
-              ptx::tma_load_2d_pair(sa, &P.tmA[w.prob], &full[stage], kb * BK, w.m_blk * BM);
               constexpr int HALF_N = BN / 2;  // this CTA's half of the B tile
               if constexpr (B_MN) {
+                // a tile of `width` columns: this CTA holds columns [half_n * rank, +half_n) as 64-column boxes (a last,
+                // partly used box is loaded whole: the tensor core reads only the first half_n columns)
+                const int half_n = CUSTOM ? w.width >> 1 : HALF_N;
+                const int nboxes = CUSTOM ? (half_n + 63) >> 6 : HALF_N / 64;
+                if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * (L::A_BYTES + static_cast<uint32_t>(nboxes) * (BK * 128)));
+                ptx::tma_load_2d_pair(sa, &P.tmA[w.prob], &full[stage], kb * BK, w.m_blk * BM);
 #pragma unroll
                 for (int nb = 0; nb < HALF_N / 64; ++nb)
-                  ptx::tma_load_2d_pair(sb + nb * (BK * 128), &P.tmB[w.prob], &full[stage],
-                                        t * BN + cta_rank * HALF_N + nb * 64, kb * BK);
+                  if (nb < nboxes)
+                    ptx::tma_load_2d_pair(sb + nb * (BK * 128), &P.tmB[w.prob], &full[stage],
+                                          w.col_base + t * BN + cta_rank * half_n + nb * 64, kb * BK);
               } else {
+                if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * L::STAGE_BYTES);
+                ptx::tma_load_2d_pair(sa, &P.tmA[w.prob], &full[stage], kb * BK, w.m_blk * BM);
                 ptx::tma_load_2d_pair(sb, &P.tmB[w.prob], &full[stage], kb * BK, t * BN + cta_rank * HALF_N);
               }
             }
@@ -297,7 +341,7 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
       uint32_t acc_phase = 0;
       uint32_t a_phase = 0;
       for (int item = cluster_id; item < g.num_items; item += num_clusters) {
-        const WorkItem w = decode_item(g, item, cta_rank);
+        const WorkItem w = decode_item<BN, CUSTOM>(g, item, cta_rank);
         if constexpr (A_RES > 0) {
           ptx::mbar_wait(afull, a_phase);
           ptx::tc_fence_after_sync();
@@ -319,9 +363,11 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
             // K-major: advance 16 elements (32 bytes) along K inside the swizzle span: +2 in 16-byte units.
             // MN-major: 16 K-rows of 128 bytes = 2048 bytes: +128.
             constexpr uint64_t B_KSTEP = B_MN ? 128 : 2;
+            // a narrower tile of an explicit schedule: the same descriptors, N taken from the item
+            const uint32_t idesc = CUSTOM ? ((g.idesc & ~(0x3Fu << 17)) | (static_cast<uint32_t>(w.width >> 3) << 17)) : g.idesc;
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              ptx::umma_f16<CL>(d_tmem, da + 2 * k, db + B_KSTEP * k, g.idesc, (kb > w.kb_begin || k > 0) ? 1u : 0u);
+              ptx::umma_f16<CL>(d_tmem, da + 2 * k, db + B_KSTEP * k, idesc, (kb > w.kb_begin || k > 0) ? 1u : 0u);
             }
             ptx::umma_commit<CL>(&empty[stage]);  // frees the smem stage (in both CTAs) once these MMAs retire
             if (++stage == STAGES) {
@@ -351,7 +397,9 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
     uint32_t acc_phase = 0;
     Epi epi(P.epi, epi_smem);
     for (int item = cluster_id; item < g.num_items; item += num_clusters) {
-      const WorkItem w = decode_item(g, item, cta_rank);
+      const WorkItem w = decode_item<BN, CUSTOM>(g, item, cta_rank);
+      if (CUSTOM && w.tile_end <= w.tile_begin) continue;  // empty slot of an explicit schedule
+      const int cpw = CUSTOM ? w.width / HALVES : COLS_PER_WARP;  // columns of a tile handled by this warp (multiple of 32)
       ItemCtx ctx;
       ctx.prob = w.prob;
       ctx.m_blk = w.m_blk;
@@ -367,20 +415,22 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
       epi.item_begin(ctx);
       for (int t = w.tile_begin; t < w.tile_end; ++t) {
         // Epilogues with global operands (EpiGrad) start loading the first chunk's rows while the MMAs finish.
-        epi.prefetch(ctx, t * BN + half * COLS_PER_WARP);
+        const int col_tile = w.col_base + t * BN;
+        epi.prefetch(ctx, col_tile + half * cpw);
         ptx::mbar_wait(&tfull[acc], acc_phase);
         ptx::tc_fence_after_sync();
 #pragma unroll(Epi::kUnrollChunks ? COLS_PER_WARP / 32 : 1)
         for (int c = 0; c < COLS_PER_WARP; c += 32) {
-          const int col_in_tile = half * COLS_PER_WARP + c;
+          if (CUSTOM && c >= cpw) break;
+          const int col_in_tile = half * cpw + c;
           const uint32_t taddr =
               tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + col_in_tile);
           uint32_t v[32];
           ptx::tmem_ld_32x32b_x32(taddr, v);
           // software pipeline: the next chunk's global operands are requested before this chunk's wait
-          epi.advance(ctx, t * BN + col_in_tile + 32, c + 32 < COLS_PER_WARP);
+          epi.advance(ctx, col_tile + col_in_tile + 32, c + 32 < cpw);
           ptx::tmem_ld_wait();
-          epi.chunk(ctx, v, t * BN + col_in_tile);
+          epi.chunk(ctx, v, col_tile + col_in_tile);
           __syncwarp();
         }
         ptx::tc_fence_before_sync();
@@ -437,6 +487,7 @@ inline void fill_shape(GemmShape* g, int problems, int M, int N, int K, int BN, 
   g->kb_per_split = g->k_blocks;
   g->num_items = problems * g->m_groups;
   g->tail_groups = g->tail_splits = g->tail_tps = 0;
+  g->n_sched = 0;
   g->idesc = ptx::umma_idesc_f16(static_cast<uint32_t>(a_fmt), static_cast<uint32_t>(b_fmt), b_mn ? 1u : 0u,
                                  static_cast<uint32_t>(BM * cl), static_cast<uint32_t>(BN));
 }

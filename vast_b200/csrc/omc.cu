@@ -35,6 +35,8 @@
 // 128 x D fp32; at D = 1024 that is 512 KB, twice the 256 KB of TMEM (512 columns x 128 lanes).
 // Staging Pt in fp16 through L2 (32 MB per direction at bs = N = 4096; the L2 holds 126 MB) keeps S at
 // one evaluation; fp32 logits / log-softmax / gradient matrices are never materialised.
+#include <cstdlib>
+#include <mutex>
 #include <type_traits>
 
 #include "common.cuh"
@@ -798,6 +800,7 @@ struct EpiGrad {
   static constexpr bool kUnrollChunks = true;  // the operand double buffer lives in registers
   static constexpr int kAuxWarps = 0;
   static constexpr bool kHasFinish = true;
+  static constexpr bool kCustomTiles = true;  // accepts an explicit schedule of tiles narrower than BN (plan_mixed_tiles)
   const Params& p;
   float* red;  // shared scratch of the final reduction
   float rho, c_t, gs, dotq, dots;
@@ -1297,6 +1300,139 @@ struct OmcPlan {
       off_dq, off_k16, total;
 };
 
+// ------------------------------------------------------------------ balanced static schedule for the dQ GEMM
+// The dQ GEMM of the headline shape is 32 row-block groups x 1024 columns = 128 tiles of 256 x 256 on 74 CTA pairs:
+// 1.73 "waves", i.e. the machine idles for 13.5 % of the kernel.  Stream-K loses more to L2 locality than it gains
+// (profiles/r01_v6_streamk_experiment.txt).  This schedule stays static and whole-K: every group's columns are cut
+// either into 256-wide tiles or into one 256-wide and 192-wide ones (tcgen05.mma takes any N % 16 == 0), and every
+// CTA pair gets ONE tile in each of two rounds such that its two tiles add up to at most 7 x 64 columns instead of
+// 8 x 64 (512 x 64-column units over 74 pairs = 6.92 each).  All tiles of a row-block group run in the same round, so
+// the group's Pt rows are fetched once, and the tiles of a round walk K in lockstep like the regular schedule.
+struct MixedPlan {
+  int U, G, C, bn_units;
+  bool ok;
+  int n_items;
+  uint32_t sched[tc::MAX_SCHED];
+};
+
+static bool solve_mixed_tiles(MixedPlan* mp) {
+  const int U = mp->U, G = mp->G, C = mp->C, BU = mp->bn_units;
+  mp->ok = false;
+  if (2 * C > tc::MAX_SCHED || U > 255 || G >= (1 << 20) || BU != 4) return false;
+  // cost in 64-column units of K-loop work on the critical path, + a fixed cost per tile (pipeline fill, epilogue tail)
+  const double tile_cost = 0.35;
+  const int reg_tiles = (U + BU - 1) / BU;
+  const long reg_items = static_cast<long>(G) * reg_tiles;
+  const double reg_cost = static_cast<double>((reg_items + C - 1) / C) * ((U < BU ? U : BU) + tile_cost);
+  struct Pat { int a4, a3; };
+  Pat pats[64];
+  int np = 0;
+  for (int a3 = 0; 3 * a3 <= U && np < 64; ++a3)
+    if ((U - 3 * a3) % 4 == 0) pats[np++] = {(U - 3 * a3) / 4, a3};
+  double best = reg_cost * 0.97;  // must beat the regular schedule by a margin
+  int bA = -1, bB = -1, b0A = 0, b0B = 0, b1A = 0, b1B = 0;
+  int r0[128], r1[128];
+  for (int ia = 0; ia < np; ++ia)
+    for (int ib = ia; ib < np; ++ib) {
+      const int tA = pats[ia].a4 + pats[ia].a3, tB = pats[ib].a4 + pats[ib].a3;
+      for (int n0A = 0; n0A <= G; ++n0A)
+        for (int n0B = 0; n0A + n0B <= G; ++n0B) {
+          if (n0A * tA + n0B * tB > C) break;
+          for (int n1A = 0; n0A + n0B + n1A <= G; ++n1A) {
+            const int n1B = G - n0A - n0B - n1A;
+            if (ib == ia && (n0B != 0 || n1B != 0)) continue;  // one pattern only: count it once
+            if (n1A * tA + n1B * tB > C) continue;
+            // round 0 widest first, round 1 narrowest first, paired by position
+            const int f0 = n0A * pats[ia].a4 + n0B * pats[ib].a4, t0 = n0A * pats[ia].a3 + n0B * pats[ib].a3;
+            const int f1 = n1A * pats[ia].a4 + n1B * pats[ib].a4, t1 = n1A * pats[ia].a3 + n1B * pats[ib].a3;
+            double worst = 0;
+            for (int i = 0; i < C; ++i) {
+              const int w0 = i < f0 ? 4 : (i < f0 + t0 ? 3 : 0);
+              const int j = C - 1 - i;  // position from the wide end of round 1
+              const int w1 = j < f1 ? 4 : (j < f1 + t1 ? 3 : 0);
+              const double c = w0 + w1 + tile_cost * ((w0 > 0) + (w1 > 0));
+              if (c > worst) worst = c;
+            }
+            if (worst < best - 1e-9) {
+              best = worst;
+              bA = ia; bB = ib; b0A = n0A; b0B = n0B; b1A = n1A; b1B = n1B;
+            }
+          }
+        }
+    }
+  if (bA < 0) return false;
+  // materialise: groups in DESCENDING order (the soft GEMM wrote the last groups' Pt rows last: they are the ones
+  // still in L2); round 0 = b0A groups of pattern A then b0B of pattern B, round 1 likewise
+  struct Tile { int grp, col, w; };
+  Tile tiles[2][128];
+  int nt[2] = {0, 0};
+  int grp = G - 1;
+  const int counts[2][2] = {{b0A, b0B}, {b1A, b1B}};
+  for (int r = 0; r < 2; ++r)
+    for (int ty = 0; ty < 2; ++ty) {
+      const Pat pt = pats[ty == 0 ? bA : bB];
+      for (int n = 0; n < counts[r][ty]; ++n, --grp) {
+        int col = 0;
+        for (int i = 0; i < pt.a4; ++i) { tiles[r][nt[r]++] = {grp, col, 4}; col += 4; }
+        for (int i = 0; i < pt.a3; ++i) { tiles[r][nt[r]++] = {grp, col, 3}; col += 3; }
+      }
+    }
+  if (grp != -1 || nt[0] > C || nt[1] > C) return false;
+  // stable sort by width: round 0 descending, round 1 ascending with the empty slots first
+  auto by_width = [](Tile* t, int n, bool desc) {
+    for (int i = 1; i < n; ++i) {
+      const Tile x = t[i];
+      int j = i - 1;
+      while (j >= 0 && (desc ? t[j].w < x.w : t[j].w > x.w)) { t[j + 1] = t[j]; --j; }
+      t[j + 1] = x;
+    }
+  };
+  by_width(tiles[0], nt[0], true);
+  by_width(tiles[1], nt[1], false);
+  for (int i = 0; i < 2 * C; ++i) mp->sched[i] = 0;
+  for (int i = 0; i < nt[0]; ++i)
+    mp->sched[i] = static_cast<uint32_t>(tiles[0][i].w) | (static_cast<uint32_t>(tiles[0][i].col) << 3) | (static_cast<uint32_t>(tiles[0][i].grp) << 11);
+  for (int i = 0; i < nt[1]; ++i) {
+    const int slot = C - nt[1] + i;
+    mp->sched[C + slot] = static_cast<uint32_t>(tiles[1][i].w) | (static_cast<uint32_t>(tiles[1][i].col) << 3) | (static_cast<uint32_t>(tiles[1][i].grp) << 11);
+  }
+  (void)r0; (void)r1;
+  mp->n_items = 2 * C;
+  mp->ok = true;
+  return true;
+}
+
+// Cached per (columns, row-block groups, clusters): the search costs a few hundred microseconds of host time.
+static bool plan_mixed_tiles(tc::GemmShape* g, int bn, int clusters) {
+  // Measured on B200 (cfg3, round 2): correct (N = 192 with cta_group::2 and the MN-major operand works) but SLOWER than
+  // the regular 2-wave tiling, 76.4 vs 72.4 us: the mainloop is bound by L2 -> SM operand traffic (~12 TB/s of L2 sector
+  // requests, the LTS cap), and a 192-wide tile fetches the same A bytes and the same two B boxes per CTA as a 256-wide
+  // one, so it is no shorter.  Kept as an opt-in experiment (VAST_OMC_MIXED_TILES=1).
+  static const bool enabled = [] {
+    const char* e = getenv("VAST_OMC_MIXED_TILES");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (!enabled || g->N % 64 != 0 || g->k_splits != 1 || bn != 256 || clusters <= 0) return false;
+  static std::mutex mu;
+  static MixedPlan cache[8];
+  static int ncache = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  const int U = g->N / 64, G = g->num_problems * g->m_groups;
+  MixedPlan* mp = nullptr;
+  for (int i = 0; i < ncache; ++i)
+    if (cache[i].U == U && cache[i].G == G && cache[i].C == clusters) mp = &cache[i];
+  if (mp == nullptr) {
+    mp = &cache[ncache < 8 ? ncache++ : 7];
+    mp->U = U; mp->G = G; mp->C = clusters; mp->bn_units = bn / 64;
+    solve_mixed_tiles(mp);
+  }
+  if (!mp->ok) return false;
+  g->n_sched = mp->n_items;
+  g->num_items = mp->n_items;
+  memcpy(g->sched, mp->sched, sizeof(uint32_t) * mp->n_items);
+  return true;
+}
+
 static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, bool need_p, bool need_grad) {
   const int sms = device_sm_count();
   const int cl = tc::pick_cluster((int)bs);
@@ -1307,8 +1443,18 @@ static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, bool
   pl->nslab = ceil_div((int)n_total, PREP_ROWS);
   pl->ncs = pl->nslab * ceil_div(2 * (int)dim, 256);
   pl->bn_dq = dim > 128 ? 256 : 128;
-  tc::fill_shape(&pl->g_dq, 2, (int)bs, (int)dim, (int)n_total, pl->bn_dq, /*a: fp16*/ 0, /*b: fp16*/ 0, /*b_mn*/ true, cl);
-  tc::choose_splits(&pl->g_dq, sms, 64, 4);
+  int cl_dq = cl, max_ks = 4;
+  // developer override for tile-shape experiments: VAST_OMC_DQ="bn,cl,max_ks" (0 keeps the default of a field)
+  if (const char* e = getenv("VAST_OMC_DQ")) {
+    int bn = 0, c = 0, ks = 0;
+    if (sscanf(e, "%d,%d,%d", &bn, &c, &ks) >= 1) {
+      if (bn == 128 || bn == 256) pl->bn_dq = bn;
+      if ((c == 1 || c == 2) && c <= cl) cl_dq = c;
+      if (ks >= 1) max_ks = ks;
+    }
+  }
+  tc::fill_shape(&pl->g_dq, 2, (int)bs, (int)dim, (int)n_total, pl->bn_dq, /*a: fp16*/ 0, /*b: fp16*/ 0, /*b_mn*/ true, cl_dq);
+  tc::choose_splits(&pl->g_dq, sms, 64, max_ks);
   size_t off = 0;
   auto take = [&](size_t bytes) {
     off = align_up(off, 256);
@@ -1570,6 +1716,9 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
       tc::KernelParams<EpiGrad::Params> P;
       memset(&P, 0, sizeof(P));
       P.g = pl.g_dq;
+      // balanced two-round schedule with 256- and 192-wide tiles where the regular tiling leaves a partial wave
+      // (needs the fused statistics / final reduction: no per-slot partial buffers in this form)
+      if (fused_stats && pl.g_dq.cl == 2) plan_mixed_tiles(&P.g, pl.bn_dq, device_sm_count() / 2);
       for (int i = 0; i < 2; ++i) {
         P.tmA[i] = tmPa[i];
         P.tmB[i] = tmKb[i];

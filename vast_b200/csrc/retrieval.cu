@@ -364,7 +364,7 @@ struct EpiTopK {
     uint32_t head = 0;
     const int k = p.k;
     for (int item = cluster_id; item < g.num_items; item += num_clusters) {
-      const tc::WorkItem w = tc::decode_item(g, item, cta_rank);
+      const tc::WorkItem w = tc::decode_item<256>(g, item, cta_rank);
       L.row_base = w.m_blk * tc::BM + quad * 32;
       const int row = L.row_base + lane;  // lane <-> row for resets / thresholds
       // ---- empty lists; admission threshold = the row's proven bound so far
