@@ -194,15 +194,18 @@ VAST_API int vast_gather_rows_concat3(const int64_t* ids_local, const int64_t* m
 
 typedef enum {
   VAST_SIM_BF16 = 0,    /* bf16 inputs, fp32 accumulate on tensor cores                         */
-  VAST_SIM_FP32X3 = 1   /* fp32 inputs split into 3 bf16 terms (6 tensor-core products): fp32-  */
-                        /* grade scores for the exact-ranking pipeline                           */
+  VAST_SIM_FP32X3 = 1,  /* fp32 inputs split into 3 bf16 terms (6 tensor-core products): fp32-  */
+                        /* grade scores (dense fp32-grade score matrix, evaluation_mm.py:223)    */
+  VAST_SIM_FP32X2 = 2   /* 2 bf16 terms, 3 products (error <= 3 * 2^-18 |q||k| + accumulation): */
+                        /* half the tensor work of FP32X3; the shortlist of the exact pipeline   */
 } vast_sim_mode;
 
 /* Build the 16-bit tensor-core operand of `x` [rows, dim] (f32 or bf16 input).
  * mode BF16:   out [rows, dim] bf16.
  * mode FP32X3: out [rows, 6*dim] bf16; as_query != 0 lays the three split terms out as
  *              (hi, hi, mid, mid, hi, lo), otherwise as (hi, mid, hi, mid, lo, hi), so that the dot
- *              product of a query row and a key row sums the six leading cross terms. */
+ *              product of a query row and a key row sums the six leading cross terms.
+ * mode FP32X2: out [rows, 3*dim] bf16; (hi, hi, mid) for queries, (hi, mid, hi) for keys. */
 VAST_API int64_t vast_sim_operand_cols(int64_t dim, int mode);
 VAST_API int vast_sim_pack_operand(const void* x, int x_dtype, int64_t rows, int64_t dim, int64_t ldx, int mode,
                           int as_query, void* out, vast_stream_t stream);
@@ -217,6 +220,17 @@ VAST_API size_t vast_sim_topk_workspace_bytes(int64_t n_q, int64_t n_k, int64_t 
 VAST_API int vast_sim_topk(const void* q_op, const void* k_op, int64_t n_q, int64_t n_k, int64_t cols, int64_t k,
                   int64_t col_offset, uint64_t* out_keys, void* workspace, size_t workspace_bytes,
                   vast_stream_t stream);
+
+/* vast_sim_topk with per-row bounds: bounds_in [n_q] (or NULL) are orderable bits (the high word of a key) of a
+ * PROVEN lower bound of each row's final k-th score over ALL columns of the problem (0 = none), e.g. the k-th
+ * score of a scan of a column sample; only scores at or above the bound are ever listed, so a column shard that
+ * starts warm does k instead of k (1 + ln(n / k)) list insertions per row.  A row's list may then hold fewer than
+ * k keys (the rest 0); the merge over all shards is still the exact global top-k.  bounds_out [n_q] (or NULL)
+ * receives the bounds proven by this call (max of bounds_in and the row's k-th listed score).  Workspace as for
+ * vast_sim_topk. */
+VAST_API int vast_sim_topk_bounded(const void* q_op, const void* k_op, int64_t n_q, int64_t n_k, int64_t cols, int64_t k,
+                          int64_t col_offset, const uint32_t* bounds_in, uint32_t* bounds_out, uint64_t* out_keys,
+                          void* workspace, size_t workspace_bytes, vast_stream_t stream);
 
 /* k-way merge of `parts` candidate lists per row ([parts, n_q, k_in] keys, e.g. the all-gather
  * of every rank's vast_sim_topk output) into the global top-k_out (score desc, index asc). */
@@ -240,6 +254,24 @@ VAST_API int vast_exact_topk_rows(const float* q, int64_t ldq, const float* kk, 
                          const int32_t* rows_list, int64_t n_rows, int64_t k, int64_t col_offset,
                          int32_t* idx_out /* [n_q, k] rows addressed by rows_list */, double* score_out,
                          vast_stream_t stream);
+
+/* Streaming rank of the ground truth, no [n_q, n_k] matrix (evaluation_mm.py:333-338 `indice_matrix[i].index(gt)`
+ * and :355-364 without the sort / .tolist()):
+ *   rank_out[i] = #{ j in [col_lo, col_lo + n_k) : s_ij > s_i,gt  or  (s_ij == s_i,gt and j < gt_col[i]) }
+ * with s the EXACT similarities of the fp32 features (fp64 accumulation in the summation order of
+ * vast_rescore_f64).  q [n_q, dim], kk [n_k_total, dim] fp32 (the FULL key matrix: the ground truth of a row may
+ * lie outside the shard); q_op [n_q, cols] / k_op [n_k, cols] are packed operands (vast_sim_pack_operand, mode
+ * FP32X2 or FP32X3) of the queries and of key rows [col_lo, col_lo + n_k).  The tensor cores count the columns
+ * surely above the ground truth; columns within delta_rel * |q_i| * max_j |k_j| of it are re-scored in fp64
+ * (rows with more than 32 of them are recounted by brute force), so the result is exact and independent of tile
+ * shapes and GPU count; delta_rel = 2^-11 bounds the split + fp32-accumulation error of both operand modes.
+ * Column shards: the ranks of disjoint shards add up (all-reduce sum) to the rank over all columns.
+ * gt_col [n_q] int32 global column index (gt_col < 0: every column counts). */
+VAST_API size_t vast_rank_of_gt_workspace_bytes(int64_t n_q, int64_t n_k, int64_t cols);
+VAST_API int vast_rank_of_gt(const float* q, int64_t ldq, const float* kk, int64_t ldk, int64_t n_q, int64_t n_k_total,
+                    int64_t dim, const void* q_op, const void* k_op, int64_t cols, int64_t col_lo, int64_t n_k,
+                    const int32_t* gt_col, float delta_rel, int32_t* rank_out, void* workspace,
+                    size_t workspace_bytes, vast_stream_t stream);
 
 /* top-k of an already materialised fp32 score matrix along rows (axis=1) or columns (axis=0),
  * ties broken by lower index -- the drop-in for `score_matrix.topk(k, dim)` at

@@ -43,10 +43,28 @@ def close(a, b):
     return np.linalg.norm(a - b) <= RTOL * np.linalg.norm(b) + 1e-6
 
 
-def check_against_oracle(out, o, bs):
+def rows_close(got, want, temp):
+    """Per-ROW gradient check (a norm-wise bound over the whole matrix lets single rows be far off).  A gradient row is
+    (1 / (2 bs tau)) (sum_j p_ij k_j - (1 - eps) k_t - (eps / N) sum_j k_j): a difference of O(1)-norm terms, so its
+    absolute error scales with g0 = 1 / (2 bs tau) whatever the row's own norm (a well-classified row's gradient nearly
+    cancels).  Bound: |err_row| <= RTOL * |want_row| + 5e-4 * g0 -- i.e. every row to 1e-3 of its own norm unless the
+    row is smaller than half the cancelling terms, and then to 5e-4 of those."""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    g0 = 1.0 / (2.0 * want.shape[0] * temp)
+    err = np.linalg.norm(got - want, axis=1)
+    lim = RTOL * np.linalg.norm(want, axis=1) + 5e-4 * g0
+    bad = np.nonzero(err > lim)[0]
+    return bad.size == 0, (bad[:8], (err / lim).max())
+
+
+def check_against_oracle(out, o, bs, temp=None):
     assert abs(out["loss"].item() - o["loss"]) <= RTOL * abs(o["loss"]) + 1e-6, (out["loss"].item(), o["loss"])
     assert close(out["grad_cond"].cpu().numpy(), o["grad_cond"]), rel(out["grad_cond"].cpu().numpy(), o["grad_cond"])
     assert close(out["grad_t"].cpu().numpy(), o["grad_t"]), rel(out["grad_t"].cpu().numpy(), o["grad_t"])
+    if temp is not None:
+        for k in ("grad_cond", "grad_t"):
+            ok, info = rows_close(out[k].cpu().numpy(), o[k], temp)
+            assert ok, (k, info)
     assert abs(out["grad_temp"].item() - o["grad_temp"]) <= RTOL * abs(o["grad_temp"]) + 1e-6
     lse = out["lse"].cpu().numpy()
     np.testing.assert_allclose(lse[0], o["lse_cond2t"], rtol=1e-4, atol=1e-4)
@@ -63,26 +81,70 @@ def check_negatives(neg, o, expo, rank, bs, floor=1e-4):
         best = key.argmax(axis=1)
         exact += int((neg[d] == best).sum())
         got = key[np.arange(bs), neg[d]]
+        # every mismatching row must be a near-tie of the race: its key within 2e-3 of the winning key (fp32 vs fp64)
         assert np.all(got >= key.max(axis=1) * (1 - 2e-3)), (d, np.nonzero(got < key.max(axis=1) * (1 - 2e-3)))
         assert np.all(neg[d] != rank * bs + np.arange(bs)), "positive sampled as negative"
     assert exact >= int(0.97 * 2 * bs), exact
 
 
+def _hier_near_tie(z, tcol, expo, units, got, floor, tol=3e-3):
+    """Why may the GPU draw `got` differ from the oracle's for this row?  Only through a numerical near-tie at one of
+    the sampler's three decisions, each re-evaluated here in fp64 with slack `tol` (the GPU keeps probabilities in fp16
+    and sums in fp32): (1) the race between chunks -- the chunk of `got` must be within tol of the winning key;
+    (2) the mixture draw softmax-part vs uniform floor part; (3) the inverse CDF inside the chunk / the uniform index
+    -- `got` must be a column whose cumulative-weight interval, widened by tol, contains the target."""
+    n = z.shape[0]
+    p = np.exp(z - (z.max() + np.log(np.exp(z - z.max()).sum())))
+    pt = p[tcol]
+    p = p.copy()
+    p[tcol] = 0.0
+    nch = (n + 31) // 32
+    pad = np.zeros(nch * 32)
+    pad[:n] = p
+    cs = pad.reshape(nch, 32).sum(axis=1)
+    key = cs / expo[:nch]
+    w_a, w_b = 1.0 - pt, floor * (n - 1)
+    mix = units[1] * (w_a + w_b)
+    can_a = mix < w_a * (1 + tol)
+    can_b = mix > w_a * (1 - tol) or cs.max() <= 0
+    ok = False
+    if can_a:
+        c = got // 32
+        if key[c] >= key.max() * (1 - tol) and pad[got] > 0:
+            seg = pad[c * 32:(c + 1) * 32]
+            pre = np.cumsum(seg)
+            j = got - c * 32
+            target = units[0] * pre[-1]
+            lo_edge = pre[j] - seg[j]
+            ok |= (lo_edge - tol * pre[-1] <= target <= pre[j] + tol * pre[-1]) or \
+                  (j == np.nonzero(seg > 0)[0][-1] and target >= lo_edge - tol * pre[-1])
+    if can_b:
+        x = units[2] * (n - 1)
+        for jj in {int(np.floor(x - 1e-3)), int(np.floor(x)), int(np.floor(x + 1e-3))}:
+            jj = min(max(jj, 0), n - 2)
+            ok |= got == (jj + 1 if jj >= tcol else jj)
+    return bool(ok)
+
+
 def check_negatives_hier(neg, o, seed, offset, rank, bs, n, floor=1e-4):
-    """Production sampler (chunk race + inverse CDF + uniform floor component) vs its oracle restatement fed
-    with the same Philox words; fp32 / fp16 near-ties may flip a few draws."""
+    """Production sampler (chunk race + inverse CDF + uniform floor component) vs its oracle restatement fed with the
+    same Philox words: index-exact, except rows where a decision of the sampler is a numerical near-tie -- every
+    mismatching row is audited (`_hier_near_tie`) and listed, and there may be only a few."""
     neg = neg.cpu().numpy()
     nch = (n + 31) // 32
-    exact = 0
+    mism = []
     for d, name in enumerate(("sim_cond2t", "sim_t2cond")):
         expo = spec.sampler_expo(seed, offset, d, bs, nch, row0=rank * bs)
         units = spec.sampler_tail_units(seed, offset, d, bs, row0=rank * bs)
         want, _, _ = spec.hardneg_hier_sample(o[name], rank, expo, units, floor)
-        exact += int((neg[d] == want).sum())
         if n > 1:
             assert np.all(neg[d] != rank * bs + np.arange(bs)), "positive sampled as negative"
             assert np.all((neg[d] >= 0) & (neg[d] < n))
-    assert exact >= int(0.97 * 2 * bs), (exact, 2 * bs)
+            for i in np.nonzero(neg[d] != want)[0]:
+                assert _hier_near_tie(np.asarray(o[name][i], dtype=np.float64), rank * bs + i, expo[i], units[i], int(neg[d][i]), floor), \
+                    ("draw differs from the oracle and is not a near-tie", d, int(i), int(neg[d][i]), int(want[i]))
+                mism.append((d, int(i)))
+    assert len(mism) <= max(2, int(0.03 * 2 * bs)), (len(mism), mism[:10])
 
 
 def test_cfg1_golden_loss_grads_and_reference_negatives(golden):
@@ -93,7 +155,7 @@ def test_cfg1_golden_loss_grads_and_reference_negatives(golden):
     noise = torch.from_numpy(np.ascontiguousarray(g["expo"][::-1])).cuda()  # ours: [0]=cond2t, [1]=t2cond
     out = run_step(g["feat_t"], g["feat_cond"], bs, 0, float(g["contra_temp"]), debug_noise=noise, want_lse=True)
     o = oracle(g["feat_t"], g["feat_cond"], bs, 0, float(g["contra_temp"]))
-    check_against_oracle(out, o, bs)
+    check_against_oracle(out, o, bs, float(g["contra_temp"]))
     # vs the reference run on un-rounded fp32 features: bf16 input rounding only
     assert abs(out["loss"].item() - float(g["loss_itc"])) < 1e-2 * float(g["loss_itc"])
     assert rel(out["grad_t"].cpu().numpy(), g["grad_t"]) < 2e-2
@@ -111,7 +173,7 @@ def test_w2_rank_offsets_golden(golden, rank):
     noise = torch.from_numpy(np.ascontiguousarray(g[f"r{rank}_expo"][::-1])).cuda()
     out = run_step(g["feat_t_all"], g["feat_cond_all"], bs, rank, temp, debug_noise=noise, want_lse=True)
     o = oracle(g["feat_t_all"], g["feat_cond_all"], bs, rank, temp)
-    check_against_oracle(out, o, bs)
+    check_against_oracle(out, o, bs, temp)
     assert abs(out["loss"].item() - float(g[f"r{rank}_loss_itc"])) < 1e-2 * float(g[f"r{rank}_loss_itc"])
     check_negatives(out["neg_idx"], o, g[f"r{rank}_expo"][::-1], rank, bs)
 
@@ -127,7 +189,7 @@ def test_ragged_shapes_philox(bs, world, rank, dim, temp, two_pass):
     seed, offset = 0x1234567887654321, (7 << 32) | 5
     out = run_step(t.numpy(), c.numpy(), bs, rank, temp, seed=seed, offset=offset, want_lse=True, two_pass=two_pass)
     o = oracle(t.numpy(), c.numpy(), bs, rank, temp)
-    check_against_oracle(out, o, bs)
+    check_against_oracle(out, o, bs, temp)
     check_negatives_hier(out["neg_idx"], o, seed, offset, rank, bs, n)
 
 
@@ -156,8 +218,8 @@ def test_single_pass_range_and_fallback(case):
     out = run_step(t.numpy(), c.numpy(), n, 0, temp, seed=seed, offset=offset, want_lse=True)
     ref = run_step(t.numpy(), c.numpy(), n, 0, temp, seed=seed, offset=offset, want_lse=True, two_pass=True)
     o = oracle(t.numpy(), c.numpy(), n, 0, temp)
-    check_against_oracle(out, o, n)
-    check_against_oracle(ref, o, n)
+    check_against_oracle(out, o, n, temp)
+    check_against_oracle(ref, o, n, temp)
     check_negatives_hier(out["neg_idx"], o, seed, offset, 0, n, n)
     if case != "untrained":       # the fallback IS the two-pass form: identical bits
         assert torch.equal(out["grad_t"], ref["grad_t"]) and torch.equal(out["neg_idx"], ref["neg_idx"])
@@ -172,7 +234,7 @@ def test_cfg3_shape_full_size():
     seed, offset = 99, 3
     out = run_step(t.numpy(), c.numpy(), n, 0, temp, seed=seed, offset=offset, want_lse=True)
     o = oracle(t.numpy(), c.numpy(), n, 0, temp)
-    check_against_oracle(out, o, n)
+    check_against_oracle(out, o, n, temp)
     check_negatives_hier(out["neg_idx"], o, seed, offset, 0, n, n)
     # determinism: same seed/offset -> identical outputs, different offset -> different draws
     out2 = run_step(t.numpy(), c.numpy(), n, 0, temp, seed=seed, offset=offset)
@@ -283,7 +345,7 @@ def test_fused_row_stats_equal_separate_kernel(bs, world, rank, dim, noise):
     assert abs(a["loss"].item() - b["loss"].item()) <= 2e-6 * abs(b["loss"].item())
     assert abs(a["grad_temp"].item() - b["grad_temp"].item()) <= 1e-5 * abs(b["grad_temp"].item()) + 1e-7
     o = oracle(t.numpy(), c.numpy(), bs, rank, 0.07)
-    check_against_oracle(a, o, bs)
+    check_against_oracle(a, o, bs, 0.07)
 
 
 @pytest.mark.parametrize("two_pass", [False, True])
@@ -305,7 +367,7 @@ def test_single_rank_step_from_features(n, dim, dtype, two_pass):
     assert torch.equal(out["pack"], ops.pack_pair(td, cd))
     tn, cn = td.float().cpu().numpy(), cd.float().cpu().numpy()
     o = oracle(tn, cn, n, 0, temp)
-    check_against_oracle(out, o, n)
+    check_against_oracle(out, o, n, temp)
     check_negatives_hier(out["neg_idx"], o, seed, offset, 0, n, n)
     # against the two-kernel form: same operands, z_t summed in another order -> agreement far inside the tolerance
     ref = ops.omc_step(ops.pack_pair(td, cd), n, 0, temp, seed=seed, offset=offset, want_lse=True, two_pass=two_pass)

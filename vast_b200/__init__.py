@@ -9,7 +9,7 @@ from .distributed import (all_gather_ids, all_gather_list, all_gather_with_grad,
                           concat_all_gather, ddp_allgather, exchange_rows)
 from .graphed import OmcGraphStep  # noqa: F401
 from .features import build_feature, l2_normalize, pool_concat  # noqa: F401
-from .retrieval import (compute_metric_ret, evaluate_ret, recall_from_candidates, recall_from_feats,  # noqa: F401
+from .retrieval import (compute_metric_ret, evaluate_ret, rank_of_gt, recall_from_candidates, recall_from_feats,  # noqa: F401
                         refine_candidates, refine_score_matrix, retrieval_topk)
 
 __version__ = "0.1.0"

@@ -34,6 +34,9 @@ SIGNATURES = {
     "vast_sim_pack_operand": (i32, [vp, i32, i64, i64, i64, i32, i32, vp, vp]),
     "vast_sim_topk_workspace_bytes": (sz, [i64, i64, i64, i64]),
     "vast_sim_topk": (i32, [vp, vp, i64, i64, i64, i64, i64, vp, vp, sz, vp]),
+    "vast_sim_topk_bounded": (i32, [vp, vp, i64, i64, i64, i64, i64, vp, vp, vp, vp, sz, vp]),
+    "vast_rank_of_gt_workspace_bytes": (sz, [i64, i64, i64]),
+    "vast_rank_of_gt": (i32, [vp, i64, vp, i64, i64, i64, i64, vp, vp, i64, i64, i64, vp, f32, vp, vp, sz, vp]),
     "vast_topk_merge": (i32, [vp, i64, i64, i64, i64, vp, vp]),
     "vast_topk_unpack": (i32, [vp, i64, vp, vp, vp]),
     "vast_rescore_f64": (i32, [vp, i64, vp, i64, i64, i64, vp, i64, i64, vp, vp]),
@@ -49,7 +52,7 @@ SIGNATURES = {
 }
 
 F32, BF16, F16 = 0, 1, 2
-SIM_BF16, SIM_FP32X3 = 0, 1
+SIM_BF16, SIM_FP32X3, SIM_FP32X2 = 0, 1, 2
 
 
 def lib():

@@ -578,6 +578,16 @@ __global__ void sim_pack_kernel(const TI* __restrict__ x, int64_t rows, int64_t 
       v = __bfloat162float(x[r * ldx + c]);
     if (mode == VAST_SIM_BF16) {
       out[r * dim + c] = __float2bfloat16_rn(v);
+    } else if (mode == VAST_SIM_FP32X2) {
+      // two bf16 terms, the three leading cross products hi.hi + hi.mid + mid.hi (dropped: <= 3 * 2^-18 |x y|)
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      const __nv_bfloat16 mid = __float2bfloat16_rn(v - __bfloat162float(hi));
+      __nv_bfloat16* o = out + r * 3 * dim + c;
+      if (as_query) {  // (hi, hi, mid)
+        o[0] = hi; o[dim] = hi; o[2 * dim] = mid;
+      } else {         // (hi, mid, hi)
+        o[0] = hi; o[dim] = mid; o[2 * dim] = hi;
+      }
     } else {
       const __nv_bfloat16 hi = __float2bfloat16_rn(v);
       const float r1 = v - __bfloat162float(hi);
@@ -905,6 +915,192 @@ __global__ void scatter_scores_kernel(const int32_t* __restrict__ text_idx, cons
 
 static inline unsigned blocks_for(int64_t n, int per_block) { return static_cast<unsigned>(ceil_div64(n, per_block)); }
 
+// ------------------------------------------------------------------ streaming rank of the ground truth
+// rank_i = #{ j : s_ij > s_i,gt  or  (s_ij == s_i,gt and j < gt_i) }  over the exact similarities of the fp32 features
+// (evaluation_mm.py:333-338 `indice_matrix[i].index(gt)` / :355-364 without the sort, the .tolist() and the [Nt, Nv]
+// matrix).  The tensor cores deliver fp32-grade APPROXIMATE scores (split operands); with a rigorous per-row error
+// bound delta_i every column is either surely above the ground truth (counted in the GEMM epilogue), surely below
+// (ignored), or inside the band |s - s_gt| <= delta_i: those few are re-scored in fp64 in the defined summation order
+// of dot_f64_lane_order and compared exactly.  Rows with more than RANK_UCAP uncertain columns are recounted
+// by brute force in fp64.  The result is independent of tile shapes, splits and GPU count.
+constexpr int RANK_UCAP = 32;
+
+struct EpiRank {
+  struct Params {
+    const float* lo;        // [M] gt score - delta, rounded down
+    const float* hi;        // [M] gt score + delta, rounded up
+    const int32_t* gt_col;  // [M] global column index of the ground truth
+    uint32_t col_offset;
+    int* count;             // [M] += columns surely above
+    int* ucount;            // [M] uncertain columns seen (may exceed RANK_UCAP: the row is then recounted exactly)
+    int32_t* ulist;         // [M][RANK_UCAP] their global indices
+  };
+  static constexpr bool kUnrollChunks = false;
+  static constexpr int kAuxWarps = 0;
+  const Params& p;
+  float lo, hi;
+  int cnt, gtc;
+  __device__ EpiRank(const Params& p_, uint8_t*) : p(p_) {}
+  __device__ __forceinline__ void item_begin(const tc::ItemCtx& c) {
+    lo = hi = INFINITY;  // rows past the end count nothing
+    gtc = -1;
+    if (c.row_valid) {
+      lo = p.lo[c.row];
+      hi = p.hi[c.row];
+      gtc = p.gt_col[c.row];
+    }
+    cnt = 0;
+  }
+  __device__ __forceinline__ void prefetch(const tc::ItemCtx&, int) {}
+  __device__ __forceinline__ void advance(const tc::ItemCtx&, int, bool) {}
+  __device__ __forceinline__ void chunk(const tc::ItemCtx& c, const uint32_t (&v)[32], int col0) {
+    if (col0 >= c.N) return;
+    const int nvalid = c.N - col0;
+    unsigned unc = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float sc = __uint_as_float(v[i]);
+      const bool ok = i < nvalid;
+      cnt += (ok && sc > hi) ? 1 : 0;
+      unc |= (ok && sc >= lo && sc <= hi) ? (1u << i) : 0u;
+    }
+    while (unc != 0) {  // rare: a handful of columns per row
+      const int i = __ffs(unc) - 1;
+      unc &= unc - 1;
+      const int col = static_cast<int>(p.col_offset) + col0 + i;
+      if (col == gtc) continue;
+      const int slot = atomicAdd(p.ucount + c.row, 1);
+      if (slot < RANK_UCAP) p.ulist[static_cast<int64_t>(c.row) * RANK_UCAP + slot] = col;
+    }
+  }
+  __device__ __forceinline__ void item_end(const tc::ItemCtx& c) {
+    if (c.row_valid && cnt != 0) atomicAdd(p.count + c.row, cnt);
+  }
+};
+
+// largest row norm of x [rows, dim] as orderable bits of a non-negative float (atomicMax); one warp per row
+__global__ void __launch_bounds__(128) max_row_norm_kernel(const float* __restrict__ x, int64_t ld, int64_t rows, int64_t dim,
+                                                          uint32_t* __restrict__ out_bits) {
+  const int64_t r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float a = 0.f;
+  for (int64_t k = lane; k < dim; k += 32) a = fmaf(x[r * ld + k], x[r * ld + k], a);
+  a = warp_sum(a);
+  if (lane == 0) atomicMax(out_bits, __float_as_uint(sqrtf(a) * 1.0001f));  // rounded up a little: it is a bound
+}
+
+// per query row: exact gt score (fp64, lane order), the band [lo, hi] = gt -/+ delta_rel * |q| * max|k|, counters cleared
+__global__ void __launch_bounds__(128) rank_prep_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ kk,
+                                                       int64_t ldk, int64_t n_q, int64_t n_k_total, int64_t dim,
+                                                       const int32_t* __restrict__ gt_col, float delta_rel,
+                                                       const uint32_t* __restrict__ kmax_bits, double* __restrict__ gscore,
+                                                       float* __restrict__ lo, float* __restrict__ hi, int* __restrict__ count,
+                                                       int* __restrict__ ucount) {
+  const int64_t r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= n_q) return;
+  const int lane = threadIdx.x & 31;
+  const int32_t g = gt_col[r];
+  const float* qr = q + r * ldq;
+  double s = -INFINITY;
+  if (g >= 0 && g < n_k_total) s = dot_f64_lane_order(qr, kk + static_cast<int64_t>(g) * ldk, dim, lane);
+  float a = 0.f;
+  for (int64_t k = lane; k < dim; k += 32) a = fmaf(qr[k], qr[k], a);
+  a = warp_sum(a);
+  if (lane == 0) {
+    const double d = static_cast<double>(delta_rel) * static_cast<double>(sqrtf(a) * 1.0001f) * static_cast<double>(__uint_as_float(*kmax_bits));
+    gscore[r] = s;
+    // a row without ground truth (-inf) counts every column: lo = hi = -inf
+    lo[r] = __double2float_rd(s - d);
+    hi[r] = __double2float_ru(s + d);
+    count[r] = 0;
+    ucount[r] = 0;
+  }
+}
+
+__device__ __forceinline__ bool ahead_of_gt(double s, int32_t j, double g, int32_t gt) { return s > g || (s == g && j < gt); }
+
+// one warp per row: the uncertain columns exactly; rows whose list overflowed are queued for the brute-force recount
+__global__ void __launch_bounds__(128) rank_resolve_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ kk,
+                                                          int64_t ldk, int64_t n_q, int64_t dim,
+                                                          const int32_t* __restrict__ gt_col, const double* __restrict__ gscore,
+                                                          const int* __restrict__ ucount, const int32_t* __restrict__ ulist,
+                                                          int* __restrict__ count, int32_t* __restrict__ bad_rows,
+                                                          int* __restrict__ n_bad) {
+  const int64_t r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= n_q) return;
+  const int lane = threadIdx.x & 31;
+  const int n = ucount[r];
+  if (n > RANK_UCAP) {
+    if (lane == 0) bad_rows[atomicAdd(n_bad, 1)] = static_cast<int32_t>(r);
+    return;
+  }
+  const double g = gscore[r];
+  const int32_t gt = gt_col[r];
+  int add = 0;
+  for (int e = 0; e < n; ++e) {
+    const int32_t j = ulist[r * RANK_UCAP + e];
+    const double sc = dot_f64_lane_order(q + r * ldq, kk + static_cast<int64_t>(j) * ldk, dim, lane);
+    add += ahead_of_gt(sc, j, g, gt) ? 1 : 0;
+  }
+  if (lane == 0 && add != 0) count[r] += add;
+}
+
+// exact recount of the queued rows over the shard's columns [col_lo, col_lo + n_k): a block per row, 8 warps stride the keys
+__global__ void __launch_bounds__(256) rank_brute_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ kk,
+                                                        int64_t ldk, int64_t col_lo, int64_t n_k, int64_t dim,
+                                                        const int32_t* __restrict__ gt_col, const double* __restrict__ gscore,
+                                                        const int32_t* __restrict__ bad_rows, const int* __restrict__ n_bad,
+                                                        int* __restrict__ count) {
+  __shared__ int part[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = *n_bad;
+  for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+    const int64_t r = bad_rows[b];
+    const double g = gscore[r];
+    const int32_t gt = gt_col[r];
+    int c = 0;
+    for (int64_t j = col_lo + warp; j < col_lo + n_k; j += 8) {
+      if (j == gt) continue;
+      const double sc = dot_f64_lane_order(q + r * ldq, kk + j * ldk, dim, lane);
+      c += ahead_of_gt(sc, static_cast<int32_t>(j), g, gt) ? 1 : 0;
+    }
+    __syncthreads();
+    if (lane == 0) part[warp] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < 8; ++w) t += part[w];
+      count[r] = t;
+    }
+  }
+}
+
+struct RankPlan {
+  tc::GemmShape g;
+  size_t off_lo, off_hi, off_g, off_cnt, off_ucnt, off_ulist, off_bad, off_scal, total;
+};
+static void rank_plan(RankPlan* pl, int64_t n_q, int64_t n_k, int64_t cols) {
+  tc::fill_shape(&pl->g, 1, (int)n_q, (int)n_k, (int)cols, 256, 1, 1, false, tc::pick_cluster((int)n_q));
+  tc::choose_splits(&pl->g, device_sm_count(), 64, 1);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    off = align_up(off, 256);
+    const size_t r = off;
+    off += bytes;
+    return r;
+  };
+  pl->off_scal = take(256);  // [0] n_bad, [1] max key norm bits
+  pl->off_lo = take(sizeof(float) * n_q);
+  pl->off_hi = take(sizeof(float) * n_q);
+  pl->off_g = take(sizeof(double) * n_q);
+  pl->off_cnt = take(sizeof(int) * n_q);
+  pl->off_ucnt = take(sizeof(int) * n_q);
+  pl->off_ulist = take(sizeof(int32_t) * n_q * RANK_UCAP);
+  pl->off_bad = take(sizeof(int32_t) * n_q);
+  pl->total = align_up(off, 256);
+}
+
 template <class T, int S, int S2, int NE_>
 struct TopkTag {
   using type = T;
@@ -964,12 +1160,15 @@ static void topk_plan(TopkPlan* pl, int64_t n_q, int64_t n_k, int64_t cols, int6
 
 using namespace vast;
 
-extern "C" int64_t vast_sim_operand_cols(int64_t dim, int mode) { return mode == VAST_SIM_FP32X3 ? 6 * dim : dim; }
+extern "C" int64_t vast_sim_operand_cols(int64_t dim, int mode) {
+  return mode == VAST_SIM_FP32X3 ? 6 * dim : (mode == VAST_SIM_FP32X2 ? 3 * dim : dim);
+}
 
 extern "C" int vast_sim_pack_operand(const void* x, int x_dtype, int64_t rows, int64_t dim, int64_t ldx, int mode,
                                      int as_query, void* out, vast_stream_t stream) {
   VAST_REQUIRE(x && out && rows >= 0 && dim > 0 && ldx >= dim, VAST_ERR_INVALID, "sim_pack_operand: bad arguments");
-  VAST_REQUIRE(mode == VAST_SIM_BF16 || mode == VAST_SIM_FP32X3, VAST_ERR_UNSUPPORTED, "sim_pack_operand: bad mode");
+  VAST_REQUIRE(mode == VAST_SIM_BF16 || mode == VAST_SIM_FP32X3 || mode == VAST_SIM_FP32X2, VAST_ERR_UNSUPPORTED,
+               "sim_pack_operand: bad mode");
   VAST_REQUIRE(dim % 8 == 0, VAST_ERR_UNSUPPORTED, "sim_pack_operand: dim must be a multiple of 8");
   if (rows == 0) return VAST_OK;
   int64_t nb = ceil_div64(rows * dim, 256);
@@ -993,9 +1192,36 @@ extern "C" size_t vast_sim_topk_workspace_bytes(int64_t n_q, int64_t n_k, int64_
   return pl.ws_bytes;
 }
 
+// bounds proven by a call: the k-th key of the row's FINAL (merged) list when the list is full -- each column range of a
+// split row only proved its own k-th score, which is lower -- else whatever bound the row started from
+__global__ void bounds_export_kernel(const uint32_t* __restrict__ thr, const uint64_t* __restrict__ keys, int k, int64_t n,
+                                     uint32_t* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t kth = static_cast<uint32_t>(keys[i * k + (k - 1)] >> 32);  // 0 when the list is not full
+  const uint32_t t = thr[i];
+  out[i] = kth > t ? kth : t;
+}
+
+static int sim_topk_impl(const void* q_op, const void* k_op, int64_t n_q, int64_t n_k, int64_t cols, int64_t k,
+                         int64_t col_offset, const uint32_t* bounds_in, uint32_t* bounds_out, uint64_t* out_keys,
+                         void* workspace, size_t workspace_bytes, vast_stream_t stream);
+
 extern "C" int vast_sim_topk(const void* q_op, const void* k_op, int64_t n_q, int64_t n_k, int64_t cols, int64_t k,
                              int64_t col_offset, uint64_t* out_keys, void* workspace, size_t workspace_bytes,
                              vast_stream_t stream) {
+  return sim_topk_impl(q_op, k_op, n_q, n_k, cols, k, col_offset, nullptr, nullptr, out_keys, workspace, workspace_bytes, stream);
+}
+
+extern "C" int vast_sim_topk_bounded(const void* q_op, const void* k_op, int64_t n_q, int64_t n_k, int64_t cols, int64_t k,
+                                     int64_t col_offset, const uint32_t* bounds_in, uint32_t* bounds_out,
+                                     uint64_t* out_keys, void* workspace, size_t workspace_bytes, vast_stream_t stream) {
+  return sim_topk_impl(q_op, k_op, n_q, n_k, cols, k, col_offset, bounds_in, bounds_out, out_keys, workspace, workspace_bytes, stream);
+}
+
+static int sim_topk_impl(const void* q_op, const void* k_op, int64_t n_q, int64_t n_k, int64_t cols, int64_t k,
+                         int64_t col_offset, const uint32_t* bounds_in, uint32_t* bounds_out, uint64_t* out_keys,
+                         void* workspace, size_t workspace_bytes, vast_stream_t stream) {
   VAST_REQUIRE(q_op && k_op && out_keys, VAST_ERR_INVALID, "sim_topk: null pointer");
   VAST_REQUIRE(n_q > 0 && n_k > 0 && cols > 0 && n_q < (1 << 30) && n_k < (1 << 30), VAST_ERR_INVALID, "sim_topk: bad sizes");
   VAST_REQUIRE(k >= 1 && k <= TOPK_MAX, VAST_ERR_UNSUPPORTED, "sim_topk: k must be in [1, %d] (got %lld)", TOPK_MAX, (long long)k);
@@ -1006,7 +1232,10 @@ extern "C" int vast_sim_topk(const void* q_op, const void* k_op, int64_t n_q, in
   VAST_REQUIRE(workspace_bytes >= pl.ws_bytes && workspace, VAST_ERR_WORKSPACE, "sim_topk: workspace %zu < required %zu",
                workspace_bytes, pl.ws_bytes);
   uint32_t* thr_shared = static_cast<uint32_t*>(workspace);
-  VAST_CUDA_OK(cudaMemsetAsync(thr_shared, 0, pl.thr_bytes, stream));
+  if (bounds_in != nullptr)  // rows start from the caller's proven bounds (0 = none) instead of cold
+    VAST_CUDA_OK(cudaMemcpyAsync(thr_shared, bounds_in, sizeof(uint32_t) * n_q, cudaMemcpyDeviceToDevice, stream));
+  else
+    VAST_CUDA_OK(cudaMemsetAsync(thr_shared, 0, pl.thr_bytes, stream));
   uint64_t* part = pl.g.n_splits > 1 ? reinterpret_cast<uint64_t*>(static_cast<char*>(workspace) + pl.thr_bytes) : out_keys;
   int rc;
   auto run = [&](auto tag) -> int {
@@ -1052,6 +1281,10 @@ extern "C" int vast_sim_topk(const void* q_op, const void* k_op, int64_t n_q, in
   if (pl.g.n_splits > 1) {
     rc = launch_topk_merge(part, k, pl.g.n_splits * k, pl.g.n_splits, (int)k, n_q, (int)k, out_keys, stream);
     if (rc) return rc;
+  }
+  if (bounds_out != nullptr) {
+    bounds_export_kernel<<<blocks_for(n_q, 256), 256, 0, stream>>>(thr_shared, out_keys, (int)k, n_q, bounds_out);
+    VAST_LAUNCH_OK("bounds_export");
   }
   return VAST_OK;
 }
@@ -1158,5 +1391,58 @@ extern "C" int vast_scatter_scores(const int32_t* text_idx, const int32_t* video
   if (n_pairs == 0) return VAST_OK;
   scatter_scores_kernel<<<blocks_for(n_pairs, 256), 256, 0, stream>>>(text_idx, video_idx, scores, n_pairs, out, ld);
   VAST_LAUNCH_OK("scatter_scores");
+  return VAST_OK;
+}
+
+extern "C" size_t vast_rank_of_gt_workspace_bytes(int64_t n_q, int64_t n_k, int64_t cols) {
+  if (n_q <= 0 || n_k <= 0 || cols <= 0) return 0;
+  RankPlan pl;
+  rank_plan(&pl, n_q, n_k, cols);
+  return pl.total;
+}
+
+extern "C" int vast_rank_of_gt(const float* q, int64_t ldq, const float* kk, int64_t ldk, int64_t n_q, int64_t n_k_total,
+                               int64_t dim, const void* q_op, const void* k_op, int64_t cols, int64_t col_lo, int64_t n_k,
+                               const int32_t* gt_col, float delta_rel, int32_t* rank_out, void* workspace,
+                               size_t workspace_bytes, vast_stream_t stream) {
+  VAST_REQUIRE(q && kk && q_op && k_op && gt_col && rank_out && workspace, VAST_ERR_INVALID, "rank_of_gt: null pointer");
+  VAST_REQUIRE(n_q > 0 && n_k > 0 && dim > 0 && n_q < (1 << 30) && n_k_total < (1ll << 31) && col_lo >= 0 &&
+                   col_lo + n_k <= n_k_total,
+               VAST_ERR_INVALID, "rank_of_gt: bad sizes");
+  VAST_REQUIRE(cols % 8 == 0 && cols >= dim, VAST_ERR_UNSUPPORTED, "rank_of_gt: operand width must be a multiple of 8");
+  VAST_REQUIRE(delta_rel >= 0.f, VAST_ERR_INVALID, "rank_of_gt: delta_rel must be non-negative");
+  RankPlan pl;
+  rank_plan(&pl, n_q, n_k, cols);
+  VAST_REQUIRE(workspace_bytes >= pl.total, VAST_ERR_WORKSPACE, "rank_of_gt: workspace %zu < required %zu", workspace_bytes, pl.total);
+  char* ws = static_cast<char*>(workspace);
+  int* scal = reinterpret_cast<int*>(ws + pl.off_scal);
+  float* lo = reinterpret_cast<float*>(ws + pl.off_lo);
+  float* hi = reinterpret_cast<float*>(ws + pl.off_hi);
+  double* gscore = reinterpret_cast<double*>(ws + pl.off_g);
+  int* ucount = reinterpret_cast<int*>(ws + pl.off_ucnt);
+  int32_t* ulist = reinterpret_cast<int32_t*>(ws + pl.off_ulist);
+  int32_t* bad = reinterpret_cast<int32_t*>(ws + pl.off_bad);
+  int* count = rank_out;  // partial counts are accumulated in place
+  VAST_CUDA_OK(cudaMemsetAsync(scal, 0, 256, stream));
+  max_row_norm_kernel<<<blocks_for(n_k, 4), 128, 0, stream>>>(kk + col_lo * ldk, ldk, n_k, dim, reinterpret_cast<uint32_t*>(scal + 1));
+  VAST_LAUNCH_OK("max_row_norm");
+  rank_prep_kernel<<<blocks_for(n_q, 4), 128, 0, stream>>>(q, ldq, kk, ldk, n_q, n_k_total, dim, gt_col, delta_rel,
+                                                           reinterpret_cast<const uint32_t*>(scal + 1), gscore, lo, hi, count, ucount);
+  VAST_LAUNCH_OK("rank_prep");
+  tc::KernelParams<EpiRank::Params> P;
+  memset(&P, 0, sizeof(P));
+  P.g = pl.g;
+  int rc = tc::make_tmap_2d(&P.tmA[0], q_op, VAST_BF16, n_q, cols, cols, tc::BM);
+  if (rc) return rc;
+  rc = tc::make_tmap_2d(&P.tmB[0], k_op, VAST_BF16, n_k, cols, cols, 256 / pl.g.cl);
+  if (rc) return rc;
+  P.epi = {lo, hi, gt_col, static_cast<uint32_t>(col_lo), count, ucount, ulist};
+  rc = tc::launch_gemm<EpiRank, 256, 4, 8>(P, stream, "rank_gemm");
+  if (rc) return rc;
+  rank_resolve_kernel<<<blocks_for(n_q, 4), 128, 0, stream>>>(q, ldq, kk, ldk, n_q, dim, gt_col, gscore, ucount, ulist, count, bad, scal);
+  VAST_LAUNCH_OK("rank_resolve");
+  rank_brute_kernel<<<static_cast<unsigned>(device_sm_count() * 4), 256, 0, stream>>>(q, ldq, kk, ldk, col_lo, n_k, dim, gt_col, gscore, bad,
+                                                                                   scal, count);
+  VAST_LAUNCH_OK("rank_brute");
   return VAST_OK;
 }

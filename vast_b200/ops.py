@@ -274,7 +274,7 @@ def gather_rows_concat3(ids_local, mask_local, ids_all, mask_all, cond_local, co
 
 
 # ------------------------------------------------------------------ retrieval scoring
-SIM_BF16, SIM_FP32X3 = _lib.SIM_BF16, _lib.SIM_FP32X3
+SIM_BF16, SIM_FP32X3, SIM_FP32X2 = _lib.SIM_BF16, _lib.SIM_FP32X3, _lib.SIM_FP32X2
 TOPK_MAX = 64
 
 
@@ -290,8 +290,12 @@ def sim_pack_operand(x: torch.Tensor, mode: int = SIM_BF16, as_query: bool = Tru
     return out
 
 
-def sim_topk(q_op: torch.Tensor, k_op: torch.Tensor, k: int, col_offset: int = 0) -> torch.Tensor:
-    """Streaming similarity + top-k on packed operands; returns sortable keys [n_q, k] (int64 storage)."""
+def sim_topk(q_op: torch.Tensor, k_op: torch.Tensor, k: int, col_offset: int = 0, bounds_in: torch.Tensor | None = None,
+             want_bounds: bool = False):
+    """Streaming similarity + top-k on packed operands; returns sortable keys [n_q, k] (int64 storage).
+    bounds_in [n_q] int32 (orderable score bits, 0 = none): proven lower bounds of every row's final k-th score over
+    ALL columns of the problem -- the lists then start warm (vast_sim_topk_bounded) and may hold fewer than k keys.
+    want_bounds: also return the bounds this call proved ([n_q] int32)."""
     require_cuda(q_op, k_op)
     assert q_op.dtype == torch.bfloat16 and k_op.dtype == torch.bfloat16 and q_op.is_contiguous() and k_op.is_contiguous()
     assert q_op.shape[1] == k_op.shape[1]
@@ -300,9 +304,41 @@ def sim_topk(q_op: torch.Tensor, k_op: torch.Tensor, k: int, col_offset: int = 0
     keys = torch.empty(n_q, k, dtype=torch.int64, device=q_op.device)
     nbytes = lib().vast_sim_topk_workspace_bytes(n_q, n_k, cols, k)
     ws = _ws(nbytes, q_op.device)
-    check(lib().vast_sim_topk(ptr(q_op), ptr(k_op), n_q, n_k, cols, k, col_offset, ptr(keys), ptr(ws), ws.numel(),
-                              stream_ptr()), "sim_topk")
-    return keys
+    if bounds_in is None and not want_bounds:
+        check(lib().vast_sim_topk(ptr(q_op), ptr(k_op), n_q, n_k, cols, k, col_offset, ptr(keys), ptr(ws), ws.numel(),
+                                  stream_ptr()), "sim_topk")
+        return keys
+    if bounds_in is not None:
+        require_cuda(bounds_in)
+        assert bounds_in.dtype == torch.int32 and bounds_in.is_contiguous() and bounds_in.numel() == n_q
+    bout = torch.empty(n_q, dtype=torch.int32, device=q_op.device) if want_bounds else None
+    check(lib().vast_sim_topk_bounded(ptr(q_op), ptr(k_op), n_q, n_k, cols, k, col_offset, ptr(bounds_in), ptr(bout),
+                                      ptr(keys), ptr(ws), ws.numel(), stream_ptr()), "sim_topk_bounded")
+    return (keys, bout) if want_bounds else keys
+
+
+def rank_of_gt(q: torch.Tensor, kk: torch.Tensor, gt_col: torch.Tensor, col_lo: int = 0, n_k: int | None = None,
+               mode: int | None = None, delta_rel: float = 2.0 ** -11) -> torch.Tensor:
+    """Streaming exact rank of the ground truth over key rows [col_lo, col_lo + n_k) of `kk` (vast_rank_of_gt):
+    #{j : s_ij > s_i,gt or (s_ij == s_i,gt and j < gt_col[i])}, s = exact fp32-feature similarities.  int32 [n_q]."""
+    require_cuda(q, kk, gt_col)
+    assert q.dtype == torch.float32 and kk.dtype == torch.float32 and q.stride(1) == 1 and kk.stride(1) == 1
+    n_q, dim = q.shape
+    n_total = kk.shape[0]
+    n_k = n_total - col_lo if n_k is None else n_k
+    mode = SIM_FP32X2 if mode is None else mode
+    gt = gt_col.int().contiguous()
+    out = torch.zeros(n_q, dtype=torch.int32, device=q.device)
+    if n_k <= 0 or n_q == 0:
+        return out
+    q_op = sim_pack_operand(q, mode, True)
+    k_op = sim_pack_operand(kk[col_lo:col_lo + n_k], mode, False)
+    cols = q_op.shape[1]
+    ws = _ws(lib().vast_rank_of_gt_workspace_bytes(n_q, n_k, cols), q.device)
+    check(lib().vast_rank_of_gt(ptr(q), q.stride(0), ptr(kk), kk.stride(0), n_q, n_total, dim, ptr(q_op), ptr(k_op), cols,
+                                col_lo, n_k, ptr(gt), float(delta_rel), ptr(out), ptr(ws), ws.numel(), stream_ptr()),
+          "rank_of_gt")
+    return out
 
 
 def topk_merge(keys_parts: torch.Tensor, k_out: int) -> torch.Tensor:

@@ -23,7 +23,7 @@ def _shard_bounds(n: int, rank: int, world: int):
 
 @torch.no_grad()
 def retrieval_topk(feat_t: torch.Tensor, feat_cond: torch.Tensor, k: int, mode: str = "bf16", shard=None,
-                   shard_mode: str = "rows"):
+                   shard_mode: str = "rows", warm_bounds: bool = True, _delta_scale: float = 1.0):
     """For every row of feat_t [Nt, D] the k best rows of feat_cond [Nv, D] by (score desc, index asc).
 
     mode "bf16": bf16 inputs, fp32 accumulate (tensor cores) -- scores are the bf16-mode similarities.
@@ -42,10 +42,12 @@ def retrieval_topk(feat_t: torch.Tensor, feat_cond: torch.Tensor, k: int, mode: 
     nt, nv = feat_t.shape[0], feat_cond.shape[0]
     rank, world = shard if shard is not None else (0, 1)
     lo, hi = _shard_bounds(nv, rank, world)
-    exact = mode == "fp32"
+    exact = mode in ("fp32", "fp32x3")
     if not exact and mode != "bf16":
         raise ValueError(mode)
-    sim_mode = ops.SIM_FP32X3 if exact else ops.SIM_BF16
+    # exact mode: the shortlist comes from 2-term bf16 splits (3 tensor-core products; "fp32x3": 3 terms, 6 products,
+    # twice the tensor work) -- either way it is re-scored in fp64 and PROVEN complete with the same error bound
+    sim_mode = (ops.SIM_FP32X3 if mode == "fp32x3" else ops.SIM_FP32X2) if exact else ops.SIM_BF16
     kl = k if not exact else min(ops.TOPK_MAX, max(2 * k, k + 16))
     if kl > ops.TOPK_MAX or k > ops.TOPK_MAX:
         raise RuntimeError(f"retrieval_topk: k={k} exceeds the supported maximum {ops.TOPK_MAX}")
@@ -67,9 +69,26 @@ def retrieval_topk(feat_t: torch.Tensor, feat_cond: torch.Tensor, k: int, mode: 
         if shard_mode not in ("cols", "rows"):
             raise ValueError(shard_mode)
         q_op = ops.sim_pack_operand(ft, sim_mode, True)
-        if hi > lo:
-            k_op = ops.sim_pack_operand(fc[lo:hi], sim_mode, False)
-            keys = ops.sim_topk(q_op, k_op, kl, col_offset=lo)
+        k_op = ops.sim_pack_operand(fc[lo:hi], sim_mode, False) if hi > lo else None
+        bounds = None
+        if world > 1 and warm_bounds:
+            # Column shards start WARM (each rank owns its videos).  A cold shard does k (1 + ln(n / (W k)))
+            # list insertions per row -- almost as many as the whole problem -- so the list work would not shrink with W.
+            # Phase A: this rank scans its slice of the QUERY rows against its own columns (1 / W^2 of the problem); the
+            # k-th score found is a proven lower bound of the row's global k-th score.  The [Nt] bounds are
+            # all-gathered (4 bytes per row) and phase B admits only scores at or above them: ~k insertions per row.
+            import torch.distributed as dist
+            per = (nt + world - 1) // world
+            rlo, rhi = min(rank * per, nt), min((rank + 1) * per, nt)
+            mine_b = torch.zeros(per, dtype=torch.int32, device=ft.device)
+            if rhi > rlo and k_op is not None and hi - lo >= kl:
+                _, b = ops.sim_topk(q_op[rlo:rhi], k_op, kl, col_offset=lo, want_bounds=True)
+                mine_b[:rhi - rlo] = b
+            allb = torch.empty(world * per, dtype=torch.int32, device=ft.device)
+            dist.all_gather_into_tensor(allb, mine_b)
+            bounds = allb[:nt].contiguous()
+        if k_op is not None:
+            keys = ops.sim_topk(q_op, k_op, kl, col_offset=lo, bounds_in=bounds)
         else:
             keys = torch.zeros(nt, kl, dtype=torch.int64, device=ft.device)
         if world > 1:
@@ -84,7 +103,7 @@ def retrieval_topk(feat_t: torch.Tensor, feat_cond: torch.Tensor, k: int, mode: 
     kk = min(k, nv)
     # proof: every column outside the shortlist has approx <= cutoff, hence exact <= cutoff + delta
     cutoff = vals[:, kl - 1].double()                         # -inf when the list is not full (all columns inside)
-    delta = (2.0 ** -11) * ft.norm(dim=1).double() * fc.norm(dim=1).max().double()
+    delta = _delta_scale * (2.0 ** -11) * ft.norm(dim=1).double() * fc.norm(dim=1).max().double()
     unproven = torch.isfinite(cutoff) & ~(s64[:, kk - 1] > cutoff + delta)
     idx_k = idx[:, :k].contiguous()
     s_k = s64[:, :k].contiguous()
@@ -92,6 +111,24 @@ def retrieval_topk(feat_t: torch.Tensor, feat_cond: torch.Tensor, k: int, mode: 
     if rows.numel() > 0:
         ops.exact_topk_rows(ft, fc, rows, k, idx_k, s_k)
     return s_k.float(), idx_k
+
+
+@torch.no_grad()
+def rank_of_gt(feat_t: torch.Tensor, feat_cond: torch.Tensor, gt_col: torch.Tensor, shard=None) -> torch.Tensor:
+    """Streaming rank of the ground truth (evaluation_mm.py:333-338 without the sort / `.tolist()` /
+    `list.index`): ranks[i] = #{j : s_ij > s_i,gt or (s_ij == s_i,gt and j < gt_col[i])} over the EXACT similarities of
+    the fp32 features -- counted inside the similarity GEMM's epilogue, near-ties of the ground truth re-scored in fp64
+    (`vast_rank_of_gt`), so the [Nt, Nv] matrix never exists and the result does not depend on tiling or GPU count.
+    shard (rank, world): every rank counts over its slice of the columns; partial counts are summed (all-reduce).
+    Returns int32 [Nt], identical on every rank."""
+    ft, fc = feat_t.float().contiguous(), feat_cond.float().contiguous()
+    rank, world = shard if shard is not None else (0, 1)
+    lo, hi = _shard_bounds(fc.shape[0], rank, world)
+    r = ops.rank_of_gt(ft, fc, gt_col, lo, hi - lo)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(r)
+    return r
 
 
 # ------------------------------------------------------------------ metrics
@@ -147,10 +184,26 @@ def compute_metric_ret(score_matrix, ids, ids_txt, direction='forward'):
 
 
 @torch.no_grad()
-def recall_from_feats(feat_t, feat_cond, ids, ids_txt, direction='forward', mode='bf16', shard=None):
-    """R@1/5/10 without the score matrix: R@K only needs the top-10 lists (the reference reports nothing
-    else: median / mean rank are computed and dropped, evaluation_mm.py:343-351)."""
+def recall_from_feats(feat_t, feat_cond, ids, ids_txt, direction='forward', mode='bf16', shard=None, method='topk'):
+    """R@1/5/10 without the score matrix.  method 'topk': R@K only needs the top-10 lists (the reference reports nothing
+    else: median / mean rank are computed and dropped, evaluation_mm.py:343-351); method 'rank': the reference's own
+    formulation -- the rank of every ground truth (`rank_of_gt`, exact fp32 semantics), then `rank < K`."""
     dev = feat_t.device
+    if method == 'rank':
+        if direction == 'forward':
+            first = _first_index(ids)
+            gt = torch.tensor([first[t] for t in ids_txt], dtype=torch.int32, device=dev)
+            rank = rank_of_gt(feat_t, feat_cond, gt, shard)
+            n = len(ids_txt)
+        else:
+            rows, cols = _backward_pairs(ids, ids_txt)                  # (text, video) ground-truth pairs
+            cols_t = torch.tensor(cols, dtype=torch.int64, device=dev)
+            r = rank_of_gt(feat_cond.float()[cols_t], feat_t, torch.tensor(rows, dtype=torch.int32, device=dev), shard)
+            rank = torch.full((len(ids),), 2 ** 30, dtype=torch.int32, device=dev)
+            rank = rank.scatter_reduce(0, cols_t, r, reduce='amin')
+            n = len(ids)
+        counts = torch.stack([(rank < 1).sum(), (rank < 5).sum(), (rank < 10).sum()]).tolist()
+        return _format(direction, counts[0] / n, counts[1] / n, counts[2] / n)
     if direction == 'forward':
         _, idx = retrieval_topk(feat_t, feat_cond, min(10, feat_cond.shape[0]), mode, shard)
         first = _first_index(ids)
