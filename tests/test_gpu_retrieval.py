@@ -556,3 +556,36 @@ def test_cfg2_real_shapes_refine_and_gather():
     assert cond3.shape == (3 * bs, S, H)
     for blk, src in ((cond3[:bs], cond[:bs]), (cond3[bs:2 * bs], cond[:n_all][neg_c]), (cond3[2 * bs:], cond[:bs])):
         assert np.array_equal(blk.cpu().numpy().view(np.uint16), src.cpu().numpy().view(np.uint16))
+
+
+class _StubPairModel(_StubModel):
+    """The same stub scorer with the batched (video index, text) pair interface of SURVEY 8 f-2."""
+
+    def compute_pair_scores(self, cond_feats, vid, ids, mask):
+        self.calls.append(ids.shape[0])
+        x = self.emb[ids] * mask.unsqueeze(-1).float()
+        ctx = cond_feats.float().mean(dim=1)[:, :self.hidden][vid][:, None, :]
+        h = torch.tanh((x + ctx) @ self.proj)
+        return torch.softmax(h[:, 0] @ self.w, dim=1)[:, 1]
+
+
+@pytest.mark.parametrize("direction", ["forward", "backward"])
+def test_rerank_batched_across_videos_equals_per_video_chunks(direction):
+    """f-2: a model that scores (video, text) PAIRS is fed batches of thousands of pairs across videos instead of <= 25
+    texts of one video (evaluation_mm.py:302); same candidates, same scores at the same positions, same metrics."""
+    from vast_b200 import retrieval
+    nt, nv, k = 900, 150, 16
+    t, v = feats(nt, nv, 64, 12, noise=3.0)
+    g = torch.Generator().manual_seed(4)
+    ids_tok = torch.randint(0, 30522, (nt, 12), generator=g).cuda()
+    mask = torch.ones(nt, 12, dtype=torch.int64).cuda()
+    cond = torch.randn(nv, 5, 16, generator=g).cuda()
+    a, b = _StubModel(), _StubPairModel()
+    i1, s1 = retrieval.refine_candidates(cond, ids_tok, mask, t.cuda(), v.cuda(), a, k, direction)
+    i2, s2 = retrieval.refine_candidates(cond, ids_tok, mask, t.cuda(), v.cuda(), b, k, direction)
+    assert torch.equal(i1, i2) and torch.allclose(s1, s2, rtol=1e-5, atol=1e-7)
+    assert max(a.calls) <= 25 and max(b.calls) > 25 and len(b.calls) < len(a.calls) / 10
+    ids = [f"v{i}" for i in range(nv)]
+    ids_txt = [f"v{i % nv}" for i in range(nt)]
+    assert retrieval.recall_from_candidates(i1, s1, ids, ids_txt, direction) == \
+        retrieval.recall_from_candidates(i2, s2, ids, ids_txt, direction)

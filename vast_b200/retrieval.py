@@ -71,7 +71,7 @@ def retrieval_topk(feat_t: torch.Tensor, feat_cond: torch.Tensor, k: int, mode: 
         q_op = ops.sim_pack_operand(ft, sim_mode, True)
         k_op = ops.sim_pack_operand(fc[lo:hi], sim_mode, False) if hi > lo else None
         bounds = None
-        if world > 1 and warm_bounds:
+        if world >= 4 and warm_bounds:    # measured (cfg5, ranks emulated): pays from 4 shards on; at 2 phase A costs what it saves
             # Column shards start WARM (each rank owns its videos).  A cold shard does k (1 + ln(n / (W k)))
             # list insertions per row -- almost as many as the whole problem -- so the list work would not shrink with W.
             # Phase A: this rank scans its slice of the QUERY rows against its own columns (1 / W^2 of the problem); the
@@ -92,10 +92,19 @@ def retrieval_topk(feat_t: torch.Tensor, feat_cond: torch.Tensor, k: int, mode: 
         else:
             keys = torch.zeros(nt, kl, dtype=torch.int64, device=ft.device)
         if world > 1:
+            # merge fused into the exchange: rank r merges the candidates of row slice r (all-to-all: every rank sends
+            # each peer only that peer's rows, (W-1)/W * Nt*k keys in and out) and the finished lists are all-gathered --
+            # W/2 x less traffic than all-gathering every rank's [Nt, k] candidates, and the merge work is sharded too
             import torch.distributed as dist
-            allk = torch.empty(world, nt, kl, dtype=torch.int64, device=keys.device)
-            dist.all_gather_into_tensor(allk, keys)
-            keys = ops.topk_merge(allk, kl)
+            per = (nt + world - 1) // world
+            send = torch.zeros(world * per, kl, dtype=torch.int64, device=keys.device)
+            send[:nt] = keys
+            recv = torch.empty(world, per, kl, dtype=torch.int64, device=keys.device)
+            dist.all_to_all_single(recv, send)
+            mine = ops.topk_merge(recv, kl)
+            allk = torch.empty(world * per, kl, dtype=torch.int64, device=keys.device)
+            dist.all_gather_into_tensor(allk, mine)
+            keys = allk[:nt].contiguous()
     vals, idx = ops.topk_unpack(keys)
     if not exact:
         return vals, idx
@@ -225,15 +234,34 @@ def recall_from_feats(feat_t, feat_cond, ids, ids_txt, direction='forward', mode
 
 # ------------------------------------------------------------------ ITM re-rank bookkeeping
 @torch.no_grad()
-def _rerank_pairs(condition_feats, input_ids, attention_mask, text_idx, video_local, model, small_batch):
+def _rerank_pairs(condition_feats, input_ids, attention_mask, text_idx, video_local, model, small_batch, pair_batch=8192):
     """Score (text, local video) candidate pairs with model.compute_slice_scores (model/vast.py:373-380),
-    per video in chunks of `small_batch` like evaluation_mm.py:292-311.  Returns (texts, videos, scores)."""
+    per video in chunks of `small_batch` like evaluation_mm.py:292-311 -- or, when the model offers
+    `compute_pair_scores(condition_feats, video_idx [b], input_ids [b, L], attention_mask [b, L]) -> [b]`, in batches of
+    `pair_batch` pairs across videos.  Returns (texts, videos, scores)."""
     nv_local = condition_feats.shape[0]
     if nv_local == 0 or text_idx.numel() == 0:   # a rank that owns no videos (ragged evaluation shards): nothing to score
         dev = condition_feats.device
         return (torch.empty(0, dtype=torch.int32, device=dev), torch.empty(0, dtype=torch.int32, device=dev),
                 torch.empty(0, dtype=torch.float32, device=dev))
     offsets, texts = ops.bucket_by_video(text_idx, video_local, nv_local)
+    if hasattr(model, "compute_pair_scores"):
+        # SURVEY 8 f-2: a scorer that takes (video index, text) PAIRS batches across videos -- `pair_batch` pairs per call
+        # instead of <= 25 texts of one video -- and can project a video's cross-attention K/V once for all its pairs.
+        # The pairs arrive grouped by video (ascending text inside a video), i.e. in the order the reference scores them.
+        n_pairs = offsets[-1:].long()                                       # device scalar: no host read on this path
+        cap = text_idx.numel()
+        vids_all = torch.searchsorted(offsets[1:].long().contiguous(), torch.arange(cap, device=offsets.device), right=True).int()
+        valid = torch.arange(cap, device=offsets.device) < n_pairs
+        vids_all = torch.where(valid, vids_all.clamp_max(nv_local - 1), torch.zeros_like(vids_all))
+        rows = torch.where(valid, texts.long().clamp_min(0), torch.zeros_like(texts.long()))
+        out_scores = torch.zeros(cap, dtype=torch.float32, device=condition_feats.device)
+        for c in range(0, cap, pair_batch):
+            sl = slice(c, min(c + pair_batch, cap))
+            out_scores[sl] = model.compute_pair_scores(condition_feats, vids_all[sl].long(), input_ids[rows[sl]],
+                                                       attention_mask[rows[sl]]).float()
+        keep = valid.nonzero().flatten()                                     # (sizes the outputs: one host read, as below)
+        return texts[keep], vids_all[keep], out_scores[keep]
     off = offsets.cpu().tolist()                       # one host read for the whole re-rank
     out_scores = torch.empty(off[-1], dtype=torch.float32, device=condition_feats.device)
     vids = torch.empty(off[-1], dtype=torch.int32, device=condition_feats.device)
@@ -286,7 +314,7 @@ def refine_score_matrix(condition_feats, input_ids, attention_mask, score_matrix
 # ------------------------------------------------------------------ streaming re-rank (no [Nt, Nv] matrix anywhere)
 @torch.no_grad()
 def refine_candidates(condition_feats, input_ids, attention_mask, feat_t, feat_cond, model, itm_rerank_num,
-                      direction='forward', mode='fp32', small_batch=25):
+                      direction='forward', mode='fp32', small_batch=25, pair_batch=8192):
     """`refine_score_matrix` (evaluation_mm.py:253-319) without the score matrix: candidates come from the streaming
     top-k over the FEATURES, the refined scores stay in the [rows, k] layout of the candidate lists.
 
@@ -318,7 +346,8 @@ def refine_candidates(condition_feats, input_ids, attention_mask, feat_t, feat_c
     start = sum(length_ls[:rank])
     local = (v_idx >= start) & (v_idx < start + cur_length) & (t_idx >= 0)
     v_local = torch.where(local, v_idx - start, torch.full_like(v_idx, -1))
-    texts, vids, scores = _rerank_pairs(condition_feats, input_ids, attention_mask, t_idx, v_local, model, small_batch)
+    texts, vids, scores = _rerank_pairs(condition_feats, input_ids, attention_mask, t_idx, v_local, model, small_batch,
+                                        pair_batch)
     # back into the list layout: both sides hold the same set of unique (text, video) pairs -> sort both by the pair key
     itm = torch.zeros(idx.numel(), dtype=torch.float32, device=dev)
     slots = local.nonzero().flatten()
