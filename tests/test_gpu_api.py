@@ -166,3 +166,71 @@ def test_build_feature_golden_and_grad(golden):
     ref.backward(go.cpu())
     for got, want in ((vis.grad, v2.grad), (aud.grad, a2.grad), (sub.grad, s2.grad)):
         np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-3, atol=1e-6)
+
+
+def test_batch_get_dropin_golden_memoised_and_delegating(golden):
+    """vast_b200.batch_get bound to a model class in place of VAST.batch_get (model/vast.py:82-312): feat_vas equals
+    the reference's own batch_get('feat_vas') golden, results are memoised in the batch (:82-83), encoder outputs come
+    through self.batch_get, every non-feature key goes to the method it replaced, and the single-modality / caption
+    keys follow the reference chain pool -> head -> normalize."""
+    import vast_b200
+    g = golden("features")
+    calls = []
+
+    class Contra(nn.Module):            # general_module.py:26-31
+        def __init__(self, i, o):
+            super().__init__()
+            self.linear = nn.Linear(i, o, bias=False)
+
+        def forward(self, x):
+            return self.linear(x)
+
+    class Bert:
+        def __call__(self, input_ids, attention_mask):
+            calls.append("bert")
+            h = torch.nn.functional.one_hot(input_ids % 24, 24).float().cuda() * attention_mask[..., None].float()
+            return types.SimpleNamespace(last_hidden_state=h)
+
+    class Model:
+        config = types.SimpleNamespace(vision_encoder_type="evaclip01_giant", audio_encoder_type="beats")
+
+        def batch_get(self, batch, key):                      # the "reference" method being replaced
+            calls.append(key)
+            if key == "vision_output":
+                batch[key] = torch.from_numpy(g["vision"]).cuda()
+            elif key == "omni_caption_tokens":
+                batch[key] = types.SimpleNamespace(input_ids=torch.arange(30).reshape(5, 6).cuda(),
+                                                   attention_mask=torch.ones(5, 6, dtype=torch.int64).cuda())
+            else:
+                raise KeyError(key)
+            return batch[key]
+
+    vast_b200.install(Model)
+    assert Model.batch_get is vast_b200.batch_get and Model.forward_ret is vast_b200.forward_ret
+    m = Model()
+    lin = nn.Linear(g["weight"].shape[1], g["weight"].shape[0]).cuda()
+    with torch.no_grad():
+        lin.weight.copy_(torch.from_numpy(g["weight"]))
+        lin.bias.copy_(torch.from_numpy(g["bias"]))
+    m.contra_head_vas = lin
+    m.contra_head_v = Contra(48, 32).cuda()
+    m.contra_head_t = Contra(24, 32).cuda()
+    m.multimodal_encoder = types.SimpleNamespace(bert=Bert())
+    batch = {"audio_output": torch.from_numpy(g["audio"]).cuda(), "subtitle_output": torch.from_numpy(g["subtitle"]).cuda()}
+    feat = m.batch_get(batch, "feat_vas")
+    np.testing.assert_allclose(feat.detach().cpu().numpy(), g["feat_vas"], rtol=2e-4, atol=2e-6)
+    assert calls == ["vision_output"]                          # fetched through the replaced method, exactly once
+    assert m.batch_get(batch, "feat_vas") is feat and "feat_vas" in batch and calls == ["vision_output"]   # memoised
+    fv = m.batch_get(batch, "feat_v")                          # reuses the memoised vision_output
+    want = torch.nn.functional.normalize(m.contra_head_v(torch.from_numpy(g["pool_v"]).cuda()), dim=-1)
+    np.testing.assert_allclose(fv.detach().cpu().numpy(), want.detach().cpu().numpy(), rtol=2e-4, atol=2e-6)
+    assert calls == ["vision_output"]
+    ft = m.batch_get(batch, "feat_t_omni_caption")             # tokens -> bert -> cls -> contra_head_t -> normalize
+    hid = Bert()(batch["omni_caption_tokens"].input_ids, batch["omni_caption_tokens"].attention_mask).last_hidden_state
+    want = torch.nn.functional.normalize(m.contra_head_t(hid[:, 0]), dim=-1)
+    np.testing.assert_allclose(ft.detach().cpu().numpy(), want.detach().cpu().numpy(), rtol=2e-4, atol=2e-6)
+    with pytest.raises(KeyError):
+        m.batch_get(batch, "no_such_key")                      # delegated: the reference method's own error
+    # preset keys are returned verbatim like the reference (:82-83)
+    sentinel = torch.zeros(1)
+    assert m.batch_get({"feat_t": sentinel}, "feat_t") is sentinel
