@@ -125,10 +125,28 @@ my_ids = [f"vid{rank}_{i}" for i in range(rank + 1)]
 ok &= vast_b200.all_gather_ids(my_ids) == [j for i in vast_b200.all_gather_list(my_ids) for j in i]
 ok &= vast_b200.all_gather_ids([rank * 10 + i for i in range(3)]) == [r * 10 + i for r in range(world) for i in range(3)]
 
-# negative-row exchange == all_gather_with_grad(x)[idx], values and gradients (NCCL all_to_all)
-xg = torch.randn(bs, 7, 16, generator=g).cuda()
-idx = torch.randint(0, n, (bs,), generator=g).cuda()
-wgt = torch.randn(bs, 7, 16, generator=g).cuda()
+# two graphed steps of the SAME shape used back to back with no host synchronisation in between (three sub-tasks per
+# training step is the natural setup): each owns its pair of symmetric buffers, so a fast rank's second push can never
+# land in a buffer a slower rank still reads.  Results must equal the single-step ones, every time.
+gs_a = vast_b200.OmcGraphStep(bs, d, tau)
+gs_b = vast_b200.OmcGraphStep(bs, d, tau)
+assert gs_a.pg is None or gs_a.pg is not gs_b.pg
+fin = []
+for it in range(6):
+    for gs in (gs_a, gs_b):
+        la, _, _ = gs(c[sl].cuda(), t[sl].cuda())
+        fin.append(la)                       # device tensors only: no .item() inside the loop
+vals = torch.stack([x.detach().clone() for x in fin[-2:]] + [fin[0].detach().clone()]).cpu()
+ok &= bool(((vals - o["loss"]).abs() < 1e-3 * abs(o["loss"])).all())
+if rank == 0:
+    print("two graphed steps, no host sync ok:", bool(ok), flush=True)
+
+# negative-row exchange == all_gather_with_grad(x)[idx], values and gradients (NCCL all_to_all).
+# Rank-dependent data and per-rank request lists: wrong-owner routing or swapped send / recv splits cannot pass.
+gr = torch.Generator().manual_seed(100 + rank)
+xg = (torch.randn(bs, 7, 16, generator=gr) + rank).cuda()
+idx = torch.randint(0, n, (bs,), generator=gr).cuda()
+wgt = torch.randn(bs, 7, 16, generator=gr).cuda()
 xa = xg.clone().requires_grad_()
 ref = vast_b200.all_gather_with_grad(xa)[idx]
 (ref * wgt).sum().backward()

@@ -91,8 +91,10 @@ class OmcGraphStep:
         self._turn = 0
         self.pg = None
         if self.world > 1 and dim % 8 == 0:
-            from .peer import packed_gather
-            self.pg = packed_gather(bs, dim, dev)
+            # its own pair of symmetric buffers: sharing the eager path's (or another step's) would let two gathers in a
+            # row target the same buffer while a slower rank still reads it
+            from .peer import private_gather
+            self.pg = private_gather(bs, dim, dev)
         if self.pg is None:
             self._pack_local = [torch.empty(bs, 2 * dim, dtype=torch.bfloat16, device=dev) for _ in range(2)]
             if self.world > 1:

@@ -65,19 +65,64 @@ class PackedGather:
 
 
 _cache: dict = {}
+_available: dict = {}
+
+
+def _single_node(group=None) -> bool:
+    """The symmetric-memory path needs every rank of the group on this node (peer / multicast mappings)."""
+    w = dist.get_world_size(group)
+    lw = os.environ.get("LOCAL_WORLD_SIZE")
+    if lw is not None:
+        return int(lw) == w
+    return torch.cuda.device_count() >= w
+
+
+def _build_collectively(bs: int, dim: int, device) -> PackedGather | None:
+    """Construct a PackedGather or return None -- the SAME answer on every rank.  Construction is collective
+    (symmetric allocation + rendezvous); if it fails on some ranks only (out of memory, a peer without P2P or multicast)
+    and those fell back to NCCL while the others waited in the symmetric-memory barrier, the job would hang: so the
+    outcome is agreed on with an all-reduce(MIN) before anyone uses it."""
+    dev = torch.device(device)
+    pg, err = None, None
+    if _single_node():
+        try:
+            pg = PackedGather(bs, dim, dev)
+        except Exception as e:  # symmetric memory not supported on this system / build
+            err = e
+    else:
+        err = RuntimeError("ranks span more than one node")
+    ok = torch.tensor([1 if pg is not None else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if ok.item() == 0:
+        if dist.get_rank() == 0:
+            import warnings
+            warnings.warn(f"vast_b200: peer-memory all-gather unavailable ({type(err).__name__ if err else 'on another rank'}: "
+                          f"{err}); using vast_pack_pair + NCCL all_gather_into_tensor")
+        return None
+    return pg
+
+
+def _enabled() -> bool:
+    return os.environ.get("VAST_PEER_GATHER", "1") == "1" and dist.is_initialized() and dist.get_world_size() > 1
 
 
 def packed_gather(bs: int, dim: int, device) -> PackedGather | None:
-    """Cached PackedGather for this shape, or None when symmetric memory is unavailable / disabled
-    (VAST_PEER_GATHER=0): the caller then uses vast_pack_pair + NCCL all_gather_into_tensor."""
-    if os.environ.get("VAST_PEER_GATHER", "1") != "1" or not dist.is_initialized() or dist.get_world_size() == 1:
+    """The EAGER path's PackedGather for this shape (cached: consecutive eager gathers alternate its two buffers), or
+    None when symmetric memory is unavailable / disabled (VAST_PEER_GATHER=0): the caller then uses vast_pack_pair +
+    NCCL all_gather_into_tensor.  Collective on first use per shape."""
+    if not _enabled():
         return None
     key = (bs, dim, torch.device(device).index)
     if key not in _cache:
-        try:
-            _cache[key] = PackedGather(bs, dim, device)
-        except Exception as e:  # symmetric memory not supported on this system / build
-            import warnings
-            warnings.warn(f"vast_b200: peer-memory all-gather unavailable ({type(e).__name__}: {e}); using NCCL")
-            _cache[key] = None
+        _cache[key] = _build_collectively(bs, dim, device)
     return _cache[key]
+
+
+def private_gather(bs: int, dim: int, device) -> PackedGather | None:
+    """A PackedGather of its OWN for a captured step (OmcGraphStep).  The write-after-read argument of the two
+    alternating buffers -- a rank that is one gather ahead never overwrites rows a slower rank still reads -- holds only
+    if consecutive gathers on a pair of buffers alternate; two graphed steps (or a graphed step and the eager path)
+    sharing one pair could push into the same buffer back to back.  Collective."""
+    if not _enabled():
+        return None
+    return _build_collectively(bs, dim, device)
