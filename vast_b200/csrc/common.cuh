@@ -120,6 +120,15 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// order-preserving map float -> uint32 (larger float <=> larger uint; 0 is below every float): atomicMax on floats
+__device__ __forceinline__ uint32_t f32_orderable(float s) {
+  const uint32_t b = __float_as_uint(s);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float f32_from_orderable(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
 // 16-byte streaming load / store (read-once, write-once data).
 __device__ __forceinline__ uint4 ld_stream16(const void* p) {
   uint4 r;

@@ -57,10 +57,16 @@ struct GemmShape {
 
 template <class EpiParams>
 struct alignas(64) KernelParams {
-  CUtensorMap tmA[MAX_PROBLEMS];
+  CUtensorMap tmA[MAX_PROBLEMS + 1];  // [MAX_PROBLEMS]: the MN-major ("transposed view") A operand of problem a_mn_prob
   CUtensorMap tmB[MAX_PROBLEMS];
   GemmShape g;
   const int* gate;  // optional device flag: the whole launch is a no-op while *gate == 0
+  // Optional MN-major A (epilogues with kAmnCapable): problem `a_mn_prob` reads its A operand as the TRANSPOSE of a
+  // row-major matrix -- A[m][k] = X[k][m], X row-major [K, M] -- through tmA[MAX_PROBLEMS] (boxes of 64 k-rows x 64
+  // m-columns, the same smem layout as the MN-major B operand) unless *a_mn_off != 0 (device flag read once per
+  // role).  a_mn_prob1 = 1 + that problem's index; 0 (what memset leaves): every problem K-major.
+  int a_mn_prob1;
+  const int* a_mn_off;
   EpiParams epi;
 };
 
@@ -164,6 +170,14 @@ struct HasCustomTiles : std::false_type {};
 template <class E>
 struct HasCustomTiles<E, std::void_t<decltype(E::kCustomTiles)>> : std::true_type {};
 template <class E, class = void>
+struct HasTileEnd : std::false_type {};
+template <class E>
+struct HasTileEnd<E, std::void_t<decltype(E::kHasTileEnd)>> : std::integral_constant<bool, E::kHasTileEnd> {};
+template <class E, class = void>
+struct HasAmn : std::false_type {};
+template <class E>
+struct HasAmn<E, std::void_t<decltype(E::kAmnCapable)>> : std::true_type {};
+template <class E, class = void>
 struct HasFinish : std::false_type {};
 template <class E>
 struct HasFinish<E, std::void_t<decltype(E::kHasFinish)>> : std::true_type {};
@@ -202,6 +216,7 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
   constexpr uint32_t TMEM_COLS = 2 * BN;
   constexpr bool PAIR = CL == 2;
   constexpr bool CUSTOM = HasCustomTiles<Epi>::value && B_MN;  // explicit single-tile work items of any width <= BN
+  constexpr bool AMN = HasAmn<Epi>::value && A_RES == 0;      // one problem may read its A operand MN-major
 
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte aligned bases (in the shared address space).
@@ -261,6 +276,12 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t a_phase = 0;
+      int amn_prob = -1;
+      if constexpr (AMN) {
+        amn_prob = P.a_mn_prob1 - 1;
+        if (amn_prob >= 0 && P.a_mn_off != nullptr && *reinterpret_cast<const volatile int*>(P.a_mn_off) != 0) amn_prob = -1;
+      }
+      (void)amn_prob;
       for (int item = cluster_id; item < g.num_items; item += num_clusters) {
         const WorkItem w = decode_item<BN, CUSTOM>(g, item, cta_rank);
         if constexpr (A_RES > 0) {
@@ -293,7 +314,12 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
               if constexpr (B_MN) {
                 const int nboxes = CUSTOM ? (w.width + 63) >> 6 : BN / 64;  // 64 K-rows x 64 columns each
                 ptx::mbar_arrive_expect_tx(&full[stage], L::A_BYTES + static_cast<uint32_t>(nboxes) * (BK * 128));
-                ptx::tma_load_2d(sa, &P.tmA[w.prob], &full[stage], kb * BK, w.m_blk * BM);
+                if (AMN && w.prob == amn_prob) {
+                  ptx::tma_load_2d(sa, &P.tmA[MAX_PROBLEMS], &full[stage], w.m_blk * BM, kb * BK);
+                  ptx::tma_load_2d(sa + BK * 128, &P.tmA[MAX_PROBLEMS], &full[stage], w.m_blk * BM + 64, kb * BK);
+                } else {
+                  ptx::tma_load_2d(sa, &P.tmA[w.prob], &full[stage], kb * BK, w.m_blk * BM);
+                }
 #pragma unroll
                 for (int nb = 0; nb < BN / 64; ++nb)
                   if (nb < nboxes)
@@ -312,7 +338,12 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
                 const int half_n = CUSTOM ? w.width >> 1 : HALF_N;
                 const int nboxes = CUSTOM ? (half_n + 63) >> 6 : HALF_N / 64;
                 if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * (L::A_BYTES + static_cast<uint32_t>(nboxes) * (BK * 128)));
-                ptx::tma_load_2d_pair(sa, &P.tmA[w.prob], &full[stage], kb * BK, w.m_blk * BM);
+                if (AMN && w.prob == amn_prob) {  // A[m][k] = X[k][m]: two boxes of 64 k-rows x 64 m-columns
+                  ptx::tma_load_2d_pair(sa, &P.tmA[MAX_PROBLEMS], &full[stage], w.m_blk * BM, kb * BK);
+                  ptx::tma_load_2d_pair(sa + BK * 128, &P.tmA[MAX_PROBLEMS], &full[stage], w.m_blk * BM + 64, kb * BK);
+                } else {
+                  ptx::tma_load_2d_pair(sa, &P.tmA[w.prob], &full[stage], kb * BK, w.m_blk * BM);
+                }
 #pragma unroll
                 for (int nb = 0; nb < HALF_N / 64; ++nb)
                   if (nb < nboxes)
@@ -340,6 +371,12 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
       int acc = 0;
       uint32_t acc_phase = 0;
       uint32_t a_phase = 0;
+      int amn_prob = -1;
+      if constexpr (AMN) {
+        amn_prob = P.a_mn_prob1 - 1;
+        if (amn_prob >= 0 && P.a_mn_off != nullptr && *reinterpret_cast<const volatile int*>(P.a_mn_off) != 0) amn_prob = -1;
+      }
+      (void)amn_prob;
       for (int item = cluster_id; item < g.num_items; item += num_clusters) {
         const WorkItem w = decode_item<BN, CUSTOM>(g, item, cta_rank);
         if constexpr (A_RES > 0) {
@@ -357,17 +394,20 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
             const uint32_t sst = ptx::smem_u32(smem + L::RING_OFFSET + stage * L::STAGE_BYTES);
             const uint32_t sa = A_RES > 0 ? ptx::smem_u32(smem + (kb - w.kb_begin) * L::A_BYTES) : sst;
             const uint32_t sbb = A_RES > 0 ? sst : sst + L::A_BYTES;
-            const uint64_t da = ptx::umma_desc_sw128_kmajor(sa);
+            const bool a_mn = AMN && w.prob == amn_prob;
+            const uint64_t da = a_mn ? ptx::umma_desc_sw128_mnmajor(sa, BK * 128) : ptx::umma_desc_sw128_kmajor(sa);
             const uint64_t db = B_MN ? ptx::umma_desc_sw128_mnmajor(sbb, BK * 128)
                                      : ptx::umma_desc_sw128_kmajor(sbb);
             // K-major: advance 16 elements (32 bytes) along K inside the swizzle span: +2 in 16-byte units.
             // MN-major: 16 K-rows of 128 bytes = 2048 bytes: +128.
             constexpr uint64_t B_KSTEP = B_MN ? 128 : 2;
+            const uint64_t a_kstep = a_mn ? 128 : 2;
             // a narrower tile of an explicit schedule: the same descriptors, N taken from the item
-            const uint32_t idesc = CUSTOM ? ((g.idesc & ~(0x3Fu << 17)) | (static_cast<uint32_t>(w.width >> 3) << 17)) : g.idesc;
+            uint32_t idesc = CUSTOM ? ((g.idesc & ~(0x3Fu << 17)) | (static_cast<uint32_t>(w.width >> 3) << 17)) : g.idesc;
+            if (a_mn) idesc |= 1u << 15;  // A operand MN-major
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              ptx::umma_f16<CL>(d_tmem, da + 2 * k, db + B_KSTEP * k, idesc, (kb > w.kb_begin || k > 0) ? 1u : 0u);
+              ptx::umma_f16<CL>(d_tmem, da + a_kstep * k, db + B_KSTEP * k, idesc, (kb > w.kb_begin || k > 0) ? 1u : 0u);
             }
             ptx::umma_commit<CL>(&empty[stage]);  // frees the smem stage (in both CTAs) once these MMAs retire
             if (++stage == STAGES) {
@@ -444,6 +484,7 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
           acc = 0;
           acc_phase ^= 1;
         }
+        if constexpr (HasTileEnd<Epi>::value) epi.tile_end(ctx, col_tile, ew, NE);
       }
       epi.item_end(ctx);
     }
@@ -491,6 +532,8 @@ inline void fill_shape(GemmShape* g, int problems, int M, int N, int K, int BN, 
   g->idesc = ptx::umma_idesc_f16(static_cast<uint32_t>(a_fmt), static_cast<uint32_t>(b_fmt), b_mn ? 1u : 0u,
                                  static_cast<uint32_t>(BM * cl), static_cast<uint32_t>(BN));
 }
+
+inline int ceil_div_i(int a, int b) { return (a + b - 1) / b; }
 
 // CTA pairs (cta_group::2) as soon as there are two 128-row blocks to pair.
 inline int pick_cluster(int M) { return ceil_div(M, BM) >= 2 ? 2 : 1; }

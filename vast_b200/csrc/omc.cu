@@ -136,8 +136,22 @@ struct EpiStats {
 // drawn by the row-finalize kernel.  ELEM = true (index-exact parity tests with injected per-element noise,
 // two-pass form only so that Pt is the softmax probability): the reference's formulation literally,
 // argmax_j (p_ij + floor) / E_ij.
-template <bool ELEM>
+// SYM = true (one rank, single-pass form): with all rows local the two directions share ONE logit matrix,
+// sim_t2cond = sim_cond2t^T, so the GEMM runs over the cond2t problem only and ONE exponent reference serves both
+// directions -- the largest target logit of the batch (omc_pack_prep publishes it) instead of each row's own:
+//   P'_ij = exp2(s_ij * scale2 - ref_all)   (diagonal zeroed)
+// is then a symmetric function of S: row i of P' holds direction cond2t's numerators of row i, COLUMN j holds direction
+// t2cond's numerators of row j (every row's softmax only needs numerators relative to a row constant).  The dQ GEMM
+// reads the same fp16 buffer K-major for cond2t and MN-major (the transposed view) for t2cond.  The epilogue adds, per
+// 32-column chunk, a transposing warp reduction (31 shuffles) that gives lane L the sum of column L over the warp's 32
+// rows: the t2cond row sums and -- a warp's 32 rows ARE one 32-column chunk of direction t2cond -- the chunk sums of
+// its hard-negative race, merged over the CTA's four row quadrants at the end of every tile (tile_end).  Half the
+// tensor work and half the Pt traffic of the two-problem form; same sampler, same Philox words.
+template <bool ELEM, bool SYM = false>
 struct EpiSoft {
+  static_assert(!(ELEM && SYM), "the reference-literal per-element race needs per-row softmax probabilities");
+  static constexpr bool kHasTileEnd = SYM;
+  static constexpr uint32_t SMEM_BYTES = SYM ? 2 * 4 * 256 * sizeof(float) : 0;
   struct Params {
     const float* ref2;  // [2][M] log2-domain exponent reference per row
     __half* P;          // [2][M][ldp] Pt (dQ GEMM A operand), target column zeroed; or nullptr
@@ -161,6 +175,7 @@ struct EpiSoft {
     const float2* stats_partial;  // [2][M][stats_slots]
     int stats_slots;
     float* ref2_out;
+    const unsigned* zmax_bits;  // SYM: orderable bits of the largest target logit (the common exponent reference)
   };
   static constexpr bool kUnrollChunks = false;
   static constexpr int kAuxWarps = 0;
@@ -169,15 +184,28 @@ struct EpiSoft {
   int bidx, tcol;
   uint32_t off_lo, off_hi;
   uint4 rnd;
-  __device__ EpiSoft(const Params& p_, uint8_t*) : p(p_) {
+  float* stage;  // SYM: [2][4][256] column sums of the current / previous tile per row quadrant
+  float ref_all;
+  int par;
+  __device__ EpiSoft(const Params& p_, uint8_t* smem) : p(p_), stage(reinterpret_cast<float*>(smem)) {
     scale2 = p.temp_dev ? kLog2e / __ldg(p.temp_dev) : p.scale2;
     unsigned long long off = (static_cast<unsigned long long>(p.off_hi) << 32) | p.off_lo;
     if (p.step_ctr != nullptr) off += *p.step_ctr;
     off_lo = static_cast<uint32_t>(off);
     off_hi = static_cast<uint32_t>(off >> 32);
+    par = 0;
+    ref_all = 0.f;
+    if constexpr (SYM) ref_all = f32_from_orderable(*reinterpret_cast<const volatile unsigned*>(p.zmax_bits)) * scale2;
   }
   __device__ __forceinline__ void item_begin(const tc::ItemCtx& c) {
     const int64_t r = static_cast<int64_t>(c.prob) * c.M + c.row;
+    if constexpr (SYM) {
+      ref = ref_all;
+      if (c.row_valid && c.n_split == 0 && c.half == 0) {  // both directions' rows use the common reference
+        p.ref2_out[c.row] = ref_all;
+        p.ref2_out[c.M + c.row] = ref_all;
+      }
+    } else
     if (p.stats_partial != nullptr) {
       ref = 0.f;
       if (c.row_valid) {
@@ -222,6 +250,52 @@ struct EpiSoft {
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         if (i == tq) pr[i] = 0.f;
+    }
+    if constexpr (SYM) {
+      if (!c.row_valid) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) pr[i] = 0.f;
+      }
+      // transposing warp reduction: lane L ends up with sum over the warp's 32 rows of column L of this chunk
+      // (a fixed tree of 31 additions: deterministic)
+      const int lane = c.lane;
+      float a[16], b[8], cc[4], d[2];
+      {
+        const bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float keep = up ? pr[k + 16] : pr[k], send = up ? pr[k] : pr[k + 16];
+          a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+      }
+      {
+        const bool up = (lane & 8) != 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float keep = up ? a[k + 8] : a[k], send = up ? a[k] : a[k + 8];
+          b[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+      }
+      {
+        const bool up = (lane & 4) != 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float keep = up ? b[k + 4] : b[k], send = up ? b[k] : b[k + 4];
+          cc[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+      }
+      {
+        const bool up = (lane & 2) != 0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const float keep = up ? cc[k + 2] : cc[k], send = up ? cc[k] : cc[k + 2];
+          d[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+      }
+      const bool up1 = (lane & 1) != 0;
+      const float colsum = (up1 ? d[1] : d[0]) + __shfl_xor_sync(0xffffffffu, up1 ? d[0] : d[1], 1);
+      const int quad = (c.row >> 5) & 3;
+      stage[(par * 4 + quad) * 256 + (col0 & 255) + lane] = colsum;
     }
     float cs = 0.f;
 #pragma unroll
@@ -283,6 +357,42 @@ struct EpiSoft {
     if (c.row_valid)
       p.partial[(static_cast<int64_t>(c.prob) * c.M + c.row) * p.num_slots + c.slot] =
           make_float4(l, bw, be, __int_as_float(bidx));
+  }
+  // SYM, after every tile (all epilogue warps): thread e of the CTA's 256 epilogue threads owns column e of the tile =
+  // row j of direction t2cond; it adds the four quadrants' column sums (fixed order) and runs the race between
+  // the four 32-column chunks of that row these 128 S rows are -- chunk (4 m_blk + quadrant), whose four Exp(1)
+  // variates are the four words of ONE Philox call, exactly the words the two-problem form uses for them -- and
+  // leaves (l, best weight, best E, best chunk) in slot m_blk of the row's partials.
+  __device__ __forceinline__ void tile_end(const tc::ItemCtx& c, int col_tile, int ew, int ne) {
+    if constexpr (SYM) {
+      asm volatile("bar.sync 2, %0;" ::"r"(ne * 32) : "memory");
+      const int e = ew * 32 + c.lane;
+      const int col = col_tile + e;
+      if (col < c.N && c.m_blk * tc::BM < c.M) {
+        const float* st = stage + par * 4 * 256 + e;
+        const float q[4] = {st[0], st[256], st[512], st[768]};
+        const float l1 = (q[0] + q[1]) + (q[2] + q[3]);
+        float w1 = 0.f, e1 = 1.f;
+        int b1 = -1;
+        if (p.do_sample) {
+          const uint4 rn = philox4x32_10(make_uint4(static_cast<uint32_t>(c.m_blk), static_cast<uint32_t>(p.row_offset + col), off_lo,
+                                                    (off_hi << 1) | 1u),
+                                         make_uint2(p.seed_lo, p.seed_hi));
+          const uint32_t wd[4] = {rn.x, rn.y, rn.z, rn.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float ex = expo_from_bits(wd[k]);
+            if (q[k] * e1 > w1 * ex) {
+              w1 = q[k];
+              e1 = ex;
+              b1 = c.m_blk * 4 + k;
+            }
+          }
+        }
+        p.partial[(static_cast<int64_t>(c.M) + col) * p.num_slots + c.m_blk] = make_float4(l1, w1, e1, __int_as_float(b1));
+      }
+      par ^= 1;
+    }
   }
 };
 
@@ -433,6 +543,7 @@ __global__ void __launch_bounds__(256) omc_prep_kernel(const __nv_bfloat16* __re
 // tile sums that tile's slab partials into ksum, the last block of a slab sums its rows' per-tile dot products
 // into z_t (and the exponent reference).
 constexpr int PP_ROWS = 64;
+constexpr float ZSPREAD_LOG2 = 9.0f;
 template <class TI>
 __device__ __forceinline__ uint4 load8_as_bf16(const TI* src) {
   uint4 o;
@@ -468,7 +579,7 @@ __global__ void __launch_bounds__(256, 4) omc_pack_prep_kernel(const TI* __restr
                                                            float* __restrict__ zt_part, float* __restrict__ zt,
                                                            float* __restrict__ ref2, float scale2,
                                                            const float* __restrict__ temp_dev, int* __restrict__ flags,
-                                                           int* __restrict__ slab_tickets) {
+                                                           int* __restrict__ slab_tickets, int want_zrange) {
   pdl_trigger();
   pdl_wait();
   __shared__ float red[8][264];
@@ -579,16 +690,37 @@ __global__ void __launch_bounds__(256, 4) omc_pack_prep_kernel(const TI* __restr
     if (threadIdx.x == 0) slab_tickets[slab] = 0;
     __threadfence();
     const int r = slab * PP_ROWS + threadIdx.x;
-    if (static_cast<int>(threadIdx.x) < PP_ROWS && r < n) {
-      float z = 0.f;
+    float z = 0.f;
+    const bool has_row = static_cast<int>(threadIdx.x) < PP_ROWS && r < n;
+    if (temp_dev) scale2 = kLog2e / __ldg(temp_dev);
+    if (has_row) {
 #pragma unroll 8
       for (int t = 0; t < ctiles; ++t) z += __ldcg(zt_part + static_cast<int64_t>(r) * ctiles + t);
       zt[r] = z;
       zt[n + r] = z;
       if (ref2 != nullptr) {
-        if (temp_dev) scale2 = kLog2e / __ldg(temp_dev);
         ref2[r] = z * scale2;
         ref2[n + r] = z * scale2;
+      }
+    }
+    if (want_zrange && warp < PP_ROWS / 32) {
+      // Symmetric single-rank form (EpiSoft<false, true>): ONE exponent reference for the whole batch, the largest
+      // target logit.  flags[4] = max z, flags[5] = max -z (orderable bits, atomicMax: order-independent), flags[6] =
+      // slabs done; the last slab checks the spread: rows whose positive lies more than ZSPREAD_LOG2 (log2 units of
+      // logit) below the reference would keep their numerators in fp16 subnormals -> raise the fallback flag.
+      float zmx = has_row ? z : -INFINITY, zmn = has_row ? -z : -INFINITY;
+      zmx = warp_max(zmx);
+      zmn = warp_max(zmn);
+      if (lane == 0) {
+        atomicMax(reinterpret_cast<unsigned*>(&flags[4]), f32_orderable(zmx));
+        atomicMax(reinterpret_cast<unsigned*>(&flags[5]), f32_orderable(zmn));
+        __threadfence();
+        if (atomicAdd(&flags[6], 1) == nslab * (PP_ROWS / 32) - 1) {
+          const float hi = f32_from_orderable(atomicMax(reinterpret_cast<unsigned*>(&flags[4]), 0u));
+          const float lo = -f32_from_orderable(atomicMax(reinterpret_cast<unsigned*>(&flags[5]), 0u));
+          if (!((hi - lo) * scale2 <= ZSPREAD_LOG2)) flags[0] = 1;
+          flags[6] = 0;
+        }
       }
     }
   }
@@ -600,7 +732,8 @@ __global__ void __launch_bounds__(256, 4) omc_pack_prep_kernel(const TI* __restr
 //   rowstat[r] = (rho = 1 / l, c_t = p_target - (1 - eps), p_target, <q, sum_j K_j>),  rowce[r] = CE row term.
 struct RowStatParams {
   const float4* partial;
-  int slots;
+  int slots;    // valid slots per row
+  int pstride;  // slots allocated per row
   int M, N, D;
   int row_offset;
   const float* ref2;
@@ -648,7 +781,7 @@ __device__ __forceinline__ float2 row_stats_warp(const RowStatParams& p, int r, 
     dot_s = fmaf(q[4], k1.x, dot_s); dot_s = fmaf(q[5], k1.y, dot_s); dot_s = fmaf(q[6], k1.z, dot_s); dot_s = fmaf(q[7], k1.w, dot_s);
   }
   // ---- merge the per-slot partials (lane-strided, then butterfly: fixed order)
-  const float4* pp = p.partial + static_cast<int64_t>(r) * p.slots;
+  const float4* pp = p.partial + static_cast<int64_t>(r) * p.pstride;
   float l = 0.f, bw = p.elem_mode ? -1.f : 0.f, be = 1.f;
   int bidx = -1;
   for (int s = lane; s < p.slots; s += 32) {
@@ -769,8 +902,14 @@ struct EpiGrad {
     // the first accumulator tile is still being multiplied; the threads of the first column range also draw the
     // hard negative and publish (rho, c_t, p_target, lse) for the final reduction.  Bit-identical to K3: the
     // lane-strided butterfly sums of the warp-per-row kernel are replayed as the same binary trees.
-    const float4* partial;  // [2][M][sslots] from EpiSoft
-    int sslots;             // <= 32
+    const float4* partial;  // [2][M][pstride] from EpiSoft
+    int sslots;             // valid slots per row (<= 32) of the two-problem form
+    int pstride;            // slots allocated per row
+    // symmetric single-rank form (EpiSoft<false, true>), in force while *sym_off == 0: direction cond2t has sslots_sym0
+    // slots per row, direction t2cond one slot per 128-row block (sslots_sym1), and t2cond's numerators are the
+    // COLUMNS of the cond2t Pt buffer
+    int sslots_sym0, sslots_sym1;
+    const int* sym_off;
     const float* ref2;
     const float* zt;
     float eps_ls, floor;
@@ -801,6 +940,7 @@ struct EpiGrad {
   static constexpr int kAuxWarps = 0;
   static constexpr bool kHasFinish = true;
   static constexpr bool kCustomTiles = true;  // accepts an explicit schedule of tiles narrower than BN (plan_mixed_tiles)
+  static constexpr bool kAmnCapable = true;   // one problem's A operand may be the transposed view of a row-major matrix
   const Params& p;
   float* red;  // shared scratch of the final reduction
   float rho, c_t, gs, dotq, dots;
@@ -822,14 +962,16 @@ struct EpiGrad {
   static __device__ __noinline__ float4 fused_row_stats(const Params& p, int prob, int M, int row, float gs, bool publish) {
     float rho, c_t;
     const int r = prob * M + row;
-    const float4* pp = p.partial + static_cast<int64_t>(r) * p.sslots;
+    const bool sym = p.sslots_sym1 > 0 && *reinterpret_cast<const volatile int*>(p.sym_off) == 0;
+    const int nslots = sym ? (prob == 0 ? p.sslots_sym0 : p.sslots_sym1) : p.sslots;
+    const float4* pp = p.partial + static_cast<int64_t>(r) * p.pstride;
     float lv[32];
     float bw = p.elem_mode ? -1.f : 0.f, be = 1.f;
     int bidx = -1;
 #pragma unroll
     for (int s = 0; s < 32; ++s) {
       lv[s] = 0.f;
-      if (s < p.sslots) {
+      if (s < nslots) {
         const float4 q = pp[s];
         lv[s] = q.x;
         const int idx = __float_as_int(q.w);
@@ -875,8 +1017,13 @@ struct EpiGrad {
         const float w_a = l, w_b = p.floor * ltot * static_cast<float>(N - 1);
         const bool take_a = bidx >= 0 && u_mix * (w_a + w_b) < w_a;
         if (take_a) {
-          const __half* src = p.Pm + static_cast<int64_t>(r) * p.ldp + bidx * 32;
           float v[32], pre[32];
+          if (sym && prob == 1) {  // the chunk is 32 consecutive ROWS of the shared buffer at column `row`
+            const __half* src = p.Pm + static_cast<int64_t>(bidx) * 32 * p.ldp + row;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = (bidx * 32 + i < N) ? __half2float(src[static_cast<int64_t>(i) * p.ldp]) : 0.f;
+          } else {
+          const __half* src = p.Pm + static_cast<int64_t>(r) * p.ldp + bidx * 32;
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8) {
             uint4 u = make_uint4(0, 0, 0, 0);
@@ -888,6 +1035,7 @@ struct EpiGrad {
               v[8 * g8 + 2 * j] = f.x;
               v[8 * g8 + 2 * j + 1] = f.y;
             }
+          }
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -1058,6 +1206,8 @@ struct EpiGrad {
       if (p.step_ctr_rw) *p.step_ctr_rw += 1;
       *p.ticket = 0;  // the step leaves its flag block as it found it (all zero): see VAST_OMC_WORKSPACE_CLEAN
       *p.ovf_reset = 0;
+      p.ovf_reset[4] = 0;  // z range of the symmetric form (flags[4], flags[5])
+      p.ovf_reset[5] = 0;
     }
   }
 };
@@ -1286,10 +1436,13 @@ __global__ void __launch_bounds__(FINAL_THREADS) omc_final_kernel(const float* _
 
 // ------------------------------------------------------------------ host orchestration
 struct OmcPlan {
-  tc::GemmShape g_s;   // S GEMMs
-  tc::GemmShape g_dq;  // dQ GEMM
+  tc::GemmShape g_s;    // S GEMMs (two problems)
+  tc::GemmShape g_sym;  // the symmetric single-rank S GEMM (one problem)
+  tc::GemmShape g_dq;   // dQ GEMM
   int bn_dq;
   int slots;
+  int slots_sym, mblk_sym;  // symmetric form: slots per cond2t row, 128-row blocks = slots per t2cond row (0: not applicable)
+  int pstride;              // partial slots allocated per row
   int nslab, ncs;
   int nslab_pp, ctiles_pp;  // fused pack + prep (single rank): PP_ROWS-row slabs x 128-column tiles
   int64_t npad;
@@ -1439,6 +1592,16 @@ static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, bool
   tc::fill_shape(&pl->g_s, 2, (int)bs, (int)n_total, (int)dim, 256, 1, 1, false, cl);
   tc::choose_splits(&pl->g_s, sms, 32, 1);
   pl->slots = pl->g_s.n_splits * 2;  // NE = 8 -> two column halves per split
+  pl->slots_sym = pl->mblk_sym = 0;
+  pl->pstride = pl->slots;
+  if (bs == n_total && tc::ceil_div_i((int)bs, tc::BM) <= 32) {
+    tc::fill_shape(&pl->g_sym, 1, (int)bs, (int)n_total, (int)dim, 256, 1, 1, false, cl);
+    tc::choose_splits(&pl->g_sym, sms, 16, 1);
+    pl->slots_sym = pl->g_sym.n_splits * 2;
+    pl->mblk_sym = tc::ceil_div_i((int)bs, tc::BM);
+    if (pl->slots_sym > pl->pstride) pl->pstride = pl->slots_sym;
+    if (pl->mblk_sym > pl->pstride) pl->pstride = pl->mblk_sym;
+  }
   pl->npad = static_cast<int64_t>(align_up(static_cast<size_t>(n_total), 8));
   pl->nslab = ceil_div((int)n_total, PREP_ROWS);
   pl->ncs = pl->nslab * ceil_div(2 * (int)dim, 256);
@@ -1466,7 +1629,7 @@ static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, bool
   pl->ctiles_pp = ceil_div((int)dim, 128);
   pl->off_flags = take(sizeof(int) * (FLAG_INTS + pl->nslab_pp));  // flags, then one ticket per pack+prep slab
   pl->off_ztpart = take(sizeof(float) * n_total * pl->ctiles_pp);
-  pl->off_partial = take(sizeof(float4) * 2 * bs * pl->slots);
+  pl->off_partial = take(sizeof(float4) * 2 * bs * pl->pstride);
   pl->off_spartial = take(sizeof(float2) * 2 * bs * pl->slots);  // statistics pass (its readers overlap the soft pass's writers)
   pl->off_ref2 = take(sizeof(float) * 2 * bs);
   pl->off_zt = take(sizeof(float) * 2 * bs);
@@ -1544,6 +1707,13 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
   float* dots = reinterpret_cast<float*>(ws + pl.off_dots);
   // K3 folded into the dQ GEMM's epilogue whenever that GEMM assembles the gradient itself (no split-K)
   const bool fused_stats = need_grad && pl.g_dq.k_splits == 1 && pl.slots <= 32 && (flags & VAST_OMC_SEPARATE_ROW_STATS) == 0;
+  // Symmetric single-rank form (see EpiSoft<false, true>): one S GEMM problem instead of two.  Needs the fused
+  // pack + prep kernel (it publishes the batch's largest target logit) and the fused statistics in the dQ epilogue.
+  static const bool sym_enabled = [] {
+    const char* e = getenv("VAST_OMC_SYM");
+    return e == nullptr || e[0] != '0';
+  }();
+  const bool sym = sym_enabled && feat_t_in != nullptr && !two_pass && fused_stats && pl.mblk_sym > 0 && pl.slots_sym <= 32;
   __half* pack16 = need_grad ? reinterpret_cast<__half*>(ws + pl.off_k16) : nullptr;
 
   const auto* pk = static_cast<const __nv_bfloat16*>(pack);
@@ -1562,7 +1732,7 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
   VAST_TIMED(stream, "omc_pack_prep",                                                                                           \
              (launch_ex(omc_pack_prep_kernel<T>, grid, 256, 0, stream, 1, static_cast<const T*>(feat_t_in),                     \
                         static_cast<const T*>(feat_cond_in), ld_in, N, D, pl.nslab_pp, pl.ctiles_pp, pko, pack16, ksump, ksum, \
-                        ztpart, zt, ref2_or_null, kLog2e * inv_tau, contra_temp_dev, wflags, wflags + FLAG_INTS)))
+                        ztpart, zt, ref2_or_null, kLog2e * inv_tau, contra_temp_dev, wflags, wflags + FLAG_INTS, sym ? 1 : 0)))
     if (in_dtype == VAST_F32)
       VAST_PACK_PREP(float);
     else if (in_dtype == VAST_BF16)
@@ -1620,7 +1790,7 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
     P.epi.P = Pbuf;
     P.epi.ldp = pl.npad;
     P.epi.partial = partial;
-    P.epi.num_slots = pl.slots;
+    P.epi.num_slots = pl.pstride;
     P.epi.scale2 = kLog2e * inv_tau;
     P.epi.temp_dev = contra_temp_dev;
     P.epi.floor = weight_floor;
@@ -1647,13 +1817,23 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
     return tc::launch_gemm<EpiSoft<false>, 256, 4, 8>(P, stream, gate ? "omc_soft_gemm_gated" : "omc_soft_gemm");
   };
 
+  auto run_soft_sym = [&]() -> int {
+    using E = EpiSoft<false, true>;
+    tc::KernelParams<E::Params> P;
+    fill_soft(P, nullptr, &wflags[0], false);
+    P.g = pl.g_sym;  // the cond2t problem only: tmA[0] = local cond rows, tmB[0] = all t rows
+    P.epi.ref2_out = ref2;
+    P.epi.zmax_bits = reinterpret_cast<const unsigned*>(&wflags[4]);
+    return tc::launch_gemm<E, 256, 4, 8>(P, stream, "omc_soft_gemm_sym", E::SMEM_BYTES);
+  };
+
   if (two_pass) {
     rc = run_stats(nullptr);
     if (rc) return rc;
     rc = run_soft(nullptr, nullptr, true);
     if (rc) return rc;
   } else {
-    rc = run_soft(nullptr, &wflags[0], false);  // K2: exponent reference = the positive pair's logit
+    rc = sym ? run_soft_sym() : run_soft(nullptr, &wflags[0], false);  // K2: exponent reference = the positive pair's logit
     if (rc) return rc;
     if (!assume_in_range) {
       rc = run_stats(&wflags[0]);        // the next two launches are no-ops unless the fp16 range overflowed
@@ -1672,6 +1852,7 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
     memset(&R, 0, sizeof(R));
     R.partial = partial;
     R.slots = pl.slots;
+    R.pstride = pl.pstride;
     R.M = M;
     R.N = N;
     R.D = D;
@@ -1735,9 +1916,19 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
       P.epi.grad_t = grad_t;
       P.epi.dotq = dotq;
       P.epi.num_slots = pl.dslots;
+      if (sym) {  // t2cond reads the cond2t Pt buffer through its transposed view unless the fallback flag was raised
+        rc = tc::make_tmap_2d(&P.tmA[tc::MAX_PROBLEMS], Pbuf, VAST_F16, n_total, bs, pl.npad, tc::BK);
+        if (rc) return rc;
+        P.a_mn_prob1 = 2;
+        P.a_mn_off = &wflags[0];
+        P.epi.sslots_sym0 = pl.slots_sym;
+        P.epi.sslots_sym1 = pl.mblk_sym;
+        P.epi.sym_off = &wflags[0];
+      }
       if (fused_stats) {
         P.epi.partial = partial;
         P.epi.sslots = pl.slots;
+        P.epi.pstride = pl.pstride;
         P.epi.ref2 = ref2;
         P.epi.zt = zt;
         P.epi.eps_ls = label_smoothing;

@@ -13,13 +13,6 @@ namespace vast {
 
 // ------------------------------------------------------------------ sortable keys
 // key = orderable(score) << 32 | (0xFFFFFFFF - index): larger key == better candidate.  0 == empty.
-__device__ __forceinline__ uint32_t f32_orderable(float s) {
-  const uint32_t b = __float_as_uint(s);
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float f32_from_orderable(uint32_t o) {
-  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
-}
 __device__ __forceinline__ uint64_t make_key(float s, uint32_t idx) {
   return (static_cast<uint64_t>(f32_orderable(s)) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - idx);
 }
