@@ -202,7 +202,8 @@ template <class Epi, int BN, int STAGES, int NE, bool B_MN, int CL, int A_RES = 
 __global__ void __launch_bounds__(64 + 32 * NE + 32 * Epi::kAuxWarps, 1)
 gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
   static_assert(NE == 4 || NE == 8, "4 or 8 epilogue warps");
-  static_assert(BN == 128 || BN == 256, "BN");
+  static_assert(BN == 128 || BN == 256 || BN == 512, "BN");
+  static_assert(BN != 512 || (B_MN && CL == 2 && A_RES == 0), "the 512-wide tile is implemented for CTA pairs with the MN-major B operand");
   static_assert(CL == 1 || CL == 2, "single CTA or CTA pair");
   static_assert(A_RES == 0 || !B_MN, "resident A is implemented for the K-major B operand");
   pdl_trigger();
@@ -213,7 +214,14 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
   using L = SmemLayout<BN, STAGES, CL, A_RES>;
   constexpr int HALVES = NE / 4;
   constexpr int COLS_PER_WARP = BN / HALVES;
-  constexpr uint32_t TMEM_COLS = 2 * BN;
+  // BN = 512: ONE accumulator stage of all 512 TMEM columns, filled by two N = 256 instructions per k-step that share
+  // the A tile -- a quarter less L2 -> SM operand traffic per FLOP than two 256-wide tiles (the mainloops here run into
+  // the L2 request rate, ~12 TB/s, before they run into the tensor pipe) at the price of an epilogue that no longer
+  // overlaps the next tile's MMAs: for GEMMs with one or two tiles per CTA pair and a long K loop (dQ = Pt . K).
+  constexpr int ACC = BN == 512 ? 1 : 2;
+  constexpr int NSUB = BN == 512 ? 2 : 1;
+  constexpr int BNI = BN / NSUB;  // columns of one tcgen05.mma
+  constexpr uint32_t TMEM_COLS = ACC * BN;
   constexpr bool PAIR = CL == 2;
   constexpr bool CUSTOM = HasCustomTiles<Epi>::value && B_MN;  // explicit single-tile work items of any width <= BN
   constexpr bool AMN = HasAmn<Epi>::value && A_RES == 0;      // one problem may read its A operand MN-major
@@ -335,8 +343,8 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
               if constexpr (B_MN) {
                 // a tile of `width` columns: this CTA holds columns [half_n * rank, +half_n) as 64-column boxes (a last,
                 // partly used box is loaded whole: the tensor core reads only the first half_n columns)
-                const int half_n = CUSTOM ? w.width >> 1 : HALF_N;
-                const int nboxes = CUSTOM ? (half_n + 63) >> 6 : HALF_N / 64;
+                const int half_n = (CUSTOM && BN != 512) ? w.width >> 1 : HALF_N;
+                const int nboxes = (CUSTOM && BN != 512) ? (half_n + 63) >> 6 : HALF_N / 64;
                 if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * (L::A_BYTES + static_cast<uint32_t>(nboxes) * (BK * 128)));
                 if (AMN && w.prob == amn_prob) {  // A[m][k] = X[k][m]: two boxes of 64 k-rows x 64 m-columns
                   ptx::tma_load_2d_pair(sa, &P.tmA[MAX_PROBLEMS], &full[stage], w.m_blk * BM, kb * BK);
@@ -344,11 +352,21 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
                 } else {
                   ptx::tma_load_2d_pair(sa, &P.tmA[w.prob], &full[stage], kb * BK, w.m_blk * BM);
                 }
+                if constexpr (BN == 512) {
+                  // per N = 256 instruction this CTA supplies 128 of its 256 columns: boxes (sub, box) at (2 sub + box) * 8 KB
+#pragma unroll
+                  for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+                    for (int nb = 0; nb < 2; ++nb)
+                      ptx::tma_load_2d_pair(sb + (sub * 2 + nb) * (BK * 128), &P.tmB[w.prob], &full[stage],
+                                            t * BN + sub * 256 + cta_rank * 128 + nb * 64, kb * BK);
+                } else {
 #pragma unroll
                 for (int nb = 0; nb < HALF_N / 64; ++nb)
                   if (nb < nboxes)
                     ptx::tma_load_2d_pair(sb + nb * (BK * 128), &P.tmB[w.prob], &full[stage],
                                           w.col_base + t * BN + cta_rank * half_n + nb * 64, kb * BK);
+                }
               } else {
                 if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * L::STAGE_BYTES);
                 ptx::tma_load_2d_pair(sa, &P.tmA[w.prob], &full[stage], kb * BK, w.m_blk * BM);
@@ -403,11 +421,15 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
             constexpr uint64_t B_KSTEP = B_MN ? 128 : 2;
             const uint64_t a_kstep = a_mn ? 128 : 2;
             // a narrower tile of an explicit schedule: the same descriptors, N taken from the item
-            uint32_t idesc = CUSTOM ? ((g.idesc & ~(0x3Fu << 17)) | (static_cast<uint32_t>(w.width >> 3) << 17)) : g.idesc;
+            uint32_t idesc = (CUSTOM && BN != 512) ? ((g.idesc & ~(0x3Fu << 17)) | (static_cast<uint32_t>(w.width >> 3) << 17)) : g.idesc;
             if (a_mn) idesc |= 1u << 15;  // A operand MN-major
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              ptx::umma_f16<CL>(d_tmem, da + a_kstep * k, db + B_KSTEP * k, idesc, (kb > w.kb_begin || k > 0) ? 1u : 0u);
+#pragma unroll
+              for (int sub = 0; sub < NSUB; ++sub)  // BN = 512: two instructions share the A descriptor
+                ptx::umma_f16<CL>(d_tmem + static_cast<uint32_t>(sub * BNI), da + a_kstep * k,
+                                  db + static_cast<uint64_t>(sub) * ((BNI / CL) * BK * 2 >> 4) + B_KSTEP * k, idesc,
+                                  (kb > w.kb_begin || k > 0) ? 1u : 0u);
             }
             ptx::umma_commit<CL>(&empty[stage]);  // frees the smem stage (in both CTAs) once these MMAs retire
             if (++stage == STAGES) {
@@ -416,7 +438,7 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
             }
           }
           ptx::umma_commit<CL>(&tfull[acc]);  // accumulator tile complete (in both CTAs' TMEM)
-          if (++acc == 2) {
+          if (++acc == ACC) {
             acc = 0;
             acc_phase ^= 1;
           }
@@ -480,7 +502,7 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
           else
             ptx::mbar_arrive(&tempty[acc]);
         }
-        if (++acc == 2) {
+        if (++acc == ACC) {
           acc = 0;
           acc_phase ^= 1;
         }
@@ -530,7 +552,7 @@ inline void fill_shape(GemmShape* g, int problems, int M, int N, int K, int BN, 
   g->tail_groups = g->tail_splits = g->tail_tps = 0;
   g->n_sched = 0;
   g->idesc = ptx::umma_idesc_f16(static_cast<uint32_t>(a_fmt), static_cast<uint32_t>(b_fmt), b_mn ? 1u : 0u,
-                                 static_cast<uint32_t>(BM * cl), static_cast<uint32_t>(BN));
+                                 static_cast<uint32_t>(BM * cl), static_cast<uint32_t>(BN > 256 ? 256 : BN));
 }
 
 inline int ceil_div_i(int a, int b) { return (a + b - 1) / b; }

@@ -1607,17 +1607,22 @@ static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, bool
   pl->ncs = pl->nslab * ceil_div(2 * (int)dim, 256);
   pl->bn_dq = dim > 128 ? 256 : 128;
   int cl_dq = cl, max_ks = 4;
+  // (512-wide tiles -- one accumulator stage, the A tile shared by two N = 256 instructions, ONE round of 64 items at the
+  // headline shape instead of 1.73 -> 2 rounds of 128 -- are implemented (gemm_tc_kernel BN = 512) and correct, but
+  // measured slower on B200: 80.0 vs 72.2 us.  A CTA pair sustains the same ~16.8 TFLOP/s whatever the tile width, so
+  // one longer round loses to two shorter ones; opt in with VAST_OMC_DQ=512,2,1.)
   // developer override for tile-shape experiments: VAST_OMC_DQ="bn,cl,max_ks" (0 keeps the default of a field)
   if (const char* e = getenv("VAST_OMC_DQ")) {
     int bn = 0, c = 0, ks = 0;
     if (sscanf(e, "%d,%d,%d", &bn, &c, &ks) >= 1) {
-      if (bn == 128 || bn == 256) pl->bn_dq = bn;
+      if (bn == 128 || bn == 256 || (bn == 512 && cl == 2)) pl->bn_dq = bn;
       if ((c == 1 || c == 2) && c <= cl) cl_dq = c;
       if (ks >= 1) max_ks = ks;
     }
   }
+  if (pl->bn_dq == 512) cl_dq = 2;
   tc::fill_shape(&pl->g_dq, 2, (int)bs, (int)dim, (int)n_total, pl->bn_dq, /*a: fp16*/ 0, /*b: fp16*/ 0, /*b_mn*/ true, cl_dq);
-  tc::choose_splits(&pl->g_dq, sms, 64, max_ks);
+  tc::choose_splits(&pl->g_dq, sms, 64, pl->bn_dq == 512 ? 1 : max_ks);
   size_t off = 0;
   auto take = [&](size_t bytes) {
     off = align_up(off, 256);
@@ -1956,8 +1961,9 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
         P.epi.M_rows = M;
         P.epi.ovf_reset = &wflags[0];
       }
-      rc = pl.bn_dq == 256 ? tc::launch_gemm<EpiGrad, 256, 4, 8, true>(P, stream, "omc_dq_gemm", 128)
-                           : tc::launch_gemm<EpiGrad, 128, 4, 8, true>(P, stream, "omc_dq_gemm", 128);
+      rc = pl.bn_dq == 512   ? tc::launch_gemm_cl<EpiGrad, 512, 4, 8, true, 2>(P, stream, "omc_dq_gemm", 128)
+           : pl.bn_dq == 256 ? tc::launch_gemm<EpiGrad, 256, 4, 8, true>(P, stream, "omc_dq_gemm", 128)
+                             : tc::launch_gemm<EpiGrad, 128, 6, 8, true, 8>(P, stream, "omc_dq_gemm", 128);
       if (rc) return rc;
     } else {  // split-K partials, summed in a fixed order by the reduce kernel
       tc::KernelParams<tc::EpiStore::Params> P;
