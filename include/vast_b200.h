@@ -91,6 +91,19 @@ VAST_API int vast_l2norm(const void* x, int x_dtype, int64_t rows, int64_t dim, 
 VAST_API int vast_l2norm_bwd(const float* grad_y, int64_t ldg, const float* y, int64_t ldy, const float* inv_norm,
                     int64_t rows, int64_t dim, float eps, float* grad_x, int64_t ldgx, vast_stream_t stream);
 
+/* Contra_head / fusion Linear + F.normalize in ONE tensor-core kernel (model/vast.py:221-279; general_module.py:26-31):
+ *   y = x . W^T + bias ;  feat = y / max(|y|_2, eps)
+ * x_op [rows, cols], w_op [dim_out, cols] are packed 16-bit operands (vast_sim_pack_operand: mode BF16 for 16-bit
+ * features and weights, FP32X3 / FP32X2 for fp32-grade results from fp32 inputs; x as_query = 1, W as_query = 0).
+ * The GEMM epilogue adds the bias, stores y and sums its squares; the last tile of every 128-row block to finish
+ * normalises the block in place (still in L2) and writes y [rows, dim_out] f32 (ld ldy), the bf16 copy y16 (ld ld16,
+ * e.g. straight into the all-gather slot; may be NULL) and inv_norm [rows] (may be NULL; saved for the backward,
+ * vast_l2norm_bwd).  Replaces cuBLAS + two normalise kernels + their HBM round trips. */
+VAST_API size_t vast_project_normalize_workspace_bytes(int64_t rows, int64_t dim_out);
+VAST_API int vast_project_normalize(const void* x_op, const void* w_op, int64_t rows, int64_t dim_out, int64_t cols,
+                           const float* bias, float eps, float* y, int64_t ldy, void* y16, int64_t ld16,
+                           float* inv_norm, void* workspace, size_t workspace_bytes, vast_stream_t stream);
+
 /* Pack the two local feature blocks into the 16-bit all-gather send buffer:
  * pack[b, 0:D] = bf16(feat_t[b]), pack[b, D:2D] = bf16(feat_cond[b])   (pack is [bs, 2D]).
  * Replaces the two separate concat_all_gather payloads of model/vast.py:395,404 by one. */
@@ -299,6 +312,17 @@ VAST_API int vast_bucket_by_video(const int32_t* text_idx, const int32_t* video_
 /* out[text, video] = score for every pair (evaluation_mm.py:313); out is pre-zeroed by the caller. */
 VAST_API int vast_scatter_scores(const int32_t* text_idx, const int32_t* video_idx, const float* scores, int64_t n_pairs,
                         float* out, int64_t ld, vast_stream_t stream);
+
+/* Match_head + softmax[:, 1] (model/general_module.py:34-42 Linear -> GELU(erf) -> LayerNorm -> Linear(2);
+ * model/vast.py:378 `F.softmax(self.itm_head(cls), dim=1)[:, 1]`) as one tensor-core GEMM with a fused epilogue:
+ * cls_op [rows, cols], w1_op [hidden, cols] packed 16-bit operands of the cls tokens and of linear1.weight; b1 =
+ * linear1.bias; u_c = linear2.weight[c] * layernorm.weight (c = 0, 1), sum_u_c their sums, v_c = linear2.weight[c] .
+ * layernorm.bias + linear2.bias[c]; eps the LayerNorm epsilon.  LayerNorm followed by a 2-row Linear needs only four
+ * sums per row, so the hidden activations never leave the accumulator.  score [rows] = P(match); logits [rows, 2]
+ * optional. */
+VAST_API int vast_match_head(const void* cls_op, const void* w1_op, int64_t rows, int64_t hidden, int64_t cols,
+                    const float* b1, const float* u0, const float* u1, float sum_u0, float sum_u1, float v0, float v1,
+                    float eps, float* score, float* logits, vast_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Generic tensor-core NT GEMM (unit-test / building block): C[m, n] = alpha * sum_k A[m,k] B[n,k]

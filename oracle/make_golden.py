@@ -269,6 +269,30 @@ def golden_features():
     print("features: feat_vas", tuple(feat.shape))
 
 
+def golden_match_head():
+    """The reference's own Match_head (model/general_module.py:34-42: Linear -> GELU(erf) -> LayerNorm(eps 1e-12) ->
+    Linear(2)) and the score `F.softmax(itm_head(cls), dim=1)[:, 1]` of compute_slice_scores (model/vast.py:378) on
+    seeded cls tokens, fp32, for the real hidden size 768 and a ragged one."""
+    G = R.load().G
+    out = {}
+    for tag, hidden, b in (("h768", 768, 37), ("h96", 96, 130)):
+        torch.manual_seed(11 + hidden)
+        head = G.Match_head(hidden)
+        with torch.no_grad():
+            head.layernorm.weight.copy_(1.0 + 0.1 * torch.randn(hidden))
+            head.layernorm.bias.copy_(0.05 * torch.randn(hidden))
+            cls = torch.randn(b, hidden) * 0.7
+            logits = head(cls)
+            score = F.softmax(logits, dim=1)[:, 1]
+        n = lambda x: x.detach().numpy()
+        out.update({f"{tag}_cls": n(cls), f"{tag}_w1": n(head.linear1.weight), f"{tag}_b1": n(head.linear1.bias),
+                    f"{tag}_gamma": n(head.layernorm.weight), f"{tag}_beta": n(head.layernorm.bias),
+                    f"{tag}_w2": n(head.linear2.weight), f"{tag}_b2": n(head.linear2.bias),
+                    f"{tag}_logits": n(logits), f"{tag}_score": n(score)})
+    np.savez_compressed(os.path.join(GOLD, "match_head.npz"), **out)
+    print("match_head:", out["h768_score"][:4])
+
+
 def golden_evaluate_ret():
     """evaluation_mm.evaluate_ret (evaluation/evaluation_mm.py:171-251) end to end: a stub model that returns
     pre-seeded evaluation dicts per batch (what VAST.forward_ret(compute_loss=False) returns, model/vast.py:468-483),
@@ -328,5 +352,6 @@ if __name__ == "__main__":
     golden_omc_w1()
     golden_retrieval()
     golden_features()
+    golden_match_head()
     golden_evaluate_ret()
     print("golden vectors written to", GOLD)

@@ -70,6 +70,21 @@ def fuse_feature(pooled, weight, bias=None):
     return l2_normalize(y)
 
 
+def match_head(cls, w1, b1, gamma, beta, w2, b2, eps=1e-12):
+    """model/general_module.py:34-42 `Match_head.forward`: linear2(layernorm(gelu(linear1(cls)))) with the reference's
+    erf GELU (:13-17) and torch LayerNorm (biased variance, eps inside the root); returns (logits [b, 2],
+    score [b] = softmax(logits, 1)[:, 1] as used by compute_slice_scores, model/vast.py:378)."""
+    from math import erf, sqrt
+    x = np.asarray(cls, dtype=np.float64) @ np.asarray(w1, dtype=np.float64).T + np.asarray(b1, dtype=np.float64)
+    g = x * 0.5 * (1.0 + np.vectorize(erf)(x / sqrt(2.0)))
+    mu = g.mean(axis=1, keepdims=True)
+    var = ((g - mu) ** 2).mean(axis=1, keepdims=True)
+    h = (g - mu) / np.sqrt(var + eps) * np.asarray(gamma, dtype=np.float64) + np.asarray(beta, dtype=np.float64)
+    z = h @ np.asarray(w2, dtype=np.float64).T + np.asarray(b2, dtype=np.float64)
+    e = np.exp(z - z.max(axis=1, keepdims=True))
+    return z, (e / e.sum(axis=1, keepdims=True))[:, 1]
+
+
 # ----------------------------------------------------------------------------
 # OMC / ITC loss (label-smoothed bidirectional softmax CE) and its backward
 # ----------------------------------------------------------------------------

@@ -23,6 +23,9 @@ SIGNATURES = {
     "vast_pool_concat_bwd": (i32, [vp, i64, i64, vp, i64, i64, i64, i32, vp, i64, i64, i64, i32, vp, i64, i64, i32, vp]),
     "vast_l2norm": (i32, [vp, i32, i64, i64, i64, f32, vp, i64, vp, i64, vp, vp]),
     "vast_l2norm_bwd": (i32, [vp, i64, vp, i64, vp, i64, i64, f32, vp, i64, vp]),
+    "vast_project_normalize_workspace_bytes": (sz, [i64, i64]),
+    "vast_project_normalize": (i32, [vp, vp, i64, i64, i64, vp, f32, vp, i64, vp, i64, vp, vp, sz, vp]),
+    "vast_match_head": (i32, [vp, vp, i64, i64, i64, vp, vp, vp, f32, f32, f32, f32, f32, vp, vp, vp]),
     "vast_pack_pair": (i32, [vp, vp, i32, i64, i64, i64, vp, vp]),
     "vast_pack_pair_push": (i32, [vp, vp, i32, i64, i64, i64, i64, vp, vp, i32, vp]),
     "vast_omc_workspace_bytes": (sz, [i64, i64, i64, i32, i32]),

@@ -1,0 +1,234 @@
+// The two small heads either side of the contrastive path, as tcgen05 GEMMs with fused epilogues:
+//
+//  * vast_project_normalize -- Contra_head / fusion Linear + F.normalize (model/vast.py:221-279):
+//      y = x . W^T + b ;  feat = y / max(|y|_2, eps)
+//    The epilogue adds the bias, stores y and accumulates each row's sum of squares across the item's tiles; the LAST
+//    work item of a 128-row block to finish (ticket) normalises the block in place while it is still in L2 and writes
+//    the bf16 copy straight into the all-gather slot: no separate normalise kernel, no cuBLAS call, no second launch.
+//
+//  * vast_match_head -- Match_head + softmax[:, 1] (model/general_module.py:34-42, model/vast.py:378):
+//      h = GELU(cls . W1^T + b1) ;  z = W2 . LayerNorm(h) + b2 ;  score = softmax(z)[1]
+//    LayerNorm followed by a 2-row Linear needs only four sums per row -- sum h, sum h^2, sum u0 h, sum u1 h with
+//    u_c = W2[c] * gamma -- so the hidden activations never leave the accumulator tile:
+//      z_c = (sum u_c h - mean sum u_c) / sqrt(var + eps) + (W2[c] . beta + b2[c]),  score = 1 / (1 + exp(z_0 - z_1)).
+//
+// Both take PACKED 16-bit operands (vast_sim_pack_operand: a plain bf16 cast, or bf16 splits of fp32 values whose
+// leading cross products give fp32-grade results), so "bf16-in / fp32-accumulate" and "fp32" are the same kernels.
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+namespace vast {
+
+// ------------------------------------------------------------------ projection + L2 normalise
+struct EpiProj {
+  struct Params {
+    const float* bias;   // [N] or nullptr
+    float* y;            // [M][ldy] out: normalised features (fp32)
+    int64_t ldy;
+    __nv_bfloat16* y16;  // [M][ld16] bf16 copy (e.g. the all-gather slot) or nullptr
+    int64_t ld16;
+    float* inv_norm;     // [M] 1 / max(|y|, eps) or nullptr
+    float* sumsq;        // [M][slots] per-item partial sums of squares
+    int slots;           // n_splits * 2
+    int* tickets;        // [m_blocks] zero-initialised
+    int items_per_block; // work items covering one 128-row block (= n_splits)
+    float eps;
+    int N;
+  };
+  static constexpr bool kUnrollChunks = false;
+  static constexpr int kAuxWarps = 0;
+  const Params& p;
+  int* flag;  // shared: this CTA is the last of its row block
+  float ss;
+  __device__ EpiProj(const Params& p_, uint8_t* smem) : p(p_), flag(reinterpret_cast<int*>(smem)) {}
+  __device__ __forceinline__ void item_begin(const tc::ItemCtx&) { ss = 0.f; }
+  __device__ __forceinline__ void prefetch(const tc::ItemCtx&, int) {}
+  __device__ __forceinline__ void advance(const tc::ItemCtx&, int, bool) {}
+  __device__ __forceinline__ void chunk(const tc::ItemCtx& c, const uint32_t (&v)[32], int col0) {
+    if (!c.row_valid || col0 >= c.N) return;
+    float* dst = p.y + static_cast<int64_t>(c.row) * p.ldy + col0;
+    const bool vec = (col0 + 32 <= c.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    if (vec) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float4 o;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+        o.x = __uint_as_float(v[i]) + b.x;
+        o.y = __uint_as_float(v[i + 1]) + b.y;
+        o.z = __uint_as_float(v[i + 2]) + b.z;
+        o.w = __uint_as_float(v[i + 3]) + b.w;
+        ss = fmaf(o.x, o.x, ss);
+        ss = fmaf(o.y, o.y, ss);
+        ss = fmaf(o.z, o.z, ss);
+        ss = fmaf(o.w, o.w, ss);
+        *reinterpret_cast<float4*>(dst + i) = o;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < c.N) {
+          const float o = __uint_as_float(v[i]) + (p.bias != nullptr ? __ldg(p.bias + col0 + i) : 0.f);
+          ss = fmaf(o, o, ss);
+          dst[i] = o;
+        }
+    }
+  }
+  // every epilogue thread, once per item: publish the partial, then the last item of the row block normalises it
+  __device__ __forceinline__ void item_end(const tc::ItemCtx& c) {
+    if (c.row_valid) p.sumsq[static_cast<int64_t>(c.row) * p.slots + c.slot] = ss;
+    __threadfence();
+    asm volatile("bar.sync 2, 256;" ::: "memory");  // the 8 epilogue warps
+    const int ew = (static_cast<int>(threadIdx.x) >> 5) - 2;
+    if (ew == 0 && c.lane == 0)  // (the odd CTA of the last pair may own no rows at all)
+      *flag = (c.m_blk * tc::BM < c.M) ? (atomicAdd(p.tickets + c.m_blk, 1) == p.items_per_block - 1) : 0;
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    if (*flag == 0) return;
+    __threadfence();
+    const int row0 = c.m_blk * tc::BM;
+    for (int r = ew; r < tc::BM; r += 8) {  // one warp per row, rows strided over the 8 warps
+      const int row = row0 + r;
+      if (row >= c.M) break;
+      // the row's sum of squares: slots in ascending order (fixed order: deterministic), every lane the same value
+      float tot = 0.f;
+      for (int sl = 0; sl < p.slots; ++sl) tot += __ldcg(p.sumsq + static_cast<int64_t>(row) * p.slots + sl);
+      const float inv = 1.0f / fmaxf(sqrtf(tot), p.eps);
+      float* yr = p.y + static_cast<int64_t>(row) * p.ldy;
+      const bool vec = (p.N % 4 == 0) && ((reinterpret_cast<uintptr_t>(yr) & 15) == 0) &&
+                       (p.y16 == nullptr || (reinterpret_cast<uintptr_t>(p.y16 + static_cast<int64_t>(row) * p.ld16) & 7) == 0);
+      if (vec) {
+        for (int d = c.lane * 4; d < p.N; d += 128) {
+          float4 x = __ldcg(reinterpret_cast<const float4*>(yr + d));
+          x.x *= inv; x.y *= inv; x.z *= inv; x.w *= inv;
+          *reinterpret_cast<float4*>(yr + d) = x;
+          if (p.y16 != nullptr) {
+            const __nv_bfloat162 a = __floats2bfloat162_rn(x.x, x.y), b = __floats2bfloat162_rn(x.z, x.w);
+            uint2 u;
+            u.x = *reinterpret_cast<const uint32_t*>(&a);
+            u.y = *reinterpret_cast<const uint32_t*>(&b);
+            *reinterpret_cast<uint2*>(p.y16 + static_cast<int64_t>(row) * p.ld16 + d) = u;
+          }
+        }
+      } else {
+        for (int d = c.lane; d < p.N; d += 32) {
+          const float x = __ldcg(yr + d) * inv;
+          yr[d] = x;
+          if (p.y16 != nullptr) p.y16[static_cast<int64_t>(row) * p.ld16 + d] = __float2bfloat16_rn(x);
+        }
+      }
+      if (c.lane == 0 && p.inv_norm != nullptr) p.inv_norm[row] = inv;
+    }
+    if (ew == 0 && c.lane == 0) p.tickets[c.m_blk] = 0;  // leave the ticket block clean
+  }
+};
+
+// ------------------------------------------------------------------ Match_head + softmax[:, 1]
+struct EpiMatch {
+  struct Params {
+    const float* b1;  // [H]
+    const float* u0;  // [H] W2[0] * gamma
+    const float* u1;  // [H] W2[1] * gamma
+    float U0, U1;     // sum u_c
+    float v0, v1;     // W2[c] . beta + b2[c]
+    float eps;
+    float* score;     // [M] softmax(z)[1]
+    float* logits;    // [M][2] or nullptr
+  };
+  static constexpr bool kUnrollChunks = false;
+  static constexpr int kAuxWarps = 0;
+  const Params& p;
+  float s1, s2, t0, t1;
+  __device__ EpiMatch(const Params& p_, uint8_t*) : p(p_) {}
+  __device__ __forceinline__ void item_begin(const tc::ItemCtx&) { s1 = s2 = t0 = t1 = 0.f; }
+  __device__ __forceinline__ void prefetch(const tc::ItemCtx&, int) {}
+  __device__ __forceinline__ void advance(const tc::ItemCtx&, int, bool) {}
+  __device__ __forceinline__ void chunk(const tc::ItemCtx& c, const uint32_t (&v)[32], int col0) {
+    if (col0 >= c.N) return;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int col = col0 + i;
+      if (col < c.N) {
+        const float h = __uint_as_float(v[i]) + __ldg(p.b1 + col);
+        const float g = h * 0.5f * (1.0f + erff(h * 0.70710678118654752f));  // the reference's erf GELU (general_module.py:13-17)
+        s1 += g;
+        s2 = fmaf(g, g, s2);
+        t0 = fmaf(__ldg(p.u0 + col), g, t0);
+        t1 = fmaf(__ldg(p.u1 + col), g, t1);
+      }
+    }
+  }
+  __device__ __forceinline__ void item_end(const tc::ItemCtx& c) {
+    if (!c.row_valid) return;
+    const float inv_h = 1.0f / static_cast<float>(c.N);
+    const float mu = s1 * inv_h;
+    const float var = fmaxf(s2 * inv_h - mu * mu, 0.f);
+    const float rs = rsqrtf(var + p.eps);
+    const float z0 = (t0 - mu * p.U0) * rs + p.v0, z1 = (t1 - mu * p.U1) * rs + p.v1;
+    p.score[c.row] = 1.0f / (1.0f + expf(z0 - z1));
+    if (p.logits != nullptr) {
+      p.logits[2 * c.row] = z0;
+      p.logits[2 * c.row + 1] = z1;
+    }
+  }
+};
+
+}  // namespace vast
+
+using namespace vast;
+
+extern "C" size_t vast_project_normalize_workspace_bytes(int64_t rows, int64_t dim_out) {
+  if (rows <= 0 || dim_out <= 0) return 0;
+  const int64_t slots = 2 * ceil_div64(dim_out, 256);
+  return align_up(sizeof(float) * rows * slots, 256) + align_up(sizeof(int) * (ceil_div64(rows, tc::BM) + 1), 256);
+}
+
+extern "C" int vast_project_normalize(const void* x_op, const void* w_op, int64_t rows, int64_t dim_out, int64_t cols,
+                                      const float* bias, float eps, float* y, int64_t ldy, void* y16, int64_t ld16,
+                                      float* inv_norm, void* workspace, size_t workspace_bytes, vast_stream_t stream) {
+  VAST_REQUIRE(x_op && w_op && y && workspace, VAST_ERR_INVALID, "project_normalize: null pointer");
+  VAST_REQUIRE(rows > 0 && dim_out > 0 && cols > 0 && rows < (1 << 30) && dim_out <= 16384, VAST_ERR_INVALID,
+               "project_normalize: bad sizes");
+  VAST_REQUIRE(cols % 8 == 0, VAST_ERR_UNSUPPORTED, "project_normalize: operand width must be a multiple of 8");
+  VAST_REQUIRE(ldy >= dim_out && (y16 == nullptr || ld16 >= dim_out), VAST_ERR_INVALID, "project_normalize: bad leading dimension");
+  VAST_REQUIRE(workspace_bytes >= vast_project_normalize_workspace_bytes(rows, dim_out), VAST_ERR_WORKSPACE,
+               "project_normalize: workspace too small");
+  using Epi = EpiProj;
+  tc::KernelParams<Epi::Params> P;
+  memset(&P, 0, sizeof(P));
+  const int cl = tc::pick_cluster((int)rows);
+  tc::fill_shape(&P.g, 1, (int)rows, (int)dim_out, (int)cols, 256, 1, 1, false, cl);
+  // one work item per (row-block group, 256-column tile): as many items as the shape offers, no K split
+  P.g.n_splits = P.g.n_tiles;
+  P.g.tiles_per_split = 1;
+  P.g.num_items = P.g.m_groups * P.g.n_splits;
+  int rc = tc::make_tmap_2d(&P.tmA[0], x_op, VAST_BF16, rows, cols, cols, tc::BM);
+  if (rc) return rc;
+  rc = tc::make_tmap_2d(&P.tmB[0], w_op, VAST_BF16, dim_out, cols, cols, 256 / cl);
+  if (rc) return rc;
+  const int slots = 2 * P.g.n_splits;
+  char* ws = static_cast<char*>(workspace);
+  float* sumsq = reinterpret_cast<float*>(ws);
+  int* tickets = reinterpret_cast<int*>(ws + align_up(sizeof(float) * rows * slots, 256));
+  VAST_CUDA_OK(cudaMemsetAsync(tickets, 0, sizeof(int) * P.g.m_blocks, stream));
+  P.epi = {bias, y, ldy, static_cast<__nv_bfloat16*>(y16), ld16, inv_norm, sumsq, slots, tickets, P.g.n_splits, eps, (int)dim_out};
+  return tc::launch_gemm<Epi, 256, 4, 8>(P, stream, "project_normalize_gemm", 16);
+}
+
+extern "C" int vast_match_head(const void* cls_op, const void* w1_op, int64_t rows, int64_t hidden, int64_t cols,
+                               const float* b1, const float* u0, const float* u1, float sum_u0, float sum_u1, float v0,
+                               float v1, float eps, float* score, float* logits, vast_stream_t stream) {
+  VAST_REQUIRE(cls_op && w1_op && b1 && u0 && u1 && score, VAST_ERR_INVALID, "match_head: null pointer");
+  VAST_REQUIRE(rows > 0 && hidden > 0 && cols > 0 && rows < (1 << 30) && hidden <= 16384, VAST_ERR_INVALID, "match_head: bad sizes");
+  VAST_REQUIRE(cols % 8 == 0, VAST_ERR_UNSUPPORTED, "match_head: operand width must be a multiple of 8");
+  using Epi = EpiMatch;
+  tc::KernelParams<Epi::Params> P;
+  memset(&P, 0, sizeof(P));
+  const int cl = tc::pick_cluster((int)rows);
+  tc::fill_shape(&P.g, 1, (int)rows, (int)hidden, (int)cols, 256, 1, 1, false, cl);  // one item per row-block group: all tiles
+  int rc = tc::make_tmap_2d(&P.tmA[0], cls_op, VAST_BF16, rows, cols, cols, tc::BM);
+  if (rc) return rc;
+  rc = tc::make_tmap_2d(&P.tmB[0], w1_op, VAST_BF16, hidden, cols, cols, 256 / cl);
+  if (rc) return rc;
+  P.epi = {b1, u0, u1, sum_u0, sum_u1, v0, v1, eps, score, logits};
+  return tc::launch_gemm<Epi, 256, 4, 4>(P, stream, "match_head_gemm");
+}

@@ -126,6 +126,71 @@ def l2norm_bwd(grad_y, y, inv_norm, eps: float = 1e-12):
     return gx
 
 
+def pair_sim(a_dtype, b_dtype, mode: str | None) -> int:
+    """packed-operand mode of a GEMM on tensors of these dtypes: 'bf16' forces the plain cast (bf16-in / fp32-
+    accumulate); otherwise values must survive exactly or to fp32 grade -- bf16 is exact in one bf16 term, fp16 needs two
+    terms (3 products), fp32 three (6 products)."""
+    if mode == "bf16":
+        return _lib.SIM_BF16
+    if torch.float32 in (a_dtype, b_dtype):
+        return _lib.SIM_FP32X3
+    if torch.float16 in (a_dtype, b_dtype):
+        return _lib.SIM_FP32X2
+    return _lib.SIM_BF16
+
+
+def _pack(t: torch.Tensor, sim: int, as_query: bool) -> torch.Tensor:
+    x = t if t.dtype in (torch.float32, torch.bfloat16) else t.float()
+    return sim_pack_operand(x.contiguous(), sim, as_query)
+
+
+def project_normalize(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None, eps: float = 1e-12,
+                      mode: str | None = None, out16: torch.Tensor | None = None, w_op: torch.Tensor | None = None):
+    """F.normalize(x @ weight.T + bias, dim=-1) in one tensor-core kernel (vast_project_normalize).
+    x [rows, K], weight [D, K]; mode None: fp32-grade for fp32 / fp16 inputs (bf16 splits), exact bf16 products for bf16
+    inputs; 'bf16': inputs rounded to bf16 (bf16-in / fp32-accumulate).  out16: optional bf16 [rows, >= D] slot (any row
+    stride) that receives the bf16 copy.  w_op: the weight already packed (cache it across calls).
+    Returns (feat f32 [rows, D], inv_norm f32 [rows], w_op)."""
+    require_cuda(x, weight)
+    assert x.dim() == 2 and weight.dim() == 2 and x.shape[1] == weight.shape[1] and x.shape[1] % 8 == 0
+    rows, dim_out = x.shape[0], weight.shape[0]
+    sim = pair_sim(x.dtype, weight.dtype, mode)
+    x_op = _pack(x, sim, True)
+    if w_op is None or w_op.shape[1] != x_op.shape[1]:
+        w_op = _pack(weight.detach(), sim, False)
+    y = torch.empty(rows, dim_out, dtype=torch.float32, device=x.device)
+    inv = torch.empty(rows, dtype=torch.float32, device=x.device)
+    b = None if bias is None else bias.detach().float().contiguous()
+    if out16 is not None:
+        assert out16.dtype == torch.bfloat16 and out16.stride(1) == 1 and out16.shape[0] == rows and out16.shape[1] >= dim_out
+    ws = _ws(lib().vast_project_normalize_workspace_bytes(rows, dim_out), x.device)
+    check(lib().vast_project_normalize(ptr(x_op), ptr(w_op), rows, dim_out, x_op.shape[1], ptr(b), float(eps), ptr(y), dim_out,
+                                       ptr(out16), out16.stride(0) if out16 is not None else 0, ptr(inv), ptr(ws),
+                                       ws.numel(), stream_ptr()), "project_normalize")
+    return y, inv, w_op
+
+
+def match_head(cls: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, u0: torch.Tensor, u1: torch.Tensor, sum_u0: float,
+               sum_u1: float, v0: float, v1: float, eps: float, mode: str | None = None, w1_op: torch.Tensor | None = None,
+               want_logits: bool = False):
+    """softmax(Linear2(LayerNorm(GELU(Linear1(cls)))))[:, 1] in one tensor-core kernel (vast_match_head); the LayerNorm
+    and the 2-row Linear are folded into u_c / sum_u_c / v_c (see include/vast_b200.h).  Returns (score [b], logits
+    [b, 2] | None, w1_op)."""
+    require_cuda(cls, w1, b1, u0, u1)
+    assert cls.dim() == 2 and cls.shape[1] == w1.shape[1] and cls.shape[1] % 8 == 0
+    rows, hidden = cls.shape[0], w1.shape[0]
+    sim = pair_sim(cls.dtype, w1.dtype, mode)
+    c_op = _pack(cls, sim, True)
+    if w1_op is None or w1_op.shape[1] != c_op.shape[1]:
+        w1_op = _pack(w1.detach(), sim, False)
+    score = torch.empty(rows, dtype=torch.float32, device=cls.device)
+    logits = torch.empty(rows, 2, dtype=torch.float32, device=cls.device) if want_logits else None
+    check(lib().vast_match_head(ptr(c_op), ptr(w1_op), rows, hidden, c_op.shape[1], ptr(b1), ptr(u0), ptr(u1), float(sum_u0),
+                                float(sum_u1), float(v0), float(v1), float(eps), ptr(score), ptr(logits), stream_ptr()),
+          "match_head")
+    return score, logits, w1_op
+
+
 def pack_pair(feat_t: torch.Tensor, feat_cond: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     """[bs, 2D] bf16 = (feat_t | feat_cond): the single all-gather payload."""
     require_cuda(feat_t, feat_cond)
