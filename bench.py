@@ -284,6 +284,9 @@ def full_path_bench(torch, vast_b200, ops, peaks, dev, bs, kern_us):
         ms_l2 = event_time(torch, lambda: ops.l2norm(x, out16=slot[:, :DIM]), flush=flush)
         ms_gather = event_time(torch, lambda: ops.gather_rows_concat3(ids, mask, ids, mask, cond, cond, neg[0], neg[1]), iters=5, flush=flush)
         ms_lin = event_time(torch, lambda: head_vas(pooled), flush=flush)
+        w_op = ops._pack(head_vas.weight.detach(), ops.SIM_BF16, False)
+        ms_proj = event_time(torch, lambda: ops.project_normalize(pooled, head_vas.weight, head_vas.bias, out16=slot[:, :DIM], w_op=w_op),
+                             flush=flush)
         ms_full = event_time(torch, step, iters=5, flush=flush)
     hbm = []
     for name, by, ms_k, shape in (
@@ -299,8 +302,11 @@ def full_path_bench(torch, vast_b200, ops, peaks, dev, bs, kern_us):
     full = {"workload": f"pool+concat -> Linear(2944,{DIM}) -> normalise (cond side), cls -> Linear(768,{DIM}) -> normalise (text side) "
                         f"-> fused contrastive step -> negative gather + 3-way concat; bs {bs}, 1 GPU, bf16 encoder outputs, L2 flushed",
             "ms_per_step": round(ms_full, 4), "value": bs / (ms_full * 1e-3), "unit": "pairs/s",
-            "stages_us": {"pool_concat": round(ms_pool * 1e3, 1), "fusion_linear_cublas": round(ms_lin * 1e3, 1),
-                          "l2norm": round(ms_l2 * 1e3, 1), "negative_gather_concat3": round(ms_gather * 1e3, 1)},
+            "stages_us": {"pool_concat": round(ms_pool * 1e3, 1),
+                          "project_normalize_fused (what the path runs: Linear + bias + L2 normalise + bf16 slot, one kernel)": round(ms_proj * 1e3, 1),
+                          "for comparison: fusion_linear_cublas": round(ms_lin * 1e3, 1), "for comparison: l2norm": round(ms_l2 * 1e3, 1),
+                          "negative_gather_concat3": round(ms_gather * 1e3, 1)},
+            "project_normalize_tflops": round(2.0 * bs * 2944 * DIM / (ms_proj * 1e-3) / 1e12, 1),
             "note": "the [3bs, S, 768] concat for the ITM head is compulsory HBM traffic larger than everything else on the path "
                     "(SURVEY 7); the contrastive step itself is the headline metric"}
     del vis, aud, sub, cap, cond, flush
