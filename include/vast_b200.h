@@ -201,6 +201,27 @@ VAST_API int vast_gather_rows_concat3(const int64_t* ids_local, const int64_t* m
                              int64_t bs, int64_t n_total, int64_t* ids_out, int64_t* mask_out, void* cond_out,
                              vast_stream_t stream);
 
+/* Negative gather + 3-way concat with the negative condition rows read STRAIGHT FROM THEIR OWNER RANKS over NVLink
+ * peer memory (replaces `all_gather_with_grad(condition_feats)` of the whole [N, S, 768] tensor,
+ * model/vast.py:422 + utils/distributed.py:12-47, followed by the index of :432-433):
+ * cond_peers[world] (HOST array) = every rank's [rows_per_rank, S*H] block in symmetric memory (this rank's own
+ * included); global row j lives on rank j / rows_per_rank.  Otherwise as vast_gather_rows_concat3. */
+VAST_API int vast_gather_rows_concat3_peer(const int64_t* ids_local, const int64_t* mask_local, const int64_t* ids_all,
+                                  const int64_t* mask_all, int64_t L, const void* cond_local, void* const* cond_peers,
+                                  int world, int64_t rows_per_rank, int64_t row_bytes_cond, const int64_t* neg_text,
+                                  const int64_t* neg_cond, int64_t bs, int64_t* ids_out, int64_t* mask_out,
+                                  void* cond_out, vast_stream_t stream);
+
+/* Its backward: out[l] = base_grad[l] (optional) + sum of grad_peers[e / bs][e % bs] over all requests e (ascending:
+ * fixed fp32 summation order) with requests[e] == row0 + l.  requests [world * bs] int64 = the all-gathered negative
+ * indices of all ranks; grad_peers[world] (HOST array) = every rank's [bs, S*H] gradient block of its fetched rows in
+ * symmetric memory; rows of `dtype`, row_bytes % 16 == 0.  The gradients travel once, to the owner only (the
+ * reference all-reduces a [W, bs, S, 768] tensor to keep one slice). */
+VAST_API size_t vast_pull_row_grads_workspace_bytes(int64_t bs);
+VAST_API int vast_pull_row_grads(const int64_t* requests, void* const* grad_peers, int world, int64_t bs, int64_t row0,
+                        int64_t row_bytes, int dtype, const void* base_grad, void* out, void* workspace,
+                        size_t workspace_bytes, vast_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Retrieval scoring   (evaluation/evaluation_mm.py:223,253-380)
  * ---------------------------------------------------------------------------------------- */

@@ -33,6 +33,9 @@ SIGNATURES = {
     "vast_omc_step_local": (i32, [vp, vp, i32, i64, vp, i64, i64, f32, vp, f32, f32, u64, u64, vp, vp, i32, vp, vp, vp, vp, vp, vp,
                                   vp, sz, vp]),
     "vast_gather_rows_concat3": (i32, [vp, vp, vp, vp, i64, vp, vp, i64, vp, vp, i64, i64, vp, vp, vp, vp]),
+    "vast_gather_rows_concat3_peer": (i32, [vp, vp, vp, vp, i64, vp, vp, i32, i64, i64, vp, vp, i64, vp, vp, vp, vp]),
+    "vast_pull_row_grads_workspace_bytes": (sz, [i64]),
+    "vast_pull_row_grads": (i32, [vp, vp, i32, i64, i64, i64, i32, vp, vp, vp, sz, vp]),
     "vast_sim_operand_cols": (i64, [i64, i32]),
     "vast_sim_pack_operand": (i32, [vp, i32, i64, i64, i64, i32, i32, vp, vp]),
     "vast_sim_topk_workspace_bytes": (sz, [i64, i64, i64, i64]),

@@ -119,6 +119,45 @@ class _GatherConcat3(torch.autograd.Function):
         return g_local, g_all, None, None, None, None, None, None
 
 
+class _PeerGatherConcat3(torch.autograd.Function):
+    """cat(cond, cond_all[neg_cond], cond) with the negative rows read from their owners over peer memory and the
+    gradients pulled back by the owners: no [N, S, H] all-gather, no index exchange in the forward, no
+    host synchronisation in either direction."""
+
+    @staticmethod
+    def forward(ctx, cond_local, ids_local, mask_local, ids_all, mask_all, neg_text, neg_cond, pr):
+        ptrs = pr.publish(cond_local.detach(), "fwd")
+        ids1, att1, cond3 = ops.gather_rows_concat3_peer(ids_local, mask_local, ids_all, mask_all, cond_local.detach(), ptrs,
+                                                         pr.bs, neg_text, neg_cond)
+        ctx.save_for_backward(neg_cond)
+        ctx.pr = pr
+        ctx.mark_non_differentiable(ids1, att1)
+        return ids1, att1, cond3
+
+    @staticmethod
+    def backward(ctx, _g1, _g2, g):
+        (neg_cond,) = ctx.saved_tensors
+        pr = ctx.pr
+        bs = neg_cond.shape[0]
+        g = g.contiguous()
+        base = g[:bs] + g[2 * bs:]                                   # the two copies of the local rows
+        ptrs = pr.publish(g[bs:2 * bs], "bwd")
+        req = torch.empty(pr.world * bs, dtype=torch.int64, device=g.device)
+        dist.all_gather_into_tensor(req, neg_cond.contiguous())
+        gx = ops.pull_row_grads(req, ptrs, bs, pr.rank * bs, g[:bs], base_grad=base)
+        return gx, None, None, None, None, None, None, None
+
+
+def gather_negatives_peer(cond_local, ids_local, mask_local, ids_all, mask_all, neg_text, neg_cond):
+    """`gather_negatives` for world_size > 1 without ever gathering condition_feats: returns None when peer memory is
+    unavailable (the caller falls back to `exchange_rows` + `gather_negatives`)."""
+    from .peer import peer_rows
+    pr = peer_rows(cond_local.shape[0], cond_local.shape[1:], cond_local.dtype, cond_local.device)
+    if pr is None or (cond_local[0].numel() * cond_local.element_size()) % 16 != 0:
+        return None
+    return _PeerGatherConcat3.apply(cond_local, ids_local, mask_local, ids_all, mask_all, neg_text, neg_cond, pr)
+
+
 def gather_negatives(cond_local, cond_all, ids_local, mask_local, ids_all, mask_all, neg_text, neg_cond):
     """(input_ids_1 [3bs,L], attention_mask_1 [3bs,L], condition_feats [3bs,S,H])  -- vast.py:429-448."""
     return _GatherConcat3.apply(cond_local, cond_all, ids_local, mask_local, ids_all, mask_all, neg_text, neg_cond)
@@ -155,7 +194,14 @@ def forward_ret(self, batch, task, compute_loss=True):
         loss, neg_text, neg_cond = omc_loss_and_negatives(feat_cond, feat_t, self.contra_temp)
         loss_itc.append(loss)
         condition_feats = self.batch_get(batch, f'condition_feats_{t[1:]}')
+        peer_out = None
         if NEGATIVE_ROW_EXCHANGE and _world() > 1:
+            # the sampled rows come straight from their owners' symmetric-memory blocks into the [3bs, S, H] ITM input
+            peer_out = gather_negatives_peer(condition_feats, input_ids, attention_mask, input_ids_collate,
+                                             attention_mask_collate, neg_text, neg_cond)
+        if peer_out is not None:
+            input_ids_1, attention_mask_1, condition_feats_3 = peer_out
+        elif NEGATIVE_ROW_EXCHANGE and _world() > 1:
             cond_neg = exchange_rows(condition_feats, neg_cond)          # [bs, S, H]: only the sampled rows travel
             own = torch.arange(cond_neg.shape[0], dtype=torch.int64, device=cond_neg.device)
             input_ids_1, attention_mask_1, condition_feats_3 = gather_negatives(

@@ -687,6 +687,237 @@ extern "C" int vast_pack_pair_push(const void* feat_t, const void* feat_cond, in
   return VAST_OK;
 }
 
+// ------------------------------------------------------------------ negative rows straight from their owners
+// The sampled negative of local row b is global row j = neg_cond[b] of the rank-ordered batch: rank j / rows_per_rank
+// holds it at local index j % rows_per_rank.  Every rank keeps its [rows_per_rank, S, H] block in symmetric memory
+// (mapped into all ranks of the node), so the middle third of the [3bs, S, H] ITM input is read over NVLink from the
+// owner's block directly into its final place: no all-gather of the whole [N, S, H] tensor with gradient
+// (model/vast.py:422), no index exchange, no intermediate buffer, no host synchronisation.
+struct PeerSrc {
+  const uint4* base[PUSH_MAX_PEERS];
+};
+__global__ void __launch_bounds__(GATHER_THREADS) gather_cond3_peer_kernel(const uint4* __restrict__ cond_local, PeerSrc peers,
+                                                                          const int64_t* __restrict__ neg_cond, int64_t bs,
+                                                                          int64_t rows_per_rank, int world, int64_t row_vecs,
+                                                                          uint4* __restrict__ out) {
+  const int64_t r = blockIdx.y;
+  const uint4* src;
+  uint4* dst0 = out + r * row_vecs;
+  uint4* dst1 = nullptr;
+  if (r < bs) {
+    src = cond_local + r * row_vecs;
+    dst1 = out + (r + 2 * bs) * row_vecs;
+  } else {
+    int64_t j = neg_cond[r - bs];
+    const int64_t n_total = rows_per_rank * world;
+    j = j < 0 ? 0 : (j >= n_total ? n_total - 1 : j);
+    const int owner = static_cast<int>(j / rows_per_rank);
+    src = peers.base[owner] + (j - owner * rows_per_rank) * row_vecs;
+  }
+  const int64_t chunk = static_cast<int64_t>(GATHER_THREADS) * GATHER_UNROLL;
+  for (int64_t base = blockIdx.x * chunk; base < row_vecs; base += gridDim.x * chunk) {
+    uint4 v[GATHER_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GATHER_UNROLL; ++u) {
+      const int64_t i = base + u * GATHER_THREADS + threadIdx.x;
+      if (i < row_vecs) v[u] = ld_stream16(src + i);
+    }
+#pragma unroll
+    for (int u = 0; u < GATHER_UNROLL; ++u) {
+      const int64_t i = base + u * GATHER_THREADS + threadIdx.x;
+      if (i < row_vecs) {
+        st_stream16(dst0 + i, v[u]);
+        if (dst1) st_stream16(dst1 + i, v[u]);
+      }
+    }
+  }
+}
+
+// Backward of the peer gather: the gradient of this rank's rows = sum of the gradient rows of every request that named
+// them.  requests [world * bs] = the all-gathered neg_cond of all ranks (request e = rank e / bs, row e % bs); the
+// requesters' gradient blocks [bs, S, H] sit in symmetric memory.  Kernel 1 lists, per local row, the requests that
+// target it in ASCENDING order (so the fp32 sums below run in a fixed order: deterministic); kernel 2 pulls and adds.
+constexpr int PULL_CAP = 16;
+__global__ void __launch_bounds__(128) pull_list_kernel(const int64_t* __restrict__ requests, int64_t n_req, int64_t row0,
+                                                       int64_t rows, int* __restrict__ counts, int* __restrict__ lists) {
+  const int64_t l = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (l >= rows) return;
+  const int lane = threadIdx.x & 31;
+  int cnt = 0;
+  for (int64_t e0 = 0; e0 < n_req; e0 += 32) {
+    const int64_t e = e0 + lane;
+    const bool hit = e < n_req && requests[e] == row0 + l;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      const int at = cnt + __popc(m & ((1u << lane) - 1u));
+      if (at < PULL_CAP) lists[l * PULL_CAP + at] = static_cast<int>(e);
+    }
+    cnt += __popc(m);
+  }
+  if (lane == 0) counts[l] = cnt;
+}
+template <class T>
+__device__ __forceinline__ void acc8(float (&a)[8], const uint4& v);
+template <>
+__device__ __forceinline__ void acc8<__nv_bfloat16>(float (&a)[8], const uint4& v) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    a[2 * j] += __uint_as_float(w[j] << 16);
+    a[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+  }
+}
+template <>
+__device__ __forceinline__ void acc8<__half>(float (&a)[8], const uint4& v) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(h[j]);
+    a[2 * j] += f.x;
+    a[2 * j + 1] += f.y;
+  }
+}
+// T = 16-bit element (8 per 16-byte vector) or float (4 per vector); out = base (optional, same dtype) + pulled sum
+template <class T>
+__global__ void __launch_bounds__(GATHER_THREADS) pull_rows_kernel(PeerSrc peers, const int64_t* __restrict__ requests,
+                                                                  int64_t n_req, int64_t bs, int64_t row0,
+                                                                  const int* __restrict__ counts, const int* __restrict__ lists,
+                                                                  const uint4* __restrict__ base_grad, int64_t row_vecs,
+                                                                  uint4* __restrict__ out) {
+  const int64_t l = blockIdx.y;
+  const int cnt = counts[l];
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(GATHER_THREADS) + threadIdx.x; i < row_vecs;
+       i += static_cast<int64_t>(gridDim.x) * GATHER_THREADS) {
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (base_grad != nullptr) {
+      const uint4 v = ld_stream16(base_grad + l * row_vecs + i);
+      if constexpr (sizeof(T) == 4) {
+        a[0] = __uint_as_float(v.x); a[1] = __uint_as_float(v.y); a[2] = __uint_as_float(v.z); a[3] = __uint_as_float(v.w);
+      } else {
+        acc8<T>(a, v);
+      }
+    }
+    auto add = [&](int e) {
+      const uint4 v = ld_stream16(peers.base[e / bs] + (e % bs) * row_vecs + i);
+      if constexpr (sizeof(T) == 4) {
+        a[0] += __uint_as_float(v.x); a[1] += __uint_as_float(v.y); a[2] += __uint_as_float(v.z); a[3] += __uint_as_float(v.w);
+      } else {
+        acc8<T>(a, v);
+      }
+    };
+    const int listed = cnt < PULL_CAP ? cnt : PULL_CAP;
+    for (int q = 0; q < listed; ++q) add(lists[l * PULL_CAP + q]);
+    if (cnt > PULL_CAP) {  // more requests than the list holds (a row sampled > 16 times): rescan, still ascending
+      int seen = 0;
+      for (int64_t e = 0; e < n_req; ++e)
+        if (requests[e] == row0 + l && seen++ >= PULL_CAP) add(static_cast<int>(e));
+    }
+    uint4 o;
+    if constexpr (sizeof(T) == 4) {
+      o = make_uint4(__float_as_uint(a[0]), __float_as_uint(a[1]), __float_as_uint(a[2]), __float_as_uint(a[3]));
+    } else if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+      uint32_t* w = &o.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a[2 * j], a[2 * j + 1]);
+        w[j] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+    } else {
+      uint32_t* w = &o.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __half2 h = __floats2half2_rn(a[2 * j], a[2 * j + 1]);
+        w[j] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+    }
+    st_stream16(out + l * row_vecs + i, o);
+  }
+}
+
+extern "C" int vast_gather_rows_concat3_peer(const int64_t* ids_local, const int64_t* mask_local, const int64_t* ids_all,
+                                             const int64_t* mask_all, int64_t L, const void* cond_local,
+                                             void* const* cond_peers, int world, int64_t rows_per_rank,
+                                             int64_t row_bytes_cond, const int64_t* neg_text, const int64_t* neg_cond,
+                                             int64_t bs, int64_t* ids_out, int64_t* mask_out, void* cond_out,
+                                             vast_stream_t stream) {
+  VAST_REQUIRE(bs >= 0 && rows_per_rank >= bs && world >= 1 && world <= PUSH_MAX_PEERS && cond_peers != nullptr, VAST_ERR_INVALID,
+               "gather_rows_concat3_peer: bad arguments");
+  if (bs == 0) return VAST_OK;
+  VAST_REQUIRE(cond_local && cond_out && neg_cond, VAST_ERR_INVALID, "gather_rows_concat3_peer: null cond pointer");
+  VAST_REQUIRE(row_bytes_cond > 0 && row_bytes_cond % 16 == 0, VAST_ERR_UNSUPPORTED,
+               "gather_rows_concat3_peer: S*H*elem_bytes (%lld) must be a multiple of 16", (long long)row_bytes_cond);
+  VAST_REQUIRE(2 * bs <= 65535, VAST_ERR_UNSUPPORTED, "gather_rows_concat3_peer: bs too large");
+  PeerSrc ps;
+  for (int r = 0; r < PUSH_MAX_PEERS; ++r) ps.base[r] = nullptr;
+  uintptr_t bits = reinterpret_cast<uintptr_t>(cond_local) | reinterpret_cast<uintptr_t>(cond_out);
+  for (int r = 0; r < world; ++r) {
+    VAST_REQUIRE(cond_peers[r] != nullptr, VAST_ERR_INVALID, "gather_rows_concat3_peer: null peer pointer %d", r);
+    ps.base[r] = static_cast<const uint4*>(cond_peers[r]);
+    bits |= reinterpret_cast<uintptr_t>(cond_peers[r]);
+  }
+  VAST_REQUIRE((bits & 15) == 0, VAST_ERR_INVALID, "gather_rows_concat3_peer: cond pointers must be 16-byte aligned");
+  const int64_t row_vecs = row_bytes_cond / 16;
+  const int64_t chunk = GATHER_THREADS * GATHER_UNROLL;
+  int64_t gx = ceil_div64(row_vecs, chunk);
+  if (gx > 64) gx = 64;
+  dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(2 * bs));
+  gather_cond3_peer_kernel<<<grid, GATHER_THREADS, 0, stream>>>(static_cast<const uint4*>(cond_local), ps, neg_cond, bs, rows_per_rank,
+                                                                world, row_vecs, static_cast<uint4*>(cond_out));
+  VAST_LAUNCH_OK("gather_cond3_peer");
+  if (ids_out || mask_out) {
+    VAST_REQUIRE(ids_out && mask_out && ids_local && mask_local && ids_all && mask_all && neg_text && L > 0,
+                 VAST_ERR_INVALID, "gather_rows_concat3_peer: null ids/mask pointer");
+    gather_ids3_kernel<<<grid_for(3 * bs * L, 256), 256, 0, stream>>>(ids_local, mask_local, ids_all, mask_all, neg_text, bs,
+                                                                      rows_per_rank * world, L, ids_out, mask_out);
+    VAST_LAUNCH_OK("gather_ids3");
+  }
+  return VAST_OK;
+}
+
+extern "C" size_t vast_pull_row_grads_workspace_bytes(int64_t bs) {
+  return bs > 0 ? align_up(sizeof(int) * bs, 256) + align_up(sizeof(int) * bs * PULL_CAP, 256) : 0;
+}
+
+extern "C" int vast_pull_row_grads(const int64_t* requests, void* const* grad_peers, int world, int64_t bs, int64_t row0,
+                                   int64_t row_bytes, int dtype, const void* base_grad, void* out, void* workspace,
+                                   size_t workspace_bytes, vast_stream_t stream) {
+  VAST_REQUIRE(requests && grad_peers && out && workspace && world >= 1 && world <= PUSH_MAX_PEERS && bs > 0, VAST_ERR_INVALID,
+               "pull_row_grads: bad arguments");
+  VAST_REQUIRE(row_bytes > 0 && row_bytes % 16 == 0 && bs <= 65535, VAST_ERR_UNSUPPORTED, "pull_row_grads: row bytes must be a multiple of 16");
+  VAST_REQUIRE(workspace_bytes >= vast_pull_row_grads_workspace_bytes(bs), VAST_ERR_WORKSPACE, "pull_row_grads: workspace too small");
+  PeerSrc ps;
+  for (int r = 0; r < PUSH_MAX_PEERS; ++r) ps.base[r] = nullptr;
+  for (int r = 0; r < world; ++r) {
+    VAST_REQUIRE(grad_peers[r] != nullptr && (reinterpret_cast<uintptr_t>(grad_peers[r]) & 15) == 0, VAST_ERR_INVALID,
+                 "pull_row_grads: bad peer pointer %d", r);
+    ps.base[r] = static_cast<const uint4*>(grad_peers[r]);
+  }
+  int* counts = static_cast<int*>(workspace);
+  int* lists = reinterpret_cast<int*>(static_cast<char*>(workspace) + align_up(sizeof(int) * bs, 256));
+  const int64_t n_req = bs * world;
+  pull_list_kernel<<<static_cast<unsigned>(ceil_div64(bs, 4)), 128, 0, stream>>>(requests, n_req, row0, bs, counts, lists);
+  VAST_LAUNCH_OK("pull_list");
+  const int64_t row_vecs = row_bytes / 16;
+  int64_t gx = ceil_div64(row_vecs, GATHER_THREADS * 4);
+  if (gx > 64) gx = 64;
+  if (gx < 1) gx = 1;
+  dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(bs));
+#define VAST_PULL(T)                                                                                                      \
+  pull_rows_kernel<T><<<grid, GATHER_THREADS, 0, stream>>>(ps, requests, n_req, bs, row0, counts, lists,                  \
+                                                          static_cast<const uint4*>(base_grad), row_vecs, static_cast<uint4*>(out))
+  if (dtype == VAST_F32)
+    VAST_PULL(float);
+  else if (dtype == VAST_BF16)
+    VAST_PULL(__nv_bfloat16);
+  else if (dtype == VAST_F16)
+    VAST_PULL(__half);
+  else
+    VAST_REQUIRE(false, VAST_ERR_UNSUPPORTED, "pull_row_grads: bad dtype");
+#undef VAST_PULL
+  VAST_LAUNCH_OK("pull_rows");
+  return VAST_OK;
+}
+
 extern "C" int vast_gather_rows_concat3(const int64_t* ids_local, const int64_t* mask_local, const int64_t* ids_all,
                                         const int64_t* mask_all, int64_t L, const void* cond_local, const void* cond_all,
                                         int64_t row_bytes_cond, const int64_t* neg_text, const int64_t* neg_cond,

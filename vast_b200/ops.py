@@ -338,6 +338,47 @@ def gather_rows_concat3(ids_local, mask_local, ids_all, mask_all, cond_local, co
     return ids_out, mask_out, cond_out
 
 
+def gather_rows_concat3_peer(ids_local, mask_local, ids_all, mask_all, cond_local, peer_ptrs, rows_per_rank: int, neg_text,
+                             neg_cond):
+    """`gather_rows_concat3` with the negative condition rows read from their owner ranks' symmetric-memory blocks
+    (peer_ptrs: one device address per rank, rank order): vast_gather_rows_concat3_peer."""
+    import ctypes
+    require_cuda(ids_local, mask_local, ids_all, mask_all, cond_local, neg_text, neg_cond)
+    bs, L = ids_local.shape
+    il, ml, ia, ma = ids_local.contiguous(), mask_local.contiguous(), ids_all.contiguous(), mask_all.contiguous()
+    cl = cond_local.contiguous()
+    row_bytes = cl[0].numel() * cl.element_size()
+    world = len(peer_ptrs)
+    ids_out = torch.empty(3 * bs, L, dtype=torch.int64, device=il.device)
+    mask_out = torch.empty(3 * bs, L, dtype=torch.int64, device=il.device)
+    cond_out = torch.empty((3 * bs,) + tuple(cl.shape[1:]), dtype=cl.dtype, device=cl.device)
+    arr = (ctypes.c_void_p * world)(*[int(p) for p in peer_ptrs])
+    check(lib().vast_gather_rows_concat3_peer(ptr(il), ptr(ml), ptr(ia), ptr(ma), L, ptr(cl), arr, world, rows_per_rank, row_bytes,
+                                              ptr(neg_text.contiguous()), ptr(neg_cond.contiguous()), bs, ptr(ids_out),
+                                              ptr(mask_out), ptr(cond_out), stream_ptr()), "gather_rows_concat3_peer")
+    return ids_out, mask_out, cond_out
+
+
+def pull_row_grads(requests: torch.Tensor, peer_ptrs, bs: int, row0: int, like: torch.Tensor, base_grad: torch.Tensor | None = None):
+    """Gradient of this rank's rows from the requesters' symmetric gradient blocks (vast_pull_row_grads): out[l] =
+    base_grad[l] + sum over requests e with requests[e] == row0 + l of block[e // bs][e % bs].  `like` [bs, ...] gives
+    shape / dtype of a block."""
+    import ctypes
+    require_cuda(requests, like)
+    assert requests.dtype == torch.int64 and requests.is_contiguous()
+    world = len(peer_ptrs)
+    out = torch.empty((bs,) + tuple(like.shape[1:]), dtype=like.dtype, device=like.device)
+    row_bytes = out[0].numel() * out.element_size()
+    if base_grad is not None:
+        base_grad = base_grad.contiguous()
+        assert base_grad.shape == out.shape and base_grad.dtype == out.dtype
+    ws = _ws(lib().vast_pull_row_grads_workspace_bytes(bs), like.device)
+    arr = (ctypes.c_void_p * world)(*[int(p) for p in peer_ptrs])
+    check(lib().vast_pull_row_grads(ptr(requests), arr, world, bs, row0, row_bytes, dtype_code(like.dtype), ptr(base_grad),
+                                    ptr(out), ptr(ws), ws.numel(), stream_ptr()), "pull_row_grads")
+    return out
+
+
 # ------------------------------------------------------------------ retrieval scoring
 SIM_BF16, SIM_FP32X3, SIM_FP32X2 = _lib.SIM_BF16, _lib.SIM_FP32X3, _lib.SIM_FP32X2
 TOPK_MAX = 64

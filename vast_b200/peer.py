@@ -64,7 +64,37 @@ class PackedGather:
         return self.bufs[i]
 
 
+class PeerRows:
+    """Per-rank [bs, ...] row blocks in symmetric memory for the negative-row exchange: the forward block
+    (this rank's condition tokens, read by whoever sampled one of its rows) and the backward block (the gradients of the
+    rows this rank fetched, pulled by their owners).  Two buffers of each alternate, one barrier per publish: a rank that
+    is a step ahead never overwrites a block a slower rank is still reading."""
+
+    def __init__(self, bs: int, row_shape, dtype, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.bs, self.row_shape, self.dtype = bs, tuple(row_shape), dtype
+        self.bufs, self.hdls = {"fwd": [], "bwd": []}, {"fwd": [], "bwd": []}
+        for kind in ("fwd", "bwd"):
+            for _ in range(2):
+                b = symm.empty((bs,) + self.row_shape, dtype=dtype, device=device)
+                self.bufs[kind].append(b)
+                self.hdls[kind].append(symm.rendezvous(b, self.group))
+        self.turn = {"fwd": 0, "bwd": 0}
+
+    @torch.no_grad()
+    def publish(self, x: torch.Tensor, kind: str = "fwd"):
+        """copy x [bs, ...] into this rank's block, barrier; returns every rank's block address (rank order)."""
+        i = self.turn[kind]
+        self.turn[kind] = i ^ 1
+        self.bufs[kind][i].copy_(x)
+        self.hdls[kind][i].barrier(channel=0)
+        return [int(p) for p in self.hdls[kind][i].buffer_ptrs]
+
+
 _cache: dict = {}
+_rows_cache: dict = {}
 _available: dict = {}
 
 
@@ -75,6 +105,38 @@ def _single_node(group=None) -> bool:
     if lw is not None:
         return int(lw) == w
     return torch.cuda.device_count() >= w
+
+
+def peer_rows(bs: int, row_shape, dtype, device) -> PeerRows | None:
+    """Cached PeerRows for this block shape, or None (symmetric memory unavailable / VAST_PEER_GATHER=0): the caller then
+    uses the all_to_all exchange.  Collective on first use per shape; the answer is the same on every rank."""
+    if not _enabled():
+        return None
+    key = (bs, tuple(row_shape), dtype, torch.device(device).index)
+    if key not in _rows_cache:
+        _rows_cache[key] = _agree(lambda: PeerRows(bs, row_shape, dtype, torch.device(device)), torch.device(device),
+                                  "peer-memory row exchange", "the all_to_all row exchange")
+    return _rows_cache[key]
+
+
+def _agree(factory, dev, what: str, fallback: str):
+    """run a collective constructor; every rank gets the object or every rank gets None (all-reduce MIN of success)."""
+    obj, err = None, None
+    if _single_node():
+        try:
+            obj = factory()
+        except Exception as e:  # symmetric memory not supported on this system / build
+            err = e
+    else:
+        err = RuntimeError("ranks span more than one node")
+    ok = torch.tensor([1 if obj is not None else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if ok.item() == 0:
+        if dist.get_rank() == 0:
+            import warnings
+            warnings.warn(f"vast_b200: {what} unavailable ({type(err).__name__ if err else 'on another rank'}: {err}); using {fallback}")
+        return None
+    return obj
 
 
 def _build_collectively(bs: int, dim: int, device) -> PackedGather | None:
