@@ -154,6 +154,33 @@ xb = xg.clone().requires_grad_()
 got = vast_b200.exchange_rows(xb, idx)
 (got * wgt).sum().backward()
 ok &= bool(torch.equal(got, ref)) and bool(torch.allclose(xb.grad, xa.grad, atol=1e-5))
+# the same exchange over peer memory, fused into the 3-way concat (what forward_ret uses): values and gradients equal
+# the reference formulation all_gather_with_grad(cond)[neg] -> cat(cond, cond_neg, cond)
+from vast_b200 import contrastive
+S2, H2, L2 = 5, 16, 6
+cond = (torch.randn(bs, S2, H2, generator=gr) + rank).cuda()
+ids_l = torch.randint(0, 1000, (bs, L2), generator=gr).cuda()
+msk_l = torch.ones(bs, L2, dtype=torch.int64).cuda()
+ids_a, msk_a = vast_b200.concat_all_gather(ids_l), vast_b200.concat_all_gather(msk_l)
+neg_t = torch.randint(0, n, (bs,), generator=gr).cuda()
+neg_c = torch.randint(0, n, (bs,), generator=gr).cuda()
+w3 = torch.randn(3 * bs, S2, H2, generator=gr).cuda()
+for it in range(3):                                  # three rounds: both alternating buffers re-used
+    ca = cond.clone().requires_grad_()
+    ref3 = torch.cat((ca, vast_b200.all_gather_with_grad(ca)[neg_c], ca))
+    (ref3 * w3).sum().backward()
+    cb = cond.clone().requires_grad_()
+    got = contrastive.gather_negatives_peer(cb, ids_l, msk_l, ids_a, msk_a, neg_t, neg_c)
+    if got is None:
+        if rank == 0:
+            print("peer row exchange: unavailable", flush=True)
+        break
+    i1, a1, c3 = got
+    (c3 * w3).sum().backward()
+    ok &= bool(torch.equal(c3, ref3)) and bool(torch.allclose(cb.grad, ca.grad, atol=1e-5))
+    ok &= bool(torch.equal(i1, torch.cat((ids_l, ids_l, ids_a[neg_t]))))
+if rank == 0:
+    print("peer row exchange ok:", bool(ok), flush=True)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:

@@ -116,3 +116,44 @@ def test_gather_matches_reference_golden(golden):
     assert np.array_equal(ids1.cpu().numpy(), g["input_ids_1"])
     assert np.array_equal(att1.cpu().numpy(), g["attention_mask_1"])
     assert np.array_equal(cond3.cpu().numpy(), g["condition_feats_3"])
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_peer_row_exchange_emulated_ranks(dtype):
+    """SURVEY 8 f-1 through the C-ABI with the ranks emulated on one GPU (every rank's block is a local buffer, the
+    'peer' pointers are their addresses): vast_gather_rows_concat3_peer == cat(cond, all_gather(cond)[neg], cond), and
+    vast_pull_row_grads == the gradient all_gather_with_grad + index would return, summed in request order."""
+    from vast_b200 import ops
+    world, bs, S, H, L = 3, 40, 7, 24, 5
+    g = torch.Generator().manual_seed(8)
+    blocks = [torch.randn(bs, S, H, generator=g).to(dtype).cuda() for _ in range(world)]
+    allc = torch.cat(blocks)
+    ids_all = torch.randint(0, 1000, (world * bs, L), generator=g).cuda()
+    mask_all = torch.randint(0, 2, (world * bs, L), generator=g).cuda()
+    negs_c = [torch.randint(0, world * bs, (bs,), generator=g).cuda() for _ in range(world)]
+    negs_c[1][:20] = 7                                  # one row requested 20 times by rank 1 (> the 16-entry request list)
+    negs_t = [torch.randint(0, world * bs, (bs,), generator=g).cuda() for _ in range(world)]
+    ptrs = [b.data_ptr() for b in blocks]
+    for r in range(world):
+        sl = slice(r * bs, (r + 1) * bs)
+        ids1, att1, cond3 = ops.gather_rows_concat3_peer(ids_all[sl], mask_all[sl], ids_all, mask_all, blocks[r], ptrs, bs,
+                                                         negs_t[r], negs_c[r])
+        assert torch.equal(cond3, torch.cat([blocks[r], allc[negs_c[r]], blocks[r]]))
+        assert torch.equal(ids1, torch.cat([ids_all[sl], ids_all[sl], ids_all[negs_t[r]]]))
+        assert torch.equal(att1, torch.cat([mask_all[sl], mask_all[sl], mask_all[negs_t[r]]]))
+    # backward: every rank's gradient block of its fetched rows; owners pull
+    gblocks = [torch.randn(bs, S, H, generator=g).to(dtype).cuda() for _ in range(world)]
+    bases = [torch.randn(bs, S, H, generator=g).to(dtype).cuda() for _ in range(world)]
+    req = torch.cat(negs_c)
+    gptrs = [b.data_ptr() for b in gblocks]
+    gall = torch.cat(gblocks).float()
+    for r in range(world):
+        out = ops.pull_row_grads(req, gptrs, bs, r * bs, gblocks[r], base_grad=bases[r])
+        want, want0 = bases[r].float().clone(), torch.zeros_like(bases[r], dtype=torch.float32)
+        for e in range(world * bs):                      # ascending request order, fp32 accumulation
+            j = int(req[e])
+            if r * bs <= j < (r + 1) * bs:
+                want[j - r * bs] += gall[e]
+                want0[j - r * bs] += gall[e]
+        assert torch.equal(out, want.to(dtype))
+        assert torch.equal(ops.pull_row_grads(req, gptrs, bs, r * bs, gblocks[r]), want0.to(dtype))   # no base gradient

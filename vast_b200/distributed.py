@@ -86,7 +86,13 @@ class _ExchangeRows(torch.autograd.Function):
         ctx.single = False
         idx_all = torch.empty(w * bs, dtype=torch.int64, device=idx.device)
         dist.all_gather_into_tensor(idx_all, idx.contiguous())
-        table = idx_all.view(w, bs).cpu()                      # the one host read: W*bs indices -> split sizes
+        # ONE BLOCKING HOST READ per call (W*bs indices -> the all_to_all split sizes): this NCCL form serialises the host
+        # with the stream.  The training path uses the peer-memory form instead (contrastive.gather_negatives_peer:
+        # rows read from their owners' symmetric blocks, no host read); this one remains for multi-node groups and
+        # systems without symmetric memory.
+        table = idx_all.view(w, bs).cpu()
+        if int(table.min()) < 0 or int(table.max()) >= w * bs:
+            raise IndexError(f"exchange_rows: row index outside [0, {w * bs}) (got min {int(table.min())}, max {int(table.max())})")
         owner, local = table // bs, table % bs
         send_rows = [local[p][owner[p] == r] for p in range(w)]   # what rank p wants from me, in its request order
         send_splits = [int(s.numel()) for s in send_rows]
