@@ -415,3 +415,31 @@ def test_assume_in_range_skips_fallback_and_poisons_on_violation(monkeypatch):
     monkeypatch.delenv("VAST_OMC_ASSUME_IN_RANGE")
     o3 = ops.omc_step(pack, n, 0, 0.07, seed=3, offset=1)          # default: the fallback handles it
     assert torch.isfinite(o3["loss"]).item()
+
+
+def test_workspace_cap_refused_cleanly_and_row_chunks_equal_whole(monkeypatch):
+    """The Pt workspace is O(bs * n_total).  Beyond the cap (VAST_OMC_MAX_WS_GB) the C-ABI refuses with
+    VAST_ERR_UNSUPPORTED and a message; the Python op runs the step on row chunks instead -- same loss, gradients, lse and
+    the SAME negatives (Philox words are keyed by the global row) as the whole step."""
+    from vast_b200 import ops
+    n, dim = 1024, 128
+    gen = torch.Generator().manual_seed(12)
+    t = torch.nn.functional.normalize(torch.randn(n, dim, generator=gen), dim=-1)
+    c = torch.nn.functional.normalize(t + 0.8 * torch.randn(n, dim, generator=gen), dim=-1)
+    pack = ops.pack_pair(t.cuda(), c.cuda())
+    whole = ops.omc_step(pack, n, 0, 0.07, seed=9, offset=4, want_lse=True)
+    need = ops.lib().vast_omc_workspace_bytes(n, n, dim, 1, 1)
+    monkeypatch.setenv("VAST_OMC_MAX_WS_GB", str(need / 2 ** 30 / 3))       # a third of what the whole step needs
+    with pytest.raises(RuntimeError, match="VAST_OMC_MAX_WS_GB"):            # the C-ABI itself refuses (status -2), no crash
+        ops.omc_step(pack, n, 0, 0.07, seed=9, offset=4, want_lse=True, buffers=whole)
+    parts = ops.omc_step(pack, n, 0, 0.07, seed=9, offset=4, want_lse=True)
+    assert parts["_ws"][0] is None                                          # went through the chunked path
+    assert torch.equal(parts["neg_idx"], whole["neg_idx"])
+    assert abs(parts["loss"].item() - whole["loss"].item()) < 1e-6 * abs(whole["loss"].item())
+    for k in ("grad_t", "grad_cond", "lse"):
+        assert torch.allclose(parts[k], whole[k], rtol=1e-5, atol=1e-9), k
+    assert abs(parts["grad_temp"].item() - whole["grad_temp"].item()) < 1e-5 * abs(whole["grad_temp"].item())
+    loc = ops.omc_step_local(t.cuda(), c.cuda(), 0.07, seed=9, offset=4)    # the single-rank entry chunks as well
+    assert torch.equal(loc["neg_idx"], whole["neg_idx"]) and torch.allclose(loc["grad_t"], whole["grad_t"], rtol=1e-5, atol=1e-9)
+    o = oracle(t.numpy(), c.numpy(), n, 0, 0.07)
+    check_against_oracle(parts, o, n, 0.07)

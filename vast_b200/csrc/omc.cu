@@ -1692,6 +1692,19 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
   const bool ws_clean = (flags & VAST_OMC_WORKSPACE_CLEAN) != 0;  // flag block already zero: skip the memset node
   OmcPlan pl;
   omc_plan(&pl, bs, n_total, dim, need_sample || need_grad, need_grad);
+  // The softmax numerators Pt are staged ONCE in fp16 ([2, bs, n_total]; the logits are evaluated a single time and
+  // never written) -- O(bs * n_total) bytes.  Beyond the cap the call is refused cleanly instead of attempting a
+  // workspace nobody sized for: any sub-block of the local rows can be processed by itself (bs / row_offset), which
+  // is what vast_b200.ops.omc_step does on its own (row chunks: O(chunk * n_total) workspace, same results).
+  const double cap_gb = [] {
+    const char* e = getenv("VAST_OMC_MAX_WS_GB");
+    const double v = e ? atof(e) : 32.0;
+    return v > 0 ? v : 32.0;
+  }();
+  VAST_REQUIRE(static_cast<double>(pl.total) <= cap_gb * 1073741824.0, VAST_ERR_UNSUPPORTED,
+               "omc_step: bs x n_total = %lld x %lld needs a %.2f GiB workspace, above the cap of %.2f GiB "
+               "(VAST_OMC_MAX_WS_GB); process the local rows in chunks (bs / row_offset select any block of rows) or "
+               "shard them over more ranks", (long long)bs, (long long)n_total, pl.total / 1073741824.0, cap_gb);
   VAST_REQUIRE(workspace_bytes >= pl.total, VAST_ERR_WORKSPACE, "omc_step: workspace %zu < required %zu", workspace_bytes, pl.total);
   VAST_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, VAST_ERR_INVALID, "omc_step: workspace must be 256-byte aligned");
 

@@ -222,6 +222,57 @@ def _omc_flags(two_pass: bool, separate_row_stats: bool | None, buffers: dict | 
         (OMC_ASSUME_IN_RANGE if assume else 0) | (OMC_WORKSPACE_CLEAN if clean else 0)
 
 
+def omc_ws_cap_bytes() -> int:
+    """workspace cap of one vast_omc_step call (VAST_OMC_MAX_WS_GB, default 32 GiB; the library refuses beyond it)."""
+    import os
+    try:
+        gb = float(os.environ.get("VAST_OMC_MAX_WS_GB", "32"))
+    except ValueError:
+        gb = 32.0
+    return int((gb if gb > 0 else 32.0) * (1 << 30))
+
+
+def _omc_step_chunked(pack, bs, row_offset, contra_temp, label_smoothing, weight_floor, seed, offset, need_sample, need_grad,
+                      debug_noise, want_lse, two_pass, step_counter, separate_row_stats):
+    """The step on row chunks when the O(bs * n_total) Pt workspace would exceed the cap: every chunk is a block of the
+    local rows with its own row_offset (the same kernels, the same Philox words -- they are keyed by the global row), the
+    loss / d tau are the row-weighted means of the chunks', gradients scale by chunk / bs.  O(chunk * n_total) workspace."""
+    n_total, dim = pack.shape[0], pack.shape[1] // 2
+    cap = omc_ws_cap_bytes()
+    rows = bs
+    while rows > 128 and lib().vast_omc_workspace_bytes(rows, n_total, dim, int(need_sample), int(need_grad)) > cap:
+        rows = max(128, (rows // 2 + 127) // 128 * 128)
+    if lib().vast_omc_workspace_bytes(rows, n_total, dim, int(need_sample), int(need_grad)) > cap:
+        raise RuntimeError(f"vast_b200.omc_step: even {rows} rows x {n_total} columns exceed the workspace cap "
+                           f"({cap / 2 ** 30:.1f} GiB, VAST_OMC_MAX_WS_GB)")
+    dev = pack.device
+    loss = torch.zeros(1, dtype=torch.float32, device=dev)
+    gtemp = torch.zeros(1, dtype=torch.float32, device=dev) if need_grad else None
+    gc = torch.empty(bs, dim, dtype=torch.float32, device=dev) if need_grad else None
+    gt = torch.empty(bs, dim, dtype=torch.float32, device=dev) if need_grad else None
+    neg = torch.empty(2, bs, dtype=torch.int64, device=dev) if need_sample else None
+    lse = torch.empty(2, bs, dtype=torch.float32, device=dev) if want_lse else None
+    ctr0 = step_counter.clone() if step_counter is not None else None
+    for r0 in range(0, bs, rows):
+        r1 = min(r0 + rows, bs)
+        if ctr0 is not None:
+            step_counter.copy_(ctr0)           # every chunk of one step draws with the same counter
+        o = omc_step(pack, r1 - r0, row_offset + r0, contra_temp, label_smoothing, weight_floor, seed, offset, need_sample,
+                     need_grad, None if debug_noise is None else debug_noise[:, r0:r1].contiguous(), want_lse, None, two_pass,
+                     step_counter, separate_row_stats)
+        w = (r1 - r0) / bs
+        loss += w * o["loss"]
+        if need_grad:
+            gc[r0:r1] = w * o["grad_cond"]
+            gt[r0:r1] = w * o["grad_t"]
+            gtemp += w * o["grad_temp"]
+        if need_sample:
+            neg[:, r0:r1] = o["neg_idx"]
+        if want_lse:
+            lse[:, r0:r1] = o["lse"]
+    return dict(loss=loss, neg_idx=neg, grad_cond=gc, grad_t=gt, grad_temp=gtemp, lse=lse, _ws=(None, None), _clean=False)
+
+
 def omc_step(pack: torch.Tensor, bs: int, row_offset: int, contra_temp, label_smoothing: float = 0.1,
              weight_floor: float = 1e-4, seed: int = 0, offset: int = 0, need_sample: bool = True,
              need_grad: bool = True, debug_noise: torch.Tensor | None = None, want_lse: bool = False,
@@ -243,6 +294,9 @@ def omc_step(pack: torch.Tensor, bs: int, row_offset: int, contra_temp, label_sm
     dev = pack.device
     if debug_noise is not None:
         assert debug_noise.shape == (2, bs, n_total) and debug_noise.dtype == torch.float32 and debug_noise.is_contiguous()
+    if buffers is None and lib().vast_omc_workspace_bytes(bs, n_total, dim, int(need_sample), int(need_grad)) > omc_ws_cap_bytes():
+        return _omc_step_chunked(pack, bs, row_offset, contra_temp, label_smoothing, weight_floor, seed, offset, need_sample,
+                                 need_grad, debug_noise, want_lse, two_pass, step_counter, separate_row_stats)
     if buffers is not None:
         loss, neg, gc, gt, gtemp, lse = (buffers[k] for k in ("loss", "neg_idx", "grad_cond", "grad_t", "grad_temp", "lse"))
         ws = buffers["_ws"][0]
@@ -284,6 +338,12 @@ def omc_step_local(feat_t: torch.Tensor, feat_cond: torch.Tensor, contra_temp, l
     dev = ft.device
     if debug_noise is not None:
         assert debug_noise.shape == (2, bs, bs) and debug_noise.dtype == torch.float32 and debug_noise.is_contiguous()
+    if buffers is None and lib().vast_omc_workspace_bytes(bs, bs, dim, int(need_sample), int(need_grad)) > omc_ws_cap_bytes():
+        pack = pack_pair(ft, fc)               # beyond the workspace cap: packed once, then the step in row chunks
+        out = omc_step(pack, bs, 0, contra_temp, label_smoothing, weight_floor, seed, offset, need_sample, need_grad, debug_noise,
+                       want_lse, None, two_pass, step_counter, separate_row_stats)
+        out["pack"] = pack
+        return out
     if buffers is not None:
         loss, neg, gc, gt, gtemp, lse, pack = (buffers[k] for k in ("loss", "neg_idx", "grad_cond", "grad_t", "grad_temp",
                                                                    "lse", "pack"))
