@@ -403,7 +403,7 @@ struct EpiSoft {
 //                    single-pass form the exponent reference ref2 = z_t * log2(e) / tau for both directions
 // Per 256-column tile, the last slab block to finish (ticket) reduces that tile's slab partials into ksum
 // in a fixed order (deterministic, and the reduction is spread over the column tiles).
-constexpr int PREP_ROWS = 128;
+constexpr int PREP_ROWS = 64;  // 64-row slabs: N / 64 x 2D / 256 blocks (512 at cfg3) are all resident at once; 128-row slabs left 256 blocks = 1.7 waves
 constexpr int FLAG_INTS = 256;  // [0] fp16-range overflow, [1] finalize ticket, [8 + ctile] prep tickets per 256-column tile
 __global__ void __launch_bounds__(256) omc_prep_kernel(const __nv_bfloat16* __restrict__ pack, int n_total, int dim, int bs,
                                                       int row_offset, int ncs, int nslab,
@@ -1623,6 +1623,18 @@ static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, bool
   if (pl->bn_dq == 512) cl_dq = 2;
   tc::fill_shape(&pl->g_dq, 2, (int)bs, (int)dim, (int)n_total, pl->bn_dq, /*a: fp16*/ 0, /*b: fp16*/ 0, /*b_mn*/ true, cl_dq);
   tc::choose_splits(&pl->g_dq, sms, 64, pl->bn_dq == 512 ? 1 : max_ks);
+  if (pl->g_dq.k_splits > 1 && getenv("VAST_OMC_DQ") == nullptr) {
+    // Small per-rank batches (cfg3 on 4 / 8 GPUs: 1024 / 512 rows) do not fill the machine with 256-wide pair tiles and
+    // would split K -- fp32 partials through HBM and a reduce kernel (measured: 25.0 + 16.9 us at 1024 rows, 20.9 +
+    // 16.7 us at 512).  128 x 128 tiles on lone CTAs give 2 x m_blocks x D / 128 whole-K items instead: one kernel with
+    // the gradient assembly, row statistics and final reduction fused (37.3 / 35.2 us), no partial buffer.
+    const int items = 2 * tc::ceil_div_i((int)bs, tc::BM) * tc::ceil_div_i((int)dim, 128);
+    if (dim > 128 && items * 10 >= sms * 3) {
+      pl->bn_dq = 128;
+      tc::fill_shape(&pl->g_dq, 2, (int)bs, (int)dim, (int)n_total, 128, 0, 0, true, 1);
+      tc::choose_splits(&pl->g_dq, sms, 64, 1);
+    }
+  }
   size_t off = 0;
   auto take = [&](size_t bytes) {
     off = align_up(off, 256);
