@@ -210,9 +210,25 @@ def parity_check(torch, dist, ops, world, rank, bs, dev_set, temp, pg):
         worst[1] = -worst[1]
         dist.all_reduce(worst, op=dist.ReduceOp.MAX)          # the worst rank decides
         out.update(grad_rel=worst[0].item(), neg_match=-worst[1].item(), loss_rel=worst[2].item(), grad_temp_rel=worst[3].item())
-        flag = torch.tensor([0 if out["fused_gather_equals_nccl"] in (True, None) else 1], device=local.device)
+        # negative-row exchange over peer memory == all_gather(cond)[neg] -> cat(cond, cond_neg, cond)
+        import vast_b200
+        from vast_b200 import contrastive
+        gp = torch.Generator(device=local.device).manual_seed(77 + rank)
+        cond = torch.randn(bs, 4, 16, generator=gp, device=local.device) + rank
+        ids_l = torch.randint(0, 1000, (bs, 4), generator=gp, device=local.device)
+        ids_a = vast_b200.concat_all_gather(ids_l)
+        neg_t = torch.randint(0, n, (bs,), generator=gp, device=local.device)
+        neg_c = torch.randint(0, n, (bs,), generator=gp, device=local.device)
+        peer = contrastive.gather_negatives_peer(cond, ids_l, ids_l, ids_a, ids_a, neg_t, neg_c)
+        rows_ok = True
+        if peer is not None:
+            want = torch.cat((cond, vast_b200.concat_all_gather(cond)[neg_c], cond))
+            rows_ok = bool(torch.equal(peer[2], want)) and bool(torch.equal(peer[0], torch.cat((ids_l, ids_l, ids_a[neg_t]))))
+        out["peer_row_exchange_equals_all_gather"] = None if peer is None else rows_ok
+        flag = torch.tensor([0 if (out["fused_gather_equals_nccl"] in (True, None) and rows_ok) else 1], device=local.device)
         dist.all_reduce(flag)
-        out["fused_gather_equals_nccl"] = None if pg is None else flag.item() == 0
+        if flag.item() != 0 and out["fused_gather_equals_nccl"] is True and rows_ok:
+            out["fused_gather_equals_nccl"] = "failed on another rank"
         ok = flag.item() == 0 and out["grad_rel"] < 1e-4 and out["neg_match"] > 0.99 and out["loss_rel"] < 1e-5 and \
             out["grad_temp_rel"] < 1e-4
     out["ok"] = bool(ok)
