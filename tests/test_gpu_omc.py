@@ -443,3 +443,42 @@ def test_workspace_cap_refused_cleanly_and_row_chunks_equal_whole(monkeypatch):
     assert torch.equal(loc["neg_idx"], whole["neg_idx"]) and torch.allclose(loc["grad_t"], whole["grad_t"], rtol=1e-5, atol=1e-9)
     o = oracle(t.numpy(), c.numpy(), n, 0, 0.07)
     check_against_oracle(parts, o, n, 0.07)
+
+
+@pytest.mark.parametrize("fused", ["0", "1"])
+@pytest.mark.parametrize("case", ["in_range", "hard_rows", "wide_spread", "small_tau"])
+def test_single_rank_symmetric_form_and_its_fallback(case, fused, monkeypatch):
+    """One rank: the symmetric form (one S GEMM problem for both directions) -- as two kernels (default) or, opt-in, as
+    ONE persistent kernel (omc_fused_gemm_kernel, VAST_OMC_FUSED=1) whose dQ items wait on per-row-block / per-column-
+    tile completion counters.  Range violations -- a negative that beats its positive by more than the fp16 range
+    ('hard_rows', 'small_tau'), or target logits spread over more than 9 log2 units ('wide_spread': half the pairs
+    untrained) -- raise the flag and the gated launches redo the step in the two-pass, two-problem form; either way the
+    result matches the oracle, and the workspace is left clean for the next step."""
+    from vast_b200 import ops
+    monkeypatch.setenv("VAST_OMC_FUSED", fused)
+    n, dim, temp = 2048, 1024, 0.07     # whole-K 256-wide pair tiles: the shape class of the headline (symmetric form in force)
+    gen = torch.Generator().manual_seed(41)
+    t0 = torch.randn(n, dim, generator=gen)
+    t = torch.nn.functional.normalize(t0, dim=-1)
+    c = torch.nn.functional.normalize(t0 + 0.5 * torch.randn(n, dim, generator=gen), dim=-1)   # trained pairs: cosine ~0.89
+    if case == "hard_rows":
+        c[3] = -t[3]
+        c[77] = t[3]
+    elif case == "wide_spread":
+        c[n // 2:] = torch.nn.functional.normalize(torch.randn(n - n // 2, dim, generator=gen), dim=-1)
+    elif case == "small_tau":
+        temp = 0.004
+    seed, offset = 23, 2
+    out = ops.omc_step_local(t.cuda(), c.cuda(), temp, seed=seed, offset=offset, want_lse=True)
+    o = oracle(t.numpy(), c.numpy(), n, 0, temp)
+    check_against_oracle(out, o, n, temp)
+    check_negatives_hier(out["neg_idx"], o, seed, offset, 0, n, n)
+    if case != "in_range":     # the fallback IS the two-pass form
+        ref = ops.omc_step_local(t.cuda(), c.cuda(), temp, seed=seed, offset=offset, want_lse=True, two_pass=True)
+        assert torch.equal(out["grad_t"], ref["grad_t"]) and torch.equal(out["neg_idx"], ref["neg_idx"])
+    # re-use of the (self-cleaned) workspace: a clean step after a fallback step gives the clean step's numbers
+    good_c = torch.nn.functional.normalize(t0 + 0.5 * torch.randn(n, dim, generator=torch.Generator().manual_seed(5)), dim=-1)
+    a = ops.omc_step_local(t.cuda(), good_c.cuda(), 0.07, seed=seed, offset=offset, want_lse=True, buffers=out)
+    b = ops.omc_step_local(t.cuda(), good_c.cuda(), 0.07, seed=seed, offset=offset)
+    torch.cuda.synchronize()
+    assert a["loss"].item() == b["loss"].item() and torch.equal(a["grad_t"], b["grad_t"]) and torch.equal(a["neg_idx"], b["neg_idx"])

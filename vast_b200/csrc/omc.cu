@@ -404,6 +404,7 @@ struct EpiSoft {
 // Per 256-column tile, the last slab block to finish (ticket) reduces that tile's slab partials into ksum
 // in a fixed order (deterministic, and the reduction is spread over the column tiles).
 constexpr int PREP_ROWS = 64;  // 64-row slabs: N / 64 x 2D / 256 blocks (512 at cfg3) are all resident at once; 128-row slabs left 256 blocks = 1.7 waves
+constexpr int DEP_INTS = 64;    // fused S + dQ kernel: done_row[<= 32 row blocks] | done_col[<= 16 column tiles]
 constexpr int FLAG_INTS = 256;  // [0] fp16-range overflow, [1] finalize ticket, [8 + ctile] prep tickets per 256-column tile
 __global__ void __launch_bounds__(256) omc_prep_kernel(const __nv_bfloat16* __restrict__ pack, int n_total, int dim, int bs,
                                                       int row_offset, int ncs, int nslab,
@@ -935,6 +936,9 @@ struct EpiGrad {
     const int* poison;
     int M_rows;
     int* ovf_reset;
+    int* dep_reset;  // fused S + dQ kernel: dependency counters the last CTA clears (or nullptr)
+    int dep_count;
+    int keep_ovf;    // the overflow flag gates fallback launches that FOLLOW this kernel: leave it for them
   };
   static constexpr bool kUnrollChunks = true;  // the operand double buffer lives in registers
   static constexpr int kAuxWarps = 0;
@@ -1198,19 +1202,311 @@ struct EpiGrad {
     }
     sa = warp_sum(sa);
     sb = warp_sum(sb);
+    for (int i = lane; i < p.dep_count; i += 32) p.dep_reset[i] = 0;
     if (lane == 0) {
       float scale = 1.0f / (2.0f * p.M_rows);
       if (p.poison != nullptr && *reinterpret_cast<const volatile int*>(p.poison) != 0) scale = __int_as_float(0x7fc00000);
-      p.loss[0] = sa * scale;
-      p.grad_temp[0] = sb * scale;
-      if (p.step_ctr_rw) *p.step_ctr_rw += 1;
+      const bool redo = p.keep_ovf && *reinterpret_cast<const volatile int*>(p.ovf_reset) != 0;  // fallback launches follow
+      if (!redo) {
+        p.loss[0] = sa * scale;
+        p.grad_temp[0] = sb * scale;
+        if (p.step_ctr_rw) *p.step_ctr_rw += 1;
+      }
       *p.ticket = 0;  // the step leaves its flag block as it found it (all zero): see VAST_OMC_WORKSPACE_CLEAN
-      *p.ovf_reset = 0;
+      if (!p.keep_ovf) *p.ovf_reset = 0;
       p.ovf_reset[4] = 0;  // z range of the symmetric form (flags[4], flags[5])
       p.ovf_reset[5] = 0;
     }
   }
 };
+
+// ------------------------------------------------------------------ K2 + K4 as ONE persistent kernel (one rank, symmetric form)
+// The symmetric S GEMM is 256 tiles on 74 CTA pairs (3.46 -> 4 rounds) and the dQ GEMM 128 tiles (1.73 -> 2 rounds):
+// as two kernels each ends in a partial round, and the second cannot start before the first has drained.  Here both
+// run as one persistent grid over ONE item list -- the 256 S tiles, then the 128 dQ tiles (direction cond2t first) --
+// dealt round-robin: a pair that got 3 S tiles gets 2 dQ tiles, one that got 4 gets 1 or 2, and a pair starts its dQ
+// tiles the moment it is out of S tiles.  A dQ tile needs finished inputs, not a finished kernel:
+//   direction cond2t, row block b : the 16 S tiles of row block b   (its Pt rows + their row partials)  -> done_row[b]
+//   direction t2cond, row block b : the 16 x 2 S tiles of column tile b / 2 (its Pt columns + column partials) -> done_col[b / 2]
+// Every S item ends with fence + barrier + one atomic per counter; the dQ item's TMA producer and epilogue warps spin
+// (acquire, watchdog) on the counter they need, then a generic->async proxy fence orders the TMA reads behind the Pt
+// stores.  No S item ever waits, and every CTA is resident (persistent grid of at most one CTA per SM), so there is no
+// cycle.  Same smem ring, same TMEM double buffer, same mbarriers across both phases; the epilogue warps run
+// EpiSoft<false, true> and then EpiGrad (whose finish hook still ends the step).
+namespace fused {
+constexpr int BN = 256, STAGES = 6, NE = 8, CL = 2;
+using L = tc::SmemLayout<BN, STAGES, CL, 0>;
+using ESoft = EpiSoft<false, true>;
+
+struct alignas(64) Params {
+  CUtensorMap tmSA, tmSB;    // S GEMM: local cond rows (K-major), all t rows (K-major)
+  CUtensorMap tmDA0, tmDA1;  // dQ GEMM A: Pt rows K-major (cond2t), Pt through its transposed view (t2cond: 64 x 64 boxes)
+  CUtensorMap tmDB0, tmDB1;  // dQ GEMM B: fp16 t rows / cond rows, row-major read MN-major
+  tc::GemmShape gs, gd;
+  int* done_row;  // [m_blocks]  S items finished per 128-row block
+  int* done_col;  // [n_tiles]   S item-CTAs finished per 256-column tile
+  int need_row, need_col;
+  ESoft::Params es;
+  EpiGrad::Params eg;
+};
+
+__device__ __forceinline__ void wait_count(const int* ctr, int need) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+  if (v >= need) return;
+  const long long t0 = clock64();
+  do {
+    __nanosleep(64);
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if (clock64() - t0 > 6000000000LL) {
+      printf("vast_b200: dependency watchdog (block %d thread %d have %d need %d)\n", (int)blockIdx.x, (int)threadIdx.x, v, need);
+      __trap();
+    }
+  } while (v < need);
+}
+
+__global__ void __launch_bounds__(64 + 32 * NE, 1) omc_fused_gemm_kernel(const __grid_constant__ Params P) {
+  pdl_trigger();
+  constexpr int HALVES = NE / 4, COLS_PER_WARP = BN / HALVES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 4);
+  uint8_t* epi_smem = smem + L::EPI_OFFSET;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta_rank = static_cast<int>(ptx::cluster_ctarank());
+  const bool leader = cta_rank == 0;
+  const int cluster_id = static_cast<int>(blockIdx.x) / CL, num_clusters = static_cast<int>(gridDim.x) / CL;
+  const tc::GemmShape& gs = P.gs;
+  const tc::GemmShape& gd = P.gd;
+  const int nA = gs.num_items, nB = gd.num_items;
+  // this pair's first dQ item: the round-robin simply continues over the concatenated list
+  const int jB0 = ((cluster_id - nA) % num_clusters + num_clusters) % num_clusters;
+
+  if (warp == 0 && lane == 0) {
+    ptx::tma_prefetch_desc(&P.tmSA);
+    ptx::tma_prefetch_desc(&P.tmSB);
+    ptx::tma_prefetch_desc(&P.tmDA0);
+    ptx::tma_prefetch_desc(&P.tmDA1);
+    ptx::tma_prefetch_desc(&P.tmDB0);
+    ptx::tma_prefetch_desc(&P.tmDB1);
+    for (int st = 0; st < STAGES; ++st) {
+      ptx::mbar_init(&full[st], 1);
+      ptx::mbar_init(&empty[st], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull[a], 1);
+      ptx::mbar_init(&tempty[a], NE * CL);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc<CL>(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish<CL>();
+  }
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto next = [&]() {
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      for (int item = cluster_id; item < nA; item += num_clusters) {
+        const tc::WorkItem w = tc::decode_item<BN>(gs, item, cta_rank);
+        for (int t = w.tile_begin; t < w.tile_end; ++t)
+          for (int kb = 0; kb < gs.k_blocks; ++kb) {
+            ptx::mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * L::STAGE_BYTES;
+            uint8_t* sb = sa + L::A_BYTES;
+            if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * L::STAGE_BYTES);
+            ptx::tma_load_2d_pair(sa, &P.tmSA, &full[stage], kb * tc::BK, w.m_blk * tc::BM);
+            ptx::tma_load_2d_pair(sb, &P.tmSB, &full[stage], kb * tc::BK, t * BN + cta_rank * (BN / 2));
+            next();
+          }
+      }
+      for (int item = jB0; item < nB; item += num_clusters) {
+        const tc::WorkItem w = tc::decode_item<BN>(gd, item, cta_rank);
+        if (w.m_blk * tc::BM < gd.M) {  // inputs of this CTA's rows complete?
+          if (w.prob == 0)
+            wait_count(P.done_row + w.m_blk, P.need_row);
+          else
+            wait_count(P.done_col + (w.m_blk >> 1), P.need_col);
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");  // Pt was written by generic-proxy stores, TMA reads it through the async proxy
+        const CUtensorMap* tb = w.prob == 0 ? &P.tmDB0 : &P.tmDB1;
+        for (int t = w.tile_begin; t < w.tile_end; ++t)
+          for (int kb = 0; kb < gd.k_blocks; ++kb) {
+            ptx::mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * L::STAGE_BYTES;
+            uint8_t* sb = sa + L::A_BYTES;
+            if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * L::STAGE_BYTES);
+            if (w.prob == 0) {
+              ptx::tma_load_2d_pair(sa, &P.tmDA0, &full[stage], kb * tc::BK, w.m_blk * tc::BM);
+            } else {  // A[m][k] = Pt[k][m]: two boxes of 64 k-rows x 64 m-columns
+              ptx::tma_load_2d_pair(sa, &P.tmDA1, &full[stage], w.m_blk * tc::BM, kb * tc::BK);
+              ptx::tma_load_2d_pair(sa + tc::BK * 128, &P.tmDA1, &full[stage], w.m_blk * tc::BM + 64, kb * tc::BK);
+            }
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb)
+              ptx::tma_load_2d_pair(sb + nb * (tc::BK * 128), tb, &full[stage], t * BN + cta_rank * (BN / 2) + nb * 64, kb * tc::BK);
+            next();
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA)
+    if (lane == 0 && leader) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      auto run_tile = [&](int k_blocks, bool a_mn, bool b_mn, uint32_t idesc) {
+        ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t sa = ptx::smem_u32(smem + stage * L::STAGE_BYTES), sb = sa + L::A_BYTES;
+          const uint64_t da = a_mn ? ptx::umma_desc_sw128_mnmajor(sa, tc::BK * 128) : ptx::umma_desc_sw128_kmajor(sa);
+          const uint64_t db = b_mn ? ptx::umma_desc_sw128_mnmajor(sb, tc::BK * 128) : ptx::umma_desc_sw128_kmajor(sb);
+          const uint64_t ak = a_mn ? 128 : 2, bk = b_mn ? 128 : 2;
+#pragma unroll
+          for (int k = 0; k < tc::BK / 16; ++k)
+            ptx::umma_f16<CL>(d_tmem, da + ak * k, db + bk * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          ptx::umma_commit<CL>(&empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ptx::umma_commit<CL>(&tfull[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      };
+      for (int item = cluster_id; item < nA; item += num_clusters) {
+        const tc::WorkItem w = tc::decode_item<BN>(gs, item, cta_rank);
+        for (int t = w.tile_begin; t < w.tile_end; ++t) run_tile(gs.k_blocks, false, false, gs.idesc);
+      }
+      for (int item = jB0; item < nB; item += num_clusters) {
+        const tc::WorkItem w = tc::decode_item<BN>(gd, item, cta_rank);
+        for (int t = w.tile_begin; t < w.tile_end; ++t)
+          run_tile(gd.k_blocks, w.prob == 1, true, w.prob == 1 ? (gd.idesc | (1u << 15)) : gd.idesc);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (both CTAs)
+    const int ew = warp - 2, q = warp & 3, half = ew >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    auto make_ctx = [&](const tc::GemmShape& g, const tc::WorkItem& w) {
+      tc::ItemCtx ctx;
+      ctx.prob = w.prob;
+      ctx.m_blk = w.m_blk;
+      ctx.n_split = w.n_split;
+      ctx.k_split = w.k_split;
+      ctx.row = w.m_blk * tc::BM + q * 32 + lane;
+      ctx.row_valid = ctx.row < g.M;
+      ctx.slot = w.n_split * HALVES + half;
+      ctx.M = g.M;
+      ctx.N = g.N;
+      ctx.lane = lane;
+      ctx.half = half;
+      return ctx;
+    };
+    {
+      ESoft epi(P.es, epi_smem);
+      for (int item = cluster_id; item < nA; item += num_clusters) {
+        const tc::WorkItem w = tc::decode_item<BN>(gs, item, cta_rank);
+        const tc::ItemCtx ctx = make_ctx(gs, w);
+        epi.item_begin(ctx);
+        for (int t = w.tile_begin; t < w.tile_end; ++t) {
+          ptx::mbar_wait(&tfull[acc], acc_phase);
+          ptx::tc_fence_after_sync();
+          for (int c = 0; c < COLS_PER_WARP; c += 32) {
+            const int col_in_tile = half * COLS_PER_WARP + c;
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + col_in_tile), v);
+            ptx::tmem_ld_wait();
+            epi.chunk(ctx, v, t * BN + col_in_tile);
+            __syncwarp();
+          }
+          ptx::tc_fence_before_sync();
+          if (lane == 0) ptx::mbar_arrive_leader(&tempty[acc]);
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+          epi.tile_end(ctx, t * BN, ew, NE);
+        }
+        epi.item_end(ctx);
+        // publish: this CTA's Pt rows x the item's column tiles and their partials are complete
+        __threadfence();
+        asm volatile("bar.sync 3, %0;" ::"r"(NE * 32) : "memory");
+        if (ew == 0 && lane == 0) {
+          if (w.m_blk * tc::BM < gs.M) atomicAdd(P.done_row + w.m_blk, 1);
+          for (int t = w.tile_begin; t < w.tile_end; ++t) atomicAdd(P.done_col + t, 1);
+        }
+      }
+    }
+    {
+      EpiGrad epi(P.eg, epi_smem);
+      for (int item = jB0; item < nB; item += num_clusters) {
+        const tc::WorkItem w = tc::decode_item<BN>(gd, item, cta_rank);
+        const tc::ItemCtx ctx = make_ctx(gd, w);
+        if (w.m_blk * tc::BM < gd.M) {  // the row statistics read the S epilogues' partials of this CTA's rows
+          if (w.prob == 0)
+            wait_count(P.done_row + w.m_blk, P.need_row);
+          else
+            wait_count(P.done_col + (w.m_blk >> 1), P.need_col);
+        }
+        epi.item_begin(ctx);
+        for (int t = w.tile_begin; t < w.tile_end; ++t) {
+          epi.prefetch(ctx, t * BN + half * COLS_PER_WARP);
+          ptx::mbar_wait(&tfull[acc], acc_phase);
+          ptx::tc_fence_after_sync();
+#pragma unroll
+          for (int c = 0; c < COLS_PER_WARP; c += 32) {
+            const int col_in_tile = half * COLS_PER_WARP + c;
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + col_in_tile), v);
+            epi.advance(ctx, t * BN + col_in_tile + 32, c + 32 < COLS_PER_WARP);
+            ptx::tmem_ld_wait();
+            epi.chunk(ctx, v, t * BN + col_in_tile);
+            __syncwarp();
+          }
+          ptx::tc_fence_before_sync();
+          if (lane == 0) ptx::mbar_arrive_leader(&tempty[acc]);
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+        epi.item_end(ctx);
+      }
+      epi.finish(ew, lane, NE);
+    }
+  }
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync_all();
+  if (warp == 1) ptx::tmem_dealloc<CL>(tmem_base, TMEM_COLS);
+}
+}  // namespace fused
 
 // block-level (sum a, sum b) in a fixed order, for 256-thread blocks
 constexpr int FINAL_THREADS = 256;
@@ -1644,7 +1940,7 @@ static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, bool
   };
   pl->nslab_pp = ceil_div((int)n_total, PP_ROWS);
   pl->ctiles_pp = ceil_div((int)dim, 128);
-  pl->off_flags = take(sizeof(int) * (FLAG_INTS + pl->nslab_pp));  // flags, then one ticket per pack+prep slab
+  pl->off_flags = take(sizeof(int) * (FLAG_INTS + pl->nslab_pp + DEP_INTS));  // flags, one ticket per pack+prep slab, dependency counters of the fused S + dQ kernel
   pl->off_ztpart = take(sizeof(float) * n_total * pl->ctiles_pp);
   pl->off_partial = take(sizeof(float4) * 2 * bs * pl->pstride);
   pl->off_spartial = take(sizeof(float2) * 2 * bs * pl->slots);  // statistics pass (its readers overlap the soft pass's writers)
@@ -1744,6 +2040,18 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
     return e == nullptr || e[0] != '0';
   }();
   const bool sym = sym_enabled && feat_t_in != nullptr && !two_pass && fused_stats && pl.mblk_sym > 0 && pl.slots_sym <= 32;
+  // ... and, opt-in (VAST_OMC_FUSED=1), the S and dQ GEMMs of that form as ONE persistent kernel (omc_fused_gemm_kernel).
+  // Built to remove both kernels' partial last rounds; correct (tests run it), but measured SLOWER on B200 at cfg3:
+  // 121.9 us against 41.4 + 75.2 us for the two kernels.  dQ tiles that start whenever their CTA pair runs out of S tiles
+  // no longer walk K in lockstep with the tiles that share their operands, and the L2 stops merging their requests -- the
+  // same effect that sank the stream-K schedule (profiles/r01_v6_streamk_experiment.txt).  The kernel boundary is what
+  // keeps the tiles of a round aligned.
+  const bool fuse_enabled = [] {
+    const char* e = getenv("VAST_OMC_FUSED");
+    return e != nullptr && e[0] == '1';
+  }();
+  const bool fuse = fuse_enabled && sym && pl.g_sym.cl == 2 && pl.g_dq.cl == 2 && pl.bn_dq == 256 && pl.g_dq.k_splits == 1 &&
+                    pl.mblk_sym <= 32 && pl.g_sym.n_tiles <= 16 && getenv("VAST_OMC_DQ") == nullptr;
   __half* pack16 = need_grad ? reinterpret_cast<__half*>(ws + pl.off_k16) : nullptr;
 
   const auto* pk = static_cast<const __nv_bfloat16*>(pack);
@@ -1753,7 +2061,7 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
 
   if (feat_t_in != nullptr) {
     // K0 + K1 in one pass over the fp features (single rank: nothing to gather in between)
-    if (!ws_clean) VAST_CUDA_OK(cudaMemsetAsync(wflags, 0, sizeof(int) * (FLAG_INTS + pl.nslab_pp), stream));
+    if (!ws_clean) VAST_CUDA_OK(cudaMemsetAsync(wflags, 0, sizeof(int) * (FLAG_INTS + pl.nslab_pp + DEP_INTS), stream));
     float* ztpart = reinterpret_cast<float*>(ws + pl.off_ztpart);
     auto* pko = const_cast<__nv_bfloat16*>(pk);
     float* ref2_or_null = two_pass ? nullptr : ref2;
@@ -1857,11 +2165,162 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
     return tc::launch_gemm<E, 256, 4, 8>(P, stream, "omc_soft_gemm_sym", E::SMEM_BYTES);
   };
 
+  // tensor maps of the dQ GEMM: A = Pt (fp16), B = the gathered features' fp16 copy read row-major (MN-major operand)
+  const float c_sm = label_smoothing / static_cast<float>(N);
+  CUtensorMap tmPa[2], tmKb[2], tmPaT;
+  if (need_grad) {
+    for (int i = 0; i < 2; ++i) {
+      rc = tc::make_tmap_2d(&tmPa[i], Pbuf + static_cast<int64_t>(i) * bs * pl.npad, VAST_F16, bs, n_total, pl.npad, tc::BM);
+      if (rc) return rc;
+      rc = tc::make_tmap_2d(&tmKb[i], pack16 + static_cast<int64_t>(i) * dim, VAST_F16, n_total, dim, 2 * dim, tc::BK);
+      if (rc) return rc;
+    }
+    if (sym) {  // t2cond reads the cond2t Pt buffer through its transposed view
+      rc = tc::make_tmap_2d(&tmPaT, Pbuf, VAST_F16, n_total, bs, pl.npad, tc::BK);
+      if (rc) return rc;
+    }
+  }
+  const bool stats_in_reduce = need_grad && pl.g_dq.k_splits > 1 && (flags & VAST_OMC_SEPARATE_ROW_STATS) == 0;
+  auto fill_grad = [&](EpiGrad::Params& e, bool sym_mode) {
+    e.rowstat = rowstat;
+    e.ksum = ksum;
+    e.pack = pk;
+    e.row_offset = static_cast<int>(row_offset);
+    e.D = D;
+    e.inv_tau = inv_tau;
+    e.temp_dev = contra_temp_dev;
+    e.c_sm = c_sm;
+    e.grad_cond = grad_cond;
+    e.grad_t = grad_t;
+    e.dotq = dotq;
+    e.num_slots = pl.dslots;
+    if (sym_mode) {  // in force while the fallback flag is clear
+      e.sslots_sym0 = pl.slots_sym;
+      e.sslots_sym1 = pl.mblk_sym;
+      e.sym_off = &wflags[0];
+    }
+    if (fused_stats) {
+      e.partial = partial;
+      e.sslots = pl.slots;
+      e.pstride = pl.pstride;
+      e.ref2 = ref2;
+      e.zt = zt;
+      e.eps_ls = label_smoothing;
+      e.floor = weight_floor;
+      e.n_total = N;
+      e.neg_idx = neg_idx;
+      e.elem_mode = elem ? 1 : 0;
+      e.Pm = Pbuf;
+      e.ldp = pl.npad;
+      e.seed_lo = static_cast<uint32_t>(seed);
+      e.seed_hi = static_cast<uint32_t>(seed >> 32);
+      e.off_lo = static_cast<uint32_t>(offset);
+      e.off_hi = static_cast<uint32_t>(offset >> 32);
+      e.step_ctr = reinterpret_cast<const unsigned long long*>(step_counter);
+      e.rowstat_out = rowstat;
+      e.lse_out = lse;
+      e.dots = dots;
+      // K5 rides on the GEMM's tail as well
+      e.cta_part = blockpart;
+      e.ticket = &wflags[1];
+      e.loss = loss;
+      e.grad_temp = grad_temp;
+      e.step_ctr_rw = reinterpret_cast<unsigned long long*>(step_counter);
+      e.poison = assume_in_range ? &wflags[0] : nullptr;
+      e.M_rows = M;
+      e.ovf_reset = &wflags[0];
+    }
+  };
+  // the dQ GEMM as a kernel of its own (gate: a no-op unless the flag is set -- the fallback of the fused S + dQ kernel)
+  auto run_dq = [&](const int* gate, bool sym_mode) -> int {
+    tc::KernelParams<EpiGrad::Params> P;
+    memset(&P, 0, sizeof(P));
+    P.g = pl.g_dq;
+    P.gate = gate;
+    // balanced two-round schedule with 256- and 192-wide tiles where the regular tiling leaves a partial wave
+    // (needs the fused statistics / final reduction: no per-slot partial buffers in this form)
+    if (fused_stats && pl.g_dq.cl == 2) plan_mixed_tiles(&P.g, pl.bn_dq, device_sm_count() / 2);
+    for (int i = 0; i < 2; ++i) {
+      P.tmA[i] = tmPa[i];
+      P.tmB[i] = tmKb[i];
+    }
+    if (sym_mode) {
+      P.tmA[tc::MAX_PROBLEMS] = tmPaT;
+      P.a_mn_prob1 = 2;
+      P.a_mn_off = &wflags[0];
+    }
+    fill_grad(P.epi, sym_mode);
+    const char* name = gate ? "omc_dq_gemm_gated" : "omc_dq_gemm";
+    return pl.bn_dq == 512   ? tc::launch_gemm_cl<EpiGrad, 512, 4, 8, true, 2>(P, stream, name, 128)
+           : pl.bn_dq == 256 ? tc::launch_gemm<EpiGrad, 256, 4, 8, true>(P, stream, name, 128)
+                             : tc::launch_gemm<EpiGrad, 128, 6, 8, true, 8>(P, stream, name, 128);
+  };
+  auto run_fused = [&]() -> int {
+    fused::Params F;
+    memset(&F, 0, sizeof(F));
+    F.tmSA = tmA[0];
+    F.tmSB = tmB[0];
+    F.tmDA0 = tmPa[0];
+    F.tmDA1 = tmPaT;
+    F.tmDB0 = tmKb[0];
+    F.tmDB1 = tmKb[1];
+    F.gs = pl.g_sym;
+    F.gd = pl.g_dq;  // one tile per work item, direction cond2t first
+    F.gd.n_splits = F.gd.n_tiles;
+    F.gd.tiles_per_split = 1;
+    F.gd.k_splits = 1;
+    F.gd.kb_per_split = F.gd.k_blocks;
+    F.gd.num_items = F.gd.num_problems * F.gd.m_groups * F.gd.n_splits;
+    F.gd.n_sched = 0;
+    int* dep = wflags + FLAG_INTS + pl.nslab_pp;
+    F.done_row = dep;
+    F.done_col = dep + 32;
+    F.need_row = F.gs.n_splits;
+    F.need_col = F.gs.m_groups * 2;
+    {
+      tc::KernelParams<fused::ESoft::Params> T;
+      fill_soft(T, nullptr, &wflags[0], false);
+      F.es = T.epi;
+      F.es.ref2_out = ref2;
+      F.es.zmax_bits = reinterpret_cast<const unsigned*>(&wflags[4]);
+    }
+    fill_grad(F.eg, true);
+    F.eg.dep_reset = dep;
+    F.eg.dep_count = DEP_INTS;
+    F.eg.keep_ovf = assume_in_range ? 0 : 1;  // the gated fallback launches that follow read the flag
+    const size_t smem = fused::L::EPI_OFFSET + fused::L::ALIGN_SLACK + fused::ESoft::SMEM_BYTES;
+    static bool attr_set = false;
+    if (!attr_set) {
+      VAST_CUDA_OK(cudaFuncSetAttribute(fused::omc_fused_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      attr_set = true;
+    }
+    const int clusters_max = device_sm_count() / 2;
+    const int items = F.gs.num_items + F.gd.num_items;
+    const int clusters = items < clusters_max ? items : clusters_max;
+    VAST_TIMED(stream, "omc_fused_gemm",
+               (launch_ex(fused::omc_fused_gemm_kernel, static_cast<unsigned>(clusters * 2), 64 + 32 * fused::NE, smem, stream, 2, F)));
+    VAST_LAUNCH_OK("omc_fused_gemm");
+    return VAST_OK;
+  };
+
+  bool dq_done = false;
   if (two_pass) {
     rc = run_stats(nullptr);
     if (rc) return rc;
     rc = run_soft(nullptr, nullptr, true);
     if (rc) return rc;
+  } else if (fuse) {
+    rc = run_fused();  // K2 + K4 (+ K3, K5) in one persistent kernel
+    if (rc) return rc;
+    dq_done = true;
+    if (!assume_in_range) {  // three no-ops unless the fp16 range or the target-logit spread was exceeded
+      rc = run_stats(&wflags[0]);
+      if (rc) return rc;
+      rc = run_soft(&wflags[0], nullptr, true);
+      if (rc) return rc;
+      rc = run_dq(&wflags[0], false);
+      if (rc) return rc;
+    }
   } else {
     rc = sym ? run_soft_sym() : run_soft(nullptr, &wflags[0], false);  // K2: exponent reference = the positive pair's logit
     if (rc) return rc;
@@ -1876,7 +2335,6 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
   // K3: row statistics + hard negatives.  Its own kernel only when nothing downstream can host it: with a
   // gradient it runs inside the dQ GEMM's epilogue (fused_stats) or inside the split-K reduce kernel (same
   // warp-per-row layout), both of which are the first consumers of its results.
-  const bool stats_in_reduce = need_grad && pl.g_dq.k_splits > 1 && (flags & VAST_OMC_SEPARATE_ROW_STATS) == 0;
   RowStatParams R;
   {
     memset(&R, 0, sizeof(R));
@@ -1914,81 +2372,9 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
   }
 
   // K4: dQ = Pt . K   (fp16 x fp16, the gathered features as the MN-major operand in their row-major layout)
-  const float c_sm = label_smoothing / static_cast<float>(N);
-  if (need_grad) {
-    CUtensorMap tmPa[2], tmKb[2];
-    for (int i = 0; i < 2; ++i) {
-      rc = tc::make_tmap_2d(&tmPa[i], Pbuf + static_cast<int64_t>(i) * bs * pl.npad, VAST_F16, bs, n_total, pl.npad, tc::BM);
-      if (rc) return rc;
-      rc = tc::make_tmap_2d(&tmKb[i], pack16 + static_cast<int64_t>(i) * dim, VAST_F16, n_total, dim, 2 * dim, tc::BK);
-      if (rc) return rc;
-    }
+  if (need_grad && !dq_done) {
     if (pl.g_dq.k_splits == 1) {  // gradient assembled in the GEMM epilogue
-      tc::KernelParams<EpiGrad::Params> P;
-      memset(&P, 0, sizeof(P));
-      P.g = pl.g_dq;
-      // balanced two-round schedule with 256- and 192-wide tiles where the regular tiling leaves a partial wave
-      // (needs the fused statistics / final reduction: no per-slot partial buffers in this form)
-      if (fused_stats && pl.g_dq.cl == 2) plan_mixed_tiles(&P.g, pl.bn_dq, device_sm_count() / 2);
-      for (int i = 0; i < 2; ++i) {
-        P.tmA[i] = tmPa[i];
-        P.tmB[i] = tmKb[i];
-      }
-      P.epi.rowstat = rowstat;
-      P.epi.ksum = ksum;
-      P.epi.pack = pk;
-      P.epi.row_offset = static_cast<int>(row_offset);
-      P.epi.D = D;
-      P.epi.inv_tau = inv_tau;
-      P.epi.temp_dev = contra_temp_dev;
-      P.epi.c_sm = c_sm;
-      P.epi.grad_cond = grad_cond;
-      P.epi.grad_t = grad_t;
-      P.epi.dotq = dotq;
-      P.epi.num_slots = pl.dslots;
-      if (sym) {  // t2cond reads the cond2t Pt buffer through its transposed view unless the fallback flag was raised
-        rc = tc::make_tmap_2d(&P.tmA[tc::MAX_PROBLEMS], Pbuf, VAST_F16, n_total, bs, pl.npad, tc::BK);
-        if (rc) return rc;
-        P.a_mn_prob1 = 2;
-        P.a_mn_off = &wflags[0];
-        P.epi.sslots_sym0 = pl.slots_sym;
-        P.epi.sslots_sym1 = pl.mblk_sym;
-        P.epi.sym_off = &wflags[0];
-      }
-      if (fused_stats) {
-        P.epi.partial = partial;
-        P.epi.sslots = pl.slots;
-        P.epi.pstride = pl.pstride;
-        P.epi.ref2 = ref2;
-        P.epi.zt = zt;
-        P.epi.eps_ls = label_smoothing;
-        P.epi.floor = weight_floor;
-        P.epi.n_total = N;
-        P.epi.neg_idx = neg_idx;
-        P.epi.elem_mode = elem ? 1 : 0;
-        P.epi.Pm = Pbuf;
-        P.epi.ldp = pl.npad;
-        P.epi.seed_lo = static_cast<uint32_t>(seed);
-        P.epi.seed_hi = static_cast<uint32_t>(seed >> 32);
-        P.epi.off_lo = static_cast<uint32_t>(offset);
-        P.epi.off_hi = static_cast<uint32_t>(offset >> 32);
-        P.epi.step_ctr = reinterpret_cast<const unsigned long long*>(step_counter);
-        P.epi.rowstat_out = rowstat;
-        P.epi.lse_out = lse;
-        P.epi.dots = dots;
-        // K5 rides on the GEMM's tail as well
-        P.epi.cta_part = blockpart;
-        P.epi.ticket = &wflags[1];
-        P.epi.loss = loss;
-        P.epi.grad_temp = grad_temp;
-        P.epi.step_ctr_rw = reinterpret_cast<unsigned long long*>(step_counter);
-        P.epi.poison = assume_in_range ? &wflags[0] : nullptr;
-        P.epi.M_rows = M;
-        P.epi.ovf_reset = &wflags[0];
-      }
-      rc = pl.bn_dq == 512   ? tc::launch_gemm_cl<EpiGrad, 512, 4, 8, true, 2>(P, stream, "omc_dq_gemm", 128)
-           : pl.bn_dq == 256 ? tc::launch_gemm<EpiGrad, 256, 4, 8, true>(P, stream, "omc_dq_gemm", 128)
-                             : tc::launch_gemm<EpiGrad, 128, 6, 8, true, 8>(P, stream, "omc_dq_gemm", 128);
+      rc = run_dq(nullptr, sym);
       if (rc) return rc;
     } else {  // split-K partials, summed in a fixed order by the reduce kernel
       tc::KernelParams<tc::EpiStore::Params> P;
