@@ -173,6 +173,13 @@ template <class E, class = void>
 struct HasTileEnd : std::false_type {};
 template <class E>
 struct HasTileEnd<E, std::void_t<decltype(E::kHasTileEnd)>> : std::integral_constant<bool, E::kHasTileEnd> {};
+// Epilogues with kSecondPass read every accumulator tile TWICE from TMEM: chunk() over the tile, then between()
+// (e.g. a cross-CTA exchange of row statistics), then chunk2() over the same tile -- the accumulator stage is
+// handed back to the MMA issuer only after the second pass.  TMEM reads are cheap; a global re-read is not.
+template <class E, class = void>
+struct HasSecondPass : std::false_type {};
+template <class E>
+struct HasSecondPass<E, std::void_t<decltype(E::kSecondPass)>> : std::integral_constant<bool, E::kSecondPass> {};
 template <class E, class = void>
 struct HasAmn : std::false_type {};
 template <class E>
@@ -494,6 +501,17 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
           ptx::tmem_ld_wait();
           epi.chunk(ctx, v, col_tile + col_in_tile);
           __syncwarp();
+        }
+        if constexpr (HasSecondPass<Epi>::value) {
+          epi.between(ctx);
+          for (int c = 0; c < COLS_PER_WARP; c += 32) {
+            const int col_in_tile = half * cpw + c;
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + col_in_tile), v);
+            ptx::tmem_ld_wait();
+            epi.chunk2(ctx, v, col_tile + col_in_tile);
+            __syncwarp();
+          }
         }
         ptx::tc_fence_before_sync();
         if (lane == 0) {

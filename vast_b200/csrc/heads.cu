@@ -2,9 +2,10 @@
 //
 //  * vast_project_normalize -- Contra_head / fusion Linear + F.normalize (model/vast.py:221-279):
 //      y = x . W^T + b ;  feat = y / max(|y|_2, eps)
-//    The epilogue adds the bias, stores y and accumulates each row's sum of squares across the item's tiles; the LAST
-//    work item of a 128-row block to finish (ticket) normalises the block in place while it is still in L2 and writes
-//    the bf16 copy straight into the all-gather slot: no separate normalise kernel, no cuBLAS call, no second launch.
+//    The epilogue reads the accumulator tile TWICE from TMEM: pass 1 sums the squares of y = acc + b over its 128 rows x
+//    256 columns; the column tiles of a row block exchange those partial sums through a ticket (they run side by
+//    side); pass 2 writes the normalised feature once -- fp32, and the bf16 copy straight into the all-gather slot.
+//    y never reaches HBM unnormalised: no separate normalise kernel, no cuBLAS call, no second launch.
 //
 //  * vast_match_head -- Match_head + softmax[:, 1] (model/general_module.py:34-42, model/vast.py:378):
 //      h = GELU(cls . W1^T + b1) ;  z = W2 . LayerNorm(h) + b2 ;  score = softmax(z)[1]
@@ -14,6 +15,8 @@
 //
 // Both take PACKED 16-bit operands (vast_sim_pack_operand: a plain bf16 cast, or bf16 splits of fp32 values whose
 // leading cross products give fp32-grade results), so "bf16-in / fp32-accumulate" and "fp32" are the same kernels.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
@@ -30,95 +33,96 @@ struct EpiProj {
     float* inv_norm;     // [M] 1 / max(|y|, eps) or nullptr
     float* sumsq;        // [M][slots] per-item partial sums of squares
     int slots;           // n_splits * 2
-    int* tickets;        // [m_blocks] zero-initialised
-    int items_per_block; // work items covering one 128-row block (= n_splits)
+    int* tickets;        // [m_blocks] zero-initialised by the host before every launch
+    int items_per_block; // work items covering one 128-row block (= column tiles)
     float eps;
     int N;
   };
   static constexpr bool kUnrollChunks = false;
   static constexpr int kAuxWarps = 0;
+  static constexpr bool kSecondPass = true;  // pass 1 over the accumulator: sum of squares; pass 2: normalise + store
   const Params& p;
-  int* flag;  // shared: this CTA is the last of its row block
-  float ss;
-  __device__ EpiProj(const Params& p_, uint8_t* smem) : p(p_), flag(reinterpret_cast<int*>(smem)) {}
-  __device__ __forceinline__ void item_begin(const tc::ItemCtx&) { ss = 0.f; }
+  float ss, inv;
+  __device__ EpiProj(const Params& p_, uint8_t*) : p(p_) {}
+  __device__ __forceinline__ void item_begin(const tc::ItemCtx&) {
+    ss = 0.f;
+    inv = 0.f;
+  }
   __device__ __forceinline__ void prefetch(const tc::ItemCtx&, int) {}
   __device__ __forceinline__ void advance(const tc::ItemCtx&, int, bool) {}
+  // pass 1: y = acc + bias, only its squares are kept
   __device__ __forceinline__ void chunk(const tc::ItemCtx& c, const uint32_t (&v)[32], int col0) {
     if (!c.row_valid || col0 >= c.N) return;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (col0 + i < c.N) {
+        const float o = __uint_as_float(v[i]) + (p.bias != nullptr ? __ldg(p.bias + col0 + i) : 0.f);
+        ss = fmaf(o, o, ss);
+      }
+  }
+  // between the passes (one 256-column tile per item): publish this thread's partial sum of squares, take a ticket,
+  // wait until all column tiles of the row block have published theirs (they run side by side on neighbouring CTA
+  // pairs; a straggler of the next round never waits on this one), add the partials in slot order (the same sum in
+  // every CTA: deterministic).  Only 4-byte partials cross CTAs; y itself never leaves the accumulator unnormalised.
+  __device__ __forceinline__ void between(const tc::ItemCtx& c) {
+    const bool owns = c.m_blk * tc::BM < c.M;  // (the odd CTA of the last pair may own no rows at all)
+    if (c.row_valid) p.sumsq[static_cast<int64_t>(c.row) * p.slots + c.slot] = ss;
+    __threadfence();
+    asm volatile("bar.sync 2, 256;" ::: "memory");  // the 8 epilogue warps
+    const int ew = (static_cast<int>(threadIdx.x) >> 5) - 2;
+    if (ew == 0 && c.lane == 0 && owns) atomicAdd(p.tickets + c.m_blk, 1);
+    if (!c.row_valid) return;
+    int v;
+    const int* t = p.tickets + c.m_blk;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(t) : "memory");
+    const long long t0 = clock64();
+    while (v < p.items_per_block) {
+      __nanosleep(100);
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(t) : "memory");
+      if (clock64() - t0 > 6000000000LL) __trap();
+    }
+    float tot = 0.f;
+    for (int sl = 0; sl < p.slots; ++sl) tot += __ldcg(p.sumsq + static_cast<int64_t>(c.row) * p.slots + sl);
+    inv = 1.0f / fmaxf(sqrtf(tot), p.eps);
+  }
+  // pass 2: the normalised feature, fp32 and bf16, written once
+  __device__ __forceinline__ void chunk2(const tc::ItemCtx& c, const uint32_t (&v)[32], int col0) {
+    if (!c.row_valid || col0 >= c.N) return;
     float* dst = p.y + static_cast<int64_t>(c.row) * p.ldy + col0;
-    const bool vec = (col0 + 32 <= c.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    __nv_bfloat16* d16 = p.y16 != nullptr ? p.y16 + static_cast<int64_t>(c.row) * p.ld16 + col0 : nullptr;
+    const bool vec = (col0 + 32 <= c.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                     (d16 == nullptr || (reinterpret_cast<uintptr_t>(d16) & 15) == 0);
     if (vec) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        float4 o;
-        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
-        o.x = __uint_as_float(v[i]) + b.x;
-        o.y = __uint_as_float(v[i + 1]) + b.y;
-        o.z = __uint_as_float(v[i + 2]) + b.z;
-        o.w = __uint_as_float(v[i + 3]) + b.w;
-        ss = fmaf(o.x, o.x, ss);
-        ss = fmaf(o.y, o.y, ss);
-        ss = fmaf(o.z, o.z, ss);
-        ss = fmaf(o.w, o.w, ss);
-        *reinterpret_cast<float4*>(dst + i) = o;
+      for (int i = 0; i < 32; i += 8) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (__uint_as_float(v[i + j]) + (p.bias != nullptr ? __ldg(p.bias + col0 + i + j) : 0.f)) * inv;
+        *reinterpret_cast<float4*>(dst + i) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(dst + i + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        if (d16 != nullptr) {
+          uint4 u;
+          uint32_t* w = &u.x;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+            w[j] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(d16 + i) = u;
+        }
       }
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         if (col0 + i < c.N) {
-          const float o = __uint_as_float(v[i]) + (p.bias != nullptr ? __ldg(p.bias + col0 + i) : 0.f);
-          ss = fmaf(o, o, ss);
+          const float o = (__uint_as_float(v[i]) + (p.bias != nullptr ? __ldg(p.bias + col0 + i) : 0.f)) * inv;
           dst[i] = o;
+          if (d16 != nullptr) d16[i] = __float2bfloat16_rn(o);
         }
     }
   }
-  // every epilogue thread, once per item: publish the partial, then the last item of the row block normalises it
   __device__ __forceinline__ void item_end(const tc::ItemCtx& c) {
-    if (c.row_valid) p.sumsq[static_cast<int64_t>(c.row) * p.slots + c.slot] = ss;
-    __threadfence();
-    asm volatile("bar.sync 2, 256;" ::: "memory");  // the 8 epilogue warps
-    const int ew = (static_cast<int>(threadIdx.x) >> 5) - 2;
-    if (ew == 0 && c.lane == 0)  // (the odd CTA of the last pair may own no rows at all)
-      *flag = (c.m_blk * tc::BM < c.M) ? (atomicAdd(p.tickets + c.m_blk, 1) == p.items_per_block - 1) : 0;
-    asm volatile("bar.sync 2, 256;" ::: "memory");
-    if (*flag == 0) return;
-    __threadfence();
-    const int row0 = c.m_blk * tc::BM;
-    for (int r = ew; r < tc::BM; r += 8) {  // one warp per row, rows strided over the 8 warps
-      const int row = row0 + r;
-      if (row >= c.M) break;
-      // the row's sum of squares: slots in ascending order (fixed order: deterministic), every lane the same value
-      float tot = 0.f;
-      for (int sl = 0; sl < p.slots; ++sl) tot += __ldcg(p.sumsq + static_cast<int64_t>(row) * p.slots + sl);
-      const float inv = 1.0f / fmaxf(sqrtf(tot), p.eps);
-      float* yr = p.y + static_cast<int64_t>(row) * p.ldy;
-      const bool vec = (p.N % 4 == 0) && ((reinterpret_cast<uintptr_t>(yr) & 15) == 0) &&
-                       (p.y16 == nullptr || (reinterpret_cast<uintptr_t>(p.y16 + static_cast<int64_t>(row) * p.ld16) & 7) == 0);
-      if (vec) {
-        for (int d = c.lane * 4; d < p.N; d += 128) {
-          float4 x = __ldcg(reinterpret_cast<const float4*>(yr + d));
-          x.x *= inv; x.y *= inv; x.z *= inv; x.w *= inv;
-          *reinterpret_cast<float4*>(yr + d) = x;
-          if (p.y16 != nullptr) {
-            const __nv_bfloat162 a = __floats2bfloat162_rn(x.x, x.y), b = __floats2bfloat162_rn(x.z, x.w);
-            uint2 u;
-            u.x = *reinterpret_cast<const uint32_t*>(&a);
-            u.y = *reinterpret_cast<const uint32_t*>(&b);
-            *reinterpret_cast<uint2*>(p.y16 + static_cast<int64_t>(row) * p.ld16 + d) = u;
-          }
-        }
-      } else {
-        for (int d = c.lane; d < p.N; d += 32) {
-          const float x = __ldcg(yr + d) * inv;
-          yr[d] = x;
-          if (p.y16 != nullptr) p.y16[static_cast<int64_t>(row) * p.ld16 + d] = __float2bfloat16_rn(x);
-        }
-      }
-      if (c.lane == 0 && p.inv_norm != nullptr) p.inv_norm[row] = inv;
-    }
-    if (ew == 0 && c.lane == 0) p.tickets[c.m_blk] = 0;  // leave the ticket block clean
+    if (c.row_valid && c.n_split == 0 && c.half == 0 && p.inv_norm != nullptr) p.inv_norm[c.row] = inv;
   }
 };
 

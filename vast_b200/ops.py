@@ -140,6 +140,8 @@ def pair_sim(a_dtype, b_dtype, mode: str | None) -> int:
 
 
 def _pack(t: torch.Tensor, sim: int, as_query: bool) -> torch.Tensor:
+    if sim == _lib.SIM_BF16 and t.dtype == torch.bfloat16 and t.is_contiguous():
+        return t                                   # already the operand: no copy
     x = t if t.dtype in (torch.float32, torch.bfloat16) else t.float()
     return sim_pack_operand(x.contiguous(), sim, as_query)
 
