@@ -53,6 +53,20 @@ struct EpiProj {
   // pass 1: y = acc + bias, only its squares are kept
   __device__ __forceinline__ void chunk(const tc::ItemCtx& c, const uint32_t (&v)[32], int col0) {
     if (!c.row_valid || col0 >= c.N) return;
+    if (col0 + 32 <= c.N && (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0)) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {  // the bias as 16-byte broadcast loads: 8 per chunk instead of 32
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+        const float o0 = __uint_as_float(v[i]) + b.x, o1 = __uint_as_float(v[i + 1]) + b.y;
+        const float o2 = __uint_as_float(v[i + 2]) + b.z, o3 = __uint_as_float(v[i + 3]) + b.w;
+        ss = fmaf(o0, o0, ss);
+        ss = fmaf(o1, o1, ss);
+        ss = fmaf(o2, o2, ss);
+        ss = fmaf(o3, o3, ss);
+      }
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < 32; ++i)
       if (col0 + i < c.N) {
@@ -91,13 +105,20 @@ struct EpiProj {
     float* dst = p.y + static_cast<int64_t>(c.row) * p.ldy + col0;
     __nv_bfloat16* d16 = p.y16 != nullptr ? p.y16 + static_cast<int64_t>(c.row) * p.ld16 + col0 : nullptr;
     const bool vec = (col0 + 32 <= c.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
-                     (d16 == nullptr || (reinterpret_cast<uintptr_t>(d16) & 15) == 0);
+                     (d16 == nullptr || (reinterpret_cast<uintptr_t>(d16) & 15) == 0) &&
+                     (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0);
     if (vec) {
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
         float o[8];
+        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+        if (p.bias != nullptr) {
+          b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+          b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i + 4));
+        }
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (__uint_as_float(v[i + j]) + (p.bias != nullptr ? __ldg(p.bias + col0 + i + j) : 0.f)) * inv;
+        for (int j = 0; j < 8; ++j) o[j] = (__uint_as_float(v[i + j]) + bb[j]) * inv;
         *reinterpret_cast<float4*>(dst + i) = make_float4(o[0], o[1], o[2], o[3]);
         *reinterpret_cast<float4*>(dst + i + 4) = make_float4(o[4], o[5], o[6], o[7]);
         if (d16 != nullptr) {

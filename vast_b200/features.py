@@ -110,13 +110,16 @@ def project_normalize(head: torch.nn.Module, pooled: torch.Tensor, eps: float = 
 def build_feature(head: torch.nn.Module, vision=None, audio=None, subtitle=None, vision_encoder_type="evaclip",
                   audio_encoder_type="beats", fused: bool | None = None) -> torch.Tensor:
     """feat_{v,a,s,va,vs,vas} (vast.py:221-279): pooled = pool_concat(...); feat = normalize(head(pooled)).
-    fused (default: whenever the head is a Linear / Contra_head with in_features % 8 == 0): projection, bias and
-    normalisation run as one tensor-core kernel (`vast_project_normalize`); otherwise the head runs as a library GEMM
-    followed by `vast_l2norm`."""
+    fused=True (needs a Linear / Contra_head with in_features % 8 == 0): projection, bias and normalisation run as one
+    tensor-core kernel (`vast_project_normalize`); default: the head runs as a library GEMM followed by
+    `vast_l2norm`.  Measured device time per call (scripts/proj_bench.py, CUDA-graph replays, K = 2944 -> D = 1024):
+    the fused kernel pays a fixed ~18 us (one long K loop per tile, ticketed exchange, two passes over the accumulator)
+    and loses to cuBLAS + vast_l2norm at these sizes, so it is opt-in (VAST_FUSED_PROJECTION=1 flips the default)."""
+    import os
     pooled = pool_concat(vision, audio, subtitle, vision_encoder_type, audio_encoder_type)
     lin = _linear_of(head)
     if fused is None:
-        fused = lin is not None and lin.in_features % 8 == 0
+        fused = os.environ.get("VAST_FUSED_PROJECTION", "0") == "1" and lin is not None and lin.in_features % 8 == 0
     if fused:
         return project_normalize(head, pooled)
     return l2_normalize(head(pooled).float())
