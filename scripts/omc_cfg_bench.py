@@ -47,6 +47,24 @@ for bs in sizes:
         for nm, ms in recs:
             agg.setdefault(nm, []).append(ms * 1e3)
         kern = {k: round(sorted(v)[len(v) // 2], 2) for k, v in agg.items()}
-        out.append(dict(bs=bs, cfg=cfg or "default", kernels_us=kern, sum_us=round(sum(kern.values()), 1),
+        # the whole step as a CUDA-graph replay (what overlaps, overlaps)
+        gs = torch.cuda.Stream()
+        gs.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(gs):
+            with torch.cuda.graph(g, stream=gs):
+                buf = ops.omc_step(pack, bs, N - bs, temp, seed=1, offset=0, buffers=buf)
+        torch.cuda.current_stream().wait_stream(gs)
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        graph_us = e0.elapsed_time(e1) / 50 * 1e3
+        out.append(dict(bs=bs, cfg=cfg or "default", kernels_us=kern, sum_us=round(sum(kern.values()), 1), graph_us=round(graph_us, 1),
                         bit_equal_to_default=same, grad_rel_diff=close, loss=buf["loss"].item()))
         print(json.dumps(out[-1]), flush=True)
