@@ -58,6 +58,29 @@ static int gemm_impl(const void* A, int64_t lda, int dtype_a, const void* B, int
     return VAST_OK;
   }
   P.epi = {C, ldc, 0, 0, alpha};
+  // diagnostics (scripts/gemm_probe.py): VAST_GEMM_PROBE = 1 tensor pipe alone, 2 operand ingest alone, 3 clusters of two
+  // pairs sharing A, 4 = 3 + 1, 5 = 3 + 2, 6 = 512-wide tiles (NN only)
+  if (const char* e = getenv("VAST_GEMM_PROBE")) {
+    const int mode = atoi(e);
+    if (cl == 2 && mode >= 1 && mode <= 6) {
+      if (mode >= 3 && mode <= 5) {
+        VAST_REQUIRE(P.g.n_tiles % 2 == 0, VAST_ERR_INVALID, "%s: probe needs an even tile count", name);
+        P.g.n_splits = P.g.n_tiles;  // one tile per item
+        P.g.tiles_per_split = 1;
+        P.g.num_items = P.g.m_groups * P.g.n_tiles;
+        rc = tc::make_tmap_2d(&P.tmA[0], A, dtype_a, M, K, lda, 64);
+        if (rc) return rc;
+      }
+      switch (mode) {
+        case 1: return tc::launch_gemm_cl<Epi, 256, 6, 4, B_MN, 2, 0, 1, 1>(P, stream, name, 0);
+        case 2: return tc::launch_gemm_cl<Epi, 256, 6, 4, B_MN, 2, 0, 1, 2>(P, stream, name, 0);
+        case 3: return tc::launch_gemm_cl<Epi, 256, 6, 4, B_MN, 2, 0, 2, 0>(P, stream, name, 0);
+        case 4: return tc::launch_gemm_cl<Epi, 256, 6, 4, B_MN, 2, 0, 2, 1>(P, stream, name, 0);
+        case 5: return tc::launch_gemm_cl<Epi, 256, 6, 4, B_MN, 2, 0, 2, 2>(P, stream, name, 0);
+        default: break;
+      }
+    }
+  }
   return tc::launch_gemm<Epi, 256, 4, 4, B_MN>(P, stream, name);
 }
 

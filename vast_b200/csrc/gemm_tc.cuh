@@ -205,9 +205,20 @@ struct HasFinish<E, std::void_t<decltype(E::kHasFinish)>> : std::true_type {};
 //         `full` barrier); only the leader issues MMAs; its tcgen05.commit is multicast to both CTAs' `empty`
 //         (stage free) and `tfull` (accumulator ready) barriers; both CTAs' epilogue warps arrive on the
 //         leader's `tempty` barrier (accumulator drained).
-template <class Epi, int BN, int STAGES, int NE, bool B_MN, int CL, int A_RES = 0>
+// MC = 2 (CTA pairs only): clusters of FOUR CTAs = two pairs that work on consecutive work items -- the same A rows, two
+//         neighbouring column ranges -- in lockstep and SHARE every A tile: each of the four CTAs fetches a 64-row
+//         slice (8 KB) of its own 128 A rows and TMA-multicasts it to the CTA of the same rank in the other pair.
+//         These mainloops are bound by the L2 -> SM request rate (ncu: lts__t_sectors at 93 % of the ~6300 B/clk the
+//         L2 slices deliver, tensor pipe at 61 %), not by the tensor pipe: 96 KB instead of 128 KB per k-block for
+//         the two tiles.  Protocol on top of the pair's: `empty` barriers count the commits of BOTH leaders (a stage
+//         is rewritten by two producers), commits to `empty` are multicast to all four CTAs; `tfull` / `tempty` stay
+//         inside a pair.  The host guarantees that items 2j, 2j+1 differ only in their column range (can_share_a()).
+// PROBE (diagnostics, scripts/gemm_probe.py): 1 = no operand loads, the MMA issuer never waits for data (the tensor
+//         pipe's own rate); 2 = loads only, stages are released without MMAs (the L2 -> SM ingest rate).  Results are garbage.
+template <class Epi, int BN, int STAGES, int NE, bool B_MN, int CL, int A_RES = 0, int MC = 1, int PROBE = 0>
 __global__ void __launch_bounds__(64 + 32 * NE + 32 * Epi::kAuxWarps, 1)
 gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
+  static_assert(MC == 1 || (MC == 2 && CL == 2 && A_RES == 0 && BN != 512), "A-sharing clusters of two CTA pairs");
   static_assert(NE == 4 || NE == 8, "4 or 8 epilogue warps");
   static_assert(BN == 128 || BN == 256 || BN == 512, "BN");
   static_assert(BN != 512 || (B_MN && CL == 2 && A_RES == 0), "the 512-wide tile is implemented for CTA pairs with the MN-major B operand");
@@ -250,8 +261,13 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const GemmShape& g = P.g;
-  const int cta_rank = PAIR ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  const int cluster_rank = PAIR ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  const int cta_rank = cluster_rank & 1;   // rank inside the CTA pair
+  const int pair_rank = cluster_rank >> 1;  // MC = 2: which of the cluster's two pairs (pair p of cluster c = pair 2c + p of the grid)
   const bool leader = cta_rank == 0;
+  const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * pair_rank));
+  const uint16_t all_mask = MC == 2 ? static_cast<uint16_t>(0xF) : pair_mask;
+  (void)pair_rank;
   const int cluster_id = static_cast<int>(blockIdx.x) / CL;
   const int num_clusters = static_cast<int>(gridDim.x) / CL;
 
@@ -262,7 +278,7 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
     }
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full[s], 1);
-      ptx::mbar_init(&empty[s], 1);
+      ptx::mbar_init(&empty[s], MC);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull[a], 1);
@@ -287,7 +303,7 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (every CTA)
-    if (lane == 0) {
+    if (lane == 0 && PROBE != 1) {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t a_phase = 0;
@@ -353,7 +369,15 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
                 const int half_n = (CUSTOM && BN != 512) ? w.width >> 1 : HALF_N;
                 const int nboxes = (CUSTOM && BN != 512) ? (half_n + 63) >> 6 : HALF_N / 64;
                 if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * (L::A_BYTES + static_cast<uint32_t>(nboxes) * (BK * 128)));
-                if (AMN && w.prob == amn_prob) {  // A[m][k] = X[k][m]: two boxes of 64 k-rows x 64 m-columns
+                if constexpr (MC == 2) {
+                  // this CTA's 64-row slice of the A rows it shares with CTA (rank ^ 2): lands in both
+                  const uint16_t share = static_cast<uint16_t>(0x5u << cta_rank);
+                  uint8_t* sl = sa + pair_rank * (BK * 128);
+                  if (AMN && w.prob == amn_prob)
+                    ptx::tma_load_2d_pair_mc(sl, &P.tmA[MAX_PROBLEMS], &full[stage], w.m_blk * BM + pair_rank * 64, kb * BK, share);
+                  else  // (tmA: 64-row boxes in this mode)
+                    ptx::tma_load_2d_pair_mc(sl, &P.tmA[w.prob], &full[stage], kb * BK, w.m_blk * BM + pair_rank * 64, share);
+                } else if (AMN && w.prob == amn_prob) {  // A[m][k] = X[k][m]: two boxes of 64 k-rows x 64 m-columns
                   ptx::tma_load_2d_pair(sa, &P.tmA[MAX_PROBLEMS], &full[stage], w.m_blk * BM, kb * BK);
                   ptx::tma_load_2d_pair(sa + BK * 128, &P.tmA[MAX_PROBLEMS], &full[stage], w.m_blk * BM + 64, kb * BK);
                 } else {
@@ -376,7 +400,11 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
                 }
               } else {
                 if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * L::STAGE_BYTES);
-                ptx::tma_load_2d_pair(sa, &P.tmA[w.prob], &full[stage], kb * BK, w.m_blk * BM);
+                if constexpr (MC == 2)
+                  ptx::tma_load_2d_pair_mc(sa + pair_rank * (BK * 128), &P.tmA[w.prob], &full[stage], kb * BK,
+                                           w.m_blk * BM + pair_rank * 64, static_cast<uint16_t>(0x5u << cta_rank));
+                else
+                  ptx::tma_load_2d_pair(sa, &P.tmA[w.prob], &full[stage], kb * BK, w.m_blk * BM);
                 ptx::tma_load_2d_pair(sb, &P.tmB[w.prob], &full[stage], kb * BK, t * BN + cta_rank * HALF_N);
               }
             }
@@ -414,7 +442,7 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
           ptx::tc_fence_after_sync();
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
           for (int kb = w.kb_begin; kb < w.kb_end; ++kb) {
-            ptx::mbar_wait(&full[stage], phase);
+            if constexpr (PROBE != 1) ptx::mbar_wait(&full[stage], phase);
             ptx::tc_fence_after_sync();
             const uint32_t sst = ptx::smem_u32(smem + L::RING_OFFSET + stage * L::STAGE_BYTES);
             const uint32_t sa = A_RES > 0 ? ptx::smem_u32(smem + (kb - w.kb_begin) * L::A_BYTES) : sst;
@@ -431,26 +459,26 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
             uint32_t idesc = (CUSTOM && BN != 512) ? ((g.idesc & ~(0x3Fu << 17)) | (static_cast<uint32_t>(w.width >> 3) << 17)) : g.idesc;
             if (a_mn) idesc |= 1u << 15;  // A operand MN-major
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
+            for (int k = 0; k < (PROBE == 2 ? 0 : BK / 16); ++k) {
 #pragma unroll
               for (int sub = 0; sub < NSUB; ++sub)  // BN = 512: two instructions share the A descriptor
                 ptx::umma_f16<CL>(d_tmem + static_cast<uint32_t>(sub * BNI), da + a_kstep * k,
                                   db + static_cast<uint64_t>(sub) * ((BNI / CL) * BK * 2 >> 4) + B_KSTEP * k, idesc,
                                   (kb > w.kb_begin || k > 0) ? 1u : 0u);
             }
-            ptx::umma_commit<CL>(&empty[stage]);  // frees the smem stage (in both CTAs) once these MMAs retire
+            ptx::umma_commit<CL>(&empty[stage], all_mask);  // frees the smem stage (in every CTA that fills it) once these MMAs retire
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
             }
           }
-          ptx::umma_commit<CL>(&tfull[acc]);  // accumulator tile complete (in both CTAs' TMEM)
+          ptx::umma_commit<CL>(&tfull[acc], pair_mask);  // accumulator tile complete (in both CTAs' TMEM)
           if (++acc == ACC) {
             acc = 0;
             acc_phase ^= 1;
           }
         }
-        if constexpr (A_RES > 0) ptx::umma_commit<CL>(aempty);  // the resident A may be replaced (in both CTAs)
+        if constexpr (A_RES > 0) ptx::umma_commit<CL>(aempty, pair_mask);  // the resident A may be replaced (in both CTAs)
       }
     }
   } else if (warp >= 2 + NE) {
@@ -578,7 +606,14 @@ inline int ceil_div_i(int a, int b) { return (a + b - 1) / b; }
 // CTA pairs (cta_group::2) as soon as there are two 128-row blocks to pair.
 inline int pick_cluster(int M) { return ceil_div(M, BM) >= 2 ? 2 : 1; }
 
-template <class Epi, int BN, int STAGES, int NE, bool B_MN, int CL, int A_RES = 0>
+// MC = 2 needs: whole-K items, an even number of equally long column ranges per row-block group (so that items 2j and
+// 2j + 1 walk the same A tiles the same number of times), a regular schedule, A tensor maps with 64-row boxes.
+inline bool can_share_a(const GemmShape& g) {
+  return g.cl == 2 && g.k_splits == 1 && g.tail_groups == 0 && g.n_sched == 0 && g.n_splits % 2 == 0 &&
+         g.n_tiles % g.n_splits == 0 && g.num_items % 2 == 0;
+}
+
+template <class Epi, int BN, int STAGES, int NE, bool B_MN, int CL, int A_RES = 0, int MC = 1, int PROBE = 0>
 int launch_gemm_cl(const KernelParams<typename Epi::Params>& P, cudaStream_t stream, const char* name, size_t epi_smem_bytes) {
   using L = SmemLayout<BN, STAGES, CL, A_RES>;
   const size_t smem = L::EPI_OFFSET + L::ALIGN_SLACK + epi_smem_bytes;
@@ -586,17 +621,41 @@ int launch_gemm_cl(const KernelParams<typename Epi::Params>& P, cudaStream_t str
   VAST_REQUIRE(P.g.cl == CL, VAST_ERR_INVALID, "%s: shape planned for clusters of %d, launched with %d", name, P.g.cl, CL);
   VAST_REQUIRE(A_RES == 0 || (P.g.k_blocks <= A_RES && P.g.k_splits == 1), VAST_ERR_INVALID,
                "%s: %d k-blocks do not fit the %d resident ones", name, P.g.k_blocks, A_RES);
-  auto kern = gemm_tc_kernel<Epi, BN, STAGES, NE, B_MN, CL, A_RES>;
+  VAST_REQUIRE(MC == 1 || can_share_a(P.g), VAST_ERR_INVALID, "%s: the work items do not pair up for A sharing", name);
+  auto kern = gemm_tc_kernel<Epi, BN, STAGES, NE, B_MN, CL, A_RES, MC, PROBE>;
+  constexpr int block = 64 + 32 * NE + 32 * Epi::kAuxWarps;
   static size_t attr_smem = 0;  // per instantiation; grows monotonically
+  static int resident = 0;      // MC = 2: clusters of four that fit the device at once
   if (smem > attr_smem) {
     VAST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr_smem = smem;
+    resident = 0;
   }
-  const int clusters_max = device_sm_count() / CL;
-  const int clusters = P.g.num_items < clusters_max ? P.g.num_items : clusters_max;
+  int clusters_max = device_sm_count() / CL;  // in CTA pairs (or lone CTAs)
+  if constexpr (MC == 2) {
+    if (resident == 0) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(static_cast<unsigned>(device_sm_count() / (CL * MC) * (CL * MC)), 1, 1);
+      cfg.blockDim = dim3(block, 1, 1);
+      cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = CL * MC;
+      attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int n = 0;
+      VAST_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+      VAST_REQUIRE(n > 0, VAST_ERR_UNSUPPORTED, "%s: no cluster of %d CTAs fits this device", name, CL * MC);
+      resident = n;
+    }
+    clusters_max = resident * MC;
+  }
+  int clusters = P.g.num_items < clusters_max ? P.g.num_items : clusters_max;
+  if (MC == 2) clusters &= ~1;
   if (clusters <= 0) return VAST_OK;
-  VAST_TIMED(stream, name,
-             (launch_ex(kern, static_cast<unsigned>(clusters * CL), 64 + 32 * NE + 32 * Epi::kAuxWarps, smem, stream, CL, P)));
+  VAST_TIMED(stream, name, (launch_ex(kern, static_cast<unsigned>(clusters * CL), block, smem, stream, CL * MC, P)));
   VAST_LAUNCH_OK(name);
   return VAST_OK;
 }

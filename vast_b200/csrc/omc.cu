@@ -2155,6 +2155,12 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
     return tc::launch_gemm<EpiSoft<false>, 256, 4, 8>(P, stream, gate ? "omc_soft_gemm_gated" : "omc_soft_gemm");
   };
 
+  // Clusters of two CTA pairs that share every A tile through TMA multicast (gemm_tc_kernel MC = 2): a quarter less
+  // L2 -> SM operand traffic, which is what binds these mainloops.  VAST_GEMM_SHARE_A=0 keeps lone pairs.
+  const bool share_a_enabled = [] {
+    const char* e = getenv("VAST_GEMM_SHARE_A");
+    return e == nullptr || e[0] != '0';
+  }();
   auto run_soft_sym = [&]() -> int {
     using E = EpiSoft<false, true>;
     tc::KernelParams<E::Params> P;
@@ -2162,15 +2168,23 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
     P.g = pl.g_sym;  // the cond2t problem only: tmA[0] = local cond rows, tmB[0] = all t rows
     P.epi.ref2_out = ref2;
     P.epi.zmax_bits = reinterpret_cast<const unsigned*>(&wflags[4]);
+    if (share_a_enabled && tc::can_share_a(P.g)) {
+      rc = tc::make_tmap_2d(&P.tmA[0], pk + row_offset * 2 * dim + dim, VAST_BF16, bs, dim, 2 * dim, 64);
+      if (rc) return rc;
+      return tc::launch_gemm_cl<E, 256, 6, 8, false, 2, 0, 2>(P, stream, "omc_soft_gemm_sym", E::SMEM_BYTES);
+    }
     return tc::launch_gemm<E, 256, 4, 8>(P, stream, "omc_soft_gemm_sym", E::SMEM_BYTES);
   };
 
   // tensor maps of the dQ GEMM: A = Pt (fp16), B = the gathered features' fp16 copy read row-major (MN-major operand)
   const float c_sm = label_smoothing / static_cast<float>(N);
   CUtensorMap tmPa[2], tmKb[2], tmPaT;
+  const bool dq_share_a = share_a_enabled && need_grad && fused_stats && pl.bn_dq == 256 && tc::can_share_a(pl.g_dq) && !fuse &&
+                          getenv("VAST_OMC_MIXED_TILES") == nullptr;
   if (need_grad) {
     for (int i = 0; i < 2; ++i) {
-      rc = tc::make_tmap_2d(&tmPa[i], Pbuf + static_cast<int64_t>(i) * bs * pl.npad, VAST_F16, bs, n_total, pl.npad, tc::BM);
+      rc = tc::make_tmap_2d(&tmPa[i], Pbuf + static_cast<int64_t>(i) * bs * pl.npad, VAST_F16, bs, n_total, pl.npad,
+                            dq_share_a ? 64 : tc::BM);
       if (rc) return rc;
       rc = tc::make_tmap_2d(&tmKb[i], pack16 + static_cast<int64_t>(i) * dim, VAST_F16, n_total, dim, 2 * dim, tc::BK);
       if (rc) return rc;
@@ -2239,7 +2253,7 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
     P.gate = gate;
     // balanced two-round schedule with 256- and 192-wide tiles where the regular tiling leaves a partial wave
     // (needs the fused statistics / final reduction: no per-slot partial buffers in this form)
-    if (fused_stats && pl.g_dq.cl == 2) plan_mixed_tiles(&P.g, pl.bn_dq, device_sm_count() / 2);
+    if (fused_stats && pl.g_dq.cl == 2 && !dq_share_a) plan_mixed_tiles(&P.g, pl.bn_dq, device_sm_count() / 2);
     for (int i = 0; i < 2; ++i) {
       P.tmA[i] = tmPa[i];
       P.tmB[i] = tmKb[i];
@@ -2251,6 +2265,7 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
     }
     fill_grad(P.epi, sym_mode);
     const char* name = gate ? "omc_dq_gemm_gated" : "omc_dq_gemm";
+    if (dq_share_a) return tc::launch_gemm_cl<EpiGrad, 256, 6, 8, true, 2, 0, 2>(P, stream, name, 128);
     return pl.bn_dq == 512   ? tc::launch_gemm_cl<EpiGrad, 512, 4, 8, true, 2>(P, stream, name, 128)
            : pl.bn_dq == 256 ? tc::launch_gemm<EpiGrad, 256, 4, 8, true>(P, stream, name, 128)
                              : tc::launch_gemm<EpiGrad, 128, 6, 8, true, 8>(P, stream, name, 128);

@@ -88,6 +88,16 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tma
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & PAIR_LEADER_MASK), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
+// The same with TMA multicast: the box lands at this offset in every CTA of `cta_mask` (bit = rank in the cluster) and
+// each copy's bytes are counted on the barrier of THAT CTA's pair leader.
+__device__ __forceinline__ void tma_load_2d_pair_mc(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c_inner,
+                                                    int32_t c_outer, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & PAIR_LEADER_MASK), "r"(c_inner), "r"(c_outer), "h"(cta_mask)
+      : "memory");
+}
 // Arrive on the leader CTA's copy of this barrier (from either CTA of the pair).
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PAIR_LEADER_MASK) : "memory");
@@ -166,11 +176,11 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 // (implies tcgen05.fence::before_thread_sync).  CG = 2: the arrival is multicast to the barrier at this
 // offset in both CTAs of the pair.
 template <int CG>
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit(uint64_t* bar, uint16_t cta_mask = 3) {
   if constexpr (CG == 2)
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                      smem_u32(bar)),
-                 "h"(static_cast<uint16_t>(3))
+                 "h"(cta_mask)
                  : "memory");
   else
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
