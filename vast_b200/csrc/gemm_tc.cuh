@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(64 + 32 * NE + 32 * Epi::kAuxWarps, 1)
 gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
   static_assert(MC == 1 || (MC == 2 && CL == 2 && A_RES == 0 && BN != 512), "A-sharing clusters of two CTA pairs");
   static_assert(NE == 4 || NE == 8, "4 or 8 epilogue warps");
-  static_assert(BN == 128 || BN == 256 || BN == 512, "BN");
+  static_assert(BN == 64 || BN == 128 || BN == 256 || BN == 512, "BN");
   static_assert(BN != 512 || (B_MN && CL == 2 && A_RES == 0), "the 512-wide tile is implemented for CTA pairs with the MN-major B operand");
   static_assert(CL == 1 || CL == 2, "single CTA or CTA pair");
   static_assert(A_RES == 0 || !B_MN, "resident A is implemented for the K-major B operand");

@@ -1911,7 +1911,7 @@ static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, bool
   if (const char* e = getenv("VAST_OMC_DQ")) {
     int bn = 0, c = 0, ks = 0;
     if (sscanf(e, "%d,%d,%d", &bn, &c, &ks) >= 1) {
-      if (bn == 128 || bn == 256 || (bn == 512 && cl == 2)) pl->bn_dq = bn;
+      if (bn == 64 || bn == 128 || bn == 256 || (bn == 512 && cl == 2)) pl->bn_dq = bn;
       if ((c == 1 || c == 2) && c <= cl) cl_dq = c;
       if (ks >= 1) max_ks = ks;
     }
@@ -1926,8 +1926,12 @@ static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, bool
     // the gradient assembly, row statistics and final reduction fused (37.3 / 35.2 us), no partial buffer.
     const int items = 2 * tc::ceil_div_i((int)bs, tc::BM) * tc::ceil_div_i((int)dim, 128);
     if (dim > 128 && items * 10 >= sms * 3) {
-      pl->bn_dq = 128;
-      tc::fill_shape(&pl->g_dq, 2, (int)bs, (int)dim, (int)n_total, 128, 0, 0, true, 1);
+      // ... and 128 x 64 tiles while those items cover less than half of the SMs: a lone CTA's mainloop is bound by
+      // its operand ingest (32 KB per k-block at 128 x 128, 24 KB at 128 x 64), so twice the CTAs at 3/4 of the bytes
+      // each finish sooner (512 rows per rank: step 53.4 -> 50.2 us; at 1024 rows the 128-wide tiles already fill the
+      // machine and 64-wide ones need two rounds: 60.9 vs 74.7 us).
+      pl->bn_dq = (items * 2 <= sms && dim % 64 == 0) ? 64 : 128;
+      tc::fill_shape(&pl->g_dq, 2, (int)bs, (int)dim, (int)n_total, pl->bn_dq, 0, 0, true, 1);
       tc::choose_splits(&pl->g_dq, sms, 64, 1);
     }
   }
@@ -2268,6 +2272,7 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
     if (dq_share_a) return tc::launch_gemm_cl<EpiGrad, 256, 6, 8, true, 2, 0, 2>(P, stream, name, 128);
     return pl.bn_dq == 512   ? tc::launch_gemm_cl<EpiGrad, 512, 4, 8, true, 2>(P, stream, name, 128)
            : pl.bn_dq == 256 ? tc::launch_gemm<EpiGrad, 256, 4, 8, true>(P, stream, name, 128)
+           : pl.bn_dq == 64  ? tc::launch_gemm<EpiGrad, 64, 8, 8, true, 8>(P, stream, name, 128)
                              : tc::launch_gemm<EpiGrad, 128, 6, 8, true, 8>(P, stream, name, 128);
   };
   auto run_fused = [&]() -> int {

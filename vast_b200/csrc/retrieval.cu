@@ -116,8 +116,12 @@ __device__ __forceinline__ void sort_desc(uint64_t (&key)[E], int lane) {
   }
 }
 
-template <int E>  // key registers per lane of a list warp: lists hold up to 32 * E keys (k <= 32 * E)
+// E: key registers per lane of a list warp: lists hold up to 32 * E keys (k <= 32 * E).
+// KCAP: list slots kept in shared memory per row (>= k).  KCAP = 16 (k <= 16, cfg5) halves the list block and buys
+// the A-stationary mainloop a fourth ring stage: that ring is latency-bound (stage bytes in flight / TMA round trip).
+template <int E, int KCAP = 32 * E>
 struct EpiTopK {
+  static_assert(KCAP == 32 * E || (E == 1 && KCAP == 16), "list slots per row");
   struct Params {
     uint64_t* out;  // [M][n_splits][k], each list sorted best-first, 0 = empty
     int k;
@@ -129,7 +133,7 @@ struct EpiTopK {
   };
   static constexpr bool kUnrollChunks = false;
   static constexpr int kAuxWarps = 4;
-  static constexpr int LSTRIDE = 32 * E + 1;  // keys per list row; odd: lanes walking 32 different rows hit different banks
+  static constexpr int LSTRIDE = KCAP + 1;  // keys per list row; odd: lanes walking 32 different rows hit different banks
   static constexpr uint32_t LIST_BYTES = tc::BM * LSTRIDE * 8;
   static constexpr uint32_t THR_OFF = LIST_BYTES;                  // [128] float admission thresholds
   static constexpr uint32_t CNT_OFF = THR_OFF + tc::BM * 4;        // [128] keys held per list
@@ -1263,7 +1267,18 @@ static int sim_topk_impl(const void* q_op, const void* k_op, int64_t n_q, int64_
     rc = tc::make_tmap_2d(&P.tmB[0], k_op, VAST_BF16, n_k, cols, cols, 256 / pl.g.cl);
     if (rc) return rc;
     P.epi = {part, static_cast<int>(k), pl.g.n_splits, 2, static_cast<uint32_t>(col_offset), thr_shared, 0};
-    rc = tc::launch_gemm_cl<EpiTopK<1>, 256, 3, 8, false, 2, 8>(P, stream, "sim_topk_gemm", EpiTopK<1>::smem_bytes());
+    static const int deep = [] {
+      const char* e = getenv("VAST_TOPK_RING4");
+      return e ? atoi(e) : 1;
+    }();
+    if (k <= 16 && deep) {
+      tc::KernelParams<typename EpiTopK<1, 16>::Params> P4;
+      memcpy(&P4, &P, sizeof(P));  // same layout: Params does not depend on KCAP
+      static_assert(sizeof(P4) == sizeof(P), "EpiTopK::Params must not depend on KCAP");
+      rc = tc::launch_gemm_cl<EpiTopK<1, 16>, 256, 4, 8, false, 2, 8>(P4, stream, "sim_topk_gemm", EpiTopK<1, 16>::smem_bytes());
+    } else {
+      rc = tc::launch_gemm_cl<EpiTopK<1>, 256, 3, 8, false, 2, 8>(P, stream, "sim_topk_gemm", EpiTopK<1>::smem_bytes());
+    }
   } else
   // <epilogue, ring depth of a lone CTA (48 KB stages), ring depth of a CTA pair (32 KB stages), filter warps>
   if (pl.e == 1)
