@@ -319,8 +319,9 @@ def full_path_bench(torch, vast_b200, ops, peaks, dev, bs, kern_us):
                         f"-> fused contrastive step -> negative gather + 3-way concat; bs {bs}, 1 GPU, bf16 encoder outputs, L2 flushed",
             "ms_per_step": round(ms_full, 4), "value": bs / (ms_full * 1e-3), "unit": "pairs/s",
             "stages_us": {"pool_concat": round(ms_pool * 1e3, 1),
-                          "project_normalize_fused (what the path runs: Linear + bias + L2 normalise + bf16 slot, one kernel)": round(ms_proj * 1e3, 1),
-                          "for comparison: fusion_linear_cublas": round(ms_lin * 1e3, 1), "for comparison: l2norm": round(ms_l2 * 1e3, 1),
+                          "fusion_linear_cublas (what build_feature runs by default)": round(ms_lin * 1e3, 1),
+                          "l2norm (default, follows the Linear)": round(ms_l2 * 1e3, 1),
+                          "for comparison: project_normalize_fused (opt-in: Linear + bias + L2 normalise + bf16 slot, one kernel)": round(ms_proj * 1e3, 1),
                           "negative_gather_concat3": round(ms_gather * 1e3, 1)},
             "project_normalize_tflops": round(2.0 * bs * 2944 * DIM / (ms_proj * 1e-3) / 1e12, 1),
             "note": "the [3bs, S, 768] concat for the ITM head is compulsory HBM traffic larger than everything else on the path "

@@ -129,7 +129,7 @@ struct EpiTopK {
     int halves;  // filter warps per quadrant (column halves of a tile) = end markers per item
     uint32_t col_offset;
     uint32_t* thr_shared;  // [M] zero-initialised orderable bits of a proven lower bound of the final k-th score
-    int debug;             // experiment switches (VAST_TOPK_DEBUG): 1 no priming, 2 list warps drop entries, 4 filters never push
+    int debug;             // experiment switches (VAST_TOPK_DEBUG): 1 no priming, 2 list warps drop entries, 4 filters never push, 8 filters drop every chunk
   };
   static constexpr bool kUnrollChunks = false;
   static constexpr int kAuxWarps = 4;
@@ -226,7 +226,7 @@ struct EpiTopK {
     __syncwarp();
   }
   __device__ __forceinline__ void chunk(const tc::ItemCtx& c, const uint32_t (&v)[32], int col0) {
-    if (col0 >= c.N) return;
+    if (col0 >= c.N || (p.debug & 8)) return;  // debug 8: scores are read from TMEM and dropped (the mainloop alone)
     const int nvalid = c.N - col0;
     const uint32_t gcol = p.col_offset + static_cast<uint32_t>(col0);
     float s[32];
@@ -1266,10 +1266,11 @@ static int sim_topk_impl(const void* q_op, const void* k_op, int64_t n_q, int64_
     if (rc) return rc;
     rc = tc::make_tmap_2d(&P.tmB[0], k_op, VAST_BF16, n_k, cols, cols, 256 / pl.g.cl);
     if (rc) return rc;
-    P.epi = {part, static_cast<int>(k), pl.g.n_splits, 2, static_cast<uint32_t>(col_offset), thr_shared, 0};
+    const char* dbg = getenv("VAST_TOPK_DEBUG");
+    P.epi = {part, static_cast<int>(k), pl.g.n_splits, 2, static_cast<uint32_t>(col_offset), thr_shared, dbg ? atoi(dbg) : 0};
     static const int deep = [] {
       const char* e = getenv("VAST_TOPK_RING4");
-      return e ? atoi(e) : 1;
+      return e ? atoi(e) : 0;  // measured at cfg5: 8.39 vs 8.37 ms -- the ring is not what binds this mainloop
     }();
     if (k <= 16 && deep) {
       tc::KernelParams<typename EpiTopK<1, 16>::Params> P4;
