@@ -121,6 +121,23 @@ VAST_API int vast_pack_pair_push(const void* feat_t, const void* feat_cond, int 
                         int64_t ld_in, int64_t row_offset, void* multicast_ptr, void* const* peer_ptrs, int world,
                         vast_stream_t stream);
 
+/* The same with ARRIVAL FLAGS instead of a barrier after the kernel: once all of this rank's stores are performed
+ * (system-scope fences, last block by ticket) the kernel release-stores its push epoch (1, 2, 3, ... per call) into
+ * entry `my_rank` of every rank's flag array (`flag_ptrs[world]`: the unicast address of each rank's uint32[world]
+ * array in symmetric memory, zeroed once and published before the first call).  `sync_state`: LOCAL int32[4], zeroed
+ * once ([0] ticket, [1] push epoch, [2] consumer epoch).  Consumers wait with vast_wait_arrivals on the same stream.
+ * The flags also make the two-buffer rule safe without a barrier: a rank can only signal step k+1 after its own
+ * kernels of step k have completed, and nobody pushes step k+2 before having seen every rank's step k+1. */
+VAST_API int vast_pack_pair_push_signal(const void* feat_t, const void* feat_cond, int dtype, int64_t bs, int64_t dim,
+                               int64_t ld_in, int64_t row_offset, void* multicast_ptr, void* const* peer_ptrs,
+                               int world, void* const* flag_ptrs, int my_rank, int* sync_state, vast_stream_t stream);
+
+/* Wait (on the device, one warp) until every rank's push of this step has arrived in this rank's buffer: entry r of
+ * `flags` (this rank's own uint32[world] array) >= consumer epoch + 1, then advance the consumer epoch.  Launched as a
+ * programmatic dependent of the push kernel, so it spins while that kernel's stores drain; kernels after it on the
+ * stream see the gathered rows.  A rank that never arrives trips a ~3 s watchdog (trap) instead of hanging. */
+VAST_API int vast_wait_arrivals(const void* flags, int world, int* sync_state, vast_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * OMC / ITC contrastive loss + hard-negative sampling + backward   (model/vast.py:405-440)
  * ---------------------------------------------------------------------------------------- */

@@ -28,6 +28,8 @@ SIGNATURES = {
     "vast_match_head": (i32, [vp, vp, i64, i64, i64, vp, vp, vp, f32, f32, f32, f32, f32, vp, vp, vp]),
     "vast_pack_pair": (i32, [vp, vp, i32, i64, i64, i64, vp, vp]),
     "vast_pack_pair_push": (i32, [vp, vp, i32, i64, i64, i64, i64, vp, vp, i32, vp]),
+    "vast_pack_pair_push_signal": (i32, [vp, vp, i32, i64, i64, i64, i64, vp, vp, i32, vp, i32, vp, vp]),
+    "vast_wait_arrivals": (i32, [vp, i32, vp, vp]),
     "vast_omc_workspace_bytes": (sz, [i64, i64, i64, i32, i32]),
     "vast_omc_step": (i32, [vp, i64, i64, i64, i64, f32, vp, f32, f32, u64, u64, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "vast_omc_step_local": (i32, [vp, vp, i32, i64, vp, i64, i64, f32, vp, f32, f32, u64, u64, vp, vp, i32, vp, vp, vp, vp, vp, vp,

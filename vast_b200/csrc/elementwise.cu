@@ -367,12 +367,34 @@ __device__ __forceinline__ void multimem_st16(void* p, uint4 v) {
                "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
                : "memory");
 }
-template <class TI>
+// Arrival flags (vast_pack_pair_push_signal): instead of a cross-rank barrier AFTER the kernel, the kernel itself tells
+// every rank "rank `me`'s rows of this step are in your buffer": every thread fences its stores at system scope, the
+// last block to finish (ticket) bumps this rank's push epoch and release-stores it into slot `me` of every rank's flag
+// array.  Consumers (vast_wait_arrivals, or the S GEMM's TMA producer) acquire-load their own array.  The kernel also
+// lets its successor in the stream start launching at once (griddepcontrol): what follows waits on the flags, not on
+// this kernel's end-of-grid flush.
+struct PushSignal {
+  unsigned* flag[PUSH_MAX_PEERS];  // every rank's flag array [world] (this rank's slot: index `me`)
+  int* state;                      // local: [0] ticket, [1] push epoch, [2] consumer epoch
+  int me;
+};
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+template <class TI, bool SIGNAL>
 __global__ void __launch_bounds__(256) pack_pair_push_kernel(const TI* __restrict__ ft, const TI* __restrict__ fc, int64_t bs,
-                                                            int dim8, int64_t ld, int64_t row_offset, const PushDst dst) {
+                                                            int dim8, int64_t ld, int64_t row_offset, const PushDst dst,
+                                                            const PushSignal sig) {
+  if constexpr (SIGNAL) pdl_trigger();
   const int64_t total = bs * 2 * dim8;
-  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (i >= total) return;
+  // (the signalling form runs a grid-stride loop over few, fat blocks: one system-scope fence per block)
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
   const int64_t b = i / (2 * dim8);
   const int v = static_cast<int>(i - b * 2 * dim8);  // 16-byte vector inside the packed row
   const bool second = v >= dim8;
@@ -405,6 +427,39 @@ __global__ void __launch_bounds__(256) pack_pair_push_kernel(const TI* __restric
   } else {
     for (int r = 0; r < dst.world; ++r) *reinterpret_cast<uint4*>(static_cast<char*>(dst.peer[r]) + off) = o;
   }
+  }
+  if constexpr (SIGNAL) {
+    __syncthreads();  // the block's stores happen before thread 0's fence, which is cumulative over them
+    if (threadIdx.x == 0) {
+      __threadfence_system();  // ... and are performed (remote ones included) before the block takes its ticket
+      if (atomicAdd(&sig.state[0], 1) == static_cast<int>(gridDim.x) - 1) {  // every block's stores are fenced
+        __threadfence_system();
+        const unsigned e = static_cast<unsigned>(sig.state[1]) + 1u;
+        sig.state[1] = static_cast<int>(e);
+        sig.state[0] = 0;
+        for (int r = 0; r < dst.world; ++r) st_release_sys_u32(sig.flag[r] + sig.me, e);
+      }
+    }
+  }
+}
+
+// One warp: lane r waits until rank r's rows of this step have arrived (flag >= consumer epoch + 1), then the consumer
+// epoch advances.  Launched as a programmatic dependent of the push kernel: it spins while that kernel's stores drain.
+__global__ void __launch_bounds__(32) wait_arrivals_kernel(const unsigned* __restrict__ flags, int world, int* __restrict__ state) {
+  pdl_trigger();
+  const unsigned want = static_cast<unsigned>(state[2]) + 1u;
+  const int r = threadIdx.x;
+  if (r < world) {
+    const long long t0 = clock64();
+    while (static_cast<int>(ld_acquire_sys_u32(flags + r) - want) < 0) {
+      if (clock64() - t0 > 6000000000LL) {  // ~3 s: a rank never pushed -- trap instead of hanging the GPU
+        printf("vast_b200: arrival watchdog (rank slot %d, want %u, have %u)\n", r, want, ld_acquire_sys_u32(flags + r));
+        __trap();
+      }
+    }
+  }
+  __syncwarp();
+  if (r == 0) state[2] = static_cast<int>(want);
 }
 
 // ------------------------------------------------------------------ negative gather + 3-way concat
@@ -651,9 +706,9 @@ extern "C" int vast_pack_pair(const void* feat_t, const void* feat_cond, int dty
   return VAST_OK;
 }
 
-extern "C" int vast_pack_pair_push(const void* feat_t, const void* feat_cond, int dtype, int64_t bs, int64_t dim, int64_t ld_in,
-                                   int64_t row_offset, void* multicast_ptr, void* const* peer_ptrs, int world,
-                                   vast_stream_t stream) {
+static int pack_pair_push_impl(const void* feat_t, const void* feat_cond, int dtype, int64_t bs, int64_t dim, int64_t ld_in,
+                               int64_t row_offset, void* multicast_ptr, void* const* peer_ptrs, int world,
+                               const PushSignal* sig, vast_stream_t stream) {
   VAST_REQUIRE(feat_t && feat_cond && dim > 0 && ld_in >= dim && bs >= 0 && row_offset >= 0, VAST_ERR_INVALID,
                "pack_pair_push: bad arguments");
   VAST_REQUIRE(world >= 1 && world <= PUSH_MAX_PEERS && (multicast_ptr != nullptr || peer_ptrs != nullptr), VAST_ERR_INVALID,
@@ -662,6 +717,7 @@ extern "C" int vast_pack_pair_push(const void* feat_t, const void* feat_cond, in
                    ((reinterpret_cast<uintptr_t>(feat_t) | reinterpret_cast<uintptr_t>(feat_cond) |
                      reinterpret_cast<uintptr_t>(multicast_ptr)) & 15) == 0,
                VAST_ERR_UNSUPPORTED, "pack_pair_push: dim and ld must be multiples of 8, pointers 16-byte aligned");
+  VAST_REQUIRE(bs > 0 || sig == nullptr, VAST_ERR_INVALID, "pack_pair_push_signal: an empty block cannot signal");
   if (bs == 0) return VAST_OK;
   PushDst dst;
   memset(&dst, 0, sizeof(dst));
@@ -673,17 +729,64 @@ extern "C" int vast_pack_pair_push(const void* feat_t, const void* feat_cond, in
                    "pack_pair_push: bad peer pointer %d", r);
       dst.peer[r] = peer_ptrs[r];
     }
+  PushSignal none;
+  memset(&none, 0, sizeof(none));
+  const PushSignal& sg = sig ? *sig : none;
   const int dim8 = static_cast<int>(dim / 8);
-  const unsigned g = static_cast<unsigned>(ceil_div64(bs * 2 * dim8, 256));
+  unsigned g = static_cast<unsigned>(ceil_div64(bs * 2 * dim8, 256));
+  if (sig != nullptr && g > static_cast<unsigned>(2 * device_sm_count())) g = static_cast<unsigned>(2 * device_sm_count());
+#define VAST_PUSH(T)                                                                                                           \
+  do {                                                                                                                         \
+    if (sig)                                                                                                                   \
+      VAST_TIMED(stream, "pack_pair_push", (pack_pair_push_kernel<T, true><<<g, 256, 0, stream>>>(                              \
+                                               static_cast<const T*>(feat_t), static_cast<const T*>(feat_cond), bs, dim8, ld_in, row_offset, dst, sg))); \
+    else                                                                                                                       \
+      VAST_TIMED(stream, "pack_pair_push", (pack_pair_push_kernel<T, false><<<g, 256, 0, stream>>>(                             \
+                                               static_cast<const T*>(feat_t), static_cast<const T*>(feat_cond), bs, dim8, ld_in, row_offset, dst, sg))); \
+  } while (0)
   if (dtype == VAST_F32)
-    VAST_TIMED(stream, "pack_pair_push", (pack_pair_push_kernel<float><<<g, 256, 0, stream>>>(static_cast<const float*>(feat_t), static_cast<const float*>(feat_cond), bs, dim8, ld_in, row_offset, dst)));
+    VAST_PUSH(float);
   else if (dtype == VAST_BF16)
-    VAST_TIMED(stream, "pack_pair_push", (pack_pair_push_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(feat_t), static_cast<const __nv_bfloat16*>(feat_cond), bs, dim8, ld_in, row_offset, dst)));
+    VAST_PUSH(__nv_bfloat16);
   else if (dtype == VAST_F16)
-    VAST_TIMED(stream, "pack_pair_push", (pack_pair_push_kernel<__half><<<g, 256, 0, stream>>>(static_cast<const __half*>(feat_t), static_cast<const __half*>(feat_cond), bs, dim8, ld_in, row_offset, dst)));
+    VAST_PUSH(__half);
   else
     VAST_REQUIRE(false, VAST_ERR_UNSUPPORTED, "pack_pair_push: bad dtype");
+#undef VAST_PUSH
   VAST_LAUNCH_OK("pack_pair_push");
+  return VAST_OK;
+}
+
+extern "C" int vast_pack_pair_push(const void* feat_t, const void* feat_cond, int dtype, int64_t bs, int64_t dim, int64_t ld_in,
+                                   int64_t row_offset, void* multicast_ptr, void* const* peer_ptrs, int world,
+                                   vast_stream_t stream) {
+  return pack_pair_push_impl(feat_t, feat_cond, dtype, bs, dim, ld_in, row_offset, multicast_ptr, peer_ptrs, world, nullptr, stream);
+}
+
+extern "C" int vast_pack_pair_push_signal(const void* feat_t, const void* feat_cond, int dtype, int64_t bs, int64_t dim,
+                                          int64_t ld_in, int64_t row_offset, void* multicast_ptr, void* const* peer_ptrs,
+                                          int world, void* const* flag_ptrs, int my_rank, int* sync_state,
+                                          vast_stream_t stream) {
+  VAST_REQUIRE(peer_ptrs != nullptr || multicast_ptr != nullptr, VAST_ERR_INVALID, "pack_pair_push_signal: no destination");
+  VAST_REQUIRE(flag_ptrs && sync_state && world >= 1 && world <= PUSH_MAX_PEERS && my_rank >= 0 && my_rank < world,
+               VAST_ERR_INVALID, "pack_pair_push_signal: bad flag arguments");
+  PushSignal sig;
+  memset(&sig, 0, sizeof(sig));
+  for (int r = 0; r < world; ++r) {
+    VAST_REQUIRE(flag_ptrs[r] != nullptr && (reinterpret_cast<uintptr_t>(flag_ptrs[r]) & 3) == 0, VAST_ERR_INVALID,
+                 "pack_pair_push_signal: bad flag pointer %d", r);
+    sig.flag[r] = static_cast<unsigned*>(flag_ptrs[r]);
+  }
+  sig.state = sync_state;
+  sig.me = my_rank;
+  return pack_pair_push_impl(feat_t, feat_cond, dtype, bs, dim, ld_in, row_offset, multicast_ptr, peer_ptrs, world, &sig, stream);
+}
+
+extern "C" int vast_wait_arrivals(const void* flags, int world, int* sync_state, vast_stream_t stream) {
+  VAST_REQUIRE(flags && sync_state && world >= 1 && world <= 32, VAST_ERR_INVALID, "wait_arrivals: bad arguments");
+  VAST_TIMED(stream, "wait_arrivals",
+             (launch_ex(wait_arrivals_kernel, 1, 32, 0, stream, 1, static_cast<const unsigned*>(flags), world, sync_state)));
+  VAST_LAUNCH_OK("wait_arrivals");
   return VAST_OK;
 }
 

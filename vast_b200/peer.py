@@ -5,8 +5,9 @@ The gathered `[N, 2D]` bf16 buffer lives in symmetric memory (`torch.distributed
 allocation mapped into every rank of the node, plus an NVSwitch multicast mapping where the driver offers one).
 `vast_pack_pair_push` converts this rank's rows and stores every 16-byte vector straight into the buffer of ALL ranks
 (one `multimem.st` to the multicast address -- more than four ranks -- or one peer store per rank); a
-symmetric-memory barrier on the same stream publishes it.  Two buffers alternate so that a rank that is one step ahead never overwrites rows a slower
-rank is still reading."""
+symmetric-memory barrier on the same stream publishes it.  Two buffers alternate so that a rank that is one step ahead
+never overwrites rows a slower rank is still reading.  (An arrival-flag protocol without the barrier exists as an opt-in
+experiment, see PackedGather.)"""
 from __future__ import annotations
 
 import ctypes
@@ -36,6 +37,25 @@ class PackedGather:
         env = os.environ.get("VAST_PEER_MULTICAST")
         self.use_multicast = (env == "1") if env in ("0", "1") else self.world > 4
         self.turn = 0
+        # Opt-in experiment (VAST_PEER_SIGNAL=1): arrival flags instead of a barrier after the push
+        # (vast_pack_pair_push_signal / vast_wait_arrivals) -- per buffer a uint32[world] array in symmetric memory that
+        # the peers' push kernels write, plus local epochs; the waiting kernel starts while the push kernel's stores
+        # still drain.  Correct (multi_gpu_check, bench parity) but measured SLOWER at 2 GPUs: 113.0 vs 106.9 us/step --
+        # system-scope fences inside the push kernel (one per block, 296 blocks) cost more than the end-of-grid flush
+        # plus the barrier kernel they replace.
+        self.use_flags = os.environ.get("VAST_PEER_SIGNAL", "0") == "1"
+        self.flags, self.fhdls, self.state = [], [], []
+        if self.use_flags:
+            for _ in range(2):
+                f = symm.empty(32, dtype=torch.int32, device=device)
+                f.zero_()
+                self.flags.append(f)
+                self.fhdls.append(symm.rendezvous(f, self.group))
+                self.state.append(torch.zeros(4, dtype=torch.int32, device=device))
+            torch.cuda.synchronize(device)
+            for h in self.fhdls:
+                h.barrier(channel=0)          # every rank's flags are zero before anyone signals
+            torch.cuda.synchronize(device)
 
     def _dst(self, i):
         h = self.hdls[i]
@@ -57,6 +77,14 @@ class PackedGather:
         self.turn = i ^ 1
         ft, fc = feat_t.contiguous(), feat_cond.contiguous()
         mc, peers = self._dst(i)
+        if self.use_flags:
+            fl = (ctypes.c_void_p * self.world)(*[int(p) for p in self.fhdls[i].buffer_ptrs])
+            check(lib().vast_pack_pair_push_signal(ptr(ft), ptr(fc), dtype_code(ft.dtype), self.bs, self.dim, self.dim,
+                                                   self.rank * self.bs, ctypes.c_void_p(mc) if mc else None, peers,
+                                                   self.world, fl, self.rank, ptr(self.state[i]), stream_ptr()),
+                  "pack_pair_push_signal")
+            check(lib().vast_wait_arrivals(ptr(self.flags[i]), self.world, ptr(self.state[i]), stream_ptr()), "wait_arrivals")
+            return self.bufs[i]
         check(lib().vast_pack_pair_push(ptr(ft), ptr(fc), dtype_code(ft.dtype), self.bs, self.dim, self.dim,
                                         self.rank * self.bs, ctypes.c_void_p(mc) if mc else None, peers, self.world,
                                         stream_ptr()), "pack_pair_push")
