@@ -482,3 +482,30 @@ def test_single_rank_symmetric_form_and_its_fallback(case, fused, monkeypatch):
     b = ops.omc_step_local(t.cuda(), good_c.cuda(), 0.07, seed=seed, offset=offset)
     torch.cuda.synchronize()
     assert a["loss"].item() == b["loss"].item() and torch.equal(a["grad_t"], b["grad_t"]) and torch.equal(a["neg_idx"], b["neg_idx"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bs", [512, 1024])
+def test_cluster_split_k_dq_equals_default(bs, monkeypatch):
+    """VAST_OMC_KSPLIT=1: the dQ GEMM of a small per-rank batch as clusters of two CTA pairs per output tile, the second
+    pair's accumulator handed over through distributed shared memory.  Same step, same negatives, gradients equal to
+    the default tiling up to the fp32 summation order."""
+    from vast_b200 import ops
+    n, dim = 4096, 1024
+    g = torch.Generator().manual_seed(11)
+    t = torch.nn.functional.normalize(torch.randn(n, dim, generator=g), dim=-1)
+    c = torch.nn.functional.normalize(t + 0.7 * torch.randn(n, dim, generator=g), dim=-1)
+    pack = ops.pack_pair(t.cuda(), c.cuda())
+    temp = torch.full((1,), 0.07, device="cuda")
+    monkeypatch.delenv("VAST_OMC_KSPLIT", raising=False)
+    ref = ops.omc_step(pack, bs, n - 2 * bs, temp, seed=5, offset=0)
+    ref = {k: ref[k].clone() for k in ("loss", "grad_t", "grad_cond", "grad_temp", "neg_idx")}
+    monkeypatch.setenv("VAST_OMC_KSPLIT", "1")
+    out = ops.omc_step(pack, bs, n - 2 * bs, temp, seed=5, offset=0)
+    torch.cuda.synchronize()
+    assert torch.equal(out["neg_idx"], ref["neg_idx"])
+    assert abs(out["loss"].item() - ref["loss"].item()) <= 1e-6 * abs(ref["loss"].item())
+    for k in ("grad_t", "grad_cond"):
+        err = (out[k] - ref[k]).norm(dim=1) / ref[k].norm(dim=1).clamp_min(1e-30)
+        assert err.max().item() < 1e-5, (k, err.max().item())
+    assert abs(out["grad_temp"].item() - ref["grad_temp"].item()) <= 1e-5 * abs(ref["grad_temp"].item()) + 1e-9

@@ -45,6 +45,16 @@ static int gemm_impl(const void* A, int64_t lda, int dtype_a, const void* B, int
   if (rc) return rc;
   rc = B_MN ? tc::make_tmap_2d(&P.tmB[0], B, dtype_b, K, N, ldb, tc::BK) : tc::make_tmap_2d(&P.tmB[0], B, dtype_b, N, K, ldb, 256 / cl);
   if (rc) return rc;
+  if (const char* e = getenv("VAST_GEMM_PROBE")) {
+    if (atoi(e) == 7 && cl == 2) {  // cluster split-K: one single-tile item per cluster of two CTA pairs
+      tc::fill_shape(&P.g, 1, (int)M, (int)N, (int)K, 256, dtype_a == VAST_BF16 ? 1 : 0, dtype_b == VAST_BF16 ? 1 : 0, B_MN, 2);
+      P.g.n_splits = P.g.n_tiles;
+      P.g.tiles_per_split = 1;
+      P.g.num_items = P.g.m_groups * P.g.n_tiles;
+      P.epi = {C, ldc, 0, 0, alpha};
+      return tc::launch_gemm_cl<Epi, 256, 6, 4, B_MN, 2, 0, 1, 0, 2>(P, stream, name, 0);
+    }
+  }
   if (P.g.k_splits > 1) {
     Workspace ws(workspace, workspace_bytes);
     float* part = ws.take<float>(static_cast<size_t>(P.g.k_splits) * M * N);
@@ -59,7 +69,7 @@ static int gemm_impl(const void* A, int64_t lda, int dtype_a, const void* B, int
   }
   P.epi = {C, ldc, 0, 0, alpha};
   // diagnostics (scripts/gemm_probe.py): VAST_GEMM_PROBE = 1 tensor pipe alone, 2 operand ingest alone, 3 clusters of two
-  // pairs sharing A, 4 = 3 + 1, 5 = 3 + 2, 6 = 512-wide tiles (NN only)
+  // pairs sharing A, 4 = 3 + 1, 5 = 3 + 2; 7 = cluster split-K (single wave of single-tile items)
   if (const char* e = getenv("VAST_GEMM_PROBE")) {
     const int mode = atoi(e);
     if (cl == 2 && mode >= 1 && mode <= 6) {

@@ -145,6 +145,15 @@ __device__ __forceinline__ WorkItem decode_item(const GemmShape& g, int idx, int
   return w;
 }
 
+// cluster split-K: pair `ks_rank` of the cluster takes its half of the item's k-blocks
+__device__ __forceinline__ void slice_k(WorkItem& w, int ks_rank) {
+  const int half = (w.kb_end - w.kb_begin + 1) >> 1;
+  if (ks_rank == 0)
+    w.kb_end = min(w.kb_begin + half, w.kb_end);
+  else
+    w.kb_begin = min(w.kb_begin + half, w.kb_end);
+}
+
 // A_RES > 0 ("A-stationary"): the CTA's whole A row block (up to A_RES k-blocks) stays resident in shared memory for
 // all N-tiles of a work item and the ring stages carry B only.  For short K (retrieval at D = 512: 8 k-blocks) the
 // operand traffic L2 -> SM is what binds the mainloop -- every 256 x 256 x 512 tile re-fetches 256 KB of A next to
@@ -160,7 +169,7 @@ struct SmemLayout {
   static constexpr uint32_t BAR_BYTES = 256;  // 2*STAGES + 6 barriers + tmem slot
   static constexpr uint32_t EPI_OFFSET = BAR_OFFSET + BAR_BYTES;
   static constexpr uint32_t ALIGN_SLACK = 1024;
-  static_assert(2 * STAGES * 8 + 6 * 8 + 8 <= BAR_BYTES, "barrier block too small");
+  static_assert(2 * STAGES * 8 + 8 * 8 + 8 <= BAR_BYTES, "barrier block too small");
 };
 
 // Epilogues that declare `static constexpr bool kHasFinish` get finish(epilogue warp, lane, NE) called by every epilogue
@@ -213,11 +222,21 @@ struct HasFinish<E, std::void_t<decltype(E::kHasFinish)>> : std::true_type {};
 //         the two tiles.  Protocol on top of the pair's: `empty` barriers count the commits of BOTH leaders (a stage
 //         is rewritten by two producers), commits to `empty` are multicast to all four CTAs; `tfull` / `tempty` stay
 //         inside a pair.  The host guarantees that items 2j, 2j+1 differ only in their column range (can_share_a()).
+// KS = 2 (CTA pairs only): CLUSTER SPLIT-K.  Clusters of four CTAs = two pairs that compute the SAME output tile, each over
+//         half of the k-blocks; when both mainloops have drained, the second pair ships its accumulator (128 x BN fp32
+//         per CTA) through distributed shared memory into the first pair's -- now idle -- operand ring, and the first
+//         pair's epilogue adds it chunk by chunk before the functor sees the values: a fixed-order sum, no partials in
+//         HBM, no reduce kernel.  For GEMMs with too few output tiles to fill the machine and a long K (dQ at small
+//         per-rank batches).  One single-tile work item per cluster (the host sizes the grid accordingly).
 // PROBE (diagnostics, scripts/gemm_probe.py): 1 = no operand loads, the MMA issuer never waits for data (the tensor
 //         pipe's own rate); 2 = loads only, stages are released without MMAs (the L2 -> SM ingest rate).  Results are garbage.
-template <class Epi, int BN, int STAGES, int NE, bool B_MN, int CL, int A_RES = 0, int MC = 1, int PROBE = 0>
+template <class Epi, int BN, int STAGES, int NE, bool B_MN, int CL, int A_RES = 0, int MC = 1, int PROBE = 0, int KS = 1>
 __global__ void __launch_bounds__(64 + 32 * NE + 32 * Epi::kAuxWarps, 1)
 gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
+  static_assert(KS == 1 || (KS == 2 && CL == 2 && MC == 1 && A_RES == 0 && BN <= 256 && Epi::kAuxWarps == 0 &&
+                            !HasSecondPass<Epi>::value && !HasTileEnd<Epi>::value),
+                "cluster split-K: two CTA pairs per output tile");
+  static_assert(KS == 1 || STAGES * (BM * BK * 2 + BN * BK * 2 / 2) >= BM * BN * 4, "the ring must hold one accumulator tile");
   static_assert(MC == 1 || (MC == 2 && CL == 2 && A_RES == 0 && BN != 512), "A-sharing clusters of two CTA pairs");
   static_assert(NE == 4 || NE == 8, "4 or 8 epilogue warps");
   static_assert(BN == 64 || BN == 128 || BN == 256 || BN == 512, "BN");
@@ -255,7 +274,9 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
   uint64_t* tempty = tfull + 2;
   uint64_t* afull = tempty + 2;   // resident A loaded (A_RES)
   uint64_t* aempty = afull + 1;   // every MMA of the item that read the resident A has retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 1);
+  uint64_t* sfull = aempty + 1;   // KS: the other pair's accumulator has landed in this CTA's ring
+  uint64_t* sfree = sfull + 1;    // KS: the first pair's ring may be overwritten (its MMAs have retired)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sfree + 1);
   uint8_t* epi_smem = smem + L::EPI_OFFSET;
 
   const int warp = threadIdx.x >> 5;
@@ -268,8 +289,9 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
   const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * pair_rank));
   const uint16_t all_mask = MC == 2 ? static_cast<uint16_t>(0xF) : pair_mask;
   (void)pair_rank;
-  const int cluster_id = static_cast<int>(blockIdx.x) / CL;
-  const int num_clusters = static_cast<int>(gridDim.x) / CL;
+  const int cluster_id = static_cast<int>(blockIdx.x) / (CL * KS);  // KS = 2: both pairs of a cluster work on the same items
+  const int num_clusters = static_cast<int>(gridDim.x) / (CL * KS);
+  const int ks_rank = KS == 2 ? pair_rank : 0;
 
   if (warp == 0 && lane == 0) {
     for (int p = 0; p < g.num_problems; ++p) {
@@ -286,6 +308,8 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
     }
     ptx::mbar_init(afull, 1);
     ptx::mbar_init(aempty, 1);
+    ptx::mbar_init(sfull, NE);
+    ptx::mbar_init(sfree, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -314,7 +338,8 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
       }
       (void)amn_prob;
       for (int item = cluster_id; item < g.num_items; item += num_clusters) {
-        const WorkItem w = decode_item<BN, CUSTOM>(g, item, cta_rank);
+        WorkItem w = decode_item<BN, CUSTOM>(g, item, cta_rank);
+        if constexpr (KS == 2) slice_k(w, ks_rank);
         if constexpr (A_RES > 0) {
           // the item's A row block, once: k-block kb at A_BYTES * kb (the previous item's MMAs must have retired)
           ptx::mbar_wait(aempty, a_phase ^ 1);
@@ -431,7 +456,8 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
       }
       (void)amn_prob;
       for (int item = cluster_id; item < g.num_items; item += num_clusters) {
-        const WorkItem w = decode_item<BN, CUSTOM>(g, item, cta_rank);
+        WorkItem w = decode_item<BN, CUSTOM>(g, item, cta_rank);
+        if constexpr (KS == 2) slice_k(w, ks_rank);
         if constexpr (A_RES > 0) {
           ptx::mbar_wait(afull, a_phase);
           ptx::tc_fence_after_sync();
@@ -493,6 +519,47 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
     int acc = 0;
     uint32_t acc_phase = 0;
     Epi epi(P.epi, epi_smem);
+    if constexpr (KS == 2) {
+      if (ks_rank == 1) {
+        // ---- second pair of a split-K cluster: no functor -- the accumulator goes to the first pair's ring
+        //      (layout: 16-byte vector j of chunk c of row r at ((c * 8 + j) * 128 + r) * 16: conflict-free on both sides)
+        const uint32_t stage_remote = ptx::mapa_u32(smem + L::RING_OFFSET, static_cast<uint32_t>(cta_rank));
+        const uint32_t sfull_remote = ptx::mapa_u32(sfull, static_cast<uint32_t>(cta_rank));
+        const int row_in_cta = q * 32 + lane;
+        for (int item = cluster_id; item < g.num_items; item += num_clusters) {
+          ptx::mbar_wait(&tfull[acc], acc_phase);
+          ptx::tc_fence_after_sync();
+          ptx::mbar_wait_cluster(sfree, 0);  // (one item per cluster: phase 0)
+#pragma unroll 1
+          for (int c = 0; c < COLS_PER_WARP; c += 32) {
+            const int col_in_tile = half * COLS_PER_WARP + c;
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + col_in_tile), v);
+            ptx::tmem_ld_wait();
+            const uint32_t dst = stage_remote + static_cast<uint32_t>(((col_in_tile >> 5) * 8 * 128 + row_in_cta) * 16);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              ptx::st_cluster_v4(dst + static_cast<uint32_t>(j * 128 * 16), __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          }
+          // every lane's stores are ordered before the warp's ONE remote arrival (fence, warp barrier, release-arrive)
+          ptx::fence_acq_rel_cluster();
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::mbar_arrive_cluster(sfull_remote);
+            ptx::mbar_arrive_leader(&tempty[acc]);
+          }
+          if (++acc == ACC) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+      }  // (finish() below: contributes zeros, takes its ticket)
+    }
+    if (KS == 2 && ks_rank == 1) {
+      // handled above
+    } else
     for (int item = cluster_id; item < g.num_items; item += num_clusters) {
       const WorkItem w = decode_item<BN, CUSTOM>(g, item, cta_rank);
       if (CUSTOM && w.tile_end <= w.tile_begin) continue;  // empty slot of an explicit schedule
@@ -516,6 +583,12 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
         epi.prefetch(ctx, col_tile + half * cpw);
         ptx::mbar_wait(&tfull[acc], acc_phase);
         ptx::tc_fence_after_sync();
+        if constexpr (KS == 2) {
+          // this pair's MMAs have retired and its producer has nothing left to load (one item per cluster): the ring
+          // is free for the other pair's accumulator
+          if (ew == 0 && lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_u32(sfree, static_cast<uint32_t>(cta_rank + 2)));
+          ptx::mbar_wait_cluster(sfull, 0);
+        }
 #pragma unroll(Epi::kUnrollChunks ? COLS_PER_WARP / 32 : 1)
         for (int c = 0; c < COLS_PER_WARP; c += 32) {
           if (CUSTOM && c >= cpw) break;
@@ -527,6 +600,17 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
           // software pipeline: the next chunk's global operands are requested before this chunk's wait
           epi.advance(ctx, col_tile + col_in_tile + 32, c + 32 < cpw);
           ptx::tmem_ld_wait();
+          if constexpr (KS == 2) {  // + the other half of K, in a fixed order
+            const float4* part = reinterpret_cast<const float4*>(smem + L::RING_OFFSET) + ((col_in_tile >> 5) * 8 * 128 + q * 32 + lane);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 x = part[j * 128];
+              v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + x.x);
+              v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + x.y);
+              v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + x.z);
+              v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + x.w);
+            }
+          }
           epi.chunk(ctx, v, col_tile + col_in_tile);
           __syncwarp();
         }
@@ -613,7 +697,29 @@ inline bool can_share_a(const GemmShape& g) {
          g.n_tiles % g.n_splits == 0 && g.num_items % 2 == 0;
 }
 
-template <class Epi, int BN, int STAGES, int NE, bool B_MN, int CL, int A_RES = 0, int MC = 1, int PROBE = 0>
+// How many clusters of `cluster` CTAs of `kern` the device holds at once (0 = none).
+template <class K>
+int resident_clusters(K kern, int cluster, int block, size_t smem) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(device_sm_count() / cluster * cluster), 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+template <class Epi, int BN, int STAGES, int NE, bool B_MN, int CL, int A_RES = 0, int MC = 1, int PROBE = 0, int KS = 1>
 int launch_gemm_cl(const KernelParams<typename Epi::Params>& P, cudaStream_t stream, const char* name, size_t epi_smem_bytes) {
   using L = SmemLayout<BN, STAGES, CL, A_RES>;
   const size_t smem = L::EPI_OFFSET + L::ALIGN_SLACK + epi_smem_bytes;
@@ -622,7 +728,9 @@ int launch_gemm_cl(const KernelParams<typename Epi::Params>& P, cudaStream_t str
   VAST_REQUIRE(A_RES == 0 || (P.g.k_blocks <= A_RES && P.g.k_splits == 1), VAST_ERR_INVALID,
                "%s: %d k-blocks do not fit the %d resident ones", name, P.g.k_blocks, A_RES);
   VAST_REQUIRE(MC == 1 || can_share_a(P.g), VAST_ERR_INVALID, "%s: the work items do not pair up for A sharing", name);
-  auto kern = gemm_tc_kernel<Epi, BN, STAGES, NE, B_MN, CL, A_RES, MC, PROBE>;
+  VAST_REQUIRE(KS == 1 || (P.g.k_splits == 1 && P.g.tiles_per_split == 1 && P.g.tail_groups == 0 && P.g.n_sched == 0),
+               VAST_ERR_INVALID, "%s: cluster split-K takes single-tile whole-K work items", name);
+  auto kern = gemm_tc_kernel<Epi, BN, STAGES, NE, B_MN, CL, A_RES, MC, PROBE, KS>;
   constexpr int block = 64 + 32 * NE + 32 * Epi::kAuxWarps;
   static size_t attr_smem = 0;  // per instantiation; grows monotonically
   static int resident = 0;      // MC = 2: clusters of four that fit the device at once
@@ -632,25 +740,21 @@ int launch_gemm_cl(const KernelParams<typename Epi::Params>& P, cudaStream_t str
     resident = 0;
   }
   int clusters_max = device_sm_count() / CL;  // in CTA pairs (or lone CTAs)
-  if constexpr (MC == 2) {
+  if constexpr (MC == 2 || KS == 2) {
     if (resident == 0) {
-      cudaLaunchConfig_t cfg;
-      memset(&cfg, 0, sizeof(cfg));
-      cfg.gridDim = dim3(static_cast<unsigned>(device_sm_count() / (CL * MC) * (CL * MC)), 1, 1);
-      cfg.blockDim = dim3(block, 1, 1);
-      cfg.dynamicSmemBytes = smem;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = CL * MC;
-      attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      int n = 0;
-      VAST_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
-      VAST_REQUIRE(n > 0, VAST_ERR_UNSUPPORTED, "%s: no cluster of %d CTAs fits this device", name, CL * MC);
-      resident = n;
+      resident = resident_clusters(kern, CL * MC * KS, block, smem);
+      VAST_REQUIRE(resident > 0, VAST_ERR_UNSUPPORTED, "%s: no cluster of %d CTAs fits this device", name, CL * MC * KS);
     }
     clusters_max = resident * MC;
+  }
+  if constexpr (KS == 2) {
+    // every work item is one cluster (two pairs), and all of them run at once
+    VAST_REQUIRE(P.g.num_items <= resident, VAST_ERR_UNSUPPORTED, "%s: %d split-K items exceed the %d resident clusters", name,
+                 P.g.num_items, resident);
+    if (P.g.num_items <= 0) return VAST_OK;
+    VAST_TIMED(stream, name, (launch_ex(kern, static_cast<unsigned>(P.g.num_items * CL * KS), block, smem, stream, CL * KS, P)));
+    VAST_LAUNCH_OK(name);
+    return VAST_OK;
   }
   int clusters = P.g.num_items < clusters_max ? P.g.num_items : clusters_max;
   if (MC == 2) clusters &= ~1;
@@ -658,6 +762,24 @@ int launch_gemm_cl(const KernelParams<typename Epi::Params>& P, cudaStream_t str
   VAST_TIMED(stream, name, (launch_ex(kern, static_cast<unsigned>(clusters * CL), block, smem, stream, CL * MC, P)));
   VAST_LAUNCH_OK(name);
   return VAST_OK;
+}
+
+// Resident clusters of the cluster split-K form of a kernel (plan-time query; -1 until first asked).
+template <class Epi, int BN, int STAGES, int NE, bool B_MN>
+int ks_resident(size_t epi_smem_bytes) {
+  static int r = -1;
+  if (r < 0) {
+    using L = SmemLayout<BN, STAGES, 2, 0>;
+    const size_t smem = L::EPI_OFFSET + L::ALIGN_SLACK + epi_smem_bytes;
+    auto kern = gemm_tc_kernel<Epi, BN, STAGES, NE, B_MN, 2, 0, 1, 0, 2>;
+    if (smem > 232448 || cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
+      cudaGetLastError();
+      r = 0;
+    } else {
+      r = resident_clusters(kern, 4, 64 + 32 * NE + 32 * Epi::kAuxWarps, smem);
+    }
+  }
+  return r;
 }
 
 // STAGES is the ring depth of a lone CTA (48 KB stages at BN = 256); a CTA pair has 32 KB stages and takes

@@ -1736,6 +1736,7 @@ struct OmcPlan {
   tc::GemmShape g_sym;  // the symmetric single-rank S GEMM (one problem)
   tc::GemmShape g_dq;   // dQ GEMM
   int bn_dq;
+  int ks_dq;  // 2: cluster split-K (two CTA pairs per output tile, reduced through distributed shared memory)
   int slots;
   int slots_sym, mblk_sym;  // symmetric form: slots per cond2t row, 128-row blocks = slots per t2cond row (0: not applicable)
   int pstride;              // partial slots allocated per row
@@ -1902,6 +1903,7 @@ static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, bool
   pl->nslab = ceil_div((int)n_total, PREP_ROWS);
   pl->ncs = pl->nslab * ceil_div(2 * (int)dim, 256);
   pl->bn_dq = dim > 128 ? 256 : 128;
+  pl->ks_dq = 1;
   int cl_dq = cl, max_ks = 4;
   // (512-wide tiles -- one accumulator stage, the A tile shared by two N = 256 instructions, ONE round of 64 items at the
   // headline shape instead of 1.73 -> 2 rounds of 128 -- are implemented (gemm_tc_kernel BN = 512) and correct, but
@@ -1924,8 +1926,35 @@ static void omc_plan(OmcPlan* pl, int64_t bs, int64_t n_total, int64_t dim, bool
     // would split K -- fp32 partials through HBM and a reduce kernel (measured: 25.0 + 16.9 us at 1024 rows, 20.9 +
     // 16.7 us at 512).  128 x 128 tiles on lone CTAs give 2 x m_blocks x D / 128 whole-K items instead: one kernel with
     // the gradient assembly, row statistics and final reduction fused (37.3 / 35.2 us), no partial buffer.
+    // Opt-in (VAST_OMC_KSPLIT=1): CLUSTER SPLIT-K (gemm_tc_kernel KS = 2).  Pair tiles keep the operand traffic per FLOP
+    // low, two pairs share one tile's K range and the second hands its accumulator to the first through distributed
+    // shared memory: no partials in HBM, the gradient assembly / statistics / final reduction stay fused.  Correct
+    // (tests run it) but measured SLOWER than the lone-CTA tiles below: dQ 43.5 vs 37.4 us at 1024 rows per rank, 35.4
+    // vs 33.2 us at 512 -- the mainloop reaches the full pair rate (0.375 us per k-block, scripts/ksplit_probe.py) but
+    // the hand-off adds ~5 us of fixed cost and the whole epilogue is exposed behind it.
+    const char* ks_env = getenv("VAST_OMC_KSPLIT");
+    if (cl == 2 && dim > 128 && dim % 128 == 0 && ks_env != nullptr && ks_env[0] == '1') {
+      const int mg = tc::ceil_div_i(tc::ceil_div_i((int)bs, tc::BM), 2);
+      const int it256 = 2 * mg * tc::ceil_div_i((int)dim, 256), it128 = 2 * mg * tc::ceil_div_i((int)dim, 128);
+      const int q256 = tc::ks_resident<EpiGrad, 256, 6, 8, true>(128), q128 = tc::ks_resident<EpiGrad, 128, 8, 8, true>(128);
+      int bn = 0;
+      if (q256 > 0 && it256 <= q256 && it256 * 4 >= q256 * 3)
+        bn = 256;
+      else if (q128 > 0 && it128 <= q128 && it128 * 2 >= q128)
+        bn = 128;
+      else if (q256 > 0 && it256 <= q256 && it256 * 2 >= q256)
+        bn = 256;
+      if (bn != 0) {
+        pl->bn_dq = bn;
+        pl->ks_dq = 2;
+        tc::fill_shape(&pl->g_dq, 2, (int)bs, (int)dim, (int)n_total, bn, 0, 0, true, 2);
+        pl->g_dq.n_splits = pl->g_dq.n_tiles;  // one tile per item = one cluster
+        pl->g_dq.tiles_per_split = 1;
+        pl->g_dq.num_items = 2 * pl->g_dq.m_groups * pl->g_dq.n_tiles;
+      }
+    }
     const int items = 2 * tc::ceil_div_i((int)bs, tc::BM) * tc::ceil_div_i((int)dim, 128);
-    if (dim > 128 && items * 10 >= sms * 3) {
+    if (pl->ks_dq == 1 && dim > 128 && items * 10 >= sms * 3) {
       // ... and 128 x 64 tiles while those items cover less than half of the SMs: a lone CTA's mainloop is bound by
       // its operand ingest (32 KB per k-block at 128 x 128, 24 KB at 128 x 64), so twice the CTAs at 3/4 of the bytes
       // each finish sooner (512 rows per rank: step 53.4 -> 50.2 us; at 1024 rows the 128-wide tiles already fill the
@@ -2183,7 +2212,7 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
   // tensor maps of the dQ GEMM: A = Pt (fp16), B = the gathered features' fp16 copy read row-major (MN-major operand)
   const float c_sm = label_smoothing / static_cast<float>(N);
   CUtensorMap tmPa[2], tmKb[2], tmPaT;
-  const bool dq_share_a = share_a_enabled && need_grad && fused_stats && pl.bn_dq == 256 && tc::can_share_a(pl.g_dq) && !fuse &&
+  const bool dq_share_a = share_a_enabled && need_grad && fused_stats && pl.bn_dq == 256 && pl.ks_dq == 1 && tc::can_share_a(pl.g_dq) && !fuse &&
                           getenv("VAST_OMC_MIXED_TILES") == nullptr;
   if (need_grad) {
     for (int i = 0; i < 2; ++i) {
@@ -2257,7 +2286,7 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
     P.gate = gate;
     // balanced two-round schedule with 256- and 192-wide tiles where the regular tiling leaves a partial wave
     // (needs the fused statistics / final reduction: no per-slot partial buffers in this form)
-    if (fused_stats && pl.g_dq.cl == 2 && !dq_share_a) plan_mixed_tiles(&P.g, pl.bn_dq, device_sm_count() / 2);
+    if (fused_stats && pl.g_dq.cl == 2 && !dq_share_a && pl.ks_dq == 1) plan_mixed_tiles(&P.g, pl.bn_dq, device_sm_count() / 2);
     for (int i = 0; i < 2; ++i) {
       P.tmA[i] = tmPa[i];
       P.tmB[i] = tmKb[i];
@@ -2270,6 +2299,9 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
     fill_grad(P.epi, sym_mode);
     const char* name = gate ? "omc_dq_gemm_gated" : "omc_dq_gemm";
     if (dq_share_a) return tc::launch_gemm_cl<EpiGrad, 256, 6, 8, true, 2, 0, 2>(P, stream, name, 128);
+    if (pl.ks_dq == 2)
+      return pl.bn_dq == 256 ? tc::launch_gemm_cl<EpiGrad, 256, 6, 8, true, 2, 0, 1, 0, 2>(P, stream, name, 128)
+                             : tc::launch_gemm_cl<EpiGrad, 128, 8, 8, true, 2, 0, 1, 0, 2>(P, stream, name, 128);
     return pl.bn_dq == 512   ? tc::launch_gemm_cl<EpiGrad, 512, 4, 8, true, 2>(P, stream, name, 128)
            : pl.bn_dq == 256 ? tc::launch_gemm<EpiGrad, 256, 4, 8, true>(P, stream, name, 128)
            : pl.bn_dq == 64  ? tc::launch_gemm<EpiGrad, 64, 8, 8, true, 8>(P, stream, name, 128)
