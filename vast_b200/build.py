@@ -49,7 +49,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OBJ_DIR, s[:-3] + ".o")
         objs.append(obj)
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_time):
-            jobs.append([nvcc, *NVCC_FLAGS, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else []))
+            jobs.append([nvcc, *NVCC_FLAGS, *os.environ.get("VAST_NVCC_EXTRA", "").split(), "-c", src, "-o", obj] +
+                        (["-Xptxas", "-v"] if verbose else []))
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -28,6 +28,20 @@
 namespace vast {
 namespace tc {
 
+// -DVAST_EPI_TRACE (developer builds only, scripts/epi_trace.py): per-CTA %globaltimer stamps of the epilogue's phases --
+// [0] roles start, [1 + 2 t] accumulator of the CTA's t-th tile ready, [2 + 2 t] its epilogue done, [15] after finish().
+#ifdef VAST_EPI_TRACE
+__device__ unsigned long long g_epi_trace[1024 * 16];
+__device__ __forceinline__ void epi_trace(int slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  if (blockIdx.x < 1024 && slot < 16) g_epi_trace[blockIdx.x * 16 + slot] = t;
+}
+#define VAST_TRACE(cond, slot) do { if (cond) ::vast::tc::epi_trace(slot); } while (0)
+#else
+#define VAST_TRACE(cond, slot) do { } while (0)
+#endif
+
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 16-bit = one 128-byte swizzle span
 constexpr int MAX_PROBLEMS = 2;
@@ -519,6 +533,9 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
     int acc = 0;
     uint32_t acc_phase = 0;
     Epi epi(P.epi, epi_smem);
+    int trace_tile = 0;
+    (void)trace_tile;
+    VAST_TRACE(ew == 0 && lane == 0, 0);
     if constexpr (KS == 2) {
       if (ks_rank == 1) {
         // ---- second pair of a split-K cluster: no functor -- the accumulator goes to the first pair's ring
@@ -583,6 +600,7 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
         epi.prefetch(ctx, col_tile + half * cpw);
         ptx::mbar_wait(&tfull[acc], acc_phase);
         ptx::tc_fence_after_sync();
+        VAST_TRACE(ew == 0 && lane == 0, 1 + 2 * trace_tile);
         if constexpr (KS == 2) {
           // this pair's MMAs have retired and its producer has nothing left to load (one item per cluster): the ring
           // is free for the other pair's accumulator
@@ -600,6 +618,7 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
           // software pipeline: the next chunk's global operands are requested before this chunk's wait
           epi.advance(ctx, col_tile + col_in_tile + 32, c + 32 < cpw);
           ptx::tmem_ld_wait();
+          VAST_TRACE(ew == 0 && lane == 0 && trace_tile == 1 && c < 128, 5 + 2 * (c >> 5));
           if constexpr (KS == 2) {  // + the other half of K, in a fixed order
             const float4* part = reinterpret_cast<const float4*>(smem + L::RING_OFFSET) + ((col_in_tile >> 5) * 8 * 128 + q * 32 + lane);
 #pragma unroll
@@ -612,6 +631,7 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
             }
           }
           epi.chunk(ctx, v, col_tile + col_in_tile);
+          VAST_TRACE(ew == 0 && lane == 0 && trace_tile == 1 && c < 128, 6 + 2 * (c >> 5));
           __syncwarp();
         }
         if constexpr (HasSecondPass<Epi>::value) {
@@ -637,10 +657,13 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
           acc_phase ^= 1;
         }
         if constexpr (HasTileEnd<Epi>::value) epi.tile_end(ctx, col_tile, ew, NE);
+        VAST_TRACE(ew == 0 && lane == 0, 2 + 2 * trace_tile);
+        ++trace_tile;
       }
       epi.item_end(ctx);
     }
     if constexpr (HasFinish<Epi>::value) epi.finish(ew, lane, NE);
+    VAST_TRACE(ew == 0 && lane == 0, 15);
   }
 
   ptx::tc_fence_before_sync();

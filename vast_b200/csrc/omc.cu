@@ -2508,3 +2508,12 @@ extern "C" int vast_omc_step_local(const void* feat_t, const void* feat_cond, in
                        weight_floor, seed, offset, step_counter, debug_noise, flags, loss, neg_idx, grad_cond, grad_t, grad_temp,
                        lse, workspace, workspace_bytes, stream);
 }
+
+#ifdef VAST_EPI_TRACE
+// developer builds only: copy the per-CTA epilogue time stamps (gemm_tc.cuh) of the last GEMM launches of THIS translation unit (the contrastive step's) to the host
+extern "C" __attribute__((visibility("default"))) int vast_debug_epi_trace(unsigned long long* out, int ctas) {
+  if (ctas > 1024) ctas = 1024;
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, vast::tc::g_epi_trace, sizeof(unsigned long long) * 16 * ctas) == cudaSuccess ? 0 : -1;
+}
+#endif
