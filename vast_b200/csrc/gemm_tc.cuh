@@ -787,14 +787,16 @@ int launch_gemm_cl(const KernelParams<typename Epi::Params>& P, cudaStream_t str
   return VAST_OK;
 }
 
-// Resident clusters of the cluster split-K form of a kernel (plan-time query; -1 until first asked).
-template <class Epi, int BN, int STAGES, int NE, bool B_MN>
-int ks_resident(size_t epi_smem_bytes) {
+// Resident clusters of four CTAs of the A-sharing (MC = 2) or cluster split-K (KS = 2) form of a kernel: a decision-time
+// query, so that a device that cannot hold such clusters simply keeps the lone-pair form (-1 until first asked).
+template <class Epi, int BN, int STAGES, int NE, bool B_MN, int MC, int KS>
+int quad_resident(size_t epi_smem_bytes) {
+  static_assert(MC * KS == 2, "clusters of two CTA pairs");
   static int r = -1;
   if (r < 0) {
     using L = SmemLayout<BN, STAGES, 2, 0>;
     const size_t smem = L::EPI_OFFSET + L::ALIGN_SLACK + epi_smem_bytes;
-    auto kern = gemm_tc_kernel<Epi, BN, STAGES, NE, B_MN, 2, 0, 1, 0, 2>;
+    auto kern = gemm_tc_kernel<Epi, BN, STAGES, NE, B_MN, 2, 0, MC, 0, KS>;
     if (smem > 232448 || cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
       cudaGetLastError();
       r = 0;
@@ -803,6 +805,10 @@ int ks_resident(size_t epi_smem_bytes) {
     }
   }
   return r;
+}
+template <class Epi, int BN, int STAGES, int NE, bool B_MN>
+int ks_resident(size_t epi_smem_bytes) {
+  return quad_resident<Epi, BN, STAGES, NE, B_MN, 1, 2>(epi_smem_bytes);
 }
 
 // STAGES is the ring depth of a lone CTA (48 KB stages at BN = 256); a CTA pair has 32 KB stages and takes

@@ -2201,7 +2201,7 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
     P.g = pl.g_sym;  // the cond2t problem only: tmA[0] = local cond rows, tmB[0] = all t rows
     P.epi.ref2_out = ref2;
     P.epi.zmax_bits = reinterpret_cast<const unsigned*>(&wflags[4]);
-    if (share_a_enabled && tc::can_share_a(P.g)) {
+    if (share_a_enabled && tc::can_share_a(P.g) && tc::quad_resident<E, 256, 6, 8, false, 2, 1>(E::SMEM_BYTES) > 0) {
       rc = tc::make_tmap_2d(&P.tmA[0], pk + row_offset * 2 * dim + dim, VAST_BF16, bs, dim, 2 * dim, 64);
       if (rc) return rc;
       return tc::launch_gemm_cl<E, 256, 6, 8, false, 2, 0, 2>(P, stream, "omc_soft_gemm_sym", E::SMEM_BYTES);
@@ -2213,7 +2213,7 @@ static int omc_step_impl(const void* feat_t_in, const void* feat_cond_in, int in
   const float c_sm = label_smoothing / static_cast<float>(N);
   CUtensorMap tmPa[2], tmKb[2], tmPaT;
   const bool dq_share_a = share_a_enabled && need_grad && fused_stats && pl.bn_dq == 256 && pl.ks_dq == 1 && tc::can_share_a(pl.g_dq) && !fuse &&
-                          getenv("VAST_OMC_MIXED_TILES") == nullptr;
+                          getenv("VAST_OMC_MIXED_TILES") == nullptr && tc::quad_resident<EpiGrad, 256, 6, 8, true, 2, 1>(128) > 0;
   if (need_grad) {
     for (int i = 0; i < 2; ++i) {
       rc = tc::make_tmap_2d(&tmPa[i], Pbuf + static_cast<int64_t>(i) * bs * pl.npad, VAST_F16, bs, n_total, pl.npad,
