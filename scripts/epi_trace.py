@@ -20,7 +20,7 @@ fn = lib().vast_debug_epi_trace
 fn.restype = ctypes.c_int
 ctas = 128
 arr = np.zeros((ctas, 16), dtype=np.uint64)
-assert fn(arr.ctypes.data_as(ctypes.c_void_p), ctas) == 0
+assert fn(arr.ctypes.data_as(ctypes.c_void_p), ctas, 0) == 0
 a = arr.astype(np.int64)
 t0 = a[:, 0].min()
 rel = (a - t0) / 1e3   # us
@@ -38,3 +38,14 @@ print("tile 2 epilogue done ", stat(rel[:, 4]), "  duration", stat(rel[:, 4] - r
 print("after finish()       ", stat(rel[:, 15]), "  since tile 2 epilogue", stat(rel[:, 15] - rel[:, 4]))
 for ch in range(4):
     print(f"tile 2 chunk {ch}: TMEM values in registers", stat(rel[:, 5 + 2 * ch] - rel[:, 3]), "  functor done", stat(rel[:, 6 + 2 * ch] - rel[:, 3]))
+
+# ---- the symmetric S GEMM (tag 1): 4 tiles per CTA pair
+arr = np.zeros((ctas, 16), dtype=np.uint64)
+assert fn(arr.ctypes.data_as(ctypes.c_void_p), ctas, 1) == 0
+a = arr.astype(np.int64)
+rel = (a - a[:, 0].min()) / 1e3
+print("--- symmetric S GEMM")
+print("roles start          ", stat(rel[:, 0]))
+for tl in range(4):
+    print(f"tile {tl + 1} acc ready     ", stat(rel[:, 1 + 2 * tl]), "  epilogue done", stat(rel[:, 2 + 2 * tl]), "  duration", stat(rel[:, 2 + 2 * tl] - rel[:, 1 + 2 * tl]))
+print("after the last item  ", stat(rel[:, 15]))

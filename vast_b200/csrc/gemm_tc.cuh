@@ -31,13 +31,13 @@ namespace tc {
 // -DVAST_EPI_TRACE (developer builds only, scripts/epi_trace.py): per-CTA %globaltimer stamps of the epilogue's phases --
 // [0] roles start, [1 + 2 t] accumulator of the CTA's t-th tile ready, [2 + 2 t] its epilogue done, [15] after finish().
 #ifdef VAST_EPI_TRACE
-__device__ unsigned long long g_epi_trace[1024 * 16];
-__device__ __forceinline__ void epi_trace(int slot) {
+__device__ unsigned long long g_epi_trace[2 * 1024 * 16];  // [epilogues with a tile_end hook (symmetric S GEMM) ? 1 : 0][CTA][slot]
+__device__ __forceinline__ void epi_trace(int slot, int tag) {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  if (blockIdx.x < 1024 && slot < 16) g_epi_trace[blockIdx.x * 16 + slot] = t;
+  if (blockIdx.x < 1024 && slot < 16) g_epi_trace[(tag * 1024 + blockIdx.x) * 16 + slot] = t;
 }
-#define VAST_TRACE(cond, slot) do { if (cond) ::vast::tc::epi_trace(slot); } while (0)
+#define VAST_TRACE(cond, slot) do { if (cond) ::vast::tc::epi_trace(slot, HasTileEnd<Epi>::value ? 1 : 0); } while (0)
 #else
 #define VAST_TRACE(cond, slot) do { } while (0)
 #endif
@@ -618,7 +618,7 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
           // software pipeline: the next chunk's global operands are requested before this chunk's wait
           epi.advance(ctx, col_tile + col_in_tile + 32, c + 32 < cpw);
           ptx::tmem_ld_wait();
-          VAST_TRACE(ew == 0 && lane == 0 && trace_tile == 1 && c < 128, 5 + 2 * (c >> 5));
+          VAST_TRACE(!HasTileEnd<Epi>::value && ew == 0 && lane == 0 && trace_tile == 1 && c < 128, 5 + 2 * (c >> 5));
           if constexpr (KS == 2) {  // + the other half of K, in a fixed order
             const float4* part = reinterpret_cast<const float4*>(smem + L::RING_OFFSET) + ((col_in_tile >> 5) * 8 * 128 + q * 32 + lane);
 #pragma unroll
@@ -631,7 +631,7 @@ gemm_tc_kernel(const __grid_constant__ KernelParams<typename Epi::Params> P) {
             }
           }
           epi.chunk(ctx, v, col_tile + col_in_tile);
-          VAST_TRACE(ew == 0 && lane == 0 && trace_tile == 1 && c < 128, 6 + 2 * (c >> 5));
+          VAST_TRACE(!HasTileEnd<Epi>::value && ew == 0 && lane == 0 && trace_tile == 1 && c < 128, 6 + 2 * (c >> 5));
           __syncwarp();
         }
         if constexpr (HasSecondPass<Epi>::value) {

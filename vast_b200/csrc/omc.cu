@@ -2511,9 +2511,10 @@ extern "C" int vast_omc_step_local(const void* feat_t, const void* feat_cond, in
 
 #ifdef VAST_EPI_TRACE
 // developer builds only: copy the per-CTA epilogue time stamps (gemm_tc.cuh) of the last GEMM launches of THIS translation unit (the contrastive step's) to the host
-extern "C" __attribute__((visibility("default"))) int vast_debug_epi_trace(unsigned long long* out, int ctas) {
+extern "C" __attribute__((visibility("default"))) int vast_debug_epi_trace(unsigned long long* out, int ctas, int tag) {
   if (ctas > 1024) ctas = 1024;
   cudaDeviceSynchronize();
-  return cudaMemcpyFromSymbol(out, vast::tc::g_epi_trace, sizeof(unsigned long long) * 16 * ctas) == cudaSuccess ? 0 : -1;
+  return cudaMemcpyFromSymbol(out, vast::tc::g_epi_trace, sizeof(unsigned long long) * 16 * ctas,
+                              sizeof(unsigned long long) * 16 * 1024 * (tag ? 1 : 0)) == cudaSuccess ? 0 : -1;
 }
 #endif
