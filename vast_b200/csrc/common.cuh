@@ -61,6 +61,18 @@ void timing_end(int slot, cudaStream_t stream);
 // Programmatic dependent launch: a kernel launched with the attribute may begin (barrier / TMEM set-up, descriptor
 // prefetch) while its predecessor in the stream drains; it must execute pdl_wait() before touching anything a
 // predecessor wrote.  pdl_trigger() lets the successor start launching once every CTA of this grid has reached it.
+// 256-bit global store (sm_100: STG.E.ENL2.256): a thread that owns a row segment writes a whole 32-byte sector per
+// instruction.  The address must be 32-byte aligned.
+__device__ __forceinline__ void st_global_v8_b32(void* p, const uint4& lo, const uint4& hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w),
+               "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_global_v8_f32(void* p, const float (&g)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(g[0]), "f"(g[1]), "f"(g[2]), "f"(g[3]),
+               "f"(g[4]), "f"(g[5]), "f"(g[6]), "f"(g[7])
+               : "memory");
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool pdl_enabled();

@@ -305,16 +305,22 @@ struct EpiSoft {
     if (p.P != nullptr && c.row_valid) {
       __half* dst = p.P + (static_cast<int64_t>(c.prob) * c.M + c.row) * p.ldp + col0;
       if (nvalid >= 32) {
+        uint4 u[4];
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
-          uint4 u;
-          uint32_t* w = &u.x;
+          uint32_t* w = &u[i >> 3].x;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const __half2 h = __floats2half2_rn(pr[i + 2 * j], pr[i + 2 * j + 1]);
             w[j] = *reinterpret_cast<const uint32_t*>(&h);
           }
-          *reinterpret_cast<uint4*>(dst + i) = u;
+        }
+        if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {  // the row's 64 bytes as two full sectors
+          st_global_v8_b32(dst, u[0], u[1]);
+          st_global_v8_b32(dst + 16, u[2], u[3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dst + 8 * i) = u[i];
         }
       } else {
 #pragma unroll
@@ -955,6 +961,7 @@ struct EpiGrad {
   uint4 nq[4], nk[4];  // operands of the NEXT chunk (requested one chunk ahead)
   uint4 cq[4], ck[4];  // operands of the current chunk
   bool cur_ok, nxt_ok;
+  bool wide;  // the gradient row is 32-byte aligned: 256-bit stores
   __device__ EpiGrad(const Params& p_, uint8_t* smem) : p(p_), red(reinterpret_cast<float*>(smem)) {
     const float inv_tau = p.temp_dev ? 1.0f / __ldg(p.temp_dev) : p.inv_tau;
     gs = inv_tau;  // scaled by 1 / (2 M) per chunk (M comes with the item)
@@ -1097,6 +1104,7 @@ struct EpiGrad {
     qrow = prow + (c.prob == 0 ? p.D : 0);  // this direction's query row
     krow = prow + (c.prob == 0 ? 0 : p.D);  // the positive row of the gathered side
     grow = (c.prob == 0 ? p.grad_cond : p.grad_t) + static_cast<int64_t>(row) * p.D;
+    wide = (reinterpret_cast<uintptr_t>(grow) & 31) == 0;
   }
   __device__ __forceinline__ void request(const tc::ItemCtx& c, int col0) {
     nxt_ok = c.row_valid && col0 + 32 <= c.N;
@@ -1143,8 +1151,12 @@ struct EpiGrad {
           dots = fmaf(q[j], sv[j], dots);
           g[j] = g1 * (fmaf(rho, a, c_t * k[j]) - p.c_sm * sv[j]);
         }
-        *reinterpret_cast<float4*>(grow + col0 + i) = make_float4(g[0], g[1], g[2], g[3]);
-        *reinterpret_cast<float4*>(grow + col0 + i + 4) = make_float4(g[4], g[5], g[6], g[7]);
+        if (wide) {  // eight columns = one full 32-byte sector per instruction
+          st_global_v8_f32(grow + col0 + i, g);
+        } else {
+          *reinterpret_cast<float4*>(grow + col0 + i) = make_float4(g[0], g[1], g[2], g[3]);
+          *reinterpret_cast<float4*>(grow + col0 + i + 4) = make_float4(g[4], g[5], g[6], g[7]);
+        }
       }
     } else {
 #pragma unroll
