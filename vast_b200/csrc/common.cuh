@@ -73,6 +73,11 @@ __device__ __forceinline__ void st_global_v8_f32(void* p, const float (&g)[8]) {
                "f"(g[4]), "f"(g[5]), "f"(g[6]), "f"(g[7])
                : "memory");
 }
+__device__ __forceinline__ void ld_global_v8_b32(const void* p, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(p));
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool pdl_enabled();

@@ -962,6 +962,7 @@ struct EpiGrad {
   uint4 cq[4], ck[4];  // operands of the current chunk
   bool cur_ok, nxt_ok;
   bool wide;  // the gradient row is 32-byte aligned: 256-bit stores
+  bool wide_in;
   __device__ EpiGrad(const Params& p_, uint8_t* smem) : p(p_), red(reinterpret_cast<float*>(smem)) {
     const float inv_tau = p.temp_dev ? 1.0f / __ldg(p.temp_dev) : p.inv_tau;
     gs = inv_tau;  // scaled by 1 / (2 M) per chunk (M comes with the item)
@@ -1105,14 +1106,23 @@ struct EpiGrad {
     krow = prow + (c.prob == 0 ? 0 : p.D);  // the positive row of the gathered side
     grow = (c.prob == 0 ? p.grad_cond : p.grad_t) + static_cast<int64_t>(row) * p.D;
     wide = (reinterpret_cast<uintptr_t>(grow) & 31) == 0;
+    wide_in = ((reinterpret_cast<uintptr_t>(qrow) | reinterpret_cast<uintptr_t>(krow)) & 31) == 0;
   }
   __device__ __forceinline__ void request(const tc::ItemCtx& c, int col0) {
     nxt_ok = c.row_valid && col0 + 32 <= c.N;
     if (nxt_ok) {
+      if (wide_in) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        nq[i] = *reinterpret_cast<const uint4*>(qrow + col0 + 8 * i);
-        nk[i] = *reinterpret_cast<const uint4*>(krow + col0 + 8 * i);
+        for (int i = 0; i < 4; i += 2) {
+          ld_global_v8_b32(qrow + col0 + 8 * i, nq[i], nq[i + 1]);
+          ld_global_v8_b32(krow + col0 + 8 * i, nk[i], nk[i + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          nq[i] = *reinterpret_cast<const uint4*>(qrow + col0 + 8 * i);
+          nk[i] = *reinterpret_cast<const uint4*>(krow + col0 + 8 * i);
+        }
       }
     }
   }
