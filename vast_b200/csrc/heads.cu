@@ -107,7 +107,9 @@ struct EpiProj {
     const bool vec = (col0 + 32 <= c.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
                      (d16 == nullptr || (reinterpret_cast<uintptr_t>(d16) & 15) == 0) &&
                      (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0);
+    const bool wide = ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) && (d16 == nullptr || (reinterpret_cast<uintptr_t>(d16) & 31) == 0);
     if (vec) {
+      uint4 u16[4];
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
         float o[8];
@@ -119,18 +121,25 @@ struct EpiProj {
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = (__uint_as_float(v[i + j]) + bb[j]) * inv;
-        *reinterpret_cast<float4*>(dst + i) = make_float4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<float4*>(dst + i + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        if (wide) {  // whole 32-byte sectors per instruction (row-per-thread stores)
+          st_global_v8_f32(dst + i, o);
+        } else {
+          *reinterpret_cast<float4*>(dst + i) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(dst + i + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
         if (d16 != nullptr) {
-          uint4 u;
-          uint32_t* w = &u.x;
+          uint32_t* w = &u16[i >> 3].x;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
             w[j] = *reinterpret_cast<const uint32_t*>(&h);
           }
-          *reinterpret_cast<uint4*>(d16 + i) = u;
+          if (!wide) *reinterpret_cast<uint4*>(d16 + i) = u16[i >> 3];
         }
+      }
+      if (wide && d16 != nullptr) {
+        st_global_v8_b32(d16, u16[0], u16[1]);
+        st_global_v8_b32(d16 + 16, u16[2], u16[3]);
       }
     } else {
 #pragma unroll
